@@ -1,0 +1,66 @@
+"""ctypes binding of include/evab200.h (the same stub a reference maintainer
+would write).  Fails loudly when the CUDA library is
+missing; never falls back to a CPU implementation."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libevab200.so")
+_lib = None
+
+vp, u64, szt, ci = C.c_void_p, C.c_uint64, C.c_size_t, C.c_int
+u64p = C.POINTER(C.c_uint64)
+
+_SIGS = {
+    "evab_last_error": (C.c_char_p, []),
+    "evab_version": (ci, []),
+    "evab_ctx_create": (ci, [u64, u64p, ci, ci, C.POINTER(vp)]),
+    "evab_ctx_destroy": (None, [vp]),
+    "evab_ctx_N": (u64, [vp]),
+    "evab_ctx_k": (ci, [vp]),
+    "evab_ctx_device": (ci, [vp]),
+    "evab_ctx_sm_count": (ci, [vp]),
+    "evab_malloc": (ci, [vp, szt, C.POINTER(vp), vp]),
+    "evab_free": (ci, [vp, vp, vp]),
+    "evab_upload": (ci, [vp, vp, vp, szt, vp]),
+    "evab_download": (ci, [vp, vp, vp, szt, vp]),
+    "evab_sync": (ci, [vp, vp]),
+    "evab_ntt_fwd": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
+    "evab_ntt_inv": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
+    "evab_add": (ci, [vp, ci, vp, vp, ci, vp, ci, vp]),
+    "evab_sub": (ci, [vp, ci, vp, vp, ci, vp, ci, vp]),
+    "evab_add_plain": (ci, [vp, ci, vp, vp, ci, vp, vp]),
+    "evab_sub_plain": (ci, [vp, ci, vp, vp, ci, vp, vp]),
+    "evab_negate": (ci, [vp, ci, vp, vp, ci, vp]),
+    "evab_mul_plain": (ci, [vp, ci, vp, vp, ci, vp, vp]),
+    "evab_mul": (ci, [vp, ci, vp, vp, vp, vp]),
+    "evab_square": (ci, [vp, ci, vp, vp, vp]),
+    "evab_rescale_work_bytes": (szt, [vp, ci]),
+    "evab_rescale": (ci, [vp, ci, vp, vp, ci, vp, vp]),
+    "evab_mod_switch": (ci, [vp, ci, vp, vp, ci, vp]),
+    "evab_keyswitch_work_bytes": (szt, [vp, ci]),
+    "evab_relinearize": (ci, [vp, ci, vp, vp, vp, vp, vp]),
+    "evab_galois_elt_from_step": (u64, [u64, ci]),
+    "evab_galois_prepare": (ci, [vp, u64]),
+    "evab_rotate": (ci, [vp, ci, vp, vp, u64, vp, vp, vp]),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "eva_b200: CUDA library %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,368 @@
+// evab200.cu -- C-ABI implementation (include/evab200.h): CUDA backend for the
+// op compositions in ops_impl.hpp, sm_100a kernels around the bodies in
+// ntt_kernels.cuh / ops_kernels.cuh.  Product code: never includes or links
+// anything under oracle/.
+#include "../../include/evab200.h"
+#include "host_tables.hpp"
+#include "ops_impl.hpp"
+#include <cuda_runtime.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return 1; }
+#define CUDA_OK(x)                                                                       \
+  do {                                                                                   \
+    cudaError_t e_ = (x);                                                                \
+    if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" const char *evab_last_error(void) { return g_err.c_str(); }
+extern "C" int evab_version(void) { return 1; }
+
+struct evab_ctx {
+  CtxView v;
+  int device, sms;
+  std::vector<u64> primes;
+  PrimeDev *d_primes = nullptr;
+  u64x2 *d_tw = nullptr;
+  u64x2 *d_qinv = nullptr;
+  u64 *d_halfmod = nullptr;
+  u64 *d_zeros = nullptr;
+  std::map<u64, u32 *> perms;  // galois elt -> device permutation table
+  std::mutex mu;
+};
+static cudaStream_t S(void *s) { return (cudaStream_t)s; }
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+template <int LOGN, bool SPLIT, int PRO, int EPI>
+__global__ void __launch_bounds__(NttGeom<LOGN>::T, 512 / NttGeom<LOGN>::T) k_ntt_fwd(const NttLaunch L) {
+  extern __shared__ __align__(16) u64 sm[];
+  typedef FwdBody<LOGN, SPLIT, PRO, EPI> B;
+  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1);
+  if (J.skip) return;
+  NttState S;
+  const u32 tid = threadIdx.x;
+  B::ph0(S, L, J, tid, sm);
+  __syncthreads();
+  B::ph1(S, L, J, tid, sm);
+  if (B::NPH == 4) {
+    __syncthreads();
+    B::ph2(S, L, J, tid, sm);
+    __syncthreads();
+    B::ph3(S, L, J, tid, sm);
+  }
+  if (SPLIT) {  // CTA pair (cluster of 2): both halves have consumed the input
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  }
+  B::phE(S, L, J, tid);
+}
+template <int LOGN, bool SPLIT, int PRO, int EPI>
+__global__ void __launch_bounds__(NttGeom<LOGN>::T, 512 / NttGeom<LOGN>::T) k_ntt_inv(const NttLaunch L) {
+  extern __shared__ __align__(16) u64 sm[];
+  typedef InvBody<LOGN, SPLIT, PRO, EPI> B;
+  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1);
+  if (J.skip) return;
+  NttState S;
+  const u32 tid = threadIdx.x;
+  B::ph0(S, L, J, tid, sm);
+  __syncthreads();
+  B::ph1(S, L, J, tid, sm);
+  if (B::NPH == 4) {
+    __syncthreads();
+    B::ph2(S, L, J, tid, sm);
+    __syncthreads();
+    B::ph3(S, L, J, tid, sm);
+  }
+}
+__global__ void __launch_bounds__(256) k_inv_last_stage(const NttLaunch L, u32 half_n) {
+  const NttJob J = ntt_job(L, blockIdx.y, 1);
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < half_n) inv_last_stage_elem(L, J, i, half_n);
+}
+template <int OP> __global__ void __launch_bounds__(256) k_dyadic(const DyArgs A) {
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
+    dyadic_elem<OP>(A, blockIdx.y, j);
+}
+template <bool SQ> __global__ void __launch_bounds__(256) k_mul_ct(const MulArgs A) {
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
+    mulct_elem<SQ>(A, blockIdx.y, j);
+}
+__global__ void __launch_bounds__(256) k_ks_inner(const IpArgs A) {
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
+    ks_inner_elem(A, blockIdx.y, j);
+}
+__global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, const u32 *perm, int N) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
+    galois_perm_elem(out, in, perm, N, blockIdx.y, j);
+}
+
+// ---------------------------------------------------------------------------
+// CUDA backend
+// ---------------------------------------------------------------------------
+template <int LOGN, bool SPLIT, int PRO, int EPI> static int launch_fwd_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  const size_t smem = (size_t)NttGeom<LOGN>::N * sizeof(u64);
+  CUDA_OK(cudaFuncSetAttribute(k_ntt_fwd<LOGN, SPLIT, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(jobs * (SPLIT ? 2 : 1)));
+  cfg.blockDim = dim3(NttGeom<LOGN>::T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = SPLIT ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, k_ntt_fwd<LOGN, SPLIT, PRO, EPI>, L));
+  return 0;
+}
+template <int LOGN, bool SPLIT> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_PLAIN, EPI_STORE>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_DIVROUND>(L, jobs, st);
+  return fail("unsupported forward NTT prologue/epilogue combination");
+}
+template <int LOGN, bool SPLIT, int EPI> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  const size_t smem = (size_t)NttGeom<LOGN>::N * sizeof(u64);
+  CUDA_OK(cudaFuncSetAttribute(k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI><<<(unsigned)(jobs * (SPLIT ? 2 : 1)), NttGeom<LOGN>::T, smem, st>>>(L);
+  CUDA_OK(cudaGetLastError());
+  if (SPLIT) {
+    const u32 half = NttGeom<LOGN>::N;
+    dim3 g((half + 255) / 256, (unsigned)jobs);
+    k_inv_last_stage<<<g, 256, 0, st>>>(L, half);
+    CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+template <int LOGN, bool SPLIT> static int launch_inv_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  if (L.pro != PRO_PLAIN) return fail("unsupported inverse NTT prologue");
+  if (L.epi == EPI_STORE) return launch_inv_m<LOGN, SPLIT, EPI_STORE>(L, jobs, st);
+  if (L.epi == EPI_ADDHALF) return launch_inv_m<LOGN, SPLIT, EPI_ADDHALF>(L, jobs, st);
+  return fail("unsupported inverse NTT epilogue");
+}
+
+struct CudaBE {
+  const evab_ctx *c;
+  cudaStream_t st;
+  int error(const char *m) { return fail(m); }
+  dim3 grid(int rows) const {
+    int per_row = (int)(c->v.N / 2 / 256);
+    if (per_row < 1) per_row = 1;
+    return dim3(per_row, rows);
+  }
+  int fwd(const NttLaunch &L, size_t jobs) {
+    switch (c->v.logN) {
+      case 10: return launch_fwd_t<10, false>(L, jobs, st);
+      case 11: return launch_fwd_t<11, false>(L, jobs, st);
+      case 12: return launch_fwd_t<12, false>(L, jobs, st);
+      case 13: return launch_fwd_t<13, false>(L, jobs, st);
+      case 14: return launch_fwd_t<14, false>(L, jobs, st);
+      case 15: return launch_fwd_t<14, true>(L, jobs, st);
+    }
+    return fail("unsupported N");
+  }
+  int inv(const NttLaunch &L, size_t jobs) {
+    switch (c->v.logN) {
+      case 10: return launch_inv_t<10, false>(L, jobs, st);
+      case 11: return launch_inv_t<11, false>(L, jobs, st);
+      case 12: return launch_inv_t<12, false>(L, jobs, st);
+      case 13: return launch_inv_t<13, false>(L, jobs, st);
+      case 14: return launch_inv_t<14, false>(L, jobs, st);
+      case 15: return launch_inv_t<14, true>(L, jobs, st);
+    }
+    return fail("unsupported N");
+  }
+  int dyadic(int op, const DyArgs &A) {
+    dim3 g = grid(A.sout * A.ell);
+    switch (op) {
+      case DY_ADD: k_dyadic<DY_ADD><<<g, 256, 0, st>>>(A); break;
+      case DY_SUB: k_dyadic<DY_SUB><<<g, 256, 0, st>>>(A); break;
+      case DY_NEG: k_dyadic<DY_NEG><<<g, 256, 0, st>>>(A); break;
+      default: k_dyadic<DY_MULPT><<<g, 256, 0, st>>>(A); break;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int mulct(bool sq, const MulArgs &A) {
+    if (sq) k_mul_ct<true><<<grid(A.ell), 256, 0, st>>>(A);
+    else k_mul_ct<false><<<grid(A.ell), 256, 0, st>>>(A);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int inner(const IpArgs &A) {
+    k_ks_inner<<<grid(A.ell + 1), 256, 0, st>>>(A);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int perm(u64 *out, const u64 *in, const u32 *p, int N, int rows) {
+    dim3 g((unsigned)((N + 255) / 256), rows);
+    k_galois_perm<<<g, 256, 0, st>>>(out, in, p, N);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" int evab_ctx_create(uint64_t N, const uint64_t *primes, int k, int device, evab_ctx **out) {
+  if (!out) return fail("evab_ctx_create: null out");
+  *out = nullptr;
+  int logN = 0;
+  while ((1ull << logN) < N) logN++;
+  if ((1ull << logN) != N || logN < 10 || logN > 15) return fail("evab_ctx_create: N must be a power of two in [2^10, 2^15]");
+  if (k < 1 || k > 24) return fail("evab_ctx_create: prime count must be in [1,24]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("evab_ctx_create: no CUDA device (this backend has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("evab_ctx_create: bad device index");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  cudaMemPool_t pool;
+  CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long thresh = ~0ull;  // keep freed blocks cached in the pool
+  cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+
+  evab_ctx *c = new evab_ctx();
+  c->device = device; c->sms = prop.multiProcessorCount;
+  c->primes.assign(primes, primes + k);
+  const size_t tw_elems = (size_t)k * 2 * N;
+  if (cudaMalloc(&c->d_tw, tw_elems * sizeof(u64x2)) != cudaSuccess) { delete c; return fail("cudaMalloc failed"); }
+  evab_host::Tables T;
+  const char *err = evab_host::build_tables(N, logN, primes, k, c->d_tw, T);
+  if (err[0]) { cudaFree(c->d_tw); delete c; return fail(std::string("evab_ctx_create: ") + err); }
+  CUDA_OK(cudaMemcpy(c->d_tw, T.tw.data(), tw_elems * sizeof(u64x2), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&c->d_primes, k * sizeof(PrimeDev)));
+  CUDA_OK(cudaMemcpy(c->d_primes, T.pd.data(), k * sizeof(PrimeDev), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&c->d_qinv, T.qinv.size() * sizeof(u64x2)));
+  CUDA_OK(cudaMemcpy(c->d_qinv, T.qinv.data(), T.qinv.size() * sizeof(u64x2), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&c->d_halfmod, T.halfmod.size() * sizeof(u64)));
+  CUDA_OK(cudaMemcpy(c->d_halfmod, T.halfmod.data(), T.halfmod.size() * sizeof(u64), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&c->d_zeros, 32 * sizeof(u64)));
+  CUDA_OK(cudaMemset(c->d_zeros, 0, 32 * sizeof(u64)));
+  c->v.N = N; c->v.logN = logN; c->v.k = k;
+  c->v.primes = c->d_primes; c->v.qinv = c->d_qinv; c->v.halfmod = c->d_halfmod; c->v.zeros = c->d_zeros;
+  *out = c;
+  return 0;
+}
+extern "C" void evab_ctx_destroy(evab_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto &kv : c->perms) cudaFree(kv.second);
+  cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_qinv); cudaFree(c->d_halfmod); cudaFree(c->d_zeros);
+  delete c;
+}
+extern "C" uint64_t evab_ctx_N(const evab_ctx *c) { return c->v.N; }
+extern "C" int evab_ctx_k(const evab_ctx *c) { return c->v.k; }
+extern "C" int evab_ctx_device(const evab_ctx *c) { return c->device; }
+extern "C" int evab_ctx_sm_count(const evab_ctx *c) { return c->sms; }
+
+extern "C" int evab_malloc(evab_ctx *c, size_t bytes, void **p, void *stream) {
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaMallocAsync(p, bytes ? bytes : 8, S(stream)));
+  return 0;
+}
+extern "C" int evab_free(evab_ctx *c, void *p, void *stream) {
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaFreeAsync(p, S(stream)));
+  return 0;
+}
+extern "C" int evab_upload(evab_ctx *c, void *d, const void *h, size_t bytes, void *stream) {
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, S(stream)));
+  return 0;
+}
+extern "C" int evab_download(evab_ctx *c, void *h, const void *d, size_t bytes, void *stream) {
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, S(stream)));
+  return 0;
+}
+extern "C" int evab_sync(evab_ctx *c, void *stream) {
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamSynchronize(S(stream)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// ops
+// ---------------------------------------------------------------------------
+#define BE_BEGIN                         \
+  CUDA_OK(cudaSetDevice(c->device));     \
+  CudaBE be{c, S(stream)};
+
+extern "C" int evab_ntt_fwd(evab_ctx *c, uint64_t *d, size_t count, const int *pidx, int np, void *stream) {
+  BE_BEGIN return ntt_batch_impl(be, c->v, false, d, count, pidx, np);
+}
+extern "C" int evab_ntt_inv(evab_ctx *c, uint64_t *d, size_t count, const int *pidx, int np, void *stream) {
+  BE_BEGIN return ntt_batch_impl(be, c->v, true, d, count, pidx, np);
+}
+extern "C" int evab_add(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *b, int sb, void *stream) {
+  BE_BEGIN return dyadic_impl<DY_ADD>(be, c->v, ell, o, a, sa, b, sb, 0);
+}
+extern "C" int evab_sub(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *b, int sb, void *stream) {
+  BE_BEGIN return dyadic_impl<DY_SUB>(be, c->v, ell, o, a, sa, b, sb, 0);
+}
+extern "C" int evab_add_plain(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt, void *stream) {
+  BE_BEGIN return dyadic_impl<DY_ADD>(be, c->v, ell, o, a, sa, pt, 1, 1);
+}
+extern "C" int evab_sub_plain(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt, void *stream) {
+  BE_BEGIN return dyadic_impl<DY_SUB>(be, c->v, ell, o, a, sa, pt, 1, 1);
+}
+extern "C" int evab_negate(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, void *stream) {
+  BE_BEGIN return dyadic_impl<DY_NEG>(be, c->v, ell, o, a, sa, (const u64 *)nullptr, 0, 0);
+}
+extern "C" int evab_mul_plain(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt, void *stream) {
+  BE_BEGIN return dyadic_impl<DY_MULPT>(be, c->v, ell, o, a, sa, pt, 1, 1);
+}
+extern "C" int evab_mul(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *b, void *stream) {
+  BE_BEGIN return mulct_impl(be, c->v, false, ell, o, a, b);
+}
+extern "C" int evab_square(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, void *stream) {
+  BE_BEGIN return mulct_impl(be, c->v, true, ell, o, a, (const u64 *)nullptr);
+}
+extern "C" int evab_mod_switch(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, void *stream) {
+  if (ell < 2 || ell > c->v.k) return fail("mod_switch needs 2 <= ell <= k");
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t row = (size_t)(ell - 1) * c->v.N * 8;
+  CUDA_OK(cudaMemcpy2DAsync(o, row, a, (size_t)ell * c->v.N * 8, row, sa, cudaMemcpyDeviceToDevice, S(stream)));
+  return 0;
+}
+extern "C" size_t evab_rescale_work_bytes(const evab_ctx *c, int sa) { return rescale_work_elems(c->v, sa) * sizeof(u64); }
+extern "C" int evab_rescale(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, void *work, void *stream) {
+  BE_BEGIN return rescale_impl(be, c->v, ell, o, a, sa, (u64 *)work);
+}
+extern "C" size_t evab_keyswitch_work_bytes(const evab_ctx *c, int ell) { return keyswitch_work_elems(c->v, ell) * sizeof(u64); }
+extern "C" int evab_relinearize(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *key, void *work, void *stream) {
+  BE_BEGIN return relinearize_impl(be, c->v, ell, o, a, key, (u64 *)work);
+}
+extern "C" uint64_t evab_galois_elt_from_step(uint64_t N, int steps) { return evab_host::galois_elt_from_step(N, steps); }
+extern "C" int evab_galois_prepare(evab_ctx *c, uint64_t elt) {
+  if (!(elt & 1) || elt >= 2 * c->v.N) return fail("galois element must be odd and < 2N");
+  std::lock_guard<std::mutex> g(c->mu);
+  if (c->perms.count(elt)) return 0;
+  CUDA_OK(cudaSetDevice(c->device));
+  std::vector<u32> tab;
+  evab_host::galois_table(c->v.N, c->v.logN, elt, tab);
+  u32 *d = nullptr;
+  CUDA_OK(cudaMalloc(&d, tab.size() * sizeof(u32)));
+  CUDA_OK(cudaMemcpy(d, tab.data(), tab.size() * sizeof(u32), cudaMemcpyHostToDevice));
+  c->perms[elt] = d;
+  return 0;
+}
+extern "C" int evab_rotate(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, uint64_t elt, const uint64_t *key, void *work, void *stream) {
+  u32 *perm = nullptr;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->perms.find(elt);
+    if (it == c->perms.end()) return fail("evab_rotate: call evab_galois_prepare(elt) first");
+    perm = it->second;
+  }
+  BE_BEGIN return rotate_impl(be, c->v, ell, o, a, perm, key, (u64 *)work);
+}

@@ -1,0 +1,164 @@
+// ops_impl.hpp -- composition of the evaluator ops out of kernel launches,
+// templated on a backend (CUDA launches in evab200.cu; serial replay in the
+// CPU emulator used by the tests).  Each function names the SEAL call it
+// replaces at the reference call site in eva/seal/seal_executor.h.
+#pragma once
+#include "ntt_kernels.cuh"
+#include "ops_kernels.cuh"
+#include <cstring>
+
+struct CtxView {
+  u64 N; int logN, k;
+  const PrimeDev *primes;   // [k]
+  const u64x2 *qinv;        // [k][k]
+  const u64 *halfmod;       // [k][k]
+  const u64 *zeros;         // [k]
+};
+
+// Backend concept:
+//   int fwd(const NttLaunch&, size_t jobs);  int inv(const NttLaunch&, size_t jobs);
+//   int dyadic(int op, const DyArgs&);       int mulct(bool square, const MulArgs&);
+//   int inner(const IpArgs&);                int perm(u64*, const u64*, const u32*, int N, int rows);
+//   int drop_last(u64* out, const u64* in, int ell, int polys, u64 N);
+//   int error(const char*);
+
+inline NttLaunch base_launch(const CtxView &c) {
+  NttLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.primes = c.primes;
+  L.inner = 1;
+  return L;
+}
+
+template <class BE>
+int ntt_batch_impl(BE &be, const CtxView &c, bool inverse, u64 *d, size_t count, const int *pidx, int np) {
+  if (np < 1 || np > 32) return be.error("evab_ntt: nprimes must be in [1,32]");
+  if (count % np) return be.error("evab_ntt: count must be a multiple of nprimes");
+  NttLaunch L = base_launch(c);
+  L.src = d; L.dst = d;
+  L.inner = np;
+  L.src_sq = L.dst_sq = (long long)np * c.N;
+  L.src_sr = L.dst_sr = (long long)c.N;
+  for (int i = 0; i < np; i++) {
+    if (pidx[i] < 0 || pidx[i] >= c.k) return be.error("evab_ntt: prime index out of range");
+    L.pmap[i] = (unsigned char)pidx[i];
+  }
+  return inverse ? be.inv(L, count) : be.fwd(L, count);
+}
+
+template <int OP, class BE>
+int dyadic_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, int sa, const u64 *b, int sb, int plain) {
+  if (ell < 1 || ell > c.k) return be.error("ell out of range");
+  if (sa < 1 || sa > 3 || (b && !plain && (sb < 1 || sb > 3))) return be.error("ciphertext size must be 1..3");
+  DyArgs A;
+  A.out = out; A.a = a; A.b = b; A.primes = c.primes; A.ell = ell; A.N = (int)c.N;
+  A.sa = sa; A.sb = sb; A.b_is_plain = plain;
+  A.sout = (plain || !b) ? sa : (sa > sb ? sa : sb);
+  return be.dyadic(OP, A);
+}
+
+template <class BE> int mulct_impl(BE &be, const CtxView &c, bool square, int ell, u64 *out, const u64 *a, const u64 *b) {
+  if (ell < 1 || ell > c.k) return be.error("ell out of range");
+  MulArgs A;
+  A.out = out; A.a = a; A.b = b; A.primes = c.primes; A.ell = ell; A.N = (int)c.N;
+  return be.mulct(square, A);
+}
+
+// RNS divide-and-round by the last residue's prime (SEAL
+// RNSTool::divide_and_round_q_last_ntt_inplace; Appendix A.6), shared by
+// rescale and the key-switch mod-down.  Poly q (< npoly) of `in` has `nres`
+// residues: prime indices pm[0..nres-2] followed by the divisor `last`.
+//   out[q][r] = (in[q][r] - NTT((iNTT(in[q][last]) + h) mod q_last mod q_r - h mod q_r)) * q_last^-1  (+ add[q][r])
+template <class BE>
+int divround_impl(BE &be, const CtxView &c, const u64 *in, long long in_poly_stride, int npoly, int nres, const unsigned char *pm,
+                  int last, u64 *out, long long out_poly_stride, const u64 *add, long long add_poly_stride, u64 *tmp) {
+  const long long N = (long long)c.N;
+  NttLaunch A = base_launch(c);
+  A.src = in + (long long)(nres - 1) * N; A.dst = tmp;
+  A.src_sq = in_poly_stride; A.dst_sq = N; A.inner = 1; A.prime_on_q = 1;
+  for (int q = 0; q < npoly; q++) A.pmap[q] = (unsigned char)last;
+  A.epi = EPI_ADDHALF;
+  if (int rc = be.inv(A, npoly)) return rc;
+  NttLaunch B = base_launch(c);
+  B.src = tmp; B.src_sq = N; B.src_sr = 0;
+  B.aux0 = in; B.aux0_sq = in_poly_stride; B.aux0_sr = N;
+  B.aux1 = add; B.aux1_sq = add_poly_stride; B.aux1_sr = N;
+  B.dst = out; B.dst_sq = out_poly_stride; B.dst_sr = N;
+  B.inner = nres - 1; B.prime_on_q = 0;
+  for (int r = 0; r < nres - 1; r++) B.pmap[r] = pm[r];
+  B.pro = PRO_MODRED; B.epi = EPI_DIVROUND;
+  B.subtab = c.halfmod + (size_t)last * c.k;
+  B.consts = c.qinv + (size_t)last * c.k;
+  return be.fwd(B, (size_t)npoly * (nres - 1));
+}
+
+inline size_t rescale_work_elems(const CtxView &c, int sa) { return (size_t)sa * c.N; }
+
+// Evaluator::rescale_to_next -- reference eva/seal/seal_executor.h:213
+template <class BE> int rescale_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, int sa, u64 *work) {
+  if (ell < 2 || ell > c.k) return be.error("rescale needs 2 <= ell <= k");
+  if (sa < 1 || sa > 3) return be.error("ciphertext size must be 1..3");
+  unsigned char pm[32];
+  for (int i = 0; i < ell; i++) pm[i] = (unsigned char)i;
+  const long long N = (long long)c.N;
+  return divround_impl(be, c, a, ell * N, sa, ell, pm, ell - 1, out, (ell - 1) * N, (const u64 *)nullptr, 0, work);
+}
+
+// workspace (in u64): that[ell] + ext[ell+1][ell] + acc[2][ell+1] + tmp[2] + permuted ct [2][ell]
+inline size_t ks_off_ext(const CtxView &c, int ell) { return (size_t)ell * c.N; }
+inline size_t ks_off_acc(const CtxView &c, int ell) { return ks_off_ext(c, ell) + (size_t)(ell + 1) * ell * c.N; }
+inline size_t ks_off_tmp(const CtxView &c, int ell) { return ks_off_acc(c, ell) + (size_t)2 * (ell + 1) * c.N; }
+inline size_t ks_off_pct(const CtxView &c, int ell) { return ks_off_tmp(c, ell) + (size_t)2 * c.N; }
+inline size_t keyswitch_work_elems(const CtxView &c, int ell) { return ks_off_pct(c, ell) + (size_t)2 * ell * c.N; }
+
+// Evaluator::switch_key_inplace (Appendix A.5): out[c][J] = base[c][J] + ks_c[J];
+// base holds `base_polys` (1 or 2) polynomials.
+template <class BE>
+int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, const u64 *key, const u64 *base, int base_polys, u64 *work) {
+  const long long N = (long long)c.N;
+  const int k = c.k, sp = k - 1;
+  if (ell < 1 || ell > k - 1) return be.error("key switching needs 1 <= ell <= k-1");
+  u64 *that = work;
+  u64 *ext = work + ks_off_ext(c, ell);
+  u64 *acc = work + ks_off_acc(c, ell);
+  u64 *tmp = work + ks_off_tmp(c, ell);
+  // 1. digits to coefficient form: that[J] = iNTT_{q_J}(t[J])
+  NttLaunch A = base_launch(c);
+  A.src = t; A.dst = that; A.inner = ell; A.src_sr = A.dst_sr = N;
+  for (int J = 0; J < ell; J++) A.pmap[J] = (unsigned char)J;
+  if (int rc = be.inv(A, ell)) return rc;
+  // 2. ext[m][J] = NTT_m(that[J] mod m) for every output modulus m != q_J
+  NttLaunch B = base_launch(c);
+  B.src = that; B.src_sq = 0; B.src_sr = N;
+  B.dst = ext; B.dst_sq = (long long)ell * N; B.dst_sr = N;
+  B.inner = ell; B.prime_on_q = 1; B.skip_diag = 1; B.pro = PRO_MODRED;
+  B.subtab = c.zeros;
+  for (int mi = 0; mi <= ell; mi++) B.pmap[mi] = (unsigned char)(mi == ell ? sp : mi);
+  for (int J = 0; J < ell; J++) B.pmap2[J] = (unsigned char)J;
+  if (int rc = be.fwd(B, (size_t)(ell + 1) * ell)) return rc;
+  // 3. inner product with the key rows of the live primes and P
+  IpArgs I;
+  I.t = t; I.ext = ext; I.key = key; I.acc = acc; I.primes = c.primes; I.ell = ell; I.k = k; I.N = (int)N;
+  if (int rc = be.inner(I)) return rc;
+  // 4. mod-down by P with rounding, fused with the accumulation into base
+  unsigned char pm[32];
+  for (int i = 0; i < ell; i++) pm[i] = (unsigned char)i;
+  if (base_polys == 2)
+    return divround_impl(be, c, acc, (long long)(ell + 1) * N, 2, ell + 1, pm, sp, out, (long long)ell * N, base, (long long)ell * N, tmp);
+  if (int rc = divround_impl(be, c, acc, 0, 1, ell + 1, pm, sp, out, 0, base, 0, tmp)) return rc;
+  return divround_impl(be, c, acc + (size_t)(ell + 1) * N, 0, 1, ell + 1, pm, sp, out + (size_t)ell * N, 0, (const u64 *)nullptr, 0, tmp + N);
+}
+
+// Evaluator::relinearize (3 -> 2) -- reference eva/seal/seal_executor.h:200
+template <class BE> int relinearize_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, const u64 *key, u64 *work) {
+  return keyswitch_impl(be, c, ell, out, a + (size_t)2 * ell * c.N, key, a, 2, work);
+}
+
+// Evaluator::rotate_vector -> apply_galois_inplace -- seal_executor.h:181,188
+template <class BE>
+int rotate_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, const u32 *perm, const u64 *key, u64 *work) {
+  if (ell < 1 || ell > c.k - 1) return be.error("rotate needs 1 <= ell <= k-1");
+  u64 *pct = work + ks_off_pct(c, ell);
+  if (int rc = be.perm(pct, a, perm, (int)c.N, 2 * ell)) return rc;
+  return keyswitch_impl(be, c, ell, out, pct + (size_t)ell * c.N, key, pct, 1, work);
+}

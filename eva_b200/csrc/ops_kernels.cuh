@@ -1,0 +1,98 @@
+// ops_kernels.cuh -- element-wise (dyadic) ciphertext kernels, the key-switch
+// inner product and the Galois permutation, as __host__ __device__ bodies
+// (two coefficients per call, 128-bit accesses) shared by the CUDA kernels and
+// the CPU emulator.  Semantics: SURVEY.md Appendix A.4 / A.5 / A.8.
+#pragma once
+#include "ntt_core.cuh"
+
+enum { DY_ADD = 0, DY_SUB = 1, DY_NEG = 2, DY_MULPT = 3 };
+
+struct DyArgs {
+  u64 *out; const u64 *a; const u64 *b;
+  const PrimeDev *primes;
+  int ell, N;
+  int sa, sb, sout;  // polys in a / b / out
+  int b_is_plain;    // b = plaintext [ell][N]: add/sub touch poly 0 only, mulpt every poly
+};
+
+EVAB_HD u64x2 ld2(const u64 *p) { return *reinterpret_cast<const u64x2 *>(p); }
+EVAB_HD void st2(u64 *p, u64x2 v) { *reinterpret_cast<u64x2 *>(p) = v; }
+
+// coefficients j, j+1 of output residue `res` (= s*ell + i)
+template <int OP> EVAB_HD void dyadic_elem(const DyArgs &A, int res, int j) {
+  const int s = res / A.ell, i = res % A.ell;
+  const PrimeDev P = A.primes[i];
+  const u64 p = P.p;
+  const size_t off = (size_t)res * A.N;
+  const bool has_a = s < A.sa;
+  const bool has_b = A.b_is_plain ? (OP == DY_MULPT || s == 0) : (s < A.sb);
+  const size_t boff = A.b_is_plain ? (size_t)i * A.N : off;
+  u64x2 va = u64x2{0, 0}, vb = u64x2{0, 0}, r;
+  if (has_a) va = ld2(A.a + off + j);
+  if (OP != DY_NEG && has_b) vb = ld2(A.b + boff + j);
+  if (OP == DY_ADD) { r.x = addmod(va.x, vb.x, p); r.y = addmod(va.y, vb.y, p); }
+  else if (OP == DY_SUB) { r.x = submod(va.x, vb.x, p); r.y = submod(va.y, vb.y, p); }
+  else if (OP == DY_NEG) { r.x = negmod(va.x, p); r.y = negmod(va.y, p); }
+  else { r.x = mulmod(va.x, vb.x, p, P.ratio_lo, P.ratio_hi); r.y = mulmod(va.y, vb.y, p, P.ratio_lo, P.ratio_hi); }
+  st2(A.out + off + j, r);
+}
+
+struct MulArgs { u64 *out; const u64 *a; const u64 *b; const PrimeDev *primes; int ell, N; };
+
+// 2x2 -> 3 tensor product (Evaluator::multiply) or square, residue i, coeffs j,j+1
+template <bool SQUARE> EVAB_HD void mulct_elem(const MulArgs &A, int i, int j) {
+  const PrimeDev P = A.primes[i];
+  const u64 p = P.p, rl = P.ratio_lo, rh = P.ratio_hi;
+  const size_t poly = (size_t)A.ell * A.N, off = (size_t)i * A.N + j;
+  const u64x2 a0 = ld2(A.a + off), a1 = ld2(A.a + poly + off);
+  u64x2 d0, d1, d2;
+  if (SQUARE) {
+    d0.x = mulmod(a0.x, a0.x, p, rl, rh); d0.y = mulmod(a0.y, a0.y, p, rl, rh);
+    u64 x0 = mulmod(a0.x, a1.x, p, rl, rh), x1 = mulmod(a0.y, a1.y, p, rl, rh);
+    d1.x = addmod(x0, x0, p); d1.y = addmod(x1, x1, p);
+    d2.x = mulmod(a1.x, a1.x, p, rl, rh); d2.y = mulmod(a1.y, a1.y, p, rl, rh);
+  } else {
+    const u64x2 b0 = ld2(A.b + off), b1 = ld2(A.b + poly + off);
+    d0.x = mulmod(a0.x, b0.x, p, rl, rh); d0.y = mulmod(a0.y, b0.y, p, rl, rh);
+    // a0*b1 + a1*b0 accumulated in 128 bits, then one reduction: same canonical value
+    u64 lo = 0, hi = 0;
+    mac128(lo, hi, a0.x, b1.x); mac128(lo, hi, a1.x, b0.x); d1.x = barrett128(lo, hi, p, rl, rh);
+    lo = hi = 0;
+    mac128(lo, hi, a0.y, b1.y); mac128(lo, hi, a1.y, b0.y); d1.y = barrett128(lo, hi, p, rl, rh);
+    d2.x = mulmod(a1.x, b1.x, p, rl, rh); d2.y = mulmod(a1.y, b1.y, p, rl, rh);
+  }
+  st2(A.out + off, d0); st2(A.out + poly + off, d1); st2(A.out + 2 * poly + off, d2);
+}
+
+// key-switch inner product over digits (Appendix A.5 step 2):
+// acc[c][m][j] = sum_J opnd(m,J)[j] * key[J][c][row(m)][j] mod m, with
+// opnd(m,J) = t[J] when row(m)==J (the digit's own modulus) else ext[m][J].
+struct IpArgs {
+  const u64 *t, *ext, *key; u64 *acc; const PrimeDev *primes;
+  int ell, k, N;
+};
+EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j) {
+  const int row = (mi == A.ell) ? A.k - 1 : mi;
+  const PrimeDev P = A.primes[row];
+  const size_t N = A.N;
+  u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
+  for (int J = 0; J < A.ell; J++) {
+    const u64 *op = (row == J) ? A.t + (size_t)J * N : A.ext + ((size_t)mi * A.ell + J) * N;
+    const u64x2 v = ld2(op + j);
+    const u64x2 k0 = ld2(A.key + (((size_t)J * 2 + 0) * A.k + row) * N + j);
+    const u64x2 k1 = ld2(A.key + (((size_t)J * 2 + 1) * A.k + row) * N + j);
+    mac128(l0x, h0x, v.x, k0.x); mac128(l0y, h0y, v.y, k0.y);
+    mac128(l1x, h1x, v.x, k1.x); mac128(l1y, h1y, v.y, k1.y);
+  }
+  u64x2 r0, r1;
+  r0.x = barrett128(l0x, h0x, P.p, P.ratio_lo, P.ratio_hi); r0.y = barrett128(l0y, h0y, P.p, P.ratio_lo, P.ratio_hi);
+  r1.x = barrett128(l1x, h1x, P.p, P.ratio_lo, P.ratio_hi); r1.y = barrett128(l1y, h1y, P.p, P.ratio_lo, P.ratio_hi);
+  st2(A.acc + ((size_t)0 * (A.ell + 1) + mi) * N + j, r0);
+  st2(A.acc + ((size_t)1 * (A.ell + 1) + mi) * N + j, r1);
+}
+
+// NTT-domain Galois automorphism: out[res][j] = in[res][perm[j]]
+EVAB_HD void galois_perm_elem(u64 *out, const u64 *in, const u32 *perm, int N, int res, int j) {
+  const size_t off = (size_t)res * N;
+  out[off + j] = EVAB_LDG(in + off + EVAB_LDG(perm + j));
+}

@@ -1,0 +1,100 @@
+/*
+ * evab200.h -- C-ABI of the B200-native CKKS evaluator that replaces the
+ * Microsoft SEAL calls made by microsoft/EVA's executor.
+ *
+ * The reference has no FFI for this path: eva/seal/seal_executor.h calls
+ * seal::Evaluator / seal::CKKSEncoder directly.  This
+ * header is the boundary a maintainer would bind instead; every entry point
+ * names the reference call site it replaces.  Plain pointers and sizes only;
+ * all `u64*` arguments named d_* are DEVICE pointers, `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  All calls enqueue
+ * work and return immediately unless stated; return 0 on success, non-zero on
+ * error with a message available from evab_last_error() (thread-local).  No
+ * exceptions cross this boundary.  There is NO CPU fallback: without a CUDA
+ * device evab_ctx_create fails.
+ *
+ * Layouts (identical to seal::Ciphertext::data() etc.):
+ *   ciphertext   u64 [size][ell][N]       NTT form, values in [0, q_i)
+ *   plaintext    u64 [ell][N]             NTT form
+ *   kswitch key  u64 [k-1][2][k][N]       (digit, component, key-level residue)
+ * k = number of primes incl. the special key-switching prime (last);
+ * EVA level j has ell = k-1-j residues (seal_executor.h:221-224).
+ */
+#ifndef EVAB200_H
+#define EVAB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct evab_ctx evab_ctx;
+
+const char *evab_last_error(void);
+int evab_version(void);
+
+/* Replaces seal::SEALContext construction (eva/seal/seal.cpp:148-172,179-184):
+ * builds NTT tables (minimal primitive 2N-th root per prime), Barrett/Shoup
+ * constants and RNS divide-and-round constants for every level on `device`.
+ * `primes` are the k moduli in SEAL order (last = special prime). N = 2^10..2^15. */
+int evab_ctx_create(uint64_t N, const uint64_t *primes, int k, int device, evab_ctx **out);
+void evab_ctx_destroy(evab_ctx *ctx);
+uint64_t evab_ctx_N(const evab_ctx *ctx);
+int evab_ctx_k(const evab_ctx *ctx);
+int evab_ctx_device(const evab_ctx *ctx);
+/* number of SMs of the context's device (grid sizing for callers/benchmarks) */
+int evab_ctx_sm_count(const evab_ctx *ctx);
+
+/* ---- device memory (stream-ordered pool) and transfers ---- */
+int evab_malloc(evab_ctx *ctx, size_t bytes, void **d_ptr, void *stream);
+int evab_free(evab_ctx *ctx, void *d_ptr, void *stream);
+int evab_upload(evab_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
+int evab_download(evab_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
+int evab_sync(evab_ctx *ctx, void *stream); /* blocks the calling thread */
+
+/* ---- negacyclic NTT / iNTT (microbenchmark entry, BASELINE config 2) ----
+ * d_data holds `count` residue polynomials of N coefficients; polynomial r is
+ * transformed in place modulo primes[prime_idx[r % nprimes]].  Semantics:
+ * seal::util::ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey
+ * (out[i] = a(psi^(2*bitrev(i)+1)), canonical output). */
+int evab_ntt_fwd(evab_ctx *ctx, uint64_t *d_data, size_t count, const int *prime_idx, int nprimes, void *stream);
+int evab_ntt_inv(evab_ctx *ctx, uint64_t *d_data, size_t count, const int *prime_idx, int nprimes, void *stream);
+
+/* ---- evaluator ops; one per SEAL call site of eva/seal/seal_executor.h ----
+ * `ell` = residues of the inputs' level.  Outputs must not alias inputs unless
+ * stated.  Sizes: sa/sb in {2,3}. */
+/* Evaluator::add :124 / sub :140 -- out size = max(sa,sb); may alias a or b */
+int evab_add(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, const uint64_t *d_b, int sb, void *stream);
+int evab_sub(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, const uint64_t *d_b, int sb, void *stream);
+/* Evaluator::add_plain :127 / sub_plain :143 -- out size = sa; may alias a */
+int evab_add_plain(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, const uint64_t *d_pt, void *stream);
+int evab_sub_plain(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, const uint64_t *d_pt, void *stream);
+/* Evaluator::negate :194 -- may alias */
+int evab_negate(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, void *stream);
+/* Evaluator::multiply_plain :168 -- may alias a */
+int evab_mul_plain(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, const uint64_t *d_pt, void *stream);
+/* Evaluator::multiply :164 (2x2 -> 3) and square :162 */
+int evab_mul(evab_ctx *ctx, int ell, uint64_t *d_out3, const uint64_t *d_a2, const uint64_t *d_b2, void *stream);
+int evab_square(evab_ctx *ctx, int ell, uint64_t *d_out3, const uint64_t *d_a2, void *stream);
+/* Evaluator::rescale_to_next :213 -- [sa][ell][N] -> [sa][ell-1][N].
+ * d_work: evab_rescale_work_bytes(ctx, sa) bytes of scratch. */
+size_t evab_rescale_work_bytes(const evab_ctx *ctx, int sa);
+int evab_rescale(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, void *d_work, void *stream);
+/* Evaluator::mod_switch_to_next :206 -- drop the last residue */
+int evab_mod_switch(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, void *stream);
+/* Evaluator::relinearize :200 (size 3 -> 2) and rotate_vector :181,188.
+ * d_key: key-switch key for relinearisation / for galois_elt, layout above.
+ * d_work: evab_keyswitch_work_bytes(ctx, ell) bytes of scratch. */
+size_t evab_keyswitch_work_bytes(const evab_ctx *ctx, int ell);
+int evab_relinearize(evab_ctx *ctx, int ell, uint64_t *d_out2, const uint64_t *d_a3, const uint64_t *d_key, void *d_work, void *stream);
+/* Galois element of rotate_vector(steps) (steps>0 left; SEAL GaloisTool::get_elt_from_step) */
+uint64_t evab_galois_elt_from_step(uint64_t N, int steps);
+/* builds and caches the NTT-domain permutation table of galois_elt on the
+ * device (blocking); must be called once before evab_rotate uses that element */
+int evab_galois_prepare(evab_ctx *ctx, uint64_t galois_elt);
+int evab_rotate(evab_ctx *ctx, int ell, uint64_t *d_out2, const uint64_t *d_a2, uint64_t galois_elt, const uint64_t *d_key, void *d_work, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,260 @@
+"""Numpy-in / numpy-out drivers for the two implementations of the C-ABI ops:
+
+* ``EmuBackend``  -- CPU replay of the CUDA kernel bodies (tests/emu/emu.cpp)
+* ``GpuBackend``  -- the real product library ``eva_b200/lib/libevab200.so``
+                     through include/evab200.h (device buffers + streams)
+
+Both expose the same methods as ``oracle.oracle.Oracle`` so the parity cases in
+tests/parity_cases.py run unchanged against either.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+u64p = C.POINTER(C.c_uint64)
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags.c_contiguous
+    return a.ctypes.data_as(u64p)
+
+
+def _elt(N, steps):
+    m = 2 * N
+    if steps == 0:
+        return m - 1
+    s = steps if steps > 0 else N // 2 - (-steps)
+    return pow(3, s, m)
+
+
+class EmuBackend:
+    name = "emu"
+
+    def __init__(self, N, primes):
+        so = os.path.join(ROOT, "tests", "emu", "libevab_emu.so")
+        src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
+        deps = [src] + [os.path.join(ROOT, "eva_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "eva_b200", "csrc"))]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
+        self.lib = C.CDLL(so)
+        self.lib.emu_ctx_create.restype = C.c_void_p
+        self.lib.emu_last_error.restype = C.c_char_p
+        for n in ("emu_rescale_work_bytes", "emu_keyswitch_work_bytes"):
+            getattr(self.lib, n).restype = C.c_size_t
+        pa = np.array(primes, dtype=np.uint64)
+        self.h = C.c_void_p(self.lib.emu_ctx_create(C.c_uint64(N), _p(pa), len(primes)))
+        if not self.h:
+            raise RuntimeError(self.lib.emu_last_error().decode())
+        self.N, self.k = N, len(primes)
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError(self.lib.emu_last_error().decode())
+
+    def ntt(self, data, prime_idx, inverse=False):
+        d = np.ascontiguousarray(data, dtype=np.uint64).copy()
+        flat = d.reshape(-1, self.N)
+        arr = (C.c_int * len(prime_idx))(*prime_idx)
+        fn = self.lib.emu_ntt_inv if inverse else self.lib.emu_ntt_fwd
+        self._chk(fn(self.h, _p(d), C.c_size_t(flat.shape[0]), arr, len(prime_idx)))
+        return d
+
+    def _bin(self, fn, a, b):
+        out = np.empty((max(a.shape[0], b.shape[0]), a.shape[1], self.N), dtype=np.uint64)
+        self._chk(getattr(self.lib, fn)(self.h, a.shape[1], _p(out), _p(a), a.shape[0], _p(b), b.shape[0]))
+        return out
+
+    def add(self, a, b): return self._bin("emu_add", a, b)
+    def sub(self, a, b): return self._bin("emu_sub", a, b)
+
+    def _plain(self, fn, a, pt):
+        out = np.empty_like(a)
+        self._chk(getattr(self.lib, fn)(self.h, a.shape[1], _p(out), _p(a), a.shape[0], _p(pt)))
+        return out
+
+    def add_plain(self, a, pt): return self._plain("emu_add_plain", a, pt)
+    def sub_plain(self, a, pt): return self._plain("emu_sub_plain", a, pt)
+    def mul_plain(self, a, pt): return self._plain("emu_mul_plain", a, pt)
+
+    def negate(self, a):
+        out = np.empty_like(a)
+        self._chk(self.lib.emu_negate(self.h, a.shape[1], _p(out), _p(a), a.shape[0]))
+        return out
+
+    def mul(self, a, b):
+        out = np.empty((3, a.shape[1], self.N), dtype=np.uint64)
+        self._chk(self.lib.emu_mul(self.h, a.shape[1], _p(out), _p(a), _p(b)))
+        return out
+
+    def square(self, a):
+        out = np.empty((3, a.shape[1], self.N), dtype=np.uint64)
+        self._chk(self.lib.emu_square(self.h, a.shape[1], _p(out), _p(a)))
+        return out
+
+    def rescale(self, a):
+        out = np.empty((a.shape[0], a.shape[1] - 1, self.N), dtype=np.uint64)
+        work = np.zeros(self.lib.emu_rescale_work_bytes(self.h, a.shape[0]) // 8, dtype=np.uint64)
+        self._chk(self.lib.emu_rescale(self.h, a.shape[1], _p(out), _p(a), a.shape[0], _p(work)))
+        return out
+
+    def mod_switch(self, a):
+        return np.ascontiguousarray(a[:, :-1])
+
+    def relinearize(self, a, rk):
+        out = np.empty((2, a.shape[1], self.N), dtype=np.uint64)
+        work = np.zeros(self.lib.emu_keyswitch_work_bytes(self.h, a.shape[1]) // 8, dtype=np.uint64)
+        self._chk(self.lib.emu_relinearize(self.h, a.shape[1], _p(out), _p(a), _p(rk), _p(work)))
+        return out
+
+    def rotate(self, a, steps, gk):
+        out = np.empty((2, a.shape[1], self.N), dtype=np.uint64)
+        work = np.zeros(self.lib.emu_keyswitch_work_bytes(self.h, a.shape[1]) // 8, dtype=np.uint64)
+        self._chk(self.lib.emu_rotate(self.h, a.shape[1], _p(out), _p(a), C.c_uint64(_elt(self.N, steps)), _p(gk), _p(work)))
+        return out
+
+
+class GpuBackend:
+    """Calls the product C-ABI (include/evab200.h).  Fails loudly if the CUDA
+    extension is missing -- there is no fallback."""
+    name = "gpu"
+
+    def __init__(self, N, primes, device=0):
+        from eva_b200 import cabi
+        self.lib = cabi.load()
+        pa = np.array(primes, dtype=np.uint64)
+        h = C.c_void_p()
+        self._chk(self.lib.evab_ctx_create(C.c_uint64(N), _p(pa), len(primes), device, C.byref(h)))
+        self.h = h
+        self.N, self.k = N, len(primes)
+        self._prepared = set()
+
+    def __del__(self):
+        try:
+            self.lib.evab_ctx_destroy(self.h)
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError(self.lib.evab_last_error().decode())
+
+    def _up(self, a):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        d = C.c_void_p()
+        self._chk(self.lib.evab_malloc(self.h, C.c_size_t(a.nbytes), C.byref(d), None))
+        self._chk(self.lib.evab_upload(self.h, d, a.ctypes.data_as(C.c_void_p), C.c_size_t(a.nbytes), None))
+        return d
+
+    def _alloc(self, nbytes):
+        d = C.c_void_p()
+        self._chk(self.lib.evab_malloc(self.h, C.c_size_t(nbytes), C.byref(d), None))
+        return d
+
+    def _down(self, d, shape):
+        out = np.empty(shape, dtype=np.uint64)
+        self._chk(self.lib.evab_download(self.h, out.ctypes.data_as(C.c_void_p), d, C.c_size_t(out.nbytes), None))
+        self._chk(self.lib.evab_sync(self.h, None))
+        return out
+
+    def _free(self, *ds):
+        for d in ds:
+            self._chk(self.lib.evab_free(self.h, d, None))
+
+    def ntt(self, data, prime_idx, inverse=False):
+        shape = np.asarray(data).shape
+        d = self._up(data)
+        arr = (C.c_int * len(prime_idx))(*prime_idx)
+        cnt = int(np.prod(shape)) // self.N
+        fn = self.lib.evab_ntt_inv if inverse else self.lib.evab_ntt_fwd
+        self._chk(fn(self.h, d, C.c_size_t(cnt), arr, len(prime_idx), None))
+        out = self._down(d, shape)
+        self._free(d)
+        return out
+
+    def _bin(self, fn, a, b):
+        shape = (max(a.shape[0], b.shape[0]), a.shape[1], self.N)
+        da, db, do = self._up(a), self._up(b), self._alloc(int(np.prod(shape)) * 8)
+        self._chk(getattr(self.lib, fn)(self.h, a.shape[1], do, da, a.shape[0], db, b.shape[0], None))
+        out = self._down(do, shape)
+        self._free(da, db, do)
+        return out
+
+    def add(self, a, b): return self._bin("evab_add", a, b)
+    def sub(self, a, b): return self._bin("evab_sub", a, b)
+
+    def _plain(self, fn, a, pt):
+        da, dp, do = self._up(a), self._up(pt), self._alloc(a.nbytes)
+        self._chk(getattr(self.lib, fn)(self.h, a.shape[1], do, da, a.shape[0], dp, None))
+        out = self._down(do, a.shape)
+        self._free(da, dp, do)
+        return out
+
+    def add_plain(self, a, pt): return self._plain("evab_add_plain", a, pt)
+    def sub_plain(self, a, pt): return self._plain("evab_sub_plain", a, pt)
+    def mul_plain(self, a, pt): return self._plain("evab_mul_plain", a, pt)
+
+    def negate(self, a):
+        da, do = self._up(a), self._alloc(a.nbytes)
+        self._chk(self.lib.evab_negate(self.h, a.shape[1], do, da, a.shape[0], None))
+        out = self._down(do, a.shape)
+        self._free(da, do)
+        return out
+
+    def mul(self, a, b):
+        shape = (3, a.shape[1], self.N)
+        da, db, do = self._up(a), self._up(b), self._alloc(int(np.prod(shape)) * 8)
+        self._chk(self.lib.evab_mul(self.h, a.shape[1], do, da, db, None))
+        out = self._down(do, shape)
+        self._free(da, db, do)
+        return out
+
+    def square(self, a):
+        shape = (3, a.shape[1], self.N)
+        da, do = self._up(a), self._alloc(int(np.prod(shape)) * 8)
+        self._chk(self.lib.evab_square(self.h, a.shape[1], do, da, None))
+        out = self._down(do, shape)
+        self._free(da, do)
+        return out
+
+    def rescale(self, a):
+        shape = (a.shape[0], a.shape[1] - 1, self.N)
+        da, do = self._up(a), self._alloc(int(np.prod(shape)) * 8)
+        dw = self._alloc(self.lib.evab_rescale_work_bytes(self.h, a.shape[0]))
+        self._chk(self.lib.evab_rescale(self.h, a.shape[1], do, da, a.shape[0], dw, None))
+        out = self._down(do, shape)
+        self._free(da, do, dw)
+        return out
+
+    def mod_switch(self, a):
+        shape = (a.shape[0], a.shape[1] - 1, self.N)
+        da, do = self._up(a), self._alloc(int(np.prod(shape)) * 8)
+        self._chk(self.lib.evab_mod_switch(self.h, a.shape[1], do, da, a.shape[0], None))
+        out = self._down(do, shape)
+        self._free(da, do)
+        return out
+
+    def relinearize(self, a, rk):
+        shape = (2, a.shape[1], self.N)
+        da, dk, do = self._up(a), self._up(rk), self._alloc(int(np.prod(shape)) * 8)
+        dw = self._alloc(self.lib.evab_keyswitch_work_bytes(self.h, a.shape[1]))
+        self._chk(self.lib.evab_relinearize(self.h, a.shape[1], do, da, dk, dw, None))
+        out = self._down(do, shape)
+        self._free(da, dk, do, dw)
+        return out
+
+    def rotate(self, a, steps, gk):
+        elt = int(self.lib.evab_galois_elt_from_step(C.c_uint64(self.N), steps))
+        assert elt == _elt(self.N, steps)
+        if elt not in self._prepared:
+            self._chk(self.lib.evab_galois_prepare(self.h, C.c_uint64(elt)))
+            self._prepared.add(elt)
+        shape = (2, a.shape[1], self.N)
+        da, dk, do = self._up(a), self._up(gk), self._alloc(int(np.prod(shape)) * 8)
+        dw = self._alloc(self.lib.evab_keyswitch_work_bytes(self.h, a.shape[1]))
+        self._chk(self.lib.evab_rotate(self.h, a.shape[1], do, da, C.c_uint64(elt), dk, dw, None))
+        out = self._down(do, shape)
+        self._free(da, dk, do, dw)
+        return out

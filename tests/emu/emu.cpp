@@ -1,0 +1,176 @@
+// emu.cpp -- CPU replay of the CUDA kernel bodies (TEST INFRASTRUCTURE).
+// Compiles eva_b200/csrc/{ntt_kernels,ops_kernels}.cuh + ops_impl.hpp with g++
+// and executes every CTA / thread / phase serially on host memory, so indexing,
+// swizzles, strides and lazy-reduction bounds are validated against the oracle
+// in a container without a GPU.  Not product code; the product path is CUDA only.
+#include "../../eva_b200/csrc/host_tables.hpp"
+#include "../../eva_b200/csrc/ops_impl.hpp"
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
+static std::string g_err;
+
+struct EmuCtx {
+  CtxView v;
+  evab_host::Tables T;
+  std::vector<u64> zeros;
+  std::map<u64, std::vector<u32>> perms;
+};
+
+template <int LOGN, bool SPLIT, bool INV, int PRO, int EPI> static void run_ntt_m(const NttLaunch &L, size_t jobs) {
+  typedef NttGeom<LOGN> G;
+  const int ctas = (int)jobs * (SPLIT ? 2 : 1);
+  std::vector<u64> sm(G::N);
+  std::vector<NttState> st(G::T);
+  if (!INV) {
+    // forward: the CTAs of one job (a cluster when SPLIT) are replayed phase by
+    // phase, with the cluster barrier before the store phase
+    constexpr int CPJ = SPLIT ? 2 : 1;
+    typedef FwdBody<LOGN, SPLIT, PRO, EPI> B;
+    std::vector<u64> smc((size_t)CPJ * G::N);
+    std::vector<NttState> stc((size_t)CPJ * G::T);
+    for (size_t job = 0; job < jobs; job++) {
+      NttJob J[CPJ];
+      for (int h = 0; h < CPJ; h++) J[h] = ntt_job(L, (u32)(job * CPJ + h), CPJ);
+      if (J[0].skip) continue;
+      for (int h = 0; h < CPJ; h++) {
+        u64 *s_ = smc.data() + (size_t)h * G::N; NttState *t_ = stc.data() + (size_t)h * G::T;
+        for (u32 t = 0; t < (u32)G::T; t++) B::ph0(t_[t], L, J[h], t, s_);
+        for (u32 t = 0; t < (u32)G::T; t++) B::ph1(t_[t], L, J[h], t, s_);
+        if (B::NPH == 4) {
+          for (u32 t = 0; t < (u32)G::T; t++) B::ph2(t_[t], L, J[h], t, s_);
+          for (u32 t = 0; t < (u32)G::T; t++) B::ph3(t_[t], L, J[h], t, s_);
+        }
+      }
+      for (int h = 0; h < CPJ; h++)
+        for (u32 t = 0; t < (u32)G::T; t++) B::phE(stc[(size_t)h * G::T + t], L, J[h], t);
+    }
+    return;
+  }
+  for (int cta = 0; cta < ctas; cta++) {
+    const NttJob J = ntt_job(L, cta, SPLIT ? 2 : 1);
+    if (J.skip) continue;
+    {
+      typedef InvBody<LOGN, SPLIT, PRO, EPI> B;
+      for (u32 t = 0; t < (u32)G::T; t++) B::ph0(st[t], L, J, t, sm.data());
+      for (u32 t = 0; t < (u32)G::T; t++) B::ph1(st[t], L, J, t, sm.data());
+      if (B::NPH == 4) {
+        for (u32 t = 0; t < (u32)G::T; t++) B::ph2(st[t], L, J, t, sm.data());
+        for (u32 t = 0; t < (u32)G::T; t++) B::ph3(st[t], L, J, t, sm.data());
+      }
+    }
+  }
+  if (INV && SPLIT)
+    for (size_t job = 0; job < jobs; job++) {
+      const NttJob J = ntt_job(L, (u32)job, 1);
+      for (u32 i = 0; i < (u32)G::N; i++) inv_last_stage_elem(L, J, i, G::N);
+    }
+}
+
+template <int LOGN, bool SPLIT, bool INV> static void run_ntt(const NttLaunch &L, size_t jobs) {
+  if (!INV) {
+    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_PLAIN, EPI_STORE>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_DIVROUND>(L, jobs);
+  } else {
+    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_STORE>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_ADDHALF>(L, jobs);
+  }
+  abort();
+}
+
+struct EmuBE {
+  const EmuCtx *c;
+  int error(const char *m) { g_err = m; return 1; }
+  int fwd(const NttLaunch &L, size_t jobs) {
+    switch (c->v.logN) {
+      case 10: run_ntt<10, false, false>(L, jobs); break;
+      case 11: run_ntt<11, false, false>(L, jobs); break;
+      case 12: run_ntt<12, false, false>(L, jobs); break;
+      case 13: run_ntt<13, false, false>(L, jobs); break;
+      case 14: run_ntt<14, false, false>(L, jobs); break;
+      case 15: run_ntt<14, true, false>(L, jobs); break;
+      default: return error("unsupported N");
+    }
+    return 0;
+  }
+  int inv(const NttLaunch &L, size_t jobs) {
+    switch (c->v.logN) {
+      case 10: run_ntt<10, false, true>(L, jobs); break;
+      case 11: run_ntt<11, false, true>(L, jobs); break;
+      case 12: run_ntt<12, false, true>(L, jobs); break;
+      case 13: run_ntt<13, false, true>(L, jobs); break;
+      case 14: run_ntt<14, false, true>(L, jobs); break;
+      case 15: run_ntt<14, true, true>(L, jobs); break;
+      default: return error("unsupported N");
+    }
+    return 0;
+  }
+  int dyadic(int op, const DyArgs &A) {
+    for (int res = 0; res < A.sout * A.ell; res++)
+      for (int j = 0; j < A.N; j += 2) switch (op) {
+          case DY_ADD: dyadic_elem<DY_ADD>(A, res, j); break;
+          case DY_SUB: dyadic_elem<DY_SUB>(A, res, j); break;
+          case DY_NEG: dyadic_elem<DY_NEG>(A, res, j); break;
+          default: dyadic_elem<DY_MULPT>(A, res, j); break;
+        }
+    return 0;
+  }
+  int mulct(bool sq, const MulArgs &A) {
+    for (int i = 0; i < A.ell; i++)
+      for (int j = 0; j < A.N; j += 2) { if (sq) mulct_elem<true>(A, i, j); else mulct_elem<false>(A, i, j); }
+    return 0;
+  }
+  int inner(const IpArgs &A) {
+    for (int mi = 0; mi <= A.ell; mi++)
+      for (int j = 0; j < A.N; j += 2) ks_inner_elem(A, mi, j);
+    return 0;
+  }
+  int perm(u64 *out, const u64 *in, const u32 *p, int N, int rows) {
+    for (int r = 0; r < rows; r++)
+      for (int j = 0; j < N; j++) galois_perm_elem(out, in, p, N, r, j);
+    return 0;
+  }
+};
+
+extern "C" {
+const char *emu_last_error() { return g_err.c_str(); }
+EmuCtx *emu_ctx_create(uint64_t N, const uint64_t *primes, int k) {
+  int logN = 0;
+  while ((1ull << logN) < N) logN++;
+  EmuCtx *c = new EmuCtx();
+  c->T.tw.resize((size_t)k * 2 * N);
+  const char *err = evab_host::build_tables(N, logN, primes, k, nullptr, c->T);
+  if (err[0]) { g_err = err; delete c; return nullptr; }
+  for (int i = 0; i < k; i++) {  // re-point the tables at the final host storage
+    c->T.pd[i].tw = c->T.tw.data() + ((size_t)i * 2 + 0) * N;
+    c->T.pd[i].itw = c->T.tw.data() + ((size_t)i * 2 + 1) * N;
+  }
+  c->zeros.assign(32, 0);
+  c->v.N = N; c->v.logN = logN; c->v.k = k;
+  c->v.primes = c->T.pd.data(); c->v.qinv = c->T.qinv.data(); c->v.halfmod = c->T.halfmod.data(); c->v.zeros = c->zeros.data();
+  return c;
+}
+void emu_ctx_destroy(EmuCtx *c) { delete c; }
+int emu_ntt_fwd(EmuCtx *c, uint64_t *d, size_t count, const int *pidx, int np) { EmuBE be{c}; return ntt_batch_impl(be, c->v, false, d, count, pidx, np); }
+int emu_ntt_inv(EmuCtx *c, uint64_t *d, size_t count, const int *pidx, int np) { EmuBE be{c}; return ntt_batch_impl(be, c->v, true, d, count, pidx, np); }
+int emu_add(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *b, int sb) { EmuBE be{c}; return dyadic_impl<DY_ADD>(be, c->v, ell, o, a, sa, b, sb, 0); }
+int emu_sub(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *b, int sb) { EmuBE be{c}; return dyadic_impl<DY_SUB>(be, c->v, ell, o, a, sa, b, sb, 0); }
+int emu_add_plain(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt) { EmuBE be{c}; return dyadic_impl<DY_ADD>(be, c->v, ell, o, a, sa, pt, 1, 1); }
+int emu_sub_plain(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt) { EmuBE be{c}; return dyadic_impl<DY_SUB>(be, c->v, ell, o, a, sa, pt, 1, 1); }
+int emu_negate(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa) { EmuBE be{c}; return dyadic_impl<DY_NEG>(be, c->v, ell, o, a, sa, (const u64 *)nullptr, 0, 0); }
+int emu_mul_plain(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt) { EmuBE be{c}; return dyadic_impl<DY_MULPT>(be, c->v, ell, o, a, sa, pt, 1, 1); }
+int emu_mul(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *b) { EmuBE be{c}; return mulct_impl(be, c->v, false, ell, o, a, b); }
+int emu_square(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a) { EmuBE be{c}; return mulct_impl(be, c->v, true, ell, o, a, (const u64 *)nullptr); }
+size_t emu_rescale_work_bytes(EmuCtx *c, int sa) { return rescale_work_elems(c->v, sa) * 8; }
+int emu_rescale(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, void *work) { EmuBE be{c}; return rescale_impl(be, c->v, ell, o, a, sa, (u64 *)work); }
+size_t emu_keyswitch_work_bytes(EmuCtx *c, int ell) { return keyswitch_work_elems(c->v, ell) * 8; }
+int emu_relinearize(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *key, void *work) { EmuBE be{c}; return relinearize_impl(be, c->v, ell, o, a, key, (u64 *)work); }
+int emu_rotate(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, uint64_t elt, const uint64_t *key, void *work) {
+  if (!c->perms.count(elt)) evab_host::galois_table(c->v.N, c->v.logN, elt, c->perms[elt]);
+  EmuBE be{c};
+  return rotate_impl(be, c->v, ell, o, a, c->perms[elt].data(), key, (u64 *)work);
+}
+}

@@ -1,0 +1,91 @@
+"""Bit-exact parity cases: implementation under test (CPU kernel replay or the
+CUDA library through the C-ABI) versus the CPU oracle on identical seeded
+inputs.  Integer pipeline => the bar is equality of every u64 word."""
+import numpy as np
+
+from oracle import oracle as o
+
+_ORACLES = {}
+
+
+def get_oracle(N, bits, seed=1):
+    key = (N, tuple(bits))
+    if key not in _ORACLES:
+        _ORACLES[key] = o.Oracle(N, list(bits)).keygen(seed)
+    return _ORACLES[key]
+
+
+def rand_ct(orc, size, ell, seed):
+    """uniform residues in [0,q_i): valid evaluator input (ops are data-independent)"""
+    return np.stack([np.stack([o.splitmix64_fill(seed * 1000 + s * 37 + i, orc.N, orc.primes[i]) for i in range(ell)])
+                     for s in range(size)])
+
+
+def eq(a, b):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        raise AssertionError("mismatch at %d/%d words, first %s: got %d want %d" % (
+            len(bad), a.size, bad[0], a[tuple(bad[0])], b[tuple(bad[0])]))
+
+
+def case_ntt(be, orc, L=None):
+    """residues seeded SplitMix64(0x5EA10000 + N + L)."""
+    N = orc.N
+    L = L or orc.k
+    data = np.stack([np.stack([o.splitmix64_fill(0x5EA10000 + N + L + 131 * b + r, N, orc.primes[r]) for r in range(L)])
+                     for b in range(2)])
+    want = np.stack([np.stack([orc.ntt_fwd(data[b, r], r) for r in range(L)]) for b in range(2)])
+    got = be.ntt(data, list(range(L)))
+    eq(got, want)
+    back = be.ntt(got, list(range(L)), inverse=True)
+    eq(back, data)
+    # edge values: 0, 1, p-1
+    edge = np.zeros((L, N), dtype=np.uint64)
+    for r in range(L):
+        edge[r, 0::3] = orc.primes[r] - 1
+        edge[r, 1::3] = 1
+    eq(be.ntt(edge, list(range(L))), np.stack([orc.ntt_fwd(edge[r], r) for r in range(L)]))
+    eq(be.ntt(edge, list(range(L)), inverse=True), np.stack([orc.ntt_inv(edge[r], r) for r in range(L)]))
+
+
+def case_dyadic(be, orc, ell):
+    a2, b2 = rand_ct(orc, 2, ell, 1), rand_ct(orc, 2, ell, 2)
+    a3, b3 = rand_ct(orc, 3, ell, 3), rand_ct(orc, 3, ell, 4)
+    pt = rand_ct(orc, 1, ell, 5)[0]
+    eq(be.add(a2, b2), orc.add(a2, b2))
+    eq(be.add(a3, b2), orc.add(a3, b2))
+    eq(be.add(a2, b3), orc.add(a2, b3))
+    eq(be.add(a3, b3), orc.add(a3, b3))
+    eq(be.sub(a2, b2), orc.sub(a2, b2))
+    eq(be.sub(a3, b2), orc.sub(a3, b2))
+    eq(be.sub(a2, b3), orc.sub(a2, b3))
+    eq(be.negate(a3), orc.negate(a3))
+    eq(be.add_plain(a2, pt), orc.add_plain(a2, pt))
+    eq(be.add_plain(a3, pt), orc.add_plain(a3, pt))
+    eq(be.sub_plain(a3, pt), orc.sub_plain(a3, pt))
+    eq(be.mul_plain(a2, pt), orc.mul_plain(a2, pt))
+    eq(be.mul_plain(a3, pt), orc.mul_plain(a3, pt))
+    eq(be.mul(a2, b2), orc.mul(a2, b2))
+    eq(be.square(a2), orc.square(a2))
+    z = np.zeros_like(a2)
+    eq(be.negate(z), z)
+    eq(be.sub(z, z), z)
+    if ell >= 2:
+        eq(be.mod_switch(a3), orc.mod_switch(a3))
+
+
+def case_rescale(be, orc, ell):
+    for size in (2, 3):
+        a = rand_ct(orc, size, ell, 10 + size)
+        eq(be.rescale(a), orc.rescale(a))
+
+
+def case_keyswitch(be, orc, ell, steps=(1, -2)):
+    a3 = rand_ct(orc, 3, ell, 21)
+    rk = orc.relin_key()
+    eq(be.relinearize(a3, rk), orc.relinearize(a3, rk))
+    a2 = rand_ct(orc, 2, ell, 22)
+    for s in steps:
+        gk = orc.galois_key(o.galois_elt_from_step(orc.N, s))
+        eq(be.rotate(a2, s, gk), orc.rotate(a2, s, gk))

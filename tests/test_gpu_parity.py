@@ -1,0 +1,80 @@
+"""GPU parity proper: the CUDA library through the C-ABI (include/evab200.h)
+versus the CPU oracle, bit-exact on identical seeded inputs."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from oracle import oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _be(N, primes):
+    from backends import GpuBackend
+    return GpuBackend(N, primes)
+
+
+@pytest.mark.parametrize("N,bits", [
+    (1024, [30, 30, 40]), (2048, [54, 55, 60]), (4096, [60, 20, 60, 60]), (8192, [60, 60, 60]),
+    (16384, [60, 60, 60, 60, 60]), (32768, [60, 20, 60, 60]),
+])
+def test_gpu_ntt(N, bits):
+    orc = pc.get_oracle(N, bits)
+    pc.case_ntt(_be(N, orc.primes), orc)
+
+
+@pytest.mark.parametrize("N,bits", [(1024, [40, 50, 60, 60]), (4096, [60, 20, 60, 60]), (8192, [60, 60, 60])])
+def test_gpu_ops_small(N, bits):
+    orc = pc.get_oracle(N, bits)
+    be = _be(N, orc.primes)
+    for ell in range(1, orc.k):
+        pc.case_dyadic(be, orc, ell)
+        pc.case_keyswitch(be, orc, ell)
+        if ell >= 2:
+            pc.case_rescale(be, orc, ell)
+
+
+def test_gpu_ops_sobel_shape():
+    """N=16384, 5x60-bit primes: the Sobel/Harris parameter set."""
+    orc = pc.get_oracle(16384, [60] * 5)
+    be = _be(16384, orc.primes)
+    for ell in (4, 3, 2, 1):
+        pc.case_dyadic(be, orc, ell)
+        pc.case_keyswitch(be, orc, ell, steps=(1, 64, 130))
+        if ell >= 2:
+            pc.case_rescale(be, orc, ell)
+
+
+def test_gpu_ops_n32768():
+    orc = pc.get_oracle(32768, [60, 20, 60, 60, 60, 60])
+    be = _be(32768, orc.primes)
+    pc.case_dyadic(be, orc, 5)
+    pc.case_rescale(be, orc, 5)
+    pc.case_keyswitch(be, orc, 5, steps=(-1,))
+    pc.case_keyswitch(be, orc, 2, steps=(3,))
+
+
+def test_gpu_ntt_large_batch_roundtrip():
+    """Full-size property check (oracle only on the first polynomials): batch
+    larger than L2, inverse(forward(x)) == x for every word."""
+    N, L, B = 16384, 4, 256
+    orc = pc.get_oracle(16384, [60] * 5)
+    be = _be(N, orc.primes)
+    data = np.stack([o.splitmix64_fill(0x5EA10000 + N + L + r, B * N, orc.primes[r]).reshape(B, N) for r in range(L)], axis=1)
+    data = np.ascontiguousarray(data)            # [B][L][N]
+    fwd = be.ntt(data, list(range(L)))
+    for b in range(2):
+        for r in range(L):
+            pc.eq(fwd[b, r], orc.ntt_fwd(data[b, r], r))
+    pc.eq(be.ntt(fwd, list(range(L)), inverse=True), data)
+
+
+def test_gpu_error_paths():
+    from eva_b200 import cabi
+    import ctypes as C
+    lib = cabi.load()
+    h = C.c_void_p()
+    bad = np.array([97, 193], dtype=np.uint64)
+    assert lib.evab_ctx_create(C.c_uint64(4096), bad.ctypes.data_as(cabi.u64p), 2, 0, C.byref(h)) != 0
+    assert b"2N" in lib.evab_last_error()
+    assert lib.evab_ctx_create(C.c_uint64(3000), bad.ctypes.data_as(cabi.u64p), 2, 0, C.byref(h)) != 0
