@@ -25,6 +25,17 @@ _SIGS = {
     "evab_upload": (ci, [vp, vp, vp, szt, vp]),
     "evab_download": (ci, [vp, vp, vp, szt, vp]),
     "evab_sync": (ci, [vp, vp]),
+    "evab_stream_create": (ci, [vp, C.POINTER(vp)]),
+    "evab_stream_destroy": (ci, [vp, vp]),
+    "evab_event_create": (ci, [vp, C.POINTER(vp)]),
+    "evab_event_destroy": (ci, [vp, vp]),
+    "evab_event_record": (ci, [vp, vp, vp]),
+    "evab_stream_wait_event": (ci, [vp, vp, vp]),
+    "evab_graph_begin": (ci, [vp, vp]),
+    "evab_graph_end": (ci, [vp, vp, C.POINTER(vp)]),
+    "evab_graph_launch": (ci, [vp, vp, vp]),
+    "evab_graph_destroy": (ci, [vp, vp]),
+    "evab_launch_count": (u64, [vp]),
     "evab_ntt_fwd": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
     "evab_ntt_inv": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
     "evab_add": (ci, [vp, ci, vp, vp, ci, vp, ci, vp]),

@@ -6,6 +6,7 @@
 #include "host_tables.hpp"
 #include "ops_impl.hpp"
 #include <cuda_runtime.h>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -33,6 +34,7 @@ struct evab_ctx {
   u64 *d_zeros = nullptr;
   std::map<u64, u32 *> perms;  // galois elt -> device permutation table
   std::mutex mu;
+  mutable std::atomic<unsigned long long> launches{0};
 };
 static cudaStream_t S(void *s) { return (cudaStream_t)s; }
 
@@ -107,7 +109,13 @@ __global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, co
 // ---------------------------------------------------------------------------
 template <int LOGN, bool SPLIT, int PRO, int EPI> static int launch_fwd_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   const size_t smem = (size_t)NttGeom<LOGN>::N * sizeof(u64);
-  CUDA_OK(cudaFuncSetAttribute(k_ntt_fwd<LOGN, SPLIT, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::atomic<bool> done[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!done[dev & 63].load()) {
+    CUDA_OK(cudaFuncSetAttribute(k_ntt_fwd<LOGN, SPLIT, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done[dev & 63].store(true);
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(jobs * (SPLIT ? 2 : 1)));
   cfg.blockDim = dim3(NttGeom<LOGN>::T);
@@ -128,7 +136,13 @@ template <int LOGN, bool SPLIT> static int launch_fwd_t(const NttLaunch &L, size
 }
 template <int LOGN, bool SPLIT, int EPI> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   const size_t smem = (size_t)NttGeom<LOGN>::N * sizeof(u64);
-  CUDA_OK(cudaFuncSetAttribute(k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::atomic<bool> done[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!done[dev & 63].load()) {
+    CUDA_OK(cudaFuncSetAttribute(k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done[dev & 63].store(true);
+  }
   k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI><<<(unsigned)(jobs * (SPLIT ? 2 : 1)), NttGeom<LOGN>::T, smem, st>>>(L);
   CUDA_OK(cudaGetLastError());
   if (SPLIT) {
@@ -150,12 +164,14 @@ struct CudaBE {
   const evab_ctx *c;
   cudaStream_t st;
   int error(const char *m) { return fail(m); }
+  void count(unsigned n = 1) const { c->launches.fetch_add(n, std::memory_order_relaxed); }
   dim3 grid(int rows) const {
     int per_row = (int)(c->v.N / 2 / 256);
     if (per_row < 1) per_row = 1;
     return dim3(per_row, rows);
   }
   int fwd(const NttLaunch &L, size_t jobs) {
+    count();
     switch (c->v.logN) {
       case 10: return launch_fwd_t<10, false>(L, jobs, st);
       case 11: return launch_fwd_t<11, false>(L, jobs, st);
@@ -167,6 +183,7 @@ struct CudaBE {
     return fail("unsupported N");
   }
   int inv(const NttLaunch &L, size_t jobs) {
+    count(c->v.logN == 15 ? 2 : 1);
     switch (c->v.logN) {
       case 10: return launch_inv_t<10, false>(L, jobs, st);
       case 11: return launch_inv_t<11, false>(L, jobs, st);
@@ -178,6 +195,7 @@ struct CudaBE {
     return fail("unsupported N");
   }
   int dyadic(int op, const DyArgs &A) {
+    count();
     dim3 g = grid(A.sout * A.ell);
     switch (op) {
       case DY_ADD: k_dyadic<DY_ADD><<<g, 256, 0, st>>>(A); break;
@@ -189,17 +207,20 @@ struct CudaBE {
     return 0;
   }
   int mulct(bool sq, const MulArgs &A) {
+    count();
     if (sq) k_mul_ct<true><<<grid(A.ell), 256, 0, st>>>(A);
     else k_mul_ct<false><<<grid(A.ell), 256, 0, st>>>(A);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
   int inner(const IpArgs &A) {
+    count();
     k_ks_inner<<<grid(A.ell + 1), 256, 0, st>>>(A);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
   int perm(u64 *out, const u64 *in, const u32 *p, int N, int rows) {
+    count();
     dim3 g((unsigned)((N + 255) / 256), rows);
     k_galois_perm<<<g, 256, 0, st>>>(out, in, p, N);
     CUDA_OK(cudaGetLastError());
@@ -289,6 +310,62 @@ extern "C" int evab_sync(evab_ctx *c, void *stream) {
   CUDA_OK(cudaStreamSynchronize(S(stream)));
   return 0;
 }
+extern "C" int evab_stream_create(evab_ctx *c, void **stream) {
+  CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t s;
+  CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = (void *)s;
+  return 0;
+}
+extern "C" int evab_stream_destroy(evab_ctx *c, void *stream) {
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamDestroy(S(stream)));
+  return 0;
+}
+extern "C" int evab_event_create(evab_ctx *c, void **event) {
+  CUDA_OK(cudaSetDevice(c->device));
+  cudaEvent_t e;
+  CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *event = (void *)e;
+  return 0;
+}
+extern "C" int evab_event_destroy(evab_ctx *c, void *event) {
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaEventDestroy((cudaEvent_t)event));
+  return 0;
+}
+extern "C" int evab_event_record(evab_ctx *c, void *event, void *stream) {
+  CUDA_OK(cudaEventRecord((cudaEvent_t)event, S(stream)));
+  return 0;
+}
+extern "C" int evab_stream_wait_event(evab_ctx *c, void *stream, void *event) {
+  CUDA_OK(cudaStreamWaitEvent(S(stream), (cudaEvent_t)event, 0));
+  return 0;
+}
+extern "C" int evab_graph_begin(evab_ctx *c, void *stream) {
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamBeginCapture(S(stream), cudaStreamCaptureModeThreadLocal));
+  return 0;
+}
+extern "C" int evab_graph_end(evab_ctx *c, void *stream, void **graph_exec) {
+  cudaGraph_t g = nullptr;
+  CUDA_OK(cudaStreamEndCapture(S(stream), &g));
+  cudaGraphExec_t ge = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+  *graph_exec = (void *)ge;
+  return 0;
+}
+extern "C" int evab_graph_launch(evab_ctx *c, void *graph_exec, void *stream) {
+  CUDA_OK(cudaGraphLaunch((cudaGraphExec_t)graph_exec, S(stream)));
+  return 0;
+}
+extern "C" int evab_graph_destroy(evab_ctx *c, void *graph_exec) {
+  CUDA_OK(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  return 0;
+}
+extern "C" uint64_t evab_launch_count(const evab_ctx *c) { return c->launches.load(); }
 
 // ---------------------------------------------------------------------------
 // ops

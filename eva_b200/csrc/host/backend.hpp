@@ -1,0 +1,195 @@
+// backend.hpp -- the B200 counterpart of the reference's SEAL backend API
+// (eva/seal/seal.h:24-97, eva/seal/seal.cpp): generateKeys, B200Public::{encrypt,
+// execute}, B200Secret::decrypt, B200Valuation.  Same argument meaning, ownership
+// and error behaviour (C++ exceptions -> Python exceptions through pybind11).
+#pragma once
+#include "executor.hpp"
+#include <tuple>
+#include <variant>
+
+namespace evab {
+
+// compiler outputs (reference eva/ckks/ckks_parameters.h:14-18, ckks_signature.h:16-36)
+struct CKKSParameters {
+  std::vector<std::uint32_t> primeBits;
+  std::set<int> rotations;
+  std::uint32_t polyModulusDegree = 0;
+};
+struct CKKSEncodingInfo {
+  Type inputType; int scale; int level;
+  CKKSEncodingInfo(Type t, int s, int l) : inputType(t), scale(s), level(l) {}
+};
+struct CKKSSignature {
+  int vecSize = 0;
+  std::map<std::string, CKKSEncodingInfo> inputs;
+  CKKSSignature() {}
+  CKKSSignature(int v, std::map<std::string, CKKSEncodingInfo> in) : vecSize(v), inputs(std::move(in)) {}
+};
+using Valuation = std::map<std::string, std::vector<double>>;
+
+// host-resident encrypted values (the reference keeps seal::Ciphertext objects
+// in host memory inside SEALValuation, eva/seal/seal.h:21-41)
+struct HostCipher { std::vector<u64> data; int size = 0, ell = 0; double scale = 0; };
+struct HostPlain { std::vector<u64> data; int ell = 0; double scale = 0; };
+using SchemeValue = std::variant<HostCipher, HostPlain, std::shared_ptr<ConstantValue>>;
+
+class B200Valuation {
+public:
+  SchemeValue &operator[](const std::string &name) { return values[name]; }
+  const SchemeValue &at(const std::string &name) const { return values.at(name); }
+  auto begin() const { return values.begin(); }
+  auto end() const { return values.end(); }
+  std::size_t size() const { return values.size(); }
+  std::map<std::string, SchemeValue> values;
+};
+
+struct Shared {
+  std::shared_ptr<Device> dev;
+  std::unique_ptr<CkksClient> client;
+  KeySet keys;
+};
+
+class B200Public {
+public:
+  explicit B200Public(std::shared_ptr<Shared> s) : s_(std::move(s)) {}
+
+  // SEALPublic::encrypt -- reference eva/seal/seal.cpp:24-102
+  B200Valuation encrypt(const Valuation &inputs, const CKKSSignature &sig) {
+    auto &enc = s_->client->encoder();
+    const std::size_t slots = enc.slotCount();
+    if (slots < (std::size_t)sig.vecSize) throw std::runtime_error("Vector size cannot be larger than slot count");
+    if (slots % sig.vecSize) throw std::runtime_error("Vector size must exactly divide the slot count");
+    B200Valuation out;
+    const u64 N = s_->dev->N();
+    for (auto &in : inputs) {
+      const auto &v = in.second;
+      if (v.size() != (std::size_t)sig.vecSize) throw std::runtime_error("Input size does not match program vector size");
+      const CKKSEncodingInfo &info = sig.inputs.at(in.first);
+      if (info.inputType == Type::Raw) { out[in.first] = std::make_shared<ConstantValue>(sig.vecSize, v); continue; }
+      const int ell = s_->dev->k() - 1 - info.level;
+      if (ell < 1) throw std::runtime_error("input level exceeds the modulus chain");
+      std::vector<double> rep;
+      rep.reserve(slots);
+      for (std::size_t r = slots / v.size(); r > 0; --r) rep.insert(rep.end(), v.begin(), v.end());
+      const double scale = std::ldexp(1.0, info.scale);
+      DBuf pt(s_->dev, (std::size_t)ell * N);
+      enc.encode(rep, scale, ell, pt.get());
+      if (info.inputType == Type::Cipher) {
+        DBuf ct = s_->client->encrypt(s_->keys, pt.get(), ell);
+        HostCipher h; h.size = 2; h.ell = ell; h.scale = scale; h.data.resize((std::size_t)2 * ell * N);
+        s_->dev->download(h.data.data(), ct.get(), h.data.size() * 8); s_->dev->sync();
+        out[in.first] = std::move(h);
+      } else {
+        HostPlain h; h.ell = ell; h.scale = scale; h.data.resize((std::size_t)ell * N);
+        s_->dev->download(h.data.data(), pt.get(), h.data.size() * 8); s_->dev->sync();
+        out[in.first] = std::move(h);
+      }
+    }
+    return out;
+  }
+
+  Executor &executorFor(Program &program) {
+    auto it = execs_.find(&program);
+    if (it == execs_.end() || it->second.second != program.termCount())
+      it = execs_.insert_or_assign(&program, std::make_pair(std::make_unique<Executor>(s_->dev, s_->client->encoder(), s_->keys, program, options), program.termCount())).first;
+    return *it->second.first;
+  }
+  void dropExecutor(Program &program) { execs_.erase(&program); }
+
+  // upload host inputs into the executor's arena (H2D on `stream`)
+  void stageInputs(Executor &ex, Program &program, const B200Valuation &inputs, void *stream) {
+    const u64 N = s_->dev->N();
+    for (auto &in : inputs) {
+      auto term = program.getInput(in.first);
+      const ValueInfo &vi = ex.info(term);
+      if (auto *c = std::get_if<HostCipher>(&in.second)) {
+        if (vi.kind != Kind::Cipher || c->ell != vi.ell || c->size != vi.size) throw std::runtime_error("input " + in.first + ": ciphertext does not match the program signature");
+        s_->dev->upload(ex.valuePtr(term), c->data.data(), c->data.size() * 8, stream);
+      } else if (auto *p = std::get_if<HostPlain>(&in.second)) {
+        if (vi.kind != Kind::Plain || p->ell != vi.ell) throw std::runtime_error("input " + in.first + ": plaintext does not match the program signature");
+        s_->dev->upload(ex.valuePtr(term), p->data.data(), (std::size_t)p->ell * N * 8, stream);
+      } else {
+        auto &cv = std::get<std::shared_ptr<ConstantValue>>(in.second);
+        std::vector<double> x;
+        cv->expandTo(x, program.getVecSize());
+        ex.setRawInput(in.first, x);
+      }
+    }
+  }
+  // SEALPublic::execute -- reference eva/seal/seal.cpp:104-122.  Host buffers in,
+  // host buffers out: H2D of the inputs, the DAG on the GPU, D2H of the outputs.
+  B200Valuation execute(Program &program, const B200Valuation &inputs) {
+    Executor &ex = executorFor(program);
+    stageInputs(ex, program, inputs, nullptr);
+    ex.run(nullptr);
+    B200Valuation out;
+    const u64 N = s_->dev->N();
+    for (auto &o : program.getOutputs()) {
+      const ValueInfo &vi = ex.info(o.second);
+      if (vi.kind == Kind::Cipher) {
+        HostCipher h; h.size = vi.size; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.size * vi.ell * N);
+        s_->dev->download(h.data.data(), ex.valuePtr(o.second), h.data.size() * 8);
+        out[o.first] = std::move(h);
+      } else if (vi.kind == Kind::Plain) {
+        HostPlain h; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.ell * N);
+        s_->dev->download(h.data.data(), ex.valuePtr(o.second), h.data.size() * 8);
+        out[o.first] = std::move(h);
+      } else {
+        out[o.first] = std::make_shared<ConstantValue>(program.getVecSize(), ex.rawValue(o.second->index));
+      }
+    }
+    s_->dev->sync();
+    return out;
+  }
+  std::shared_ptr<Shared> shared() const { return s_; }
+  ExecOptions options;
+
+private:
+  std::shared_ptr<Shared> s_;
+  std::map<Program *, std::pair<std::unique_ptr<Executor>, std::uint64_t>> execs_;
+};
+
+class B200Secret {
+public:
+  explicit B200Secret(std::shared_ptr<Shared> s) : s_(std::move(s)) {}
+  // SEALSecret::decrypt -- reference eva/seal/seal.cpp:124-146
+  Valuation decrypt(const B200Valuation &enc, const CKKSSignature &sig) {
+    Valuation out;
+    const u64 N = s_->dev->N();
+    auto &encoder = s_->client->encoder();
+    for (auto &e : enc) {
+      if (auto *c = std::get_if<HostCipher>(&e.second)) {
+        DBuf ct(s_->dev, c->data.size());
+        s_->dev->upload(ct.get(), c->data.data(), c->data.size() * 8);
+        DBuf pt = s_->client->decrypt(s_->keys, ct.get(), c->size, c->ell);
+        out[e.first] = encoder.decode(pt.get(), c->ell, c->scale);
+      } else if (auto *p = std::get_if<HostPlain>(&e.second)) {
+        DBuf pt(s_->dev, (std::size_t)p->ell * N);
+        s_->dev->upload(pt.get(), p->data.data(), (std::size_t)p->ell * N * 8);
+        out[e.first] = encoder.decode(pt.get(), p->ell, p->scale);
+      } else {
+        std::get<std::shared_ptr<ConstantValue>>(e.second)->expandTo(out[e.first], sig.vecSize);
+      }
+      out.at(e.first).resize(sig.vecSize);
+    }
+    return out;
+  }
+private:
+  std::shared_ptr<Shared> s_;
+};
+
+// generateKeys -- reference eva/seal/seal.cpp:174-203
+inline std::tuple<std::unique_ptr<B200Public>, std::unique_ptr<B200Secret>>
+generateKeys(const CKKSParameters &params, int device = 0, std::uint64_t seed = 0) {
+  std::vector<int> bits(params.primeBits.begin(), params.primeBits.end());
+  auto primes = hmod::createCoeffModulus(params.polyModulusDegree, bits);
+  auto s = std::make_shared<Shared>();
+  s->dev = std::make_shared<Device>(params.polyModulusDegree, primes, device);
+  if (!seed) { std::random_device rd; seed = ((std::uint64_t)rd() << 32) ^ rd(); }
+  s->client = std::make_unique<CkksClient>(s->dev, seed);
+  std::vector<int> rots(params.rotations.begin(), params.rotations.end());
+  s->client->keygen(s->keys, rots);
+  return std::make_tuple(std::make_unique<B200Public>(s), std::make_unique<B200Secret>(s));
+}
+
+}  // namespace evab

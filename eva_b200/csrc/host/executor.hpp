@@ -1,0 +1,385 @@
+// executor.hpp -- B200 executor + stream/graph DAG scheduler for compiled EVA
+// programs.  Replaces, for the hot path,
+//   SEALExecutor::operator()/setInputs/getOutputs/free  (reference eva/seal/seal_executor.h:264-436)
+//   ProgramTraversal / MulticoreProgramTraversal::forwardPass
+//                                                       (eva/common/program_traversal.h:36-88,
+//                                                        eva/common/multicore_program_traversal.h:24-84)
+// Instead of interpreting the DAG term by term on CPU threads, the program is
+// lowered ONCE into a static plan (value kinds, levels, scales, device buffer
+// offsets, stream assignment, event edges); every execute() then replays the
+// plan: independent terms run concurrently on different CUDA streams, cross-
+// stream dependencies are events, and the whole replay can be captured into a
+// CUDA graph so that one execute() costs a single graph launch.
+#pragma once
+#include "ckks_client.hpp"
+#include "ir.hpp"
+#include <cmath>
+#include <functional>
+#include <set>
+#include <unordered_map>
+
+namespace evab {
+
+enum class Kind : int { None = 0, Cipher = 1, Plain = 2, Raw = 3 };
+
+struct ValueInfo {
+  Kind kind = Kind::None;
+  int size = 0;        // ciphertext polynomials
+  int ell = 0;         // residues
+  double scale = 0.0;  // absolute scale (always an exact power of two in EVA)
+  std::size_t off = 0; // word offset into the arena (Cipher / Plain)
+  bool alias = false;  // shares its operand's storage (Output, step-0 rotation)
+};
+
+struct Step {
+  const Term *term;
+  Op op;
+  int stream = 0;
+  std::vector<int> waits;  // event ids to wait for before issuing
+  int record = -1;         // event id recorded after issuing
+  std::size_t work = 0;    // scratch word offset in the stream's workspace (0 = none)
+};
+
+struct ExecOptions {
+  int numStreams = 8;
+  bool useGraph = true;
+  bool cacheConstants = true;  // encode plan-time-constant plaintexts once per plan instead of on every run
+};
+
+class Executor {
+public:
+  Executor(std::shared_ptr<Device> dev, CkksEncoder &enc, const KeySet &keys, Program &program, ExecOptions opt = {})
+      : dev_(std::move(dev)), enc_(enc), keys_(keys), prog_(program), opt_(opt), N_(dev_->N()), k_(dev_->k()) {
+    buildPlan();
+  }
+  ~Executor() {
+    if (graph_) evab_graph_destroy(dev_->ctx(), graph_);
+    for (void *e : events_) evab_event_destroy(dev_->ctx(), e);
+    for (void *s : streams_) evab_stream_destroy(dev_->ctx(), s);
+  }
+  Executor(const Executor &) = delete;
+
+  std::size_t cipherOpCount() const { return cipherOps_; }
+  const ValueInfo &info(const Term::Ptr &t) const { return vals_.at(t->index); }
+  u64 *valuePtr(const Term::Ptr &t) const { return arena_.get() + vals_.at(t->index).off; }
+  u64 *valuePtr(std::uint64_t index) const { return arena_.get() + vals_.at(index).off; }
+  const ValueInfo &info(std::uint64_t index) const { return vals_.at(index); }
+  const std::vector<double> &rawValue(std::uint64_t index) const { return raws_.at(index); }
+
+  // device-resident run: inputs must already be in valuePtr(input term); raw
+  // inputs set through setRawInput.  Enqueues the whole program on `stream`
+  // (graph launch or multi-stream replay); does not synchronise.
+  void run(void *stream) {
+    if (rawDirty_ || !opt_.cacheConstants) { evalRawAndEncodes(stream); rawDirty_ = false; }
+    if (opt_.useGraph) {
+      if (!graph_ || !graphValid_) capture();
+      check(evab_graph_launch(dev_->ctx(), graph_, stream));
+    } else {
+      replay(stream);
+    }
+  }
+  void setRawInput(const std::string &name, const std::vector<double> &v) {
+    auto t = prog_.getInput(name);
+    if (vals_.at(t->index).kind != Kind::Raw) throw std::runtime_error("input " + name + " is not a raw input");
+    std::vector<double> x;
+    ConstantValue(prog_.getVecSize(), v).expandTo(x, prog_.getVecSize());
+    raws_[t->index] = x;
+    rawDirty_ = true;
+  }
+
+private:
+  // ---------------------------------------------------------------- planning
+  void buildPlan() {
+    order_ = prog_.toposort();
+    vals_.assign(prog_.termCount(), ValueInfo{});
+    raws_.resize(prog_.termCount());
+    std::size_t arenaWords = 0;
+    auto place = [&](ValueInfo &v) { v.off = arenaWords; arenaWords += (std::size_t)(v.kind == Kind::Cipher ? v.size : 1) * v.ell * N_; };
+    for (auto &t : order_) {
+      ValueInfo &v = vals_[t->index];
+      auto a = [&](int i) -> const ValueInfo & { return vals_[t->operandAt(i)->index]; };
+      switch (t->op) {
+        case Op::Input: {
+          const Type ty = t->type.value_or(Type::Cipher);
+          if (ty == Type::Raw) { v.kind = Kind::Raw; rawInputs_ = true; break; }
+          if (!t->encodeAtScale || !t->encodeAtLevel) throw std::runtime_error("input term lacks scale/level (program not compiled?)");
+          v.kind = ty == Type::Cipher ? Kind::Cipher : Kind::Plain;
+          v.size = 2; v.ell = levelToEll(*t->encodeAtLevel); v.scale = std::ldexp(1.0, (int)*t->encodeAtScale);
+          place(v);
+        } break;
+        case Op::Constant:
+          v.kind = Kind::Raw;
+          t->constant->expandTo(raws_[t->index], prog_.getVecSize());
+          break;
+        case Op::Encode:
+          if (a(0).kind != Kind::Raw) throw std::runtime_error("Encode expects a raw operand");
+          v.kind = Kind::Plain; v.ell = levelToEll(t->encodeAtLevel.value()); v.scale = std::ldexp(1.0, (int)t->encodeAtScale.value());
+          place(v);
+          break;
+        case Op::Add: case Op::Sub: case Op::Mul: {
+          const ValueInfo &x = a(0), &y = a(1);
+          if (x.kind == Kind::Raw && y.kind == Kind::Raw) { v.kind = Kind::Raw; break; }
+          if (x.kind == Kind::Raw || y.kind == Kind::Raw) throw std::runtime_error("Unsupported operation encountered");
+          if (x.kind != Kind::Cipher && y.kind != Kind::Cipher) throw std::runtime_error("Unsupported operation encountered");
+          if (x.ell != y.ell) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+          const ValueInfo &c = x.kind == Kind::Cipher ? x : y, &o = x.kind == Kind::Cipher ? y : x;
+          v.kind = Kind::Cipher; v.ell = x.ell;
+          if (t->op == Op::Mul) {
+            v.scale = x.scale * y.scale;
+            if (o.kind == Kind::Cipher) {
+              if (x.size != 2 || y.size != 2) throw std::runtime_error("ciphertext multiplication expects size-2 operands");
+              v.size = 3;
+            } else v.size = c.size;
+          } else {
+            if (x.scale != y.scale) throw std::invalid_argument("scale mismatch");
+            v.scale = x.scale;
+            v.size = o.kind == Kind::Cipher ? std::max(x.size, y.size) : c.size;
+            if (t->op == Op::Sub && x.kind != Kind::Cipher) throw std::runtime_error("plain - cipher must be lowered before execution");
+          }
+          place(v);
+        } break;
+        case Op::Negate:
+          if (a(0).kind == Kind::Raw) { v.kind = Kind::Raw; break; }
+          v = a(0); v.alias = false; place(v);
+          break;
+        case Op::RotateLeftConst: case Op::RotateRightConst:
+          if (a(0).kind == Kind::Raw) { v.kind = Kind::Raw; break; }
+          if (a(0).kind != Kind::Cipher || a(0).size != 2) throw std::runtime_error("rotation expects a size-2 ciphertext");
+          v = a(0); v.alias = false; place(v);
+          break;
+        case Op::Relinearize:
+          if (a(0).kind != Kind::Cipher) throw std::runtime_error("Relinearize expects a ciphertext");
+          v = a(0); v.alias = false; v.size = 2; place(v);
+          break;
+        case Op::ModSwitch: case Op::Rescale:
+          if (a(0).kind != Kind::Cipher) throw std::runtime_error("ModSwitch/Rescale expects a ciphertext");
+          if (a(0).ell < 2) throw std::invalid_argument("end of modulus switching chain reached");
+          v = a(0); v.alias = false; v.ell = a(0).ell - 1;
+          if (t->op == Op::Rescale) v.scale = a(0).scale / std::ldexp(1.0, (int)t->rescaleDivisor.value());
+          place(v);
+          break;
+        case Op::Output:
+          v = a(0); v.alias = true;
+          break;
+        default: throw std::runtime_error(std::string("Unhandled op ") + opName(t->op));
+      }
+      if (v.kind == Kind::Cipher && t->op != Op::Input && t->op != Op::Output) cipherOps_++;
+    }
+    // ---- stream assignment + event edges
+    const int S = std::max(1, opt_.numStreams);
+    std::vector<int> streamOf(prog_.termCount(), -1), eventOf(prog_.termCount(), -1);
+    std::vector<char> chainTaken(prog_.termCount(), 0);
+    std::vector<std::size_t> workWords(S, 0);
+    int rr = 0;
+    for (auto &t : order_) {
+      const ValueInfo &v = vals_[t->index];
+      const bool device = (v.kind == Kind::Cipher || v.kind == Kind::Plain) && t->op != Op::Input && !v.alias;
+      if (!device) {
+        if (v.alias) streamOf[t->index] = streamOf[t->operandAt(0)->index];
+        continue;
+      }
+      Step st;
+      st.term = t.get(); st.op = t->op;
+      // continue the chain of a device operand nobody continued yet, else take a new stream round-robin
+      int chosen = -1;
+      for (auto &o : t->getOperands()) {
+        const int so = streamOf[o->index];
+        if (so >= 0 && !chainTaken[o->index] && o->op != Op::Input) { chosen = so; chainTaken[o->index] = 1; break; }
+      }
+      if (chosen < 0) chosen = (rr++) % S;
+      st.stream = chosen;
+      for (auto &o : t->getOperands()) {
+        const int so = streamOf[o->index];
+        if (so >= 0 && so != chosen && o->op != Op::Input) {
+          std::uint64_t src = o->index;
+          if (eventOf[src] < 0) { eventOf[src] = numEvents_++; recordAfter_[src] = eventOf[src]; }
+          if (std::find(st.waits.begin(), st.waits.end(), eventOf[src]) == st.waits.end()) st.waits.push_back(eventOf[src]);
+        }
+      }
+      std::size_t w = 0;
+      if (t->op == Op::Relinearize || ((t->op == Op::RotateLeftConst || t->op == Op::RotateRightConst) && *t->rotation != 0))
+        w = evab_keyswitch_work_bytes(dev_->ctx(), vals_[t->operandAt(0)->index].ell) / 8;
+      else if (t->op == Op::Rescale)
+        w = evab_rescale_work_bytes(dev_->ctx(), vals_[t->operandAt(0)->index].size) / 8;
+      workWords[chosen] = std::max(workWords[chosen], w);
+      streamOf[t->index] = chosen;
+      steps_.push_back(st);
+    }
+    // resolve alias chains (Output of X shares X's storage; Output(Output) never occurs)
+    for (auto &t : order_) {
+      ValueInfo &v = vals_[t->index];
+      if (v.alias) { const ValueInfo &src = vals_[t->operandAt(0)->index]; v.off = src.off; }
+    }
+    for (auto &st : steps_) {
+      auto it = recordAfter_.find(st.term->index);
+      if (it != recordAfter_.end()) st.record = it->second;
+    }
+    // last step of every stream must be joined back into the caller's stream
+    usedStreams_ = 0;
+    for (auto &st : steps_) usedStreams_ = std::max(usedStreams_, st.stream + 1);
+    workOff_.assign(usedStreams_, 0);
+    for (int s = 0; s < usedStreams_; s++) { workOff_[s] = arenaWords; arenaWords += workWords[s]; }
+    arena_ = DBuf(dev_, arenaWords + 8);
+    for (int s = 0; s < usedStreams_; s++) { void *h; check(evab_stream_create(dev_->ctx(), &h)); streams_.push_back(h); }
+    for (int e = 0; e < numEvents_ + usedStreams_ + 1; e++) { void *h; check(evab_event_create(dev_->ctx(), &h)); events_.push_back(h); }
+    // plan-time constants: raw values and (optionally) their encodings
+    evalRawAndEncodes(nullptr);
+    rawDirty_ = false;
+    // galois tables for every rotation in the program
+    for (auto &st : steps_)
+      if ((st.op == Op::RotateLeftConst || st.op == Op::RotateRightConst) && *st.term->rotation != 0) {
+        const u64 elt = galoisElt(*st.term);
+        if (!keys_.galois.count(elt)) throw std::invalid_argument("Galois key not present");
+        check(evab_galois_prepare(dev_->ctx(), elt));
+      }
+  }
+  int levelToEll(std::uint32_t level) const {
+    const int ell = k_ - 1 - (int)level;
+    if (ell < 1) throw std::runtime_error("level exceeds the modulus chain");
+    return ell;
+  }
+  u64 galoisElt(const Term &t) const {
+    const int steps = t.op == Op::RotateLeftConst ? *t.rotation : -*t.rotation;
+    const u64 elt = evab_galois_elt_from_step(N_, steps);
+    if (!elt) throw std::invalid_argument("step count too large");
+    return elt;
+  }
+
+  // raw (vector<double>) terms run on the host (reference seal_executor.h:63-112);
+  // Encode terms whose operand does not depend on raw inputs are encoded once.
+  void evalRawAndEncodes(void *stream) {
+    hasDynamicEncodes_ = false;
+    std::vector<char> dyn(prog_.termCount(), 0);
+    for (auto &t : order_) {
+      const ValueInfo &v = vals_[t->index];
+      bool d = (t->op == Op::Input && v.kind == Kind::Raw);
+      for (auto &o : t->getOperands()) d = d || dyn[o->index];
+      dyn[t->index] = d;
+      if (v.kind == Kind::Raw && t->op != Op::Input && t->op != Op::Constant) {
+        auto &out = raws_[t->index];
+        auto &x = raws_[t->operandAt(0)->index];
+        if (t->op == Op::Output) { out = x; continue; }
+        if (x.empty()) { out.clear(); continue; }  // raw input not provided yet
+        const std::size_t n = x.size();
+        out.resize(n);
+        if (t->op == Op::Negate) for (std::size_t i = 0; i < n; i++) out[i] = -x[i];
+        else if (t->op == Op::RotateLeftConst || t->op == Op::RotateRightConst) {
+          long long sh = *t->rotation;
+          if (t->op == Op::RotateRightConst) sh = -sh;
+          sh %= (long long)n; if (sh < 0) sh += n;
+          for (std::size_t i = 0; i < n; i++) out[i] = x[(i + sh) % n];
+        } else {
+          auto &y = raws_[t->operandAt(1)->index];
+          if (y.empty()) { out.clear(); continue; }
+          for (std::size_t i = 0; i < n; i++) out[i] = t->op == Op::Add ? x[i] + y[i] : t->op == Op::Sub ? x[i] - y[i] : x[i] * y[i];
+        }
+      }
+      if (t->op == Op::Encode) {
+        const bool dynamic = dyn[t->index] || !opt_.cacheConstants;
+        hasDynamicEncodes_ = hasDynamicEncodes_ || dynamic;
+        if (encoded_.count(t->index) && !dynamic) continue;
+        auto &x = raws_[t->operandAt(0)->index];
+        if (x.empty()) continue;
+        encodeTerm(*t, x, stream);
+        encoded_.insert(t->index);
+      }
+    }
+  }
+  void encodeTerm(const Term &t, const std::vector<double> &x, void *stream) {
+    const ValueInfo &v = vals_[t.index];
+    const u64 slots = N_ / 2;
+    if (slots % x.size()) throw std::runtime_error("Vector size must exactly divide the slot count");
+    std::vector<double> rep;
+    rep.reserve(slots);
+    for (u64 r = slots / x.size(); r > 0; --r) rep.insert(rep.end(), x.begin(), x.end());  // seal_executor.h:229-240
+    enc_.encode(rep, v.scale, v.ell, arena_.get() + v.off, stream);
+  }
+
+  // ---------------------------------------------------------------- execution
+  void issue(const Step &st, void *stream) {
+    const Term &t = *st.term;
+    evab_ctx *c = dev_->ctx();
+    const ValueInfo &o = vals_[t.index];
+    u64 *out = arena_.get() + o.off;
+    auto V = [&](int i) -> const ValueInfo & { return vals_[t.operandAt(i)->index]; };
+    auto P = [&](int i) -> const u64 * { return arena_.get() + vals_[t.operandAt(i)->index].off; };
+    u64 *work = arena_.get() + workOff_[st.stream];
+    switch (t.op) {
+      case Op::Encode:
+        break;  // produced by evalRawAndEncodes
+      case Op::Add: case Op::Sub: case Op::Mul: {
+        int ci = V(0).kind == Kind::Cipher ? 0 : 1, oi = 1 - ci;
+        if (V(oi).kind == Kind::Cipher) {
+          if (t.op == Op::Add) check(evab_add(c, o.ell, out, P(0), V(0).size, P(1), V(1).size, stream));
+          else if (t.op == Op::Sub) check(evab_sub(c, o.ell, out, P(0), V(0).size, P(1), V(1).size, stream));
+          else if (t.operandAt(0) == t.operandAt(1)) check(evab_square(c, o.ell, out, P(0), stream));  // seal_executor.h:161
+          else check(evab_mul(c, o.ell, out, P(0), P(1), stream));
+        } else {
+          if (t.op == Op::Add) check(evab_add_plain(c, o.ell, out, P(ci), V(ci).size, P(oi), stream));
+          else if (t.op == Op::Sub) check(evab_sub_plain(c, o.ell, out, P(0), V(0).size, P(1), stream));
+          else check(evab_mul_plain(c, o.ell, out, P(ci), V(ci).size, P(oi), stream));
+        }
+      } break;
+      case Op::Negate: check(evab_negate(c, o.ell, out, P(0), V(0).size, stream)); break;
+      case Op::RotateLeftConst: case Op::RotateRightConst:
+        if (*t.rotation == 0) check(evab_add_plain(c, o.ell, out, P(0), 2, enc_.zeroPlain(o.ell), stream));  // rotate_vector(0): copy
+        else { const u64 elt = galoisElt(t); check(evab_rotate(c, o.ell, out, P(0), elt, keys_.galois.at(elt).get(), work, stream)); }
+        break;
+      case Op::Relinearize: check(evab_relinearize(c, o.ell, out, P(0), keys_.relin.get(), work, stream)); break;
+      case Op::ModSwitch: check(evab_mod_switch(c, V(0).ell, out, P(0), V(0).size, stream)); break;
+      case Op::Rescale: check(evab_rescale(c, V(0).ell, out, P(0), V(0).size, work, stream)); break;
+      default: throw std::runtime_error(std::string("Unhandled op ") + opName(t.op));
+    }
+  }
+  // fork from `stream` into the plan's streams, issue every step, join back
+  void replay(void *stream) {
+    evab_ctx *c = dev_->ctx();
+    void *forkEv = events_[numEvents_ + usedStreams_];
+    check(evab_event_record(c, forkEv, stream));
+    for (int s = 0; s < usedStreams_; s++) check(evab_stream_wait_event(c, streams_[s], forkEv));
+    for (auto &st : steps_) {
+      void *s = streams_[st.stream];
+      for (int e : st.waits) check(evab_stream_wait_event(c, s, events_[e]));
+      issue(st, s);
+      if (st.record >= 0) check(evab_event_record(c, events_[st.record], s));
+    }
+    for (int s = 0; s < usedStreams_; s++) {
+      check(evab_event_record(c, events_[numEvents_ + s], streams_[s]));
+      check(evab_stream_wait_event(c, stream, events_[numEvents_ + s]));
+    }
+  }
+  void capture() {
+    evab_ctx *c = dev_->ctx();
+    if (graph_) { evab_graph_destroy(c, graph_); graph_ = nullptr; }
+    if (!capStream_) { check(evab_stream_create(c, &capStream_)); streams_.push_back(capStream_); }
+    enc_.zeroPlain(k_);  // make sure lazily-created helpers exist before capture
+    check(evab_graph_begin(c, capStream_));
+    try { replay(capStream_); } catch (...) { void *g = nullptr; evab_graph_end(c, capStream_, &g); throw; }
+    check(evab_graph_end(c, capStream_, &graph_));
+    graphValid_ = true;
+  }
+
+  std::shared_ptr<Device> dev_;
+  CkksEncoder &enc_;
+  const KeySet &keys_;
+  Program &prog_;
+  ExecOptions opt_;
+  u64 N_;
+  int k_;
+  std::vector<Term::Ptr> order_;
+  std::vector<ValueInfo> vals_;
+  std::vector<std::vector<double>> raws_;
+  std::vector<Step> steps_;
+  std::unordered_map<std::uint64_t, int> recordAfter_;
+  std::unordered_set<std::uint64_t> encoded_;
+  std::vector<std::size_t> workOff_;
+  std::vector<void *> streams_, events_;
+  void *capStream_ = nullptr;
+  void *graph_ = nullptr;
+  bool graphValid_ = false, rawDirty_ = false, rawInputs_ = false, hasDynamicEncodes_ = false;
+  int numEvents_ = 0, usedStreams_ = 0;
+  std::size_t cipherOps_ = 0;
+  DBuf arena_;
+};
+
+}  // namespace evab

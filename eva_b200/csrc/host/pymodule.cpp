@@ -1,0 +1,186 @@
+// pymodule.cpp -- pybind11 module `eva_b200._eva_b200`: the Python-facing
+// surface of the backend, name-compatible with the reference's `_eva` module
+// (python/eva/wrapper.cpp:26-246) for Program/Term/Op/Type/evaluate/
+// CKKSParameters/CKKSSignature/CKKSEncodingInfo/generate_keys/*Valuation/
+// *Public.encrypt/execute/*Secret.decrypt, plus a few test/benchmark hooks
+// (raw key/ciphertext injection, device-resident execution).
+#include "backend.hpp"
+#include "reference_eval.hpp"
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+namespace py = pybind11;
+using namespace evab;
+typedef py::array_t<std::uint64_t, py::array::c_style | py::array::forcecast> u64arr;
+
+static std::vector<u64> toVec(const u64arr &a) { return std::vector<u64>(a.data(), a.data() + a.size()); }
+
+PYBIND11_MODULE(_eva_b200, m) {
+  m.doc() = "B200-native EVA backend";
+
+  py::enum_<Op>(m, "Op")
+      .value("Undef", Op::Undef).value("Input", Op::Input).value("Output", Op::Output).value("Constant", Op::Constant)
+      .value("Negate", Op::Negate).value("Add", Op::Add).value("Sub", Op::Sub).value("Mul", Op::Mul)
+      .value("RotateLeftConst", Op::RotateLeftConst).value("RotateRightConst", Op::RotateRightConst)
+      .value("Relinearize", Op::Relinearize).value("ModSwitch", Op::ModSwitch).value("Rescale", Op::Rescale).value("Encode", Op::Encode);
+  py::enum_<Type>(m, "Type").value("Undef", Type::Undef).value("Cipher", Type::Cipher).value("Raw", Type::Raw).value("Plain", Type::Plain);
+
+  py::class_<Term, std::shared_ptr<Term>>(m, "Term", "EVA's native Term class")
+      .def_readonly("op", &Term::op, "The operation performed by this term")
+      .def_readonly("index", &Term::index)
+      .def_property_readonly("operands", &Term::getOperands)
+      .def_property_readonly("attributes", [](const Term &t) {
+        py::dict d;
+        if (t.rescaleDivisor) d["RescaleDivisorAttribute"] = *t.rescaleDivisor;
+        if (t.rotation) d["RotationAttribute"] = *t.rotation;
+        if (t.type) d["TypeAttribute"] = *t.type;
+        if (t.range) d["RangeAttribute"] = *t.range;
+        if (t.encodeAtScale) d["EncodeAtScaleAttribute"] = *t.encodeAtScale;
+        if (t.encodeAtLevel) d["EncodeAtLevelAttribute"] = *t.encodeAtLevel;
+        if (t.constant) d["ConstantValueAttribute"] = t.constant->values();
+        return d;
+      })
+      .def("_set_attributes", [](Term &t, const py::dict &d) {  // fixture loading / tests
+        for (auto item : d) {
+          const std::string k = py::cast<std::string>(item.first);
+          if (k == "RescaleDivisorAttribute") t.rescaleDivisor = py::cast<std::uint32_t>(item.second);
+          else if (k == "RotationAttribute") t.rotation = py::cast<std::int32_t>(item.second);
+          else if (k == "TypeAttribute") t.type = py::cast<Type>(item.second);
+          else if (k == "RangeAttribute") t.range = py::cast<std::uint32_t>(item.second);
+          else if (k == "EncodeAtScaleAttribute") t.encodeAtScale = py::cast<std::uint32_t>(item.second);
+          else if (k == "EncodeAtLevelAttribute") t.encodeAtLevel = py::cast<std::uint32_t>(item.second);
+          else throw std::runtime_error("unknown attribute " + k);
+        }
+      });
+
+  py::class_<Program>(m, "Program", "EVA's native Program class")
+      .def(py::init<std::string, std::uint64_t>(), py::arg("name"), py::arg("vec_size"))
+      .def_property("name", &Program::getName, &Program::setName, "The name of this program")
+      .def_property_readonly("vec_size", &Program::getVecSize, "The number of elements for all vectors in this program")
+      .def_property_readonly("inputs", py::cpp_function(&Program::getInputs, py::keep_alive<0, 1>()), "A dictionary from input names to terms")
+      .def_property_readonly("outputs", py::cpp_function(&Program::getOutputs, py::keep_alive<0, 1>()), "A dictionary from output names to terms")
+      .def("set_output_ranges", [](const Program &p, std::uint32_t range) { for (auto &e : p.getOutputs()) e.second->range = range; }, py::arg("range"))
+      .def("set_input_scales", [](const Program &p, std::uint32_t scale) { for (auto &s : p.getSources()) s->encodeAtScale = scale; }, py::arg("scale"))
+      .def("to_DOT", &Program::toDOT)
+      .def("terms", &Program::toposort, "All live terms in topological order")
+      .def("_make_term", &Program::makeTerm, py::keep_alive<0, 1>())
+      .def("_make_left_rotation", &Program::makeLeftRotation, py::keep_alive<0, 1>())
+      .def("_make_right_rotation", &Program::makeRightRotation, py::keep_alive<0, 1>())
+      .def("_make_dense_constant", &Program::makeDenseConstant, py::keep_alive<0, 1>())
+      .def("_make_uniform_constant", &Program::makeUniformConstant, py::keep_alive<0, 1>())
+      .def("_make_input", &Program::makeInput, py::keep_alive<0, 1>())
+      .def("_make_output", &Program::makeOutput, py::keep_alive<0, 1>());
+
+  m.def("evaluate", &evaluate, py::arg("program"), py::arg("inputs"), "Evaluate the program without homomorphic encryption");
+  m.def("set_num_threads", [](int) {}, py::arg("num_threads"),
+        "Kept for API compatibility: the DAG is scheduled on CUDA streams, not CPU threads.");
+  py::class_<int>(m, "_GaloisGuard").def(py::init());
+
+  py::module mckks = m.def_submodule("_ckks", "CKKS compiler types");
+  py::class_<CKKSParameters>(mckks, "CKKSParameters", "Abstract encryption parameters for CKKS")
+      .def(py::init([](std::vector<std::uint32_t> bits, std::set<int> rots, std::uint32_t n) { CKKSParameters p; p.primeBits = bits; p.rotations = rots; p.polyModulusDegree = n; return p; }),
+           py::arg("prime_bits"), py::arg("rotations"), py::arg("poly_modulus_degree"))
+      .def_readonly("prime_bits", &CKKSParameters::primeBits)
+      .def_readonly("rotations", &CKKSParameters::rotations)
+      .def_readonly("poly_modulus_degree", &CKKSParameters::polyModulusDegree);
+  py::class_<CKKSEncodingInfo>(mckks, "CKKSEncodingInfo")
+      .def(py::init<Type, int, int>(), py::arg("input_type"), py::arg("scale"), py::arg("level"))
+      .def_readonly("input_type", &CKKSEncodingInfo::inputType)
+      .def_readonly("scale", &CKKSEncodingInfo::scale)
+      .def_readonly("level", &CKKSEncodingInfo::level);
+  py::class_<CKKSSignature>(mckks, "CKKSSignature")
+      .def(py::init<int, std::map<std::string, CKKSEncodingInfo>>(), py::arg("vec_size"), py::arg("inputs"))
+      .def_readonly("vec_size", &CKKSSignature::vecSize)
+      .def_readonly("inputs", &CKKSSignature::inputs);
+
+  py::module mb = m.def_submodule("_b200", "B200 CUDA backend (replaces the reference's _seal submodule)");
+  py::class_<B200Valuation>(mb, "B200Valuation", "A valuation for inputs or outputs holding encrypted values")
+      .def(py::init<>())
+      .def("names", [](const B200Valuation &v) { std::vector<std::string> n; for (auto &e : v) n.push_back(e.first); return n; })
+      .def("set_cipher", [](B200Valuation &v, const std::string &name, const u64arr &data, double scale) {
+        if (data.ndim() != 3) throw std::runtime_error("ciphertext array must be [size][ell][N]");
+        HostCipher h; h.data = toVec(data); h.size = (int)data.shape(0); h.ell = (int)data.shape(1); h.scale = scale;
+        v[name] = std::move(h);
+      }, "test/benchmark hook: inject a raw ciphertext [size][ell][N]")
+      .def("set_plain", [](B200Valuation &v, const std::string &name, const u64arr &data, double scale) {
+        HostPlain h; h.data = toVec(data); h.ell = (int)data.shape(0); h.scale = scale; v[name] = std::move(h);
+      })
+      .def("set_raw", [](B200Valuation &v, const std::string &name, const std::vector<double> &x) { v[name] = std::make_shared<ConstantValue>(x.size(), x); })
+      .def("get", [](const B200Valuation &v, const std::string &name) -> py::object {
+        const SchemeValue &sv = v.at(name);
+        if (auto *c = std::get_if<HostCipher>(&sv)) {
+          const std::size_t N = c->data.size() / ((std::size_t)c->size * c->ell);
+          u64arr a({(std::size_t)c->size, (std::size_t)c->ell, N});
+          std::memcpy(a.mutable_data(), c->data.data(), c->data.size() * 8);
+          return py::make_tuple("cipher", a, c->scale);
+        }
+        if (auto *p = std::get_if<HostPlain>(&sv)) {
+          const std::size_t N = p->data.size() / (std::size_t)p->ell;
+          u64arr a({(std::size_t)p->ell, N});
+          std::memcpy(a.mutable_data(), p->data.data(), p->data.size() * 8);
+          return py::make_tuple("plain", a, p->scale);
+        }
+        return py::make_tuple("raw", std::get<std::shared_ptr<ConstantValue>>(sv)->values(), 0.0);
+      });
+
+  py::class_<B200Public>(mb, "B200Public", "The public part of the context: encryption and execution on the GPU")
+      .def("encrypt", &B200Public::encrypt, py::arg("inputs"), py::arg("signature"))
+      .def("execute", &B200Public::execute, py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>())
+      .def("set_options", [](B200Public &p, int streams, bool graph, bool cache) { p.options.numStreams = streams; p.options.useGraph = graph; p.options.cacheConstants = cache; },
+           py::arg("num_streams") = 8, py::arg("use_graph") = true, py::arg("cache_constants") = true)
+      .def("drop_plan", &B200Public::dropExecutor)
+      .def("cipher_op_count", [](B200Public &p, Program &prog) { return p.executorFor(prog).cipherOpCount(); })
+      .def("launch_count", [](B200Public &p) { return evab_launch_count(p.shared()->dev->ctx()); })
+      .def("primes", [](B200Public &p) { return p.shared()->dev->primes(); })
+      // ---- benchmark hooks: device-resident execution on a caller-provided stream
+      .def("stage_inputs", [](B200Public &p, Program &prog, const B200Valuation &in, std::uintptr_t stream) { p.stageInputs(p.executorFor(prog), prog, in, (void *)stream); })
+      .def("run_resident", [](B200Public &p, Program &prog, std::uintptr_t stream) { p.executorFor(prog).run((void *)stream); },
+           py::call_guard<py::gil_scoped_release>())
+      .def("sync", [](B200Public &p, std::uintptr_t stream) { p.shared()->dev->sync((void *)stream); }, py::call_guard<py::gil_scoped_release>())
+      // ---- test hooks
+      .def("debug_value", [](B200Public &p, Program &prog, std::uint64_t index) -> py::object {
+        Executor &ex = p.executorFor(prog);
+        const ValueInfo &vi = ex.info(index);
+        auto dev = p.shared()->dev;
+        if (vi.kind == Kind::Raw) return py::cast(ex.rawValue(index));
+        if (vi.kind == Kind::None) return py::none();
+        const std::size_t polys = vi.kind == Kind::Cipher ? vi.size : 1;
+        u64arr a({polys, (std::size_t)vi.ell, (std::size_t)dev->N()});
+        dev->sync();
+        dev->download(a.mutable_data(), ex.valuePtr(index), a.size() * 8);
+        dev->sync();
+        return py::make_tuple(a, vi.scale);
+      })
+      .def("encode", [](B200Public &p, const std::vector<double> &values, double scale, int ell) {
+        auto dev = p.shared()->dev;
+        DBuf pt(dev, (std::size_t)ell * dev->N());
+        p.shared()->client->encoder().encode(values, scale, ell, pt.get());
+        u64arr a({(std::size_t)ell, (std::size_t)dev->N()});
+        dev->download(a.mutable_data(), pt.get(), a.size() * 8);
+        dev->sync();
+        return a;
+      });
+  py::class_<B200Secret>(mb, "B200Secret", "The secret part of the context: decryption")
+      .def("decrypt", &B200Secret::decrypt, py::arg("enc_outputs"), py::arg("signature"));
+
+  mb.def("generate_keys", [](const CKKSParameters &p, int device, std::uint64_t seed) { return generateKeys(p, device, seed); },
+         py::arg("abstract_params"), py::arg("device") = 0, py::arg("seed") = 0);
+  // test/benchmark hook: evaluation context from externally supplied key material
+  mb.def("context_from_raw_keys", [](std::uint64_t N, const std::vector<u64> &primes, const u64arr &relin, const std::map<u64, u64arr> &galois, int device) {
+    auto s = std::make_shared<Shared>();
+    s->dev = std::make_shared<Device>(N, primes, device);
+    s->client = std::make_unique<CkksClient>(s->dev, 1);
+    s->keys.relin = DBuf(s->dev, relin.size());
+    s->dev->upload(s->keys.relin.get(), relin.data(), relin.size() * 8);
+    for (auto &g : galois) {
+      check(evab_galois_prepare(s->dev->ctx(), g.first));
+      DBuf d(s->dev, g.second.size());
+      s->dev->upload(d.get(), g.second.data(), g.second.size() * 8);
+      s->keys.galois.emplace(g.first, std::move(d));
+    }
+    s->dev->sync();
+    return std::make_unique<B200Public>(s);
+  }, py::arg("N"), py::arg("primes"), py::arg("relin_key"), py::arg("galois_keys"), py::arg("device") = 0);
+  mb.def("create_coeff_modulus", [](std::uint64_t N, const std::vector<int> &bits) { return hmod::createCoeffModulus(N, bits); });
+}

@@ -52,6 +52,26 @@ int evab_upload(evab_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, voi
 int evab_download(evab_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
 int evab_sync(evab_ctx *ctx, void *stream); /* blocks the calling thread */
 
+/* ---- scheduler glue: streams, events and CUDA-graph capture.  These replace
+ * the Galois worklist + atomics of MulticoreProgramTraversal::forwardPass
+ * (eva/common/multicore_program_traversal.h:24-84): independent DAG terms are
+ * enqueued on different streams, dependencies become events, and a whole
+ * execute() can be captured once and replayed as one graph launch. ---- */
+int evab_stream_create(evab_ctx *ctx, void **stream);
+int evab_stream_destroy(evab_ctx *ctx, void *stream);
+int evab_event_create(evab_ctx *ctx, void **event);            /* timing disabled */
+int evab_event_destroy(evab_ctx *ctx, void *event);
+int evab_event_record(evab_ctx *ctx, void *event, void *stream);
+int evab_stream_wait_event(evab_ctx *ctx, void *stream, void *event);
+/* begin/end capture on `stream` (other streams join through event waits);
+ * end returns an executable graph handle */
+int evab_graph_begin(evab_ctx *ctx, void *stream);
+int evab_graph_end(evab_ctx *ctx, void *stream, void **graph_exec);
+int evab_graph_launch(evab_ctx *ctx, void *graph_exec, void *stream);
+int evab_graph_destroy(evab_ctx *ctx, void *graph_exec);
+/* number of kernel launches issued through this context so far */
+uint64_t evab_launch_count(const evab_ctx *ctx);
+
 /* ---- negacyclic NTT / iNTT (microbenchmark entry, BASELINE config 2) ----
  * d_data holds `count` residue polynomials of N coefficients; polynomial r is
  * transformed in place modulo primes[prime_idx[r % nprimes]].  Semantics:

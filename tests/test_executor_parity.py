@@ -1,0 +1,104 @@
+"""Executor parity on whole programs: the product executor (C++ plan + CUDA
+streams/graph, C-ABI kernels) versus the oracle runner, on programs compiled by
+the REFERENCE compiler (tests/golden/programs).  Bit-exact on every intermediate
+ciphertext; decrypted outputs also checked against the reference's own
+acceptance criterion (tests/common.py:34, MSE < 0.01) using reference_outputs."""
+import numpy as np
+import pytest
+
+from eva_b200 import program_io as gl
+from oracle import oracle as o
+from oracle_exec import OracleProgram
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(name, seed=1, use_graph=True, streams=8):
+    from eva_b200 import b200
+    d = gl.load_json(name)
+    prog, params, sig, terms = gl.build_program(d)
+    N = d["poly_modulus_degree"]
+    orc = o.Oracle(N, d["prime_bits"]).keygen(seed)
+    op = OracleProgram(d, orc)
+    op.prepare_keys()
+    assert b200.create_coeff_modulus(N, d["prime_bits"]) == orc.primes
+    pub = b200.context_from_raw_keys(N, orc.primes, op.rk, {int(e): k for e, k in op.gks.items()})
+    pub.set_options(num_streams=streams, use_graph=use_graph, cache_constants=True)
+    rng = np.random.default_rng(seed)
+    inputs_o, val, plain_inputs = {}, b200.B200Valuation(), {}
+    for name_, info in d["signature"].items():
+        x = rng.uniform(-1, 1, d["vec_size"])
+        plain_inputs[name_] = x
+        ell = orc.k - 1 - info["level"]
+        if info["type"] == "Cipher":
+            ct = orc.encrypt(orc.encode(x, 2.0 ** info["scale"], ell), seed=11)
+            inputs_o[name_] = ("cipher", ct, 2.0 ** info["scale"])
+            val.set_cipher(name_, ct, 2.0 ** info["scale"])
+        elif info["type"] == "Raw":
+            inputs_o[name_] = ("raw", x)
+            val.set_raw(name_, list(x))
+        else:
+            pt = orc.encode(x, 2.0 ** info["scale"], ell)
+            inputs_o[name_] = ("plain", pt, 2.0 ** info["scale"])
+            val.set_plain(name_, pt, 2.0 ** info["scale"])
+    V = op.run(inputs_o)
+    out = pub.execute(prog, val)
+    out2 = pub.execute(prog, val)   # second run replays the captured graph
+    n_checked = 0
+    for t in d["terms"]:
+        want = V[t["id"]]
+        got = pub.debug_value(prog, terms[t["id"]].index)
+        if want[0] == "raw":
+            assert np.allclose(np.asarray(got), want[1])
+            continue
+        arr, scale = got
+        w = want[1] if want[0] == "cipher" else want[1][None]
+        assert arr.shape == w.shape, (t, arr.shape, w.shape)
+        assert scale == want[2], (t, scale, want[2])
+        assert np.array_equal(arr, w), "term %d (%s) differs" % (t["id"], t["op"])
+        n_checked += 1
+    for oname, oid in d["outputs"].items():
+        for res in (out, out2):
+            kind, arr, scale = res.get(oname)
+            want = V[oid]
+            if kind == "cipher":
+                assert np.array_equal(arr, want[1]) and scale == want[2]
+    assert pub.cipher_op_count(prog) == op.cipher_op_count()
+    return d, orc, V, plain_inputs, n_checked
+
+
+@pytest.mark.parametrize("name", ["polynomial", "feat_bin_mul_11", "feat_bin_sub_01", "feat_unary", "feat_rot_m1", "feat_rot_0",
+                                  "feat_mixed", "feat_transparent", "feat_hsum", "feat_deep"])
+def test_small_programs_bit_exact(name):
+    run_both(name)
+
+
+def test_sobel_bit_exact_and_accurate():
+    d, orc, V, x, n = run_both("sobel")
+    assert n >= 61
+    assert sum(1 for t in d["terms"] if t["op"] in ("Add", "Sub", "Mul", "Negate", "RotateLeftConst", "RotateRightConst",
+                                                    "Relinearize", "ModSwitch", "Rescale")) == 61
+    oid = d["outputs"]["image"]
+    dec = orc.decode(orc.decrypt(V[oid][1]), V[oid][2])[:d["vec_size"]]
+    # plaintext semantics of the Sobel program computed directly (reference examples/image_processing.py:39-63)
+    img = x["image"]
+    F = [[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]]
+    ix = sum(np.roll(img, -(i * 64 + j)) * F[i][j] for i in range(3) for j in range(3))
+    iy = sum(np.roll(img, -(i * 64 + j)) * F[j][i] for i in range(3) for j in range(3))
+    dsq = ix ** 2 + iy ** 2
+    ref = dsq * 2.2137874823876622 + dsq ** 2 * -1.0984324107372518 + dsq ** 3 * 0.17254603006834726
+    assert np.mean((dec - ref) ** 2) < 0.01
+
+
+def test_harris_bit_exact():
+    d, orc, V, x, n = run_both("harris")
+    assert n >= 143
+
+
+@pytest.mark.parametrize("graph,streams", [(False, 1), (False, 8), (True, 4)])
+def test_scheduler_modes_agree(graph, streams):
+    run_both("sobel", use_graph=graph, streams=streams)
+
+
+def test_wide_dag():
+    run_both("wide64")
