@@ -4,6 +4,7 @@
 // and error behaviour (C++ exceptions -> Python exceptions through pybind11).
 #pragma once
 #include "executor.hpp"
+#include <atomic>
 #include <tuple>
 #include <variant>
 
@@ -49,9 +50,20 @@ struct Shared {
   KeySet keys;
 };
 
+// the cached plan of one (program, context) pair; owned by the Program
+struct PlanHolder {
+  std::shared_ptr<Shared> keepAlive;  // the plan references the context's encoder and keys
+  std::unique_ptr<Executor> exec;
+  std::uint64_t termCount = 0;
+  ExecOptions opt;
+};
+
 class B200Public {
 public:
-  explicit B200Public(std::shared_ptr<Shared> s) : s_(std::move(s)) {}
+  explicit B200Public(std::shared_ptr<Shared> s) : s_(std::move(s)) {
+    static std::atomic<std::uint64_t> next{1};
+    id_ = next.fetch_add(1);
+  }
 
   // SEALPublic::encrypt -- reference eva/seal/seal.cpp:24-102
   B200Valuation encrypt(const Valuation &inputs, const CKKSSignature &sig) {
@@ -89,12 +101,17 @@ public:
   }
 
   Executor &executorFor(Program &program) {
-    auto it = execs_.find(&program);
-    if (it == execs_.end() || it->second.second != program.termCount())
-      it = execs_.insert_or_assign(&program, std::make_pair(std::make_unique<Executor>(s_->dev, s_->client->encoder(), s_->keys, program, options), program.termCount())).first;
-    return *it->second.first;
+    auto h = std::static_pointer_cast<PlanHolder>(program.attachment(id_));
+    if (!h || h->termCount != program.termCount()) {
+      h = std::make_shared<PlanHolder>();
+      h->keepAlive = s_;
+      h->exec = std::make_unique<Executor>(s_->dev, s_->client->encoder(), s_->keys, program, options);
+      h->termCount = program.termCount();
+      program.attach(id_, h);
+    }
+    return *h->exec;
   }
-  void dropExecutor(Program &program) { execs_.erase(&program); }
+  void dropExecutor(Program &program) { program.attach(id_, nullptr); }
 
   // upload host inputs into the executor's arena (H2D on `stream`)
   void stageInputs(Executor &ex, Program &program, const B200Valuation &inputs, void *stream) {
@@ -146,7 +163,7 @@ public:
 
 private:
   std::shared_ptr<Shared> s_;
-  std::map<Program *, std::pair<std::unique_ptr<Executor>, std::uint64_t>> execs_;
+  std::uint64_t id_ = 0;
 };
 
 class B200Secret {

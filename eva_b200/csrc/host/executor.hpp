@@ -90,7 +90,7 @@ public:
 private:
   // ---------------------------------------------------------------- planning
   void buildPlan() {
-    order_ = prog_.toposort();
+    for (auto &t : prog_.toposort()) order_.push_back(t.get());  // raw: the plan lives inside the Program (attachment)
     vals_.assign(prog_.termCount(), ValueInfo{});
     raws_.resize(prog_.termCount());
     std::size_t arenaWords = 0;
@@ -179,7 +179,7 @@ private:
         continue;
       }
       Step st;
-      st.term = t.get(); st.op = t->op;
+      st.term = t; st.op = t->op;
       // continue the chain of a device operand nobody continued yet, else take a new stream round-robin
       int chosen = -1;
       for (auto &o : t->getOperands()) {
@@ -366,7 +366,7 @@ private:
   ExecOptions opt_;
   u64 N_;
   int k_;
-  std::vector<Term::Ptr> order_;
+  std::vector<Term *> order_;
   std::vector<ValueInfo> vals_;
   std::vector<std::vector<double>> raws_;
   std::vector<Step> steps_;

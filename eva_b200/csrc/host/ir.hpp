@@ -131,10 +131,14 @@ public:
   }
   Program(const Program &) = delete;
   ~Program() {
+    attachments_.clear();  // backend plans hold raw Term pointers: they die with the program
     // release the roots first; Terms deregister themselves from sources_/sinks_
     outputs_.clear();
     inputs_.clear();
   }
+  // opaque per-backend state (e.g. a cached execution plan) that must not outlive the program
+  std::shared_ptr<void> attachment(std::uint64_t key) const { auto it = attachments_.find(key); return it == attachments_.end() ? nullptr : it->second; }
+  void attach(std::uint64_t key, std::shared_ptr<void> v) { if (v) attachments_[key] = std::move(v); else attachments_.erase(key); }
 
   Term::Ptr makeTerm(Op op, const std::vector<Term::Ptr> &operands = {}) {
     auto t = std::make_shared<Term>(op, *this);
@@ -196,6 +200,7 @@ private:
   std::uint64_t nextIndex_ = 0;
   std::unordered_set<Term *> sources_, sinks_;
   std::vector<TermMapBase *> maps_;
+  std::map<std::uint64_t, std::shared_ptr<void>> attachments_;
   // roots last: their destruction tears the graph down while the sets above are alive
   std::map<std::string, Term::Ptr> outputs_, inputs_;
 };
