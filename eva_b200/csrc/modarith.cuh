@@ -49,6 +49,12 @@ EVAB_HD u64 shoup_lazy(u64 y, u64 w, u64 ws, u64 p) {
   return w * y - q * p;
 }
 EVAB_HD u64 shoup_mul(u64 y, u64 w, u64 ws, u64 p) { return csub(shoup_lazy(y, w, ws, p), p); }
+// same with the caller supplying np = 2^64 - p: w*y + q*np (mod 2^64) saves the
+// negation of q in the multiply-accumulate chain
+EVAB_HD u64 shoup_lazy_n(u64 y, u64 w, u64 ws, u64 np) {
+  u64 q = mulhi64(ws, y);
+  return w * y + q * np;
+}
 
 // canonical add / sub / neg for operands already in [0,p)
 EVAB_HD u64 addmod(u64 a, u64 b, u64 p) { return csub(a + b, p); }

@@ -125,17 +125,17 @@ EVAB_HD void xchg_write_c(const u64 (&x)[32], u64 *sm, u32 tid) {
 // `root` is the twiddle root prefix: 1 for a full transform; 2+h for the h-th
 // half of an n+1 transform (twiddle index = (root << s) + group).
 // ---------------------------------------------------------------------------
-EVAB_HD void ct_bfly(u64 &X, u64 &Y, const u64x2 w, u64 p, u64 two_p, bool fix, u64 eight_p) {
+EVAB_HD void ct_bfly(u64 &X, u64 &Y, const u64x2 w, u64 np, u64 two_p, bool fix, u64 eight_p) {
   u64 x = X;
   if (fix) x = csub(x, eight_p);
-  u64 t = shoup_lazy(Y, w.x, w.y, p);
+  u64 t = shoup_lazy_n(Y, w.x, w.y, np);
   X = x + t;
   Y = x - t + two_p;
 }
 // one forward stage over the 32 registers: pair distance d (in k), 16/d groups
 // of twiddles starting at table index tw0 (consecutive).
 template <int D> EVAB_HD void fwd_stage(u64 (&x)[32], const u64x2 *tw, u32 tw0, u64 p, int &b) {
-  const u64 two_p = 2 * p, eight_p = 8 * p;
+  const u64 two_p = 2 * p, eight_p = 8 * p, np = 0 - p;
   const bool fix = b > 14;
   if (fix) b = 8;
 #pragma unroll
@@ -144,7 +144,7 @@ template <int D> EVAB_HD void fwd_stage(u64 (&x)[32], const u64x2 *tw, u32 tw0, 
 #pragma unroll
     for (int j = 0; j < D; j++) {
       const int k = g * 2 * D + j;
-      ct_bfly(x[k], x[k + D], w, p, two_p, fix, eight_p);
+      ct_bfly(x[k], x[k + D], w, np, two_p, fix, eight_p);
     }
   }
   b += 2;
@@ -193,7 +193,7 @@ EVAB_HD void canon(u64 (&x)[32], u64 p, int b) {
 template <int D> EVAB_HD void inv_stage(u64 (&x)[32], const u64x2 *tw, u32 tw0, u64 p, int &b) {
   // entry bound b in {1,2,4,8}; sums are reduced by 8p only once they could
   // reach 16p.
-  const u64 eight_p = 8 * p;
+  const u64 eight_p = 8 * p, np = 0 - p;
   const u64 bias = (u64)b * p;
   const bool fix = b > 4;
 #pragma unroll
@@ -206,7 +206,7 @@ template <int D> EVAB_HD void inv_stage(u64 (&x)[32], const u64x2 *tw, u32 tw0, 
       u64 s = X + Y;
       if (fix) s = csub(s, eight_p);
       x[k] = s;
-      x[k + D] = shoup_lazy(X - Y + bias, w.x, w.y, p);
+      x[k + D] = shoup_lazy_n(X - Y + bias, w.x, w.y, np);
     }
   }
   b = fix ? 8 : 2 * b;
