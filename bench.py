@@ -101,23 +101,32 @@ def synthetic_inputs(d, primes, seed):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from concurrent.futures import ThreadPoolExecutor
     from eva_b200 import b200, program_io
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     d = program_io.load_json(WORKLOAD)
-    prog, params, sig, terms = program_io.build_program(d)
+    B = args.instances
     N = d["poly_modulus_degree"]
     primes = b200.create_coeff_modulus(N, d["prime_bits"])
     relin, galois, cts = synthetic_inputs(d, primes, seed=1234 + rank)
     pub = b200.context_from_raw_keys(N, primes, relin, galois, local)
     pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache)
-    val = b200.B200Valuation()
-    for name, (ct, scale) in cts.items():
-        val.set_cipher(name, ct, scale)
-    nops = pub.cipher_op_count(prog)
-    stream = torch.cuda.current_stream().cuda_stream
+    # B independent program instances (one plan + arena each), same keys, different input ciphertexts
+    progs, vals = [], []
+    for i in range(B):
+        prog, params, sig, terms = program_io.build_program(d)
+        progs.append((prog, terms))
+        _, _, cts_i = synthetic_inputs({**d, "terms": []}, primes, seed=77 * (rank + 1) + i)
+        val = b200.B200Valuation()
+        for name, (ct, scale) in cts_i.items():
+            val.set_cipher(name, ct, scale)
+        vals.append(val)
+    nops = pub.cipher_op_count(progs[0][0])
+    main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(B)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -125,26 +134,34 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (plan build, graph capture, clocks)
-    l0 = pub.launch_count()
-    pub.stage_inputs(prog, val, stream)
-    for _ in range(max(3, args.warmup)):
-        pub.run_resident(prog, stream)
-    torch.cuda.synchronize()
-    out = pub.execute(prog, val)
-    launches_warm = pub.launch_count() - l0
-    # launches per step: count one un-graphed replay
-    pub2_launch0 = pub.launch_count()
+    def step_resident():
+        """one step = B independent Sobel instances, each replayed as one CUDA graph on its own stream"""
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for i in range(B):
+            streams[i].wait_event(fork)
+            pub.run_resident(progs[i][0], streams[i].cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(streams[i])
+            main.wait_event(ev)
+
+    # ---- launches per step (one un-graphed replay of one instance), then plans + graphs
     pub.set_options(num_streams=args.streams, use_graph=False, cache_constants=not args.no_const_cache)
-    pub.drop_plan(prog)
-    pub.stage_inputs(prog, val, stream); pub.run_resident(prog, stream); torch.cuda.synchronize()
-    launches_per_step = pub.launch_count() - pub2_launch0
-    pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache)
-    pub.drop_plan(prog)
-    pub.stage_inputs(prog, val, stream)
-    for _ in range(3):
-        pub.run_resident(prog, stream)
+    pub.stage_inputs(progs[0][0], vals[0], main.cuda_stream)
+    l0 = pub.launch_count()
+    pub.run_resident(progs[0][0], main.cuda_stream)
     torch.cuda.synchronize()
+    launches_per_instance = pub.launch_count() - l0
+    pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache)
+    pub.drop_plan(progs[0][0])
+    for i in range(B):
+        pub.stage_inputs(progs[i][0], vals[i], main.cuda_stream)
+    torch.cuda.synchronize()
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    torch.cuda.synchronize()
+    pool = ThreadPoolExecutor(max_workers=B)
+    outs = list(pool.map(lambda i: pub.execute(progs[i][0], vals[i]), range(B)))   # warm the e2e path
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -153,25 +170,32 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         flush.zero_()
-        ev[i][0].record()
-        pub.run_resident(prog, stream)
-        ev[i][1].record()
+        ev[i][0].record(main)
+        step_resident()
+        ev[i][1].record(main)
     barrier()
     t_res = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
-    # ---- e2e through the public API: host buffers in/out, H2D + D2H inside the timed region
+    # ---- single-instance latency (one graph launch, nothing else on the GPU)
+    lat = []
+    for i in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(main); pub.run_resident(progs[0][0], main.cuda_stream); b.record(main)
+        torch.cuda.synchronize()
+        lat.append(a.elapsed_time(b))
+    lat.sort()
+    # ---- e2e through the public API: host buffers in/out (H2D + D2H inside the timed region),
+    #      B concurrent execute() calls per step from B host threads
     barrier()
     t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     for i in range(args.steps):
-        out = pub.execute(prog, val)
-    e1.record()
+        outs = list(pool.map(lambda j: pub.execute(progs[j][0], vals[j]), range(B)))
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
     barrier()
-    t_e2e = e0.elapsed_time(e1) * 1e-3
     clocks = sampler.finish()
-    h2d = sum(ct.nbytes for ct, _ in cts.values())
-    okind, oarr, _ = out.get(list(d["outputs"].keys())[0])
-    d2h = int(oarr.nbytes)
+    h2d = sum(ct.nbytes for ct, _ in cts.values()) * B
+    okind, oarr, _ = outs[0].get(list(d["outputs"].keys())[0])
+    d2h = int(oarr.nbytes) * B
     # ---- final gather of the outputs on rank 0 (north_star: NCCL only for the final gather)
     if world > 1:
         o_dev = torch.from_numpy(oarr.view(np.int64)).cuda()
@@ -180,23 +204,26 @@ def run_ours(args):
         tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_res, t_e2e = tt.tolist()
-    total_ops = nops * args.steps * world
+    total_ops = nops * B * args.steps * world
     result = {
         "metric": METRIC, "value": total_ops / t_res, "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "sobel_64x64 (examples/image_processing.py) compiled by the reference compiler: N=16384, prime_bits=[60]*5, 61 ciphertext ops, 1 program instance per GPU per step",
-                   "parallelism": "replicas x%d (independent program instances, no data-path collective; NCCL gather of outputs)" % world,
-                   "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("cuda-graph" if not args.no_graph else "streams") + " x%d streams" % args.streams,
+        "config": {"workload": "sobel_64x64 (examples/image_processing.py) compiled by the reference compiler: N=16384, prime_bits=[60]*5, 61 ciphertext ops per instance; one step = batch of %d independent program instances (images) per GPU" % B,
+                   "instances_per_gpu": B,
+                   "parallelism": "replicas x%d GPUs (independent program instances, no data-path collective; NCCL gather of outputs)" % world,
+                   "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("cuda-graph per instance" if not args.no_graph else "streams") + ", %d streams/plan" % args.streams,
                    "const_encode": "cached per plan" if not args.no_const_cache else "every step"},
-        "e2e": {"value": total_ops / t_e2e, "unit": "ops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3},
-        "gpu_launches": int(launches_per_step * args.steps),
+        "e2e": {"value": total_ops / t_e2e, "unit": "ops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,
+                "note": "B200Public.execute() with host numpy buffers, %d concurrent calls per step (host wall clock incl. H2D/D2H)" % B},
+        "single_instance": {"latency_ms": lat[len(lat) // 2], "ops_per_s": nops / (lat[len(lat) // 2] * 1e-3)},
+        "gpu_launches": int(launches_per_instance * B * args.steps),
         "clocks": clocks,
     }
     if rank == 0:
-        result["roofline"] = ntt_roofline(pub, primes, N, stream)
+        result["roofline"] = ntt_roofline(pub, primes, N, main.cuda_stream)
         if world == 1 and not args.no_cpu:
-            result["cpu_baseline"] = cpu_baseline(d, sample_runs=2)
+            result["cpu_baseline"] = cpu_baseline(d, B, sample_steps=1)
         print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
@@ -238,30 +265,34 @@ def ntt_roofline(pub, primes, N, stream):
             "algorithmic_bytes_per_launch": algo, "launch_ms": ms}
 
 
-def cpu_baseline(d, sample_runs=2, threads=None):
-    """the oracle port of the reference's CPU path on the host cores (bounded sample)"""
+def cpu_baseline(d, B, sample_steps=1, threads=None):
+    """the oracle port of the reference's CPU path on the host cores: the same step
+    (a batch of B Sobel instances) scheduled on one dependency-counting thread pool"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import oracle as o
-    from oracle_exec import OracleProgram
+    from oracle_exec import OracleProgram, run_many
     threads = threads or len(os.sched_getaffinity(0))
     N = d["poly_modulus_degree"]
     orc = o.Oracle(N, d["prime_bits"]).keygen(1)
     op = OracleProgram(d, orc)
     op.prepare_keys()
     rng = np.random.default_rng(0)
-    inputs = {}
-    for name, info in d["signature"].items():
-        ell = orc.k - 1 - info["level"]
-        inputs[name] = ("cipher", orc.encrypt(orc.encode(rng.uniform(-1, 1, d["vec_size"]), 2.0 ** info["scale"], ell)), 2.0 ** info["scale"])
+    batch = []
+    for i in range(B):
+        inputs = {}
+        for name, info in d["signature"].items():
+            ell = orc.k - 1 - info["level"]
+            inputs[name] = ("cipher", orc.encrypt(orc.encode(rng.uniform(0, 0.2, d["vec_size"]), 2.0 ** info["scale"], ell), seed=i), 2.0 ** info["scale"])
+        batch.append(inputs)
     nops = op.cipher_op_count()
-    op.run(inputs, threads=threads)  # warm-up
+    run_many(op, batch[:max(1, min(B, threads // 8))], threads)  # warm-up
     t0 = time.perf_counter()
-    for _ in range(sample_runs):
-        op.run(inputs, threads=threads)
+    for _ in range(sample_steps):
+        run_many(op, batch, threads)
     dt = time.perf_counter() - t0
-    return {"value": nops * sample_runs / dt, "unit": "ops/s", "cores": threads, "kind": "port",
-            "sample": "%d full Sobel execute() calls (61 ops each) on the oracle port (not SEAL), dependency-counting thread pool over %d threads" % (sample_runs, threads),
-            "ms_per_execute": dt / sample_runs * 1e3}
+    return {"value": nops * B * sample_steps / dt, "unit": "ops/s", "cores": threads, "kind": "port",
+            "sample": "%d step(s) of %d Sobel instances (61 ops each) on the oracle port (not SEAL), one dependency-counting thread pool over %d threads" % (sample_steps, B, threads),
+            "ms_per_step": dt / sample_steps * 1e3}
 
 
 def run_reference(args):
@@ -272,11 +303,12 @@ def run_reference(args):
     d = program_io.load_json(WORKLOAD)
     cb = None
     t0 = time.perf_counter()
-    cb = cpu_baseline(d, sample_runs=max(1, args.steps))
+    cb = cpu_baseline(d, args.instances, sample_steps=max(1, args.steps))
     dt = time.perf_counter() - t0
     res = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": cb["ms_per_execute"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": "sobel_64x64 (examples/image_processing.py) compiled by the reference compiler: N=16384, prime_bits=[60]*5, 61 ciphertext ops",
+           "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": "sobel_64x64 (examples/image_processing.py) compiled by the reference compiler: N=16384, prime_bits=[60]*5, 61 ciphertext ops per instance; one step = batch of %d independent program instances" % args.instances,
+                      "instances_per_gpu": args.instances,
                       "note": "reference SEAL+Galois path cannot be built (SEAL absent); CPU oracle port of the same path, all host threads"},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": dt}
     print(json.dumps(res))
@@ -289,6 +321,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--instances", type=int, default=16, help="independent Sobel program instances per GPU per step")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-const-cache", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -137,25 +137,26 @@ public:
   // host buffers out: H2D of the inputs, the DAG on the GPU, D2H of the outputs.
   B200Valuation execute(Program &program, const B200Valuation &inputs) {
     Executor &ex = executorFor(program);
-    stageInputs(ex, program, inputs, nullptr);
-    ex.run(nullptr);
+    void *st = ex.mainStream();
+    stageInputs(ex, program, inputs, st);
+    ex.run(st);
     B200Valuation out;
     const u64 N = s_->dev->N();
     for (auto &o : program.getOutputs()) {
       const ValueInfo &vi = ex.info(o.second);
       if (vi.kind == Kind::Cipher) {
         HostCipher h; h.size = vi.size; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.size * vi.ell * N);
-        s_->dev->download(h.data.data(), ex.valuePtr(o.second), h.data.size() * 8);
+        s_->dev->download(h.data.data(), ex.valuePtr(o.second), h.data.size() * 8, st);
         out[o.first] = std::move(h);
       } else if (vi.kind == Kind::Plain) {
         HostPlain h; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.ell * N);
-        s_->dev->download(h.data.data(), ex.valuePtr(o.second), h.data.size() * 8);
+        s_->dev->download(h.data.data(), ex.valuePtr(o.second), h.data.size() * 8, st);
         out[o.first] = std::move(h);
       } else {
         out[o.first] = std::make_shared<ConstantValue>(program.getVecSize(), ex.rawValue(o.second->index));
       }
     }
-    s_->dev->sync();
+    s_->dev->sync(st);
     return out;
   }
   std::shared_ptr<Shared> shared() const { return s_; }

@@ -60,6 +60,12 @@ public:
   Executor(const Executor &) = delete;
 
   std::size_t cipherOpCount() const { return cipherOps_; }
+  // private stream used by B200Public::execute for H2D -> run -> D2H of this plan,
+  // so that execute() calls on different programs overlap on the GPU
+  void *mainStream() {
+    if (!mainStream_) { check(evab_stream_create(dev_->ctx(), &mainStream_)); streams_.push_back(mainStream_); }
+    return mainStream_;
+  }
   const ValueInfo &info(const Term::Ptr &t) const { return vals_.at(t->index); }
   u64 *valuePtr(const Term::Ptr &t) const { return arena_.get() + vals_.at(t->index).off; }
   u64 *valuePtr(std::uint64_t index) const { return arena_.get() + vals_.at(index).off; }
@@ -220,6 +226,7 @@ private:
     workOff_.assign(usedStreams_, 0);
     for (int s = 0; s < usedStreams_; s++) { workOff_[s] = arenaWords; arenaWords += workWords[s]; }
     arena_ = DBuf(dev_, arenaWords + 8);
+    dev_->sync();  // stream-ordered allocation made on the null stream: publish it to the plan's streams
     for (int s = 0; s < usedStreams_; s++) { void *h; check(evab_stream_create(dev_->ctx(), &h)); streams_.push_back(h); }
     for (int e = 0; e < numEvents_ + usedStreams_ + 1; e++) { void *h; check(evab_event_create(dev_->ctx(), &h)); events_.push_back(h); }
     // plan-time constants: raw values and (optionally) their encodings
@@ -375,6 +382,7 @@ private:
   std::vector<std::size_t> workOff_;
   std::vector<void *> streams_, events_;
   void *capStream_ = nullptr;
+  void *mainStream_ = nullptr;
   void *graph_ = nullptr;
   bool graphValid_ = false, rawDirty_ = false, rawInputs_ = false, hasDynamicEncodes_ = false;
   int numEvents_ = 0, usedStreams_ = 0;

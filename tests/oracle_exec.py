@@ -152,3 +152,55 @@ class OracleProgram:
         if errors:
             raise errors[0]
         return V
+
+
+def run_many(op, inputs_list, threads):
+    """Runs several instances of one compiled program concurrently on ONE thread pool
+    (instances x DAG parallelism), the CPU analogue of a batched GPU step."""
+    uses = {tid: [] for tid in op.order}
+    base_pending = {}
+    for tid in op.order:
+        args = op.terms[tid]["args"]
+        base_pending[tid] = len(args)
+        for a in args:
+            uses[a].append(tid)
+    lock = threading.Lock()
+    done = threading.Event()
+    errors = []
+    Vs = []
+    pend = []
+    for inputs in inputs_list:
+        V = {}
+        for tid, name in op.in_names.items():
+            V[tid] = inputs[name]
+        Vs.append(V)
+        pend.append(dict(base_pending))
+    remaining = [len(op.order) * len(inputs_list)]
+    pool = ThreadPoolExecutor(max_workers=max(1, threads))
+
+    def work(i, tid):
+        try:
+            Vs[i][tid] = op.exec_term(op.terms[tid], Vs[i])
+        except BaseException as e:
+            errors.append(e)
+            done.set()
+            return
+        ready = []
+        with lock:
+            for u in uses[tid]:
+                pend[i][u] -= 1
+                if pend[i][u] == 0:
+                    ready.append(u)
+            remaining[0] -= 1
+            if remaining[0] == 0:
+                done.set()
+        for u in ready:
+            pool.submit(work, i, u)
+    initial = [(i, tid) for i in range(len(inputs_list)) for tid in op.order if base_pending[tid] == 0]
+    for i, tid in initial:
+        pool.submit(work, i, tid)
+    done.wait()
+    pool.shutdown(wait=True)
+    if errors:
+        raise errors[0]
+    return Vs
