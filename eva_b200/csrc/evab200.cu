@@ -41,23 +41,23 @@ static cudaStream_t S(void *s) { return (cudaStream_t)s; }
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
+struct BlockSync {
+  EVAB_HD void operator()() const {
+#if defined(__CUDA_ARCH__)
+    __syncthreads();
+#endif
+  }
+};
+// one CTA = one residue (or one half of a 2^15 residue); T = N/16 threads, 64 registers
 template <int LOGN, bool SPLIT, int PRO, int EPI>
-__global__ void __launch_bounds__(NttGeom<LOGN>::T, 512 / NttGeom<LOGN>::T) k_ntt_fwd(const NttLaunch L) {
+__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_fwd(const NttLaunch L) {
   extern __shared__ __align__(16) u64 sm[];
   typedef FwdBody<LOGN, SPLIT, PRO, EPI> B;
   const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1);
   if (J.skip) return;
   NttState S;
   const u32 tid = threadIdx.x;
-  B::ph0(S, L, J, tid, sm);
-  __syncthreads();
-  B::ph1(S, L, J, tid, sm);
-  if (B::NPH == 4) {
-    __syncthreads();
-    B::ph2(S, L, J, tid, sm);
-    __syncthreads();
-    B::ph3(S, L, J, tid, sm);
-  }
+  PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, sm, BlockSync());
   if (SPLIT) {  // CTA pair (cluster of 2): both halves have consumed the input
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -65,22 +65,13 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T, 512 / NttGeom<LOGN>::T) k_nt
   B::phE(S, L, J, tid);
 }
 template <int LOGN, bool SPLIT, int PRO, int EPI>
-__global__ void __launch_bounds__(NttGeom<LOGN>::T, 512 / NttGeom<LOGN>::T) k_ntt_inv(const NttLaunch L) {
+__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_inv(const NttLaunch L) {
   extern __shared__ __align__(16) u64 sm[];
   typedef InvBody<LOGN, SPLIT, PRO, EPI> B;
   const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1);
   if (J.skip) return;
   NttState S;
-  const u32 tid = threadIdx.x;
-  B::ph0(S, L, J, tid, sm);
-  __syncthreads();
-  B::ph1(S, L, J, tid, sm);
-  if (B::NPH == 4) {
-    __syncthreads();
-    B::ph2(S, L, J, tid, sm);
-    __syncthreads();
-    B::ph3(S, L, J, tid, sm);
-  }
+  PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, sm, BlockSync());
 }
 __global__ void __launch_bounds__(256) k_inv_last_stage(const NttLaunch L, u32 half_n) {
   const NttJob J = ntt_job(L, blockIdx.y, 1);

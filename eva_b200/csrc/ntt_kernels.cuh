@@ -36,13 +36,7 @@ struct NttLaunch {
   unsigned char pmap2[32];
 };
 
-struct NttState { u64 x[32]; int b; u32 pi; u64 p; };
-
-template <int LOGN, bool SPLIT> struct NttJobGeom {
-  typedef NttGeom<LOGN> G;
-  static constexpr int CTAS_PER_JOB = SPLIT ? 2 : 1;
-  static constexpr int NFULL = SPLIT ? 2 * G::N : G::N;
-};
+struct NttState { u64 x[NTT_E]; int b; };
 
 struct NttJob {
   const u64 *src; u64 *dst; const u64 *aux0; const u64 *aux1;
@@ -70,158 +64,148 @@ template <int PRO> EVAB_HD u64 pro_load(const NttLaunch &L, const NttJob &J, con
   return v;
 }
 
+// 16 contiguous coefficients with 256-bit accesses (full 32-byte sectors per lane)
+EVAB_HD void load16(u64 (&a)[NTT_E], const u64 *p) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int c = 0; c < NTT_E / 4; c++) {
+    u64 v0, v1, v2, v3;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(p + 4 * c));
+    a[4 * c] = v0; a[4 * c + 1] = v1; a[4 * c + 2] = v2; a[4 * c + 3] = v3;
+  }
+#else
+  for (int k = 0; k < NTT_E; k++) a[k] = p[k];
+#endif
+}
+EVAB_HD void store16(u64 *p, const u64 (&a)[NTT_E]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int c = 0; c < NTT_E / 4; c++)
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4 * c), "l"(a[4 * c]), "l"(a[4 * c + 1]), "l"(a[4 * c + 2]), "l"(a[4 * c + 3]) : "memory");
+#else
+  for (int k = 0; k < NTT_E; k++) p[k] = a[k];
+#endif
+}
+
 // ------------------------------ forward ------------------------------------
+// Phases (separated by block barriers), P = NttGeom::P register passes:
+//   0          : load (layout of pass 0) [+ split stage] + pass 0 + exchange write
+//   2j-1, 2j   : exchange read + pass j   |   exchange write        (1 <= j <= P-2)
+//   2(P-1)-1   : exchange read + last (contiguous) pass
+//   phE        : fused epilogue + store
 template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct FwdBody {
   typedef NttGeom<LOGN> G;
-  static constexpr int NPH = (G::NC > 0) ? 4 : 2;
+  static constexpr int NPH = G::NPH;
 
-  // phase 0: load (layout A) + optional split stage + pass A + exchange write
-  static EVAB_HD void ph0(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
+  template <int PH> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
     const PrimeDev P = L.primes[J.pi];
-    S.p = P.p; S.pi = J.pi;
-    const u64 sub = (PRO == PRO_MODRED) ? EVAB_LDG(L.subtab + J.pi) : 0;
-    u32 root = 1;
-    if (!SPLIT) {
+    const u32 root = SPLIT ? 2 + J.h : 1;
+    if constexpr (PH == 0) {
+      const u64 sub = (PRO == PRO_MODRED) ? EVAB_LDG(L.subtab + J.pi) : 0;
+      if (!SPLIT) {
 #pragma unroll
-      for (int k = 0; k < 32; k++) S.x[k] = pro_load<PRO>(L, J, P, idx_a<LOGN>(tid, k), sub);
-      S.b = 1;
-    } else {
-      // first stage of the 2N transform: pairs (i, i + N) with twiddle tw[1];
-      // this CTA keeps the h-th output half and continues with root prefix 2+h
-      const u64x2 w = ldg_tw(P.tw + 1);
-      const u64 two_p = 2 * P.p;
+        for (int k = 0; k < NTT_E; k++) S.x[k] = pro_load<PRO>(L, J, P, idx_s<LOGN, 0>(tid, k), sub);
+        S.b = 1;
+      } else {
+        // first stage of the 2N transform: pairs (i, i + N) with twiddle tw[1];
+        // this CTA keeps the h-th output half and continues with root prefix 2+h
+        const u64x2 w = ldg_tw(P.tw + 1);
+        const u64 two_p = 2 * P.p;
 #pragma unroll
-      for (int k = 0; k < 32; k++) {
-        u32 i = idx_a<LOGN>(tid, k);
-        u64 X = pro_load<PRO>(L, J, P, i, sub), Y = pro_load<PRO>(L, J, P, i + G::N, sub);
-        u64 t = shoup_lazy(Y, w.x, w.y, P.p);
-        S.x[k] = J.h ? X - t + two_p : X + t;
+        for (int k = 0; k < NTT_E; k++) {
+          const u32 i = idx_s<LOGN, 0>(tid, k);
+          const u64 X = pro_load<PRO>(L, J, P, i, sub), Y = pro_load<PRO>(L, J, P, i + G::N, sub);
+          const u64 t = shoup_lazy(Y, w.x, w.y, P.p);
+          S.x[k] = J.h ? X - t + two_p : X + t;
+        }
+        S.b = 3;
       }
-      S.b = 3;
-      root = 2 + J.h;
+      fwd_pass_s<LOGN, 0>(S.x, P.tw, root, P.p, tid, S.b);
+      xchg_write_s<LOGN, 0, 1>(S.x, sm, tid);
+    } else if constexpr (PH == NPH - 1) {
+      xchg_read_c<LOGN>(S.x, sm, tid);
+      fwd_pass_c<LOGN>(S.x, P.tw, root, P.p, tid, S.b);
+    } else if constexpr (PH % 2 == 1) {
+      constexpr int j = (PH + 1) / 2;
+      xchg_read_s<LOGN, j, j>(S.x, sm, tid);
+      fwd_pass_s<LOGN, j>(S.x, P.tw, root, P.p, tid, S.b);
+    } else {
+      constexpr int j = PH / 2;
+      if constexpr (j + 1 == G::P - 1) xchg_write_sc<LOGN, j>(S.x, sm, tid);
+      else xchg_write_s<LOGN, j, j + 1>(S.x, sm, tid);
     }
-    fwd_pass_a<LOGN>(S.x, P.tw, root, P.p, S.b);
-    xchg_write_a<LOGN>(S.x, sm, tid);
   }
-  // phase 1: exchange read + pass B (+ final epilogue when there is no pass C)
-  static EVAB_HD void ph1(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
-    const PrimeDev P = L.primes[J.pi];
-    xchg_read_b_ab<LOGN>(S.x, sm, tid);
-    fwd_pass_b<LOGN>(S.x, P.tw, SPLIT ? 2 + J.h : 1, P.p, tid, S.b);
-  }
-  static EVAB_HD void ph2(NttState &S, const NttLaunch &, const NttJob &, u32 tid, u64 *sm) {
-    xchg_write_b_bc<LOGN>(S.x, sm, tid);
-  }
-  static EVAB_HD void ph3(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
-    const PrimeDev P = L.primes[J.pi];
-    xchg_read_c(S.x, sm, tid);
-    fwd_pass_c<LOGN>(S.x, P.tw, SPLIT ? 2 + J.h : 1, P.p, tid, S.b);
-  }
-  // final phase: fused epilogue + store of 32 contiguous coefficients (layout C).
+  // final phase: fused epilogue + store of 16 contiguous coefficients.
   // SPLIT: the two CTAs of a job both read the whole input, so for in-place
   // transforms the caller must barrier the CTA pair (cluster) before this phase.
   static EVAB_HD void phE(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid) {
     const PrimeDev P = L.primes[J.pi];
     canon(S.x, P.p, S.b);
-    const size_t base = (size_t)(SPLIT ? J.h * G::N : 0) + ((size_t)tid << 5);
+    const size_t base = (size_t)(SPLIT ? J.h * G::N : 0) + ((size_t)tid << NTT_EL);
     if (EPI == EPI_DIVROUND) {
       const u64x2 c = ldg_tw(L.consts + J.pi);
-      u64 a[32];
-      load32(a, J.aux0 + base);
+      u64 a[NTT_E];
+      load16(a, J.aux0 + base);
 #pragma unroll
-      for (int k = 0; k < 32; k++) S.x[k] = shoup_mul(submod(a[k], S.x[k], P.p), c.x, c.y, P.p);
+      for (int k = 0; k < NTT_E; k++) S.x[k] = shoup_mul(submod(a[k], S.x[k], P.p), c.x, c.y, P.p);
       if (J.aux1) {
-        load32(a, J.aux1 + base);
+        load16(a, J.aux1 + base);
 #pragma unroll
-        for (int k = 0; k < 32; k++) S.x[k] = addmod(S.x[k], a[k], P.p);
+        for (int k = 0; k < NTT_E; k++) S.x[k] = addmod(S.x[k], a[k], P.p);
       }
     }
-    store32(J.dst + base, S.x);
-  }
-  static EVAB_HD void load32(u64 (&a)[32], const u64 *p) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-      u64 v0, v1, v2, v3;
-      asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(p + 4 * c));
-      a[4 * c] = v0; a[4 * c + 1] = v1; a[4 * c + 2] = v2; a[4 * c + 3] = v3;
-    }
-#else
-    for (int k = 0; k < 32; k++) a[k] = p[k];
-#endif
-  }
-  static EVAB_HD void store32(u64 *p, const u64 (&a)[32]) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int c = 0; c < 8; c++)
-      asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4 * c), "l"(a[4 * c]), "l"(a[4 * c + 1]), "l"(a[4 * c + 2]), "l"(a[4 * c + 3]) : "memory");
-#else
-    for (int k = 0; k < 32; k++) p[k] = a[k];
-#endif
+    store16(J.dst + base, S.x);
   }
 };
 
 // ------------------------------ inverse ------------------------------------
+// Phases: 0: contiguous load + last-pass stages + exchange write;
+//         then for j = P-2 .. 1: exchange read + pass j | exchange write;
+//         last: exchange read + pass 0 + scale by N^-1 + epilogue store (strided, coalesced).
 // SPLIT: each CTA runs the LOGN-stage inverse on one half (root prefix 2+h) and
-// stores lazily-reduced values; k_inv_last_stage then finishes the transform.
+// stores lazily-reduced values; inv_last_stage_elem then finishes the transform.
 template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct InvBody {
   typedef NttGeom<LOGN> G;
-  typedef FwdBody<LOGN, SPLIT> F;
-  static constexpr int NPH = (G::NC > 0) ? 4 : 2;
+  static constexpr int NPH = G::NPH;
 
-  static EVAB_HD void load_c(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid) {
-    const size_t base = (size_t)(SPLIT ? J.h * G::N : 0) + ((size_t)tid << 5);
-    if (PRO == PRO_GATHER) {
-#pragma unroll
-      for (int k = 0; k < 32; k++) S.x[k] = EVAB_LDG(J.src + EVAB_LDG(L.perm + base + k));
-    } else {
-      F::load32(S.x, J.src + base);
-    }
-    S.b = 1;
-  }
-  static EVAB_HD void ph0(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
+  template <int PH> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
     const PrimeDev P = L.primes[J.pi];
-    S.p = P.p; S.pi = J.pi;
-    load_c(S, L, J, tid);
-    if (G::NC > 0) {
-      inv_pass_c<LOGN>(S.x, P.itw, SPLIT ? 2 + J.h : 1, P.p, tid, S.b);
-      xchg_write_c(S.x, sm, tid);
-    } else {
-      inv_pass_b<LOGN>(S.x, P.itw, SPLIT ? 2 + J.h : 1, P.p, tid, S.b);
-      xchg_write_b_ab<LOGN>(S.x, sm, tid);
-    }
-  }
-  static EVAB_HD void ph1(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
-    const PrimeDev P = L.primes[J.pi];
-    if (G::NC > 0) {
-      xchg_read_b_bc<LOGN>(S.x, sm, tid);
-      inv_pass_b<LOGN>(S.x, P.itw, SPLIT ? 2 + J.h : 1, P.p, tid, S.b);
-    } else {
-      finish(S, L, J, P, tid, sm);
-    }
-  }
-  static EVAB_HD void ph2(NttState &S, const NttLaunch &, const NttJob &, u32 tid, u64 *sm) {
-    xchg_write_b_ab<LOGN>(S.x, sm, tid);
-  }
-  static EVAB_HD void ph3(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
-    const PrimeDev P = L.primes[J.pi];
-    finish(S, L, J, P, tid, sm);
-  }
-  static EVAB_HD void finish(NttState &S, const NttLaunch &L, const NttJob &J, const PrimeDev &P, u32 tid, u64 *sm) {
-    xchg_read_a<LOGN>(S.x, sm, tid);
-    inv_pass_a<LOGN>(S.x, P.itw, SPLIT ? 2 + J.h : 1, P.p, S.b);
-    if (SPLIT) {  // leave < 8p values for the last-stage kernel
+    const u32 root = SPLIT ? 2 + J.h : 1;
+    if constexpr (PH == 0) {
+      const size_t base = (size_t)(SPLIT ? J.h * G::N : 0) + ((size_t)tid << NTT_EL);
+      if (PRO == PRO_GATHER) {
 #pragma unroll
-      for (int k = 0; k < 32; k++) J.dst[(size_t)J.h * G::N + idx_a<LOGN>(tid, k)] = S.x[k];
-      return;
-    }
-    scale_canon(S.x, P.ninv, P.ninv_s, P.p);
-    const u64 half = P.p >> 1;
+        for (int k = 0; k < NTT_E; k++) S.x[k] = EVAB_LDG(J.src + EVAB_LDG(L.perm + base + k));
+      } else {
+        load16(S.x, J.src + base);
+      }
+      S.b = 1;
+      inv_pass_c<LOGN>(S.x, P.itw, root, P.p, tid, S.b);
+      xchg_write_c<LOGN>(S.x, sm, tid);
+    } else if constexpr (PH == NPH - 1) {
+      xchg_read_s<LOGN, 0, 1>(S.x, sm, tid);
+      inv_pass_s<LOGN, 0>(S.x, P.itw, root, P.p, tid, S.b);
+      if (SPLIT) {  // leave < 8p values for the last-stage kernel
 #pragma unroll
-    for (int k = 0; k < 32; k++) {
-      u64 v = S.x[k];
-      if (EPI == EPI_ADDHALF) v = addmod(v, half, P.p);
-      J.dst[idx_a<LOGN>(tid, k)] = v;
+        for (int k = 0; k < NTT_E; k++) J.dst[(size_t)J.h * G::N + idx_s<LOGN, 0>(tid, k)] = S.x[k];
+        return;
+      }
+      scale_canon(S.x, P.ninv, P.ninv_s, P.p);
+      const u64 half = P.p >> 1;
+#pragma unroll
+      for (int k = 0; k < NTT_E; k++) {
+        u64 v = S.x[k];
+        if (EPI == EPI_ADDHALF) v = addmod(v, half, P.p);
+        J.dst[idx_s<LOGN, 0>(tid, k)] = v;
+      }
+    } else if constexpr (PH % 2 == 1) {
+      constexpr int j = G::P - 2 - (PH - 1) / 2;
+      if constexpr (j == G::P - 2) xchg_read_sc<LOGN, j>(S.x, sm, tid);
+      else xchg_read_s<LOGN, j, j + 1>(S.x, sm, tid);
+      inv_pass_s<LOGN, j>(S.x, P.itw, root, P.p, tid, S.b);
+    } else {
+      constexpr int j = G::P - 2 - (PH - 2) / 2;   // pass that just ran
+      xchg_write_s<LOGN, j, j>(S.x, sm, tid);
     }
   }
 };
@@ -239,3 +223,15 @@ EVAB_HD void inv_last_stage_elem(const NttLaunch &L, const NttJob &J, u32 i, u32
   if (L.epi == EPI_ADDHALF) { const u64 h = P.p >> 1; a = addmod(a, h, P.p); b = addmod(b, h, P.p); }
   J.dst[i] = a; J.dst[i + half_n] = b;
 }
+
+// compile-time loop over the barrier-separated phases
+template <class B, int PH, int NPH> struct PhaseLoop {
+  template <class Sync> static EVAB_HD void run(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm, Sync sync) {
+    B::template phase<PH>(S, L, J, tid, sm);
+    if (PH + 1 < NPH) sync();
+    PhaseLoop<B, PH + 1, NPH>::run(S, L, J, tid, sm, sync);
+  }
+};
+template <class B, int NPH> struct PhaseLoop<B, NPH, NPH> {
+  template <class Sync> static EVAB_HD void run(NttState &, const NttLaunch &, const NttJob &, u32, u64 *, Sync) {}
+};

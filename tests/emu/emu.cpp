@@ -19,47 +19,38 @@ struct EmuCtx {
   std::map<u64, std::vector<u32>> perms;
 };
 
+// run phase PH of body B for every thread of one CTA, then recurse to PH+1
+template <class B, int PH, int NPH> struct EmuPhases {
+  static void run(NttState *st, int T, const NttLaunch &L, const NttJob &J, u64 *sm) {
+    for (u32 t = 0; t < (u32)T; t++) B::template phase<PH>(st[t], L, J, t, sm);
+    EmuPhases<B, PH + 1, NPH>::run(st, T, L, J, sm);
+  }
+};
+template <class B, int NPH> struct EmuPhases<B, NPH, NPH> {
+  static void run(NttState *, int, const NttLaunch &, const NttJob &, u64 *) {}
+};
+
 template <int LOGN, bool SPLIT, bool INV, int PRO, int EPI> static void run_ntt_m(const NttLaunch &L, size_t jobs) {
   typedef NttGeom<LOGN> G;
-  const int ctas = (int)jobs * (SPLIT ? 2 : 1);
-  std::vector<u64> sm(G::N);
-  std::vector<NttState> st(G::T);
-  if (!INV) {
-    // forward: the CTAs of one job (a cluster when SPLIT) are replayed phase by
-    // phase, with the cluster barrier before the store phase
-    constexpr int CPJ = SPLIT ? 2 : 1;
-    typedef FwdBody<LOGN, SPLIT, PRO, EPI> B;
-    std::vector<u64> smc((size_t)CPJ * G::N);
-    std::vector<NttState> stc((size_t)CPJ * G::T);
-    for (size_t job = 0; job < jobs; job++) {
-      NttJob J[CPJ];
-      for (int h = 0; h < CPJ; h++) J[h] = ntt_job(L, (u32)(job * CPJ + h), CPJ);
-      if (J[0].skip) continue;
-      for (int h = 0; h < CPJ; h++) {
-        u64 *s_ = smc.data() + (size_t)h * G::N; NttState *t_ = stc.data() + (size_t)h * G::T;
-        for (u32 t = 0; t < (u32)G::T; t++) B::ph0(t_[t], L, J[h], t, s_);
-        for (u32 t = 0; t < (u32)G::T; t++) B::ph1(t_[t], L, J[h], t, s_);
-        if (B::NPH == 4) {
-          for (u32 t = 0; t < (u32)G::T; t++) B::ph2(t_[t], L, J[h], t, s_);
-          for (u32 t = 0; t < (u32)G::T; t++) B::ph3(t_[t], L, J[h], t, s_);
-        }
-      }
+  constexpr int CPJ = SPLIT ? 2 : 1;
+  std::vector<u64> smc((size_t)CPJ * G::N);
+  std::vector<NttState> stc((size_t)CPJ * G::T);
+  for (size_t job = 0; job < jobs; job++) {
+    NttJob J[CPJ];
+    for (int h = 0; h < CPJ; h++) J[h] = ntt_job(L, (u32)(job * CPJ + h), CPJ);
+    if (J[0].skip) continue;
+    if (!INV) {
+      // forward: the CTAs of one job (a cluster when SPLIT) run all compute phases,
+      // then the cluster barrier, then the store phase
+      typedef FwdBody<LOGN, SPLIT, PRO, EPI> B;
+      for (int h = 0; h < CPJ; h++)
+        EmuPhases<B, 0, B::NPH>::run(stc.data() + (size_t)h * G::T, G::T, L, J[h], smc.data() + (size_t)h * G::N);
       for (int h = 0; h < CPJ; h++)
         for (u32 t = 0; t < (u32)G::T; t++) B::phE(stc[(size_t)h * G::T + t], L, J[h], t);
-    }
-    return;
-  }
-  for (int cta = 0; cta < ctas; cta++) {
-    const NttJob J = ntt_job(L, cta, SPLIT ? 2 : 1);
-    if (J.skip) continue;
-    {
+    } else {
       typedef InvBody<LOGN, SPLIT, PRO, EPI> B;
-      for (u32 t = 0; t < (u32)G::T; t++) B::ph0(st[t], L, J, t, sm.data());
-      for (u32 t = 0; t < (u32)G::T; t++) B::ph1(st[t], L, J, t, sm.data());
-      if (B::NPH == 4) {
-        for (u32 t = 0; t < (u32)G::T; t++) B::ph2(st[t], L, J, t, sm.data());
-        for (u32 t = 0; t < (u32)G::T; t++) B::ph3(st[t], L, J, t, sm.data());
-      }
+      for (int h = 0; h < CPJ; h++)
+        EmuPhases<B, 0, B::NPH>::run(stc.data() + (size_t)h * G::T, G::T, L, J[h], smc.data() + (size_t)h * G::N);
     }
   }
   if (INV && SPLIT)
