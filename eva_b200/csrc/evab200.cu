@@ -7,6 +7,7 @@
 #include "ops_impl.hpp"
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>

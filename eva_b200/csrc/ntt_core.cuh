@@ -53,6 +53,9 @@ template <int LOGN> struct NttGeom {
   static constexpr int P = (LOGN + NTT_EL - 1) / NTT_EL;       // register passes
   static constexpr int R = LOGN - NTT_EL * (P - 1);            // stages of the last pass (1..4)
   static constexpr int NPH = 2 * (P - 1);                      // barrier-separated phases before the epilogue
+#if defined(__CUDACC__)
+  __host__ __device__
+#endif
   static constexpr int lowbits(int j) { return LOGN - NTT_EL * (j + 1); }
 };
 
