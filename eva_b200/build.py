@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     if force or _newer(ext, host_src + [LIB]):
         import pybind11
         import sysconfig
-        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fvisibility=hidden",
                "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"],
                os.path.join(HOST, "pymodule.cpp"), "-o", ext, "-L" + LIBDIR, "-levab200", "-Wl,-rpath,$ORIGIN/lib"]
         subprocess.check_call(cmd)

@@ -14,7 +14,6 @@
 #include <map>
 #include <memory>
 #include <optional>
-#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <unordered_set>
@@ -330,17 +329,16 @@ inline std::unique_ptr<Program> Program::deepCopy() const {
   return np;
 }
 inline std::string Program::toDOT() const {
-  std::ostringstream s;
-  s << "digraph \"" << name_ << "\" {\n";
+  std::string s = "digraph \"" + name_ + "\" {\n";
   for (auto &t : toposort()) {
-    s << "t" << t->index << " [label=\"" << opName(t->op);
-    if (t->rotation) s << "(" << *t->rotation << ")";
-    if (t->rescaleDivisor) s << "(" << *t->rescaleDivisor << ")";
-    s << "\"];\n";
-    for (auto &o : t->getOperands()) s << "t" << o->index << " -> t" << t->index << ";\n";
+    s += "t" + std::to_string(t->index) + " [label=\"" + opName(t->op);
+    if (t->rotation) s += "(" + std::to_string(*t->rotation) + ")";
+    if (t->rescaleDivisor) s += "(" + std::to_string(*t->rescaleDivisor) + ")";
+    s += "\"];\n";
+    for (auto &o : t->getOperands()) s += "t" + std::to_string(o->index) + " -> t" + std::to_string(t->index) + ";\n";
   }
-  s << "}\n";
-  return s.str();
+  s += "}\n";
+  return s;
 }
 
 }  // namespace evab

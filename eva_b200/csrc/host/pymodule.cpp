@@ -5,6 +5,7 @@
 // *Public.encrypt/execute/*Secret.decrypt, plus a few test/benchmark hooks
 // (raw key/ciphertext injection, device-resident execution).
 #include "backend.hpp"
+#include "compiler.hpp"
 #include "reference_eval.hpp"
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
@@ -58,8 +59,8 @@ PYBIND11_MODULE(_eva_b200, m) {
       .def(py::init<std::string, std::uint64_t>(), py::arg("name"), py::arg("vec_size"))
       .def_property("name", &Program::getName, &Program::setName, "The name of this program")
       .def_property_readonly("vec_size", &Program::getVecSize, "The number of elements for all vectors in this program")
-      .def_property_readonly("inputs", py::cpp_function(&Program::getInputs, py::keep_alive<0, 1>()), "A dictionary from input names to terms")
-      .def_property_readonly("outputs", py::cpp_function(&Program::getOutputs, py::keep_alive<0, 1>()), "A dictionary from output names to terms")
+      .def_property_readonly("inputs", &Program::getInputs, "A dictionary from input names to terms")
+      .def_property_readonly("outputs", &Program::getOutputs, "A dictionary from output names to terms")
       .def("set_output_ranges", [](const Program &p, std::uint32_t range) { for (auto &e : p.getOutputs()) e.second->range = range; }, py::arg("range"))
       .def("set_input_scales", [](const Program &p, std::uint32_t scale) { for (auto &s : p.getSources()) s->encodeAtScale = scale; }, py::arg("scale"))
       .def("to_DOT", &Program::toDOT)
@@ -78,6 +79,11 @@ PYBIND11_MODULE(_eva_b200, m) {
   py::class_<int>(m, "_GaloisGuard").def(py::init());
 
   py::module mckks = m.def_submodule("_ckks", "CKKS compiler types");
+  py::class_<CKKSCompiler>(mckks, "CKKSCompiler")
+      .def(py::init(), "Create a compiler with the default config")
+      .def(py::init<std::unordered_map<std::string, std::string>>(), py::arg("config"), "Create a compiler with a custom config (dict from strings to strings)")
+      .def("compile", &CKKSCompiler::compile, py::arg("program"),
+           "Compile a program for CKKS; returns (compiled Program, CKKSParameters, CKKSSignature)");
   py::class_<CKKSParameters>(mckks, "CKKSParameters", "Abstract encryption parameters for CKKS")
       .def(py::init([](std::vector<std::uint32_t> bits, std::set<int> rots, std::uint32_t n) { CKKSParameters p; p.primeBits = bits; p.rotations = rots; p.polyModulusDegree = n; return p; }),
            py::arg("prime_bits"), py::arg("rotations"), py::arg("poly_modulus_degree"))

@@ -1,0 +1,129 @@
+"""End to end through the user-facing API, in the style of the reference's own
+acceptance tests (tests/common.py:12-36): DSL -> CKKSCompiler -> generate_keys ->
+encrypt -> execute (GPU) -> decrypt, compared with evaluate() by MSE < 0.01
+(HE vs plaintext) and < 1e-10 (compiled vs source)."""
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def check(prog, inputs, config=None):
+    from eva import evaluate
+    from eva.ckks import CKKSCompiler
+    from eva.metric import valuation_mse
+    from eva.seal import generate_keys
+    compiler = CKKSCompiler(config) if config else CKKSCompiler()
+    compiled, params, signature = compiler.compile(prog)
+    reference = evaluate(prog, inputs)
+    reference_compiled = evaluate(compiled, inputs)
+    assert valuation_mse(reference, reference_compiled) < 1e-10
+    public_ctx, secret_ctx = generate_keys(params)
+    enc_inputs = public_ctx.encrypt(inputs, signature)
+    enc_outputs = public_ctx.execute(compiled, enc_inputs)
+    outputs = secret_ctx.decrypt(enc_outputs, signature)
+    assert valuation_mse(outputs, reference) < 0.01
+    return params
+
+
+def test_readme_polynomial():
+    from eva import EvaProgram, Input, Output
+    poly = EvaProgram('Polynomial', vec_size=1024)
+    with poly:
+        x = Input('x')
+        Output('y', 3 * x ** 2 + 5 * x - 2)
+    poly.set_output_ranges(30)
+    poly.set_input_scales(30)
+    p = check(poly, {'x': [i / 1024.0 for i in range(1024)]})
+    assert list(p.prime_bits) == [60, 60, 60] and p.poly_modulus_degree == 8192
+
+
+@pytest.mark.parametrize("is_enc", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("op", ["add", "sub", "mul"])
+def test_binary_ops(op, is_enc):
+    from eva import EvaProgram, Input, Output
+    random.seed(1)
+    prog = EvaProgram('bin', vec_size=64)
+    with prog:
+        a, b = Input('a', is_enc[0]), Input('b', is_enc[1])
+        Output('y', a + b if op == "add" else a - b if op == "sub" else a * b)
+    prog.set_output_ranges(20)
+    prog.set_input_scales(30)
+    check(prog, {'a': [random.uniform(-2, 2) for _ in range(64)], 'b': [random.uniform(-2, 2) for _ in range(64)]})
+
+
+def test_rotations_and_unary():
+    from eva import EvaProgram, Input, Output
+    random.seed(2)
+    prog = EvaProgram('rot', vec_size=8)
+    with prog:
+        x = Input('x')
+        Output('l', x << 1)
+        Output('r', x >> 2)
+        Output('n', -x)
+        Output('c', x ** 3)
+    prog.set_output_ranges(20)
+    prog.set_input_scales(30)
+    check(prog, {'x': [random.uniform(-2, 2) for _ in range(8)]})
+
+
+def test_horizontal_sum_and_mixed():
+    from eva import EvaProgram, Input, Output
+    from eva.std.numeric import horizontal_sum
+    random.seed(3)
+    prog = EvaProgram('hsum', vec_size=2048)
+    with prog:
+        x = Input('x')
+        c = Input('c', False)
+        Output('y', horizontal_sum(x) * 0.001 + c)
+    prog.set_output_ranges(25)
+    prog.set_input_scales(25)
+    check(prog, {'x': [random.uniform(-1, 1) for _ in range(2048)], 'c': [random.uniform(-1, 1) for _ in range(2048)]})
+
+
+@pytest.mark.parametrize("rescaler", ["lazy_waterline", "eager_waterline", "always"])
+def test_sobel_image(rescaler):
+    """examples/image_processing.py:39-63 on a smooth synthetic image"""
+    from eva import EvaProgram, Input, Output
+    import math
+    h = w = 64
+    sobel = EvaProgram('sobel', vec_size=h * w)
+    with sobel:
+        image = Input('image')
+        F = [[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]]
+        for i in range(3):
+            for j in range(3):
+                rot = image << (i * w + j)
+                hor, ver = rot * F[i][j], rot * F[j][i]
+                if i == 0 and j == 0:
+                    Ix, Iy = hor, ver
+                else:
+                    Ix += hor
+                    Iy += ver
+        d = Ix ** 2 + Iy ** 2
+        d2 = d * d
+        d3 = d2 * d
+        Output('image', d * 2.2137874823876622 + d2 * -1.0984324107372518 + d3 * 0.17254603006834726)
+    sobel.set_input_scales(25)
+    sobel.set_output_ranges(10)
+    img = [0.5 + 0.25 * math.sin(0.1 * (k % w)) * math.cos(0.07 * (k // w)) for k in range(h * w)]
+    p = check(sobel, {'image': img}, {"rescaler": rescaler})
+    if rescaler == "lazy_waterline":
+        assert list(p.prime_bits) == [60] * 5 and p.poly_modulus_degree == 16384
+
+
+def test_security_levels_and_error_paths():
+    from eva import EvaProgram, Input, Output
+    from eva.ckks import CKKSCompiler
+    prog = EvaProgram('sec', vec_size=64)
+    with prog:
+        x = Input('x')
+        Output('y', x * x)
+    prog.set_output_ranges(20)
+    prog.set_input_scales(30)
+    for s in ("128", "192", "256"):
+        for q in ("false", "true"):
+            check(prog, {'x': [0.5] * 64}, {"security_level": s, "quantum_safe": q, "warn_vec_size": "false"})
+    with pytest.raises(RuntimeError):
+        CKKSCompiler({"security_level": "1024"}).compile(prog)
