@@ -1,0 +1,106 @@
+// encode_kernels.cuh -- CKKS encoder on the device:
+// seal::CKKSEncoder::encode as called at reference eva/seal/seal_executor.h:242 /
+// seal.cpp:68,80.  values (vec_size doubles, replicated over N/2 slots) ->
+// inverse canonical-embedding FFT in FP64 -> round(x * scale / N) -> residues
+// mod each prime; the forward NTT of the residues is done by the NTT kernel.
+//
+// FP64 arithmetic is written with explicit round-to-nearest operations (no FMA
+// contraction) in the same order as the host encoders, so device, host and
+// oracle encodings agree bit for bit; twiddles come from the host (libm).
+// Bodies are __host__ __device__ so the tests replay them on the CPU.
+#pragma once
+#include "modarith.cuh"
+#include <math.h>
+
+struct __align__(16) cplx { double re, im; };
+
+#if defined(__CUDA_ARCH__)
+#define D_ADD(a, b) __dadd_rn(a, b)
+#define D_SUB(a, b) __dsub_rn(a, b)
+#define D_MUL(a, b) __dmul_rn(a, b)
+#else
+#define D_ADD(a, b) ((a) + (b))
+#define D_SUB(a, b) ((a) - (b))
+#define D_MUL(a, b) ((a) * (b))
+#endif
+
+#define ENC_MAX_BATCH 32
+struct EncBatch {
+  const double *vals[ENC_MAX_BATCH];  // device: vec_size values each
+  u32 vec[ENC_MAX_BATCH];
+  double scale[ENC_MAX_BATCH];
+  cplx *work;                         // [count][N]
+  u64 *out;                           // [count][ell][N] coefficient-form residues
+  const cplx *roots;                  // [N] zeta^bitrev(i)
+  const u32 *slot_index;              // [N]
+  const PrimeDev *primes;
+  const u64 *pow2;                    // [k][128]: 2^i mod p
+  u32 N, ell, count;
+};
+
+// scatter: slot i (and its conjugate slot) <- values[i mod vec]
+EVAB_HD void enc_scatter(const EncBatch &B, u32 e, u32 i) {
+  const u32 slots = B.N >> 1;
+  const double v = B.vals[e][i % B.vec[e]];
+  cplx *w = B.work + (size_t)e * B.N;
+  cplx c; c.re = v; c.im = 0.0;
+  w[B.slot_index[i]] = c;
+  w[B.slot_index[slots + i]] = c;
+}
+
+// one Gentleman-Sande butterfly with the conjugate twiddle of roots[idx]
+EVAB_HD void enc_bfly(cplx &x, cplx &y, const cplx r) {
+  const double wr = r.re, wi = -r.im;
+  const double ur = x.re, ui = x.im, vr = y.re, vi = y.im;
+  x.re = D_ADD(ur, vr); x.im = D_ADD(ui, vi);
+  const double dr = D_SUB(ur, vr), di = D_SUB(ui, vi);
+  y.re = D_SUB(D_MUL(dr, wr), D_MUL(di, wi));
+  y.im = D_ADD(D_MUL(dr, wi), D_MUL(di, wr));
+}
+// NS consecutive inverse-FFT stages (gaps g, 2g, .. 2^(NS-1) g) on one closed set of
+// 2^NS elements spaced g apart; set u of N / 2^NS
+template <int NS> EVAB_HD void enc_fft_set(const EncBatch &B, u32 e, u32 u, u32 g) {
+  constexpr int M = 1 << NS;
+  cplx *w = B.work + (size_t)e * B.N;
+  const u32 low = u % g, high = u / g;
+  const u32 base = high * (M * g) + low;
+  cplx x[M];
+#pragma unroll
+  for (int j = 0; j < M; j++) x[j] = w[base + j * g];
+#pragma unroll
+  for (int st = 0; st < NS; st++) {
+    const int d = 1 << st;                 // pair distance in units of g
+    const u32 gap = g << st;
+    const u32 m = B.N / (2 * gap);
+#pragma unroll
+    for (int j = 0; j < M; j++)
+      if (!(j & d)) enc_bfly(x[j], x[j + d], B.roots[m + (base + j * g) / (2 * gap)]);
+  }
+#pragma unroll
+  for (int j = 0; j < M; j++) w[base + j * g] = x[j];
+}
+// thread t of N/8 handles 8 elements = 8 / 2^nstages closed sets
+EVAB_HD void enc_fft8(const EncBatch &B, u32 e, u32 t, u32 g, int nstages) {
+  if (nstages == 3) enc_fft_set<3>(B, e, t, g);
+  else if (nstages == 2) { enc_fft_set<2>(B, e, 2 * t, g); enc_fft_set<2>(B, e, 2 * t + 1, g); }
+  else { for (u32 s = 0; s < 4; s++) enc_fft_set<1>(B, e, 4 * t + s, g); }
+}
+
+// coefficient j: round(re * scale / N) -> residue mod prime i (sign-aware; exact for
+// magnitudes beyond 2^64 through mantissa * 2^shift)
+EVAB_HD void enc_round(const EncBatch &B, u32 e, u32 j, int k) {
+  const double fix = B.scale[e] / (double)B.N;
+  const double c = round(D_MUL(B.work[(size_t)e * B.N + j].re, fix));
+  const bool neg = signbit(c);
+  const double mag = fabs(c);
+  u64 mant; int sh = 0;
+  if (mag < 18446744073709551616.0) mant = (u64)mag;
+  else { int ex; const double fr = frexp(mag, &ex); mant = (u64)ldexp(fr, 64); sh = ex - 64; }
+  for (u32 i = 0; i < B.ell; i++) {
+    const PrimeDev P = B.primes[i];
+    u64 v = barrett64(mant, P.p, P.ratio64);
+    if (sh) v = mulmod(v, B.pow2[(size_t)i * 128 + (sh > 127 ? 127 : sh)], P.p, P.ratio_lo, P.ratio_hi);
+    B.out[((size_t)e * B.ell + i) * B.N + j] = (neg && v) ? P.p - v : v;
+  }
+  (void)k;
+}

@@ -33,6 +33,9 @@ struct evab_ctx {
   u64x2 *d_qinv = nullptr;
   u64 *d_halfmod = nullptr;
   u64 *d_zeros = nullptr;
+  cplx *d_roots = nullptr;
+  u32 *d_slot = nullptr;
+  u64 *d_pow2 = nullptr;
   std::map<u64, u32 *> perms;  // galois elt -> device permutation table
   std::mutex mu;
   mutable std::atomic<unsigned long long> launches{0};
@@ -90,6 +93,15 @@ template <bool SQ> __global__ void __launch_bounds__(256) k_mul_ct(const MulArgs
 __global__ void __launch_bounds__(256) k_ks_inner(const IpArgs A) {
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
     ks_inner_elem(A, blockIdx.y, j);
+}
+__global__ void __launch_bounds__(256) k_enc_scatter(const EncBatch B) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B.N / 2; i += gridDim.x * blockDim.x) enc_scatter(B, blockIdx.y, i);
+}
+__global__ void __launch_bounds__(256) k_enc_fft(const EncBatch B, u32 g, int nstages) {
+  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < B.N / 8; t += gridDim.x * blockDim.x) enc_fft8(B, blockIdx.y, t, g, nstages);
+}
+__global__ void __launch_bounds__(256) k_enc_round(const EncBatch B) {
+  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < B.N; j += gridDim.x * blockDim.x) enc_round(B, blockIdx.y, j, 0);
 }
 __global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, const u32 *perm, int N) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
@@ -211,6 +223,24 @@ struct CudaBE {
     CUDA_OK(cudaGetLastError());
     return 0;
   }
+  int enc_scatter(const EncBatch &B) {
+    count();
+    k_enc_scatter<<<dim3((B.N / 2 + 255) / 256, B.count), 256, 0, st>>>(B);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int enc_fft(const EncBatch &B, u32 g, int ns) {
+    count();
+    k_enc_fft<<<dim3((B.N / 8 + 255) / 256, B.count), 256, 0, st>>>(B, g, ns);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int enc_round(const EncBatch &B) {
+    count();
+    k_enc_round<<<dim3((B.N + 255) / 256, B.count), 256, 0, st>>>(B);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   int perm(u64 *out, const u64 *in, const u32 *p, int N, int rows) {
     count();
     dim3 g((unsigned)((N + 255) / 256), rows);
@@ -259,6 +289,13 @@ extern "C" int evab_ctx_create(uint64_t N, const uint64_t *primes, int k, int de
   CUDA_OK(cudaMemcpy(c->d_halfmod, T.halfmod.data(), T.halfmod.size() * sizeof(u64), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&c->d_zeros, 32 * sizeof(u64)));
   CUDA_OK(cudaMemset(c->d_zeros, 0, 32 * sizeof(u64)));
+  CUDA_OK(cudaMalloc(&c->d_roots, N * sizeof(cplx)));
+  CUDA_OK(cudaMemcpy(c->d_roots, T.roots.data(), N * sizeof(cplx), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&c->d_slot, N * sizeof(u32)));
+  CUDA_OK(cudaMemcpy(c->d_slot, T.slot_index.data(), N * sizeof(u32), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&c->d_pow2, T.pow2.size() * sizeof(u64)));
+  CUDA_OK(cudaMemcpy(c->d_pow2, T.pow2.data(), T.pow2.size() * sizeof(u64), cudaMemcpyHostToDevice));
+  c->v.roots = c->d_roots; c->v.slot_index = c->d_slot; c->v.pow2 = c->d_pow2;
   c->v.N = N; c->v.logN = logN; c->v.k = k;
   c->v.primes = c->d_primes; c->v.qinv = c->d_qinv; c->v.halfmod = c->d_halfmod; c->v.zeros = c->d_zeros;
   *out = c;
@@ -270,6 +307,7 @@ extern "C" void evab_ctx_destroy(evab_ctx *c) {
   cudaDeviceSynchronize();
   for (auto &kv : c->perms) cudaFree(kv.second);
   cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_qinv); cudaFree(c->d_halfmod); cudaFree(c->d_zeros);
+  cudaFree(c->d_roots); cudaFree(c->d_slot); cudaFree(c->d_pow2);
   delete c;
 }
 extern "C" uint64_t evab_ctx_N(const evab_ctx *c) { return c->v.N; }
@@ -371,6 +409,10 @@ extern "C" int evab_ntt_fwd(evab_ctx *c, uint64_t *d, size_t count, const int *p
 }
 extern "C" int evab_ntt_inv(evab_ctx *c, uint64_t *d, size_t count, const int *pidx, int np, void *stream) {
   BE_BEGIN return ntt_batch_impl(be, c->v, true, d, count, pidx, np);
+}
+extern "C" int evab_encode(evab_ctx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell,
+                           uint64_t *out, void *work, void *stream) {
+  BE_BEGIN return encode_impl(be, c->v, count, vals, vec, scales, ell, out, (cplx *)work);
 }
 extern "C" int evab_add(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *b, int sb, void *stream) {
   BE_BEGIN return dyadic_impl<DY_ADD>(be, c->v, ell, o, a, sa, b, sb, 0);

@@ -74,14 +74,25 @@ public:
     }
   }
   // encode into device memory d_pt[ell][N] in NTT form (seal::CKKSEncoder::encode)
+  // device path: the batched encoder kernels behind evab_encode (FP64 FFT + NTT on the GPU)
   void encode(const std::vector<double> &values, double scale, int ell, u64 *d_pt, void *stream = nullptr) const {
+    if (values.empty() || (N_ / 2) % values.size()) throw std::invalid_argument("values size must divide the slot count");
+    DBuf vals(dev_, values.size()), work(dev_, (std::size_t)N_ * 2);
+    dev_->upload(vals.get(), values.data(), values.size() * 8, stream);
+    const double *ptr = reinterpret_cast<const double *>(vals.get());
+    const std::uint32_t vec = (std::uint32_t)values.size();
+    check(evab_encode(dev_->ctx(), 1, &ptr, &vec, &scale, ell, d_pt, work.get(), stream));
+    dev_->sync(stream);  // staging buffers are released at scope exit
+  }
+  // host path (same arithmetic, kept as a cross-check of the device encoder)
+  void encodeHost(const std::vector<double> &values, double scale, int ell, u64 *d_pt, void *stream = nullptr) const {
     std::vector<u64> coef;
     embed(values, scale, ell, coef);
     dev_->upload(d_pt, coef.data(), coef.size() * 8, stream);
     std::vector<int> idx(ell);
     for (int i = 0; i < ell; i++) idx[i] = i;
     check(evab_ntt_fwd(dev_->ctx(), d_pt, (std::size_t)ell, idx.data(), ell, stream));
-    dev_->sync(stream);  // coef is a stack-lifetime staging buffer
+    dev_->sync(stream);
   }
   // decode device plaintext d_pt[ell][N] (NTT form) -> N/2 real slot values
   std::vector<double> decode(const u64 *d_pt, int ell, double scale) const {

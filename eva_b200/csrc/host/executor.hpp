@@ -16,6 +16,7 @@
 #include <cmath>
 #include <functional>
 #include <set>
+#include <unordered_set>
 #include <unordered_map>
 
 namespace evab {
@@ -39,6 +40,9 @@ struct Step {
   int record = -1;         // event id recorded after issuing
   std::size_t work = 0;    // scratch word offset in the stream's workspace (0 = none)
 };
+
+// Encode terms of one level that are encoded by a single batched device launch sequence
+struct EncodeGroup { int ell; bool dynamic; std::vector<Term *> members; std::size_t outOff, workOff, rawOff; int stream = -1; };
 
 struct ExecOptions {
   int numStreams = 8;
@@ -76,7 +80,7 @@ public:
   // inputs set through setRawInput.  Enqueues the whole program on `stream`
   // (graph launch or multi-stream replay); does not synchronise.
   void run(void *stream) {
-    if (rawDirty_ || !opt_.cacheConstants) { evalRawAndEncodes(stream); rawDirty_ = false; }
+    if (rawDirty_) { evalRawAndEncodes(stream); rawDirty_ = false; }
     if (opt_.useGraph) {
       if (!graph_ || !graphValid_) capture();
       check(evab_graph_launch(dev_->ctx(), graph_, stream));
@@ -120,7 +124,7 @@ private:
         case Op::Encode:
           if (a(0).kind != Kind::Raw) throw std::runtime_error("Encode expects a raw operand");
           v.kind = Kind::Plain; v.ell = levelToEll(t->encodeAtLevel.value()); v.scale = std::ldexp(1.0, (int)t->encodeAtScale.value());
-          place(v);
+          encodeTerms_.push_back(t);   // placed below, contiguous per (level, static/dynamic) group
           break;
         case Op::Add: case Op::Sub: case Op::Mul: {
           const ValueInfo &x = a(0), &y = a(1);
@@ -171,6 +175,32 @@ private:
       }
       if (v.kind == Kind::Cipher && t->op != Op::Input && t->op != Op::Output) cipherOps_++;
     }
+    // ---- Encode groups: one batched device encode per (ell, input-dependent?) group.
+    // Static groups (constants only) are encoded once per plan when cacheConstants is
+    // set, otherwise every run like the reference (seal_executor.h:303-308).
+    {
+      std::vector<char> dyn(prog_.termCount(), 0);
+      for (auto &t : order_) {
+        bool d = (t->op == Op::Input && vals_[t->index].kind == Kind::Raw);
+        for (auto &o : t->getOperands()) d = d || dyn[o->index];
+        dyn[t->index] = d;
+      }
+      std::map<std::pair<int, int>, int> groupOf;
+      for (Term *t : encodeTerms_) {
+        auto key = std::make_pair(vals_[t->index].ell, (int)dyn[t->index]);
+        auto it = groupOf.find(key);
+        if (it == groupOf.end()) { it = groupOf.emplace(key, (int)groups_.size()).first; groups_.push_back(EncodeGroup{key.first, key.second != 0, {}, 0, 0, 0}); }
+        groups_[it->second].members.push_back(t);
+        groupIndex_[t->index] = it->second;
+      }
+      for (auto &g : groups_) {
+        g.outOff = arenaWords;
+        for (Term *t : g.members) { vals_[t->index].off = arenaWords; arenaWords += (std::size_t)g.ell * N_; }
+        g.workOff = arenaWords; arenaWords += g.members.size() * N_ * 2;
+        g.rawOff = rawWords_;
+        for (Term *t : g.members) { rawOff_[t->index] = rawWords_; rawWords_ += prog_.getVecSize(); }
+      }
+    }
     // ---- stream assignment + event edges
     const int S = std::max(1, opt_.numStreams);
     std::vector<int> streamOf(prog_.termCount(), -1), eventOf(prog_.termCount(), -1);
@@ -188,6 +218,11 @@ private:
       st.term = t; st.op = t->op;
       // continue the chain of a device operand nobody continued yet, else take a new stream round-robin
       int chosen = -1;
+      if (t->op == Op::Encode) {
+        EncodeGroup &g = groups_[groupIndex_.at(t->index)];
+        if (g.stream < 0) g.stream = (rr++) % S;
+        chosen = g.stream;
+      }
       for (auto &o : t->getOperands()) {
         const int so = streamOf[o->index];
         if (so >= 0 && !chainTaken[o->index] && o->op != Op::Input) { chosen = so; chainTaken[o->index] = 1; break; }
@@ -226,6 +261,7 @@ private:
     workOff_.assign(usedStreams_, 0);
     for (int s = 0; s < usedStreams_; s++) { workOff_[s] = arenaWords; arenaWords += workWords[s]; }
     arena_ = DBuf(dev_, arenaWords + 8);
+    rawArena_ = DBuf(dev_, rawWords_ + 8);
     dev_->sync();  // stream-ordered allocation made on the null stream: publish it to the plan's streams
     for (int s = 0; s < usedStreams_; s++) { void *h; check(evab_stream_create(dev_->ctx(), &h)); streams_.push_back(h); }
     for (int e = 0; e < numEvents_ + usedStreams_ + 1; e++) { void *h; check(evab_event_create(dev_->ctx(), &h)); events_.push_back(h); }
@@ -282,26 +318,34 @@ private:
         }
       }
       if (t->op == Op::Encode) {
-        const bool dynamic = dyn[t->index] || !opt_.cacheConstants;
-        hasDynamicEncodes_ = hasDynamicEncodes_ || dynamic;
-        if (encoded_.count(t->index) && !dynamic) continue;
         auto &x = raws_[t->operandAt(0)->index];
         if (x.empty()) continue;
-        encodeTerm(*t, x, stream);
-        encoded_.insert(t->index);
+        if (dyn[t->index]) hasDynamicEncodes_ = true;
+        if (!rawUploaded_.count(t->index) || dyn[t->index]) {
+          if ((N_ / 2) % x.size()) throw std::runtime_error("Vector size must exactly divide the slot count");
+          dev_->upload(rawArena_.get() + rawOff_.at(t->index), x.data(), x.size() * 8, stream);
+          rawUploaded_.insert(t->index);
+        }
       }
     }
+    dev_->sync(stream);  // the staged host vectors are temporaries of this call
+    if (opt_.cacheConstants && !staticEncoded_) {
+      for (auto &g : groups_) if (!g.dynamic) issueEncodeGroup(g, stream);
+      dev_->sync(stream);
+      staticEncoded_ = true;
+    }
   }
-  void encodeTerm(const Term &t, const std::vector<double> &x, void *stream) {
-    const ValueInfo &v = vals_[t.index];
-    const u64 slots = N_ / 2;
-    if (slots % x.size()) throw std::runtime_error("Vector size must exactly divide the slot count");
-    std::vector<double> rep;
-    rep.reserve(slots);
-    for (u64 r = slots / x.size(); r > 0; --r) rep.insert(rep.end(), x.begin(), x.end());  // seal_executor.h:229-240
-    enc_.encode(rep, v.scale, v.ell, arena_.get() + v.off, stream);
+  // one batched device encode (scatter -> inverse FFT -> round/reduce -> NTT) for a group
+  void issueEncodeGroup(const EncodeGroup &g, void *stream) {
+    std::vector<const double *> ptrs; std::vector<std::uint32_t> vec; std::vector<double> sc;
+    for (Term *t : g.members) {
+      ptrs.push_back(reinterpret_cast<const double *>(rawArena_.get() + rawOff_.at(t->index)));
+      vec.push_back((std::uint32_t)raws_[t->operandAt(0)->index].size());
+      sc.push_back(vals_[t->index].scale);
+    }
+    check(evab_encode(dev_->ctx(), (int)g.members.size(), ptrs.data(), vec.data(), sc.data(), g.ell, arena_.get() + g.outOff,
+                      arena_.get() + g.workOff, stream));
   }
-
   // ---------------------------------------------------------------- execution
   void issue(const Step &st, void *stream) {
     const Term &t = *st.term;
@@ -312,8 +356,10 @@ private:
     auto P = [&](int i) -> const u64 * { return arena_.get() + vals_[t.operandAt(i)->index].off; };
     u64 *work = arena_.get() + workOff_[st.stream];
     switch (t.op) {
-      case Op::Encode:
-        break;  // produced by evalRawAndEncodes
+      case Op::Encode: {
+        const EncodeGroup &g = groups_[groupIndex_.at(t.index)];
+        if (g.members.front() == &t && (g.dynamic || !opt_.cacheConstants)) issueEncodeGroup(g, stream);
+      } break;
       case Op::Add: case Op::Sub: case Op::Mul: {
         int ci = V(0).kind == Kind::Cipher ? 0 : 1, oi = 1 - ci;
         if (V(oi).kind == Kind::Cipher) {
@@ -376,6 +422,14 @@ private:
   std::vector<Term *> order_;
   std::vector<ValueInfo> vals_;
   std::vector<std::vector<double>> raws_;
+  std::vector<EncodeGroup> groups_;
+  std::vector<Term *> encodeTerms_;
+  std::unordered_map<std::uint64_t, int> groupIndex_;
+  std::unordered_map<std::uint64_t, std::size_t> rawOff_;
+  std::unordered_set<std::uint64_t> rawUploaded_;
+  std::size_t rawWords_ = 0;
+  bool staticEncoded_ = false;
+  DBuf rawArena_;
   std::vector<Step> steps_;
   std::unordered_map<std::uint64_t, int> recordAfter_;
   std::unordered_set<std::uint64_t> encoded_;

@@ -158,14 +158,24 @@ PYBIND11_MODULE(_eva_b200, m) {
         dev->sync();
         return py::make_tuple(a, vi.scale);
       })
-      .def("encode", [](B200Public &p, const std::vector<double> &values, double scale, int ell) {
+      .def("encode", [](B200Public &p, const std::vector<double> &values, double scale, int ell, bool host) {
         auto dev = p.shared()->dev;
         DBuf pt(dev, (std::size_t)ell * dev->N());
-        p.shared()->client->encoder().encode(values, scale, ell, pt.get());
+        std::vector<double> rep;
+        const std::size_t slots = dev->N() / 2;
+        for (std::size_t r = slots / values.size(); r > 0; --r) rep.insert(rep.end(), values.begin(), values.end());
+        if (host) p.shared()->client->encoder().encodeHost(rep, scale, ell, pt.get());
+        else p.shared()->client->encoder().encode(values, scale, ell, pt.get());
         u64arr a({(std::size_t)ell, (std::size_t)dev->N()});
         dev->download(a.mutable_data(), pt.get(), a.size() * 8);
         dev->sync();
         return a;
+      }, py::arg("values"), py::arg("scale"), py::arg("ell"), py::arg("host") = false)
+      .def("decode", [](B200Public &p, const u64arr &pt, double scale) {
+        auto dev = p.shared()->dev;
+        DBuf d(dev, pt.size());
+        dev->upload(d.get(), pt.data(), pt.size() * 8);
+        return p.shared()->client->encoder().decode(d.get(), (int)pt.shape(0), scale);
       });
   py::class_<B200Secret>(mb, "B200Secret", "The secret part of the context: decryption")
       .def("decrypt", &B200Secret::decrypt, py::arg("enc_outputs"), py::arg("signature"));

@@ -4,6 +4,7 @@
 // emulator used by the tests.
 #pragma once
 #include "modarith.cuh"
+#include <cmath>
 #include <vector>
 
 namespace evab_host {
@@ -30,7 +31,22 @@ inline u64 min_root(u64 N, u64 p) {
   return best;
 }
 
+struct cplxh { double re, im; };
+// e^(2 pi i index / degree) from the first octant + symmetries (SEAL ComplexRoots::get_root)
+inline void unit_root(u64 index, u64 degree, double &re, double &im) {
+  const double PI = 3.1415926535897932384626433832795028842;
+  index &= degree - 1;
+  double a, b;
+  if (index <= degree / 8) { const double ang = 2.0 * PI * (double)index / (double)degree; re = cos(ang); im = sin(ang); }
+  else if (index <= degree / 4) { unit_root(degree / 4 - index, degree, a, b); re = b; im = a; }
+  else if (index <= degree / 2) { unit_root(degree / 2 - index, degree, a, b); re = -a; im = b; }
+  else if (index <= 3 * degree / 4) { unit_root(index - degree / 2, degree, a, b); re = -a; im = -b; }
+  else { unit_root(degree - index, degree, a, b); re = a; im = -b; }
+}
 struct Tables {
+  std::vector<cplxh> roots;        // [N] zeta^bitrev(i), zeta = e^(2 pi i / 2N)   (CKKS encoder)
+  std::vector<u32> slot_index;     // [N] matrix_reps_index_map
+  std::vector<u64> pow2;           // [k][128] 2^i mod p
   std::vector<u64x2> tw;       // [k][2][N]  forward / inverse {w, shoup(w)} in bit-reversed power order
   std::vector<PrimeDev> pd;    // tw / itw pointers are filled relative to `tw_base`
   std::vector<u64x2> qinv;     // [last][i]  {q_last^-1 mod q_i, shoup}
@@ -63,6 +79,16 @@ inline const char *build_tables(u64 N, int logN, const u64 *primes, int k, const
     P.tw = tw_base + ((size_t)i * 2 + 0) * N;
     P.itw = tw_base + ((size_t)i * 2 + 1) * N;
   }
+  T.roots.resize(N); T.slot_index.resize(N);
+  for (u64 i = 0; i < N; i++) unit_root(bitrev((u32)i, logN), 2 * N, T.roots[i].re, T.roots[i].im);
+  { const u64 m = 2 * N, slots = N / 2; u64 pos = 1;
+    for (u64 i = 0; i < slots; i++) {
+      T.slot_index[i] = bitrev((u32)((pos - 1) >> 1), logN);
+      T.slot_index[slots | i] = bitrev((u32)((m - pos - 1) >> 1), logN);
+      pos = (pos * 3) & (m - 1);
+    } }
+  T.pow2.assign((size_t)k * 128, 0);
+  for (int i = 0; i < k; i++) { u64 v = 1 % primes[i]; for (int e = 0; e < 128; e++) { T.pow2[(size_t)i * 128 + e] = v; v = mulmod(v, 2, primes[i]); } }
   T.qinv.assign((size_t)k * k, u64x2{0, 0});
   T.halfmod.assign((size_t)k * k, 0);
   for (int last = 0; last < k; last++)

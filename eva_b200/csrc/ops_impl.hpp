@@ -5,6 +5,7 @@
 #pragma once
 #include "ntt_kernels.cuh"
 #include "ops_kernels.cuh"
+#include "encode_kernels.cuh"
 #include <cstring>
 
 struct CtxView {
@@ -13,6 +14,9 @@ struct CtxView {
   const u64x2 *qinv;        // [k][k]
   const u64 *halfmod;       // [k][k]
   const u64 *zeros;         // [k]
+  const cplx *roots;        // [N]   CKKS encoder tables
+  const u32 *slot_index;    // [N]
+  const u64 *pow2;          // [k][128]
 };
 
 // Backend concept:
@@ -20,6 +24,7 @@ struct CtxView {
 //   int dyadic(int op, const DyArgs&);       int mulct(bool square, const MulArgs&);
 //   int inner(const IpArgs&);                int perm(u64*, const u64*, const u32*, int N, int rows);
 //   int drop_last(u64* out, const u64* in, int ell, int polys, u64 N);
+//   int enc_scatter(const EncBatch&);  int enc_fft(const EncBatch&, u32 gap, int nstages);  int enc_round(const EncBatch&);
 //   int error(const char*);
 
 inline NttLaunch base_launch(const CtxView &c) {
@@ -161,4 +166,40 @@ int rotate_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, const
   u64 *pct = work + ks_off_pct(c, ell);
   if (int rc = be.perm(pct, a, perm, (int)c.N, 2 * ell)) return rc;
   return keyswitch_impl(be, c, ell, out, pct + (size_t)ell * c.N, key, pct, 1, work);
+}
+
+
+// seal::CKKSEncoder::encode (vector overload) for a batch of vectors -- reference
+// eva/seal/seal_executor.h:242.  d_values/vec/scale are host arrays of `count` entries.
+template <class BE>
+int encode_impl(BE &be, const CtxView &c, int count, const double *const *d_values, const u32 *vec, const double *scale, int ell,
+                u64 *out, cplx *work) {
+  if (ell < 1 || ell > c.k) return be.error("encode: ell out of range");
+  const u32 slots = (u32)(c.N / 2);
+  for (int e0 = 0; e0 < count; e0 += ENC_MAX_BATCH) {
+    EncBatch B;
+    memset(&B, 0, sizeof(B));
+    B.count = (u32)((count - e0) < ENC_MAX_BATCH ? (count - e0) : ENC_MAX_BATCH);
+    for (u32 e = 0; e < B.count; e++) {
+      if (vec[e0 + e] == 0 || slots % vec[e0 + e]) return be.error("Vector size must exactly divide the slot count");
+      B.vals[e] = d_values[e0 + e]; B.vec[e] = vec[e0 + e]; B.scale[e] = scale[e0 + e];
+    }
+    B.work = work + (size_t)e0 * c.N; B.out = out + (size_t)e0 * ell * c.N;
+    B.roots = c.roots; B.slot_index = c.slot_index; B.primes = c.primes; B.pow2 = c.pow2;
+    B.N = (u32)c.N; B.ell = (u32)ell;
+    if (int rc = be.enc_scatter(B)) return rc;
+    int done = 0;
+    for (u32 g = 1; done < c.logN;) {
+      const int ns = (c.logN - done) >= 3 ? 3 : (c.logN - done);
+      if (int rc = be.enc_fft(B, g, ns)) return rc;   // N/8 threads, 8 elements each
+      done += ns; g <<= ns;
+    }
+    if (int rc = be.enc_round(B)) return rc;
+  }
+  // forward NTT of every residue, batched: job (q = vector, r = residue)
+  NttLaunch L = base_launch(c);
+  L.src = out; L.dst = out; L.inner = ell;
+  L.src_sq = L.dst_sq = (long long)ell * c.N; L.src_sr = L.dst_sr = (long long)c.N;
+  for (int i = 0; i < ell; i++) L.pmap[i] = (unsigned char)i;
+  return be.fwd(L, (size_t)count * ell);
 }

@@ -80,6 +80,14 @@ uint64_t evab_launch_count(const evab_ctx *ctx);
 int evab_ntt_fwd(evab_ctx *ctx, uint64_t *d_data, size_t count, const int *prime_idx, int nprimes, void *stream);
 int evab_ntt_inv(evab_ctx *ctx, uint64_t *d_data, size_t count, const int *prime_idx, int nprimes, void *stream);
 
+/* ---- CKKS encoder on the device: seal::CKKSEncoder::encode at seal_executor.h:242
+ * (and seal.cpp:68,80).  Encodes `count` vectors in one batch: vector e has
+ * vec_sizes[e] doubles at d_values[e] (device), is replicated over the N/2 slots
+ * and encoded at absolute scale scales[e] into d_out[e][ell][N] (NTT form).
+ * h_* arguments are host arrays read during the call.  d_work: count*N*16 bytes. ---- */
+int evab_encode(evab_ctx *ctx, int count, const double *const *h_d_values, const uint32_t *h_vec_sizes, const double *h_scales,
+                int ell, uint64_t *d_out, void *d_work, void *stream);
+
 /* ---- evaluator ops; one per SEAL call site of eva/seal/seal_executor.h ----
  * `ell` = residues of the inputs' level.  Outputs must not alias inputs unless
  * stated.  Sizes: sa/sb in {2,3}. */

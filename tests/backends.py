@@ -38,7 +38,7 @@ class EmuBackend:
         src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
         deps = [src] + [os.path.join(ROOT, "eva_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "eva_b200", "csrc"))]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", src, "-o", so])
         self.lib = C.CDLL(so)
         self.lib.emu_ctx_create.restype = C.c_void_p
         self.lib.emu_last_error.restype = C.c_char_p

@@ -119,6 +119,18 @@ struct EmuBE {
       for (int j = 0; j < A.N; j += 2) ks_inner_elem(A, mi, j);
     return 0;
   }
+  int enc_scatter(const EncBatch &B) {
+    for (u32 e = 0; e < B.count; e++) for (u32 i = 0; i < B.N / 2; i++) ::enc_scatter(B, e, i);
+    return 0;
+  }
+  int enc_fft(const EncBatch &B, u32 g, int ns) {
+    for (u32 e = 0; e < B.count; e++) for (u32 t = 0; t < B.N / 8; t++) enc_fft8(B, e, t, g, ns);
+    return 0;
+  }
+  int enc_round(const EncBatch &B) {
+    for (u32 e = 0; e < B.count; e++) for (u32 j = 0; j < B.N; j++) ::enc_round(B, e, j, 0);
+    return 0;
+  }
   int perm(u64 *out, const u64 *in, const u32 *p, int N, int rows) {
     for (int r = 0; r < rows; r++)
       for (int j = 0; j < N; j++) galois_perm_elem(out, in, p, N, r, j);
@@ -142,6 +154,7 @@ EmuCtx *emu_ctx_create(uint64_t N, const uint64_t *primes, int k) {
   c->zeros.assign(32, 0);
   c->v.N = N; c->v.logN = logN; c->v.k = k;
   c->v.primes = c->T.pd.data(); c->v.qinv = c->T.qinv.data(); c->v.halfmod = c->T.halfmod.data(); c->v.zeros = c->zeros.data();
+  c->v.roots = reinterpret_cast<const cplx *>(c->T.roots.data()); c->v.slot_index = c->T.slot_index.data(); c->v.pow2 = c->T.pow2.data();
   return c;
 }
 void emu_ctx_destroy(EmuCtx *c) { delete c; }
@@ -155,6 +168,10 @@ int emu_negate(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa) { Emu
 int emu_mul_plain(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt) { EmuBE be{c}; return dyadic_impl<DY_MULPT>(be, c->v, ell, o, a, sa, pt, 1, 1); }
 int emu_mul(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *b) { EmuBE be{c}; return mulct_impl(be, c->v, false, ell, o, a, b); }
 int emu_square(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a) { EmuBE be{c}; return mulct_impl(be, c->v, true, ell, o, a, (const u64 *)nullptr); }
+int emu_encode(EmuCtx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell, uint64_t *out, void *work) {
+  EmuBE be{c};
+  return encode_impl(be, c->v, count, vals, vec, scales, ell, out, (cplx *)work);
+}
 size_t emu_rescale_work_bytes(EmuCtx *c, int sa) { return rescale_work_elems(c->v, sa) * 8; }
 int emu_rescale(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, void *work) { EmuBE be{c}; return rescale_impl(be, c->v, ell, o, a, sa, (u64 *)work); }
 size_t emu_keyswitch_work_bytes(EmuCtx *c, int ell) { return keyswitch_work_elems(c->v, ell) * 8; }

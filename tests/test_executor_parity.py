@@ -13,7 +13,7 @@ from oracle_exec import OracleProgram
 pytestmark = pytest.mark.gpu
 
 
-def run_both(name, seed=1, use_graph=True, streams=8, lo=-1.0, hi=1.0):
+def run_both(name, seed=1, use_graph=True, streams=8, lo=-1.0, hi=1.0, cache=True):
     from eva_b200 import b200
     d = gl.load_json(name)
     prog, params, sig, terms = gl.build_program(d)
@@ -23,7 +23,7 @@ def run_both(name, seed=1, use_graph=True, streams=8, lo=-1.0, hi=1.0):
     op.prepare_keys()
     assert b200.create_coeff_modulus(N, d["prime_bits"]) == orc.primes
     pub = b200.context_from_raw_keys(N, orc.primes, op.rk, {int(e): k for e, k in op.gks.items()})
-    pub.set_options(num_streams=streams, use_graph=use_graph, cache_constants=True)
+    pub.set_options(num_streams=streams, use_graph=use_graph, cache_constants=cache)
     rng = np.random.default_rng(seed)
     inputs_o, val, plain_inputs = {}, b200.B200Valuation(), {}
     for name_, info in d["signature"].items():
@@ -98,6 +98,12 @@ def test_harris_bit_exact():
 @pytest.mark.parametrize("graph,streams", [(False, 1), (False, 8), (True, 4)])
 def test_scheduler_modes_agree(graph, streams):
     run_both("sobel", use_graph=graph, streams=streams)
+
+
+@pytest.mark.parametrize("name", ["sobel", "feat_mixed", "polynomial"])
+def test_constants_encoded_every_run(name):
+    """cache_constants=False: Encode terms run on the GPU inside every execute (as the reference does)"""
+    run_both(name, cache=False)
 
 
 def test_wide_dag():

@@ -78,3 +78,26 @@ def test_gpu_error_paths():
     assert lib.evab_ctx_create(C.c_uint64(4096), bad.ctypes.data_as(cabi.u64p), 2, 0, C.byref(h)) != 0
     assert b"2N" in lib.evab_last_error()
     assert lib.evab_ctx_create(C.c_uint64(3000), bad.ctypes.data_as(cabi.u64p), 2, 0, C.byref(h)) != 0
+
+
+@pytest.mark.parametrize("N,bits", [(4096, [60, 40, 60]), (16384, [60] * 5), (32768, [60, 20, 60, 60])])
+def test_gpu_encoder_bit_exact(N, bits):
+    """SURVEY 8a row E: device encoder (FP64 FFT + rounding + NTT) == host encoder == oracle, bit for bit;
+    decode(encode(x)) ~ x."""
+    from eva_b200 import b200
+    orc = pc.get_oracle(N, bits)
+    k = len(orc.primes)
+    z = np.zeros((k - 1, 2, k, N), dtype=np.uint64)
+    pub = b200.context_from_raw_keys(N, orc.primes, z, {})
+    rng = np.random.default_rng(N)
+    for vals, sb in ((rng.uniform(-2, 2, N // 2), 30), (np.array([0.17254603006834726]), 60), (rng.uniform(-1, 1, 64), 90),
+                     (np.zeros(8), 40)):
+        for ell in (k - 1, 1):
+            want = orc.encode(vals, 2.0 ** sb, ell)
+            dev = pub.encode(list(vals), 2.0 ** sb, ell)
+            host = pub.encode(list(vals), 2.0 ** sb, ell, True)
+            pc.eq(dev, want)
+            pc.eq(host, want)
+    x = rng.uniform(-2, 2, N // 2)
+    dec = np.array(pub.decode(pub.encode(list(x), 2.0 ** 40, k - 1), 2.0 ** 40))
+    assert np.abs(dec - x).max() < 1e-6
