@@ -101,7 +101,6 @@ def synthetic_inputs(d, primes, seed):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from concurrent.futures import ThreadPoolExecutor
     from eva_b200 import b200, program_io
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -114,19 +113,18 @@ def run_ours(args):
     relin, galois, cts = synthetic_inputs(d, primes, seed=1234 + rank)
     pub = b200.context_from_raw_keys(N, primes, relin, galois, local)
     pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache)
-    # B independent program instances (one plan + arena each), same keys, different input ciphertexts
-    progs, vals = [], []
+    # B independent program instances (different input ciphertexts, same keys) executed by ONE
+    # batched plan: every kernel launch covers all B instances (execute_batch / evab_set_batch)
+    prog, params, sig, terms = program_io.build_program(d)
+    vals = []
     for i in range(B):
-        prog, params, sig, terms = program_io.build_program(d)
-        progs.append((prog, terms))
         _, _, cts_i = synthetic_inputs({**d, "terms": []}, primes, seed=77 * (rank + 1) + i)
         val = b200.B200Valuation()
         for name, (ct, scale) in cts_i.items():
             val.set_cipher(name, ct, scale)
         vals.append(val)
-    nops = pub.cipher_op_count(progs[0][0])
+    nops = pub.cipher_op_count(prog)
     main = torch.cuda.current_stream()
-    streams = [torch.cuda.Stream() for _ in range(B)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -134,34 +132,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        """one step = B independent Sobel instances, each replayed as one CUDA graph on its own stream"""
-        fork = torch.cuda.Event()
-        fork.record(main)
-        for i in range(B):
-            streams[i].wait_event(fork)
-            pub.run_resident(progs[i][0], streams[i].cuda_stream)
-            ev = torch.cuda.Event()
-            ev.record(streams[i])
-            main.wait_event(ev)
-
-    # ---- launches per step (one un-graphed replay of one instance), then plans + graphs
+    # ---- launches per step: one un-graphed replay of the batched plan
     pub.set_options(num_streams=args.streams, use_graph=False, cache_constants=not args.no_const_cache)
-    pub.stage_inputs(progs[0][0], vals[0], main.cuda_stream)
-    l0 = pub.launch_count()
-    pub.run_resident(progs[0][0], main.cuda_stream)
+    pub.stage_inputs(prog, vals, main.cuda_stream)
+    pub.run_resident(prog, main.cuda_stream, B)
     torch.cuda.synchronize()
-    launches_per_instance = pub.launch_count() - l0
+    l0 = pub.launch_count()
+    pub.run_resident(prog, main.cuda_stream, B)
+    torch.cuda.synchronize()
+    launches_per_step = pub.launch_count() - l0
     pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache)
-    pub.drop_plan(progs[0][0])
-    for i in range(B):
-        pub.stage_inputs(progs[i][0], vals[i], main.cuda_stream)
+    pub.drop_plan(prog, B)
+    pub.stage_inputs(prog, vals, main.cuda_stream)
     torch.cuda.synchronize()
     for _ in range(max(3, args.warmup)):
-        step_resident()
+        pub.run_resident(prog, main.cuda_stream, B)
     torch.cuda.synchronize()
-    pool = ThreadPoolExecutor(max_workers=B)
-    outs = list(pool.map(lambda i: pub.execute(progs[i][0], vals[i]), range(B)))   # warm the e2e path
+    outs = pub.execute_batch(prog, vals)   # warm the e2e path
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -171,24 +158,27 @@ def run_ours(args):
     for i in range(args.steps):
         flush.zero_()
         ev[i][0].record(main)
-        step_resident()
+        pub.run_resident(prog, main.cuda_stream, B)
         ev[i][1].record(main)
     barrier()
     t_res = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
-    # ---- single-instance latency (one graph launch, nothing else on the GPU)
+    # ---- single-instance latency (batch-1 plan, one graph launch, nothing else on the GPU)
+    pub.stage_inputs(prog, vals[:1], main.cuda_stream)
+    for _ in range(3):
+        pub.run_resident(prog, main.cuda_stream, 1)
+    torch.cuda.synchronize()
     lat = []
     for i in range(10):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(main); pub.run_resident(progs[0][0], main.cuda_stream); b.record(main)
+        a.record(main); pub.run_resident(prog, main.cuda_stream, 1); b.record(main)
         torch.cuda.synchronize()
         lat.append(a.elapsed_time(b))
     lat.sort()
-    # ---- e2e through the public API: host buffers in/out (H2D + D2H inside the timed region),
-    #      B concurrent execute() calls per step from B host threads
+    # ---- e2e through the public API: host buffers in/out (H2D + D2H inside the timed region)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        outs = list(pool.map(lambda j: pub.execute(progs[j][0], vals[j]), range(B)))
+        outs = pub.execute_batch(prog, vals)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
@@ -212,12 +202,12 @@ def run_ours(args):
         "config": {"workload": "sobel_64x64 (examples/image_processing.py) compiled by the reference compiler: N=16384, prime_bits=[60]*5, 61 ciphertext ops per instance; one step = batch of %d independent program instances (images) per GPU" % B,
                    "instances_per_gpu": B,
                    "parallelism": "replicas x%d GPUs (independent program instances, no data-path collective; NCCL gather of outputs)" % world,
-                   "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("cuda-graph per instance" if not args.no_graph else "streams") + ", %d streams/plan" % args.streams,
+                   "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("one cuda-graph per step" if not args.no_graph else "streams") + ", %d streams, kernels batched over the %d instances" % (args.streams, B),
                    "const_encode": "cached per plan" if not args.no_const_cache else "23 Encode terms run on the GPU inside every execute (FP64 FFT + NTT), as in the reference"},
         "e2e": {"value": total_ops / t_e2e, "unit": "ops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,
-                "note": "B200Public.execute() with host numpy buffers, %d concurrent calls per step (host wall clock incl. H2D/D2H)" % B},
+                "note": "B200Public.execute_batch() on %d host-resident valuations per step (host wall clock incl. H2D/D2H)" % B},
         "single_instance": {"latency_ms": lat[len(lat) // 2], "ops_per_s": nops / (lat[len(lat) // 2] * 1e-3)},
-        "gpu_launches": int(launches_per_instance * B * args.steps),
+        "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
     }
     if rank == 0:

@@ -42,6 +42,20 @@ struct evab_ctx {
 };
 static cudaStream_t S(void *s) { return (cudaStream_t)s; }
 
+// thread-local batched-issue state (evab_set_batch)
+struct BatchState { int batch = 1; long long stride = 0, vstride = 0; };
+static thread_local BatchState g_batch;
+extern "C" int evab_set_batch(int batch, size_t stride_words, size_t value_stride) {
+  if (batch < 1 || batch > 65535) return fail("evab_set_batch: batch must be in [1, 65535]");
+  g_batch.batch = batch; g_batch.stride = (long long)stride_words; g_batch.vstride = (long long)value_stride;
+  return 0;
+}
+__device__ __forceinline__ void shift(NttLaunch &L, long long off) {
+  L.src += off; L.dst += off;
+  if (L.aux0) L.aux0 += off;
+  if (L.aux1) L.aux1 += off;
+}
+
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
@@ -54,8 +68,9 @@ struct BlockSync {
 };
 // one CTA = one residue (or one half of a 2^15 residue); T = N/16 threads, 64 registers
 template <int LOGN, bool SPLIT, int PRO, int EPI>
-__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_fwd(const NttLaunch L) {
+__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_fwd(NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
+  shift(L, (long long)blockIdx.y * bstride);
   typedef FwdBody<LOGN, SPLIT, PRO, EPI> B;
   const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1);
   if (J.skip) return;
@@ -69,41 +84,54 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_n
   B::phE(S, L, J, tid);
 }
 template <int LOGN, bool SPLIT, int PRO, int EPI>
-__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_inv(const NttLaunch L) {
+__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_inv(NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
+  shift(L, (long long)blockIdx.y * bstride);
   typedef InvBody<LOGN, SPLIT, PRO, EPI> B;
   const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1);
   if (J.skip) return;
   NttState S;
   PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, sm, BlockSync());
 }
-__global__ void __launch_bounds__(256) k_inv_last_stage(const NttLaunch L, u32 half_n) {
+__global__ void __launch_bounds__(256) k_inv_last_stage(NttLaunch L, u32 half_n, const long long bstride) {
+  shift(L, (long long)blockIdx.z * bstride);
   const NttJob J = ntt_job(L, blockIdx.y, 1);
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < half_n) inv_last_stage_elem(L, J, i, half_n);
 }
-template <int OP> __global__ void __launch_bounds__(256) k_dyadic(const DyArgs A) {
+template <int OP> __global__ void __launch_bounds__(256) k_dyadic(DyArgs A, const long long bstride) {
+  { const long long off = (long long)blockIdx.z * bstride; A.out += off; if (A.a) A.a += off; if (A.b) A.b += off; }
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
     dyadic_elem<OP>(A, blockIdx.y, j);
 }
-template <bool SQ> __global__ void __launch_bounds__(256) k_mul_ct(const MulArgs A) {
+template <bool SQ> __global__ void __launch_bounds__(256) k_mul_ct(MulArgs A, const long long bstride) {
+  { const long long off = (long long)blockIdx.z * bstride; A.out += off; A.a += off; if (A.b) A.b += off; }
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
     mulct_elem<SQ>(A, blockIdx.y, j);
 }
-__global__ void __launch_bounds__(256) k_ks_inner(const IpArgs A) {
+__global__ void __launch_bounds__(256) k_ks_inner(IpArgs A, const long long bstride) {
+  { const long long off = (long long)blockIdx.z * bstride; A.t += off; A.ext += off; A.acc += off; }
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
     ks_inner_elem(A, blockIdx.y, j);
 }
-__global__ void __launch_bounds__(256) k_enc_scatter(const EncBatch B) {
+__device__ __forceinline__ void shift(EncBatch &B, long long off, long long voff) {
+  B.work += off / 2; B.out += off;   // work is addressed in 16-byte complex elements
+  for (u32 e = 0; e < B.count; e++) B.vals[e] += voff;
+}
+__global__ void __launch_bounds__(256) k_enc_scatter(EncBatch B, const long long bstride, const long long vstride) {
+  shift(B, (long long)blockIdx.z * bstride, (long long)blockIdx.z * vstride);
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B.N / 2; i += gridDim.x * blockDim.x) enc_scatter(B, blockIdx.y, i);
 }
-__global__ void __launch_bounds__(256) k_enc_fft(const EncBatch B, u32 g, int nstages) {
+__global__ void __launch_bounds__(256) k_enc_fft(EncBatch B, u32 g, int nstages, const long long bstride) {
+  B.work += (long long)blockIdx.z * bstride / 2;
   for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < B.N / 8; t += gridDim.x * blockDim.x) enc_fft8(B, blockIdx.y, t, g, nstages);
 }
-__global__ void __launch_bounds__(256) k_enc_round(const EncBatch B) {
+__global__ void __launch_bounds__(256) k_enc_round(EncBatch B, const long long bstride) {
+  { const long long off = (long long)blockIdx.z * bstride; B.work += off / 2; B.out += off; }
   for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < B.N; j += gridDim.x * blockDim.x) enc_round(B, blockIdx.y, j, 0);
 }
-__global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, const u32 *perm, int N) {
+__global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, const u32 *perm, int N, const long long bstride) {
+  out += (long long)blockIdx.z * bstride; in += (long long)blockIdx.z * bstride;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
     galois_perm_elem(out, in, perm, N, blockIdx.y, j);
 }
@@ -121,7 +149,7 @@ template <int LOGN, bool SPLIT, int PRO, int EPI> static int launch_fwd_m(const 
     done[dev & 63].store(true);
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(jobs * (SPLIT ? 2 : 1)));
+  cfg.gridDim = dim3((unsigned)(jobs * (SPLIT ? 2 : 1)), (unsigned)g_batch.batch);
   cfg.blockDim = dim3(NttGeom<LOGN>::T);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -129,7 +157,7 @@ template <int LOGN, bool SPLIT, int PRO, int EPI> static int launch_fwd_m(const 
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = SPLIT ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  CUDA_OK(cudaLaunchKernelEx(&cfg, k_ntt_fwd<LOGN, SPLIT, PRO, EPI>, L));
+  CUDA_OK(cudaLaunchKernelEx(&cfg, k_ntt_fwd<LOGN, SPLIT, PRO, EPI>, L, g_batch.stride));
   return 0;
 }
 template <int LOGN, bool SPLIT> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
@@ -147,12 +175,12 @@ template <int LOGN, bool SPLIT, int EPI> static int launch_inv_m(const NttLaunch
     CUDA_OK(cudaFuncSetAttribute(k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done[dev & 63].store(true);
   }
-  k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI><<<(unsigned)(jobs * (SPLIT ? 2 : 1)), NttGeom<LOGN>::T, smem, st>>>(L);
+  k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI><<<dim3((unsigned)(jobs * (SPLIT ? 2 : 1)), (unsigned)g_batch.batch), NttGeom<LOGN>::T, smem, st>>>(L, g_batch.stride);
   CUDA_OK(cudaGetLastError());
   if (SPLIT) {
     const u32 half = NttGeom<LOGN>::N;
-    dim3 g((half + 255) / 256, (unsigned)jobs);
-    k_inv_last_stage<<<g, 256, 0, st>>>(L, half);
+    dim3 g((half + 255) / 256, (unsigned)jobs, (unsigned)g_batch.batch);
+    k_inv_last_stage<<<g, 256, 0, st>>>(L, half, g_batch.stride);
     CUDA_OK(cudaGetLastError());
   }
   return 0;
@@ -172,7 +200,7 @@ struct CudaBE {
   dim3 grid(int rows) const {
     int per_row = (int)(c->v.N / 2 / 256);
     if (per_row < 1) per_row = 1;
-    return dim3(per_row, rows);
+    return dim3(per_row, rows, g_batch.batch);
   }
   int fwd(const NttLaunch &L, size_t jobs) {
     count();
@@ -202,49 +230,50 @@ struct CudaBE {
     count();
     dim3 g = grid(A.sout * A.ell);
     switch (op) {
-      case DY_ADD: k_dyadic<DY_ADD><<<g, 256, 0, st>>>(A); break;
-      case DY_SUB: k_dyadic<DY_SUB><<<g, 256, 0, st>>>(A); break;
-      case DY_NEG: k_dyadic<DY_NEG><<<g, 256, 0, st>>>(A); break;
-      default: k_dyadic<DY_MULPT><<<g, 256, 0, st>>>(A); break;
+      case DY_ADD: k_dyadic<DY_ADD><<<g, 256, 0, st>>>(A, g_batch.stride); break;
+      case DY_SUB: k_dyadic<DY_SUB><<<g, 256, 0, st>>>(A, g_batch.stride); break;
+      case DY_NEG: k_dyadic<DY_NEG><<<g, 256, 0, st>>>(A, g_batch.stride); break;
+      case DY_COPY: k_dyadic<DY_COPY><<<g, 256, 0, st>>>(A, g_batch.stride); break;
+      default: k_dyadic<DY_MULPT><<<g, 256, 0, st>>>(A, g_batch.stride); break;
     }
     CUDA_OK(cudaGetLastError());
     return 0;
   }
   int mulct(bool sq, const MulArgs &A) {
     count();
-    if (sq) k_mul_ct<true><<<grid(A.ell), 256, 0, st>>>(A);
-    else k_mul_ct<false><<<grid(A.ell), 256, 0, st>>>(A);
+    if (sq) k_mul_ct<true><<<grid(A.ell), 256, 0, st>>>(A, g_batch.stride);
+    else k_mul_ct<false><<<grid(A.ell), 256, 0, st>>>(A, g_batch.stride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
   int inner(const IpArgs &A) {
     count();
-    k_ks_inner<<<grid(A.ell + 1), 256, 0, st>>>(A);
+    k_ks_inner<<<grid(A.ell + 1), 256, 0, st>>>(A, g_batch.stride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
   int enc_scatter(const EncBatch &B) {
     count();
-    k_enc_scatter<<<dim3((B.N / 2 + 255) / 256, B.count), 256, 0, st>>>(B);
+    k_enc_scatter<<<dim3((B.N / 2 + 255) / 256, B.count, g_batch.batch), 256, 0, st>>>(B, g_batch.stride, g_batch.vstride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
   int enc_fft(const EncBatch &B, u32 g, int ns) {
     count();
-    k_enc_fft<<<dim3((B.N / 8 + 255) / 256, B.count), 256, 0, st>>>(B, g, ns);
+    k_enc_fft<<<dim3((B.N / 8 + 255) / 256, B.count, g_batch.batch), 256, 0, st>>>(B, g, ns, g_batch.stride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
   int enc_round(const EncBatch &B) {
     count();
-    k_enc_round<<<dim3((B.N + 255) / 256, B.count), 256, 0, st>>>(B);
+    k_enc_round<<<dim3((B.N + 255) / 256, B.count, g_batch.batch), 256, 0, st>>>(B, g_batch.stride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
   int perm(u64 *out, const u64 *in, const u32 *p, int N, int rows) {
     count();
-    dim3 g((unsigned)((N + 255) / 256), rows);
-    k_galois_perm<<<g, 256, 0, st>>>(out, in, p, N);
+    dim3 g((unsigned)((N + 255) / 256), rows, g_batch.batch);
+    k_galois_perm<<<g, 256, 0, st>>>(out, in, p, N, g_batch.stride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -440,10 +469,10 @@ extern "C" int evab_square(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a,
 }
 extern "C" int evab_mod_switch(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, void *stream) {
   if (ell < 2 || ell > c->v.k) return fail("mod_switch needs 2 <= ell <= k");
-  CUDA_OK(cudaSetDevice(c->device));
-  const size_t row = (size_t)(ell - 1) * c->v.N * 8;
-  CUDA_OK(cudaMemcpy2DAsync(o, row, a, (size_t)ell * c->v.N * 8, row, sa, cudaMemcpyDeviceToDevice, S(stream)));
-  return 0;
+  BE_BEGIN return copy_impl(be, c->v, ell, ell - 1, o, a, sa);
+}
+extern "C" int evab_copy(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, void *stream) {
+  BE_BEGIN return copy_impl(be, c->v, ell, ell, o, a, sa);
 }
 extern "C" size_t evab_rescale_work_bytes(const evab_ctx *c, int sa) { return rescale_work_elems(c->v, sa) * sizeof(u64); }
 extern "C" int evab_rescale(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, void *work, void *stream) {

@@ -100,64 +100,82 @@ public:
     return out;
   }
 
-  Executor &executorFor(Program &program) {
-    auto h = std::static_pointer_cast<PlanHolder>(program.attachment(id_));
+  Executor &executorFor(Program &program, int batch = 1) {
+    const std::uint64_t key = id_ * 65536ull + (std::uint64_t)batch;
+    auto h = std::static_pointer_cast<PlanHolder>(program.attachment(key));
     if (!h || h->termCount != program.termCount()) {
       h = std::make_shared<PlanHolder>();
       h->keepAlive = s_;
-      h->exec = std::make_unique<Executor>(s_->dev, s_->client->encoder(), s_->keys, program, options);
+      ExecOptions o = options;
+      o.batch = batch;
+      h->exec = std::make_unique<Executor>(s_->dev, s_->client->encoder(), s_->keys, program, o);
       h->termCount = program.termCount();
-      program.attach(id_, h);
+      program.attach(key, h);
     }
     return *h->exec;
   }
-  void dropExecutor(Program &program) { program.attach(id_, nullptr); }
+  void dropExecutor(Program &program, int batch = 1) { program.attach(id_ * 65536ull + (std::uint64_t)batch, nullptr); }
 
   // upload host inputs into the executor's arena (H2D on `stream`)
-  void stageInputs(Executor &ex, Program &program, const B200Valuation &inputs, void *stream) {
+  void stageInputs(Executor &ex, Program &program, const B200Valuation &inputs, void *stream, int b = 0) {
     const u64 N = s_->dev->N();
     for (auto &in : inputs) {
       auto term = program.getInput(in.first);
       const ValueInfo &vi = ex.info(term);
       if (auto *c = std::get_if<HostCipher>(&in.second)) {
         if (vi.kind != Kind::Cipher || c->ell != vi.ell || c->size != vi.size) throw std::runtime_error("input " + in.first + ": ciphertext does not match the program signature");
-        s_->dev->upload(ex.valuePtr(term), c->data.data(), c->data.size() * 8, stream);
+        s_->dev->upload(ex.valuePtr(term, b), c->data.data(), c->data.size() * 8, stream);
       } else if (auto *p = std::get_if<HostPlain>(&in.second)) {
         if (vi.kind != Kind::Plain || p->ell != vi.ell) throw std::runtime_error("input " + in.first + ": plaintext does not match the program signature");
-        s_->dev->upload(ex.valuePtr(term), p->data.data(), (std::size_t)p->ell * N * 8, stream);
+        s_->dev->upload(ex.valuePtr(term, b), p->data.data(), (std::size_t)p->ell * N * 8, stream);
       } else {
         auto &cv = std::get<std::shared_ptr<ConstantValue>>(in.second);
         std::vector<double> x;
         cv->expandTo(x, program.getVecSize());
-        ex.setRawInput(in.first, x);
+        ex.setRawInput(in.first, x, b);
       }
     }
   }
   // SEALPublic::execute -- reference eva/seal/seal.cpp:104-122.  Host buffers in,
   // host buffers out: H2D of the inputs, the DAG on the GPU, D2H of the outputs.
   B200Valuation execute(Program &program, const B200Valuation &inputs) {
-    Executor &ex = executorFor(program);
+    std::vector<const B200Valuation *> in{&inputs};
+    return std::move(executeMany(program, in)[0]);
+  }
+  // Batched execute: N valuations of the same program run as ONE plan replay whose kernels
+  // each cover all instances (horizontal fusion).  Results are identical
+  // to N separate execute() calls.
+  std::vector<B200Valuation> executeBatch(Program &program, const std::vector<B200Valuation> &inputs) {
+    std::vector<const B200Valuation *> in;
+    for (auto &v : inputs) in.push_back(&v);
+    return executeMany(program, in);
+  }
+  std::vector<B200Valuation> executeMany(Program &program, const std::vector<const B200Valuation *> &inputs) {
+    const int B = (int)inputs.size();
+    if (B < 1) throw std::invalid_argument("execute needs at least one valuation");
+    Executor &ex = executorFor(program, B);
     void *st = ex.mainStream();
-    stageInputs(ex, program, inputs, st);
+    for (int b = 0; b < B; b++) stageInputs(ex, program, *inputs[b], st, b);
     ex.run(st);
-    B200Valuation out;
+    std::vector<B200Valuation> outs(B);
     const u64 N = s_->dev->N();
-    for (auto &o : program.getOutputs()) {
-      const ValueInfo &vi = ex.info(o.second);
-      if (vi.kind == Kind::Cipher) {
-        HostCipher h; h.size = vi.size; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.size * vi.ell * N);
-        s_->dev->download(h.data.data(), ex.valuePtr(o.second), h.data.size() * 8, st);
-        out[o.first] = std::move(h);
-      } else if (vi.kind == Kind::Plain) {
-        HostPlain h; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.ell * N);
-        s_->dev->download(h.data.data(), ex.valuePtr(o.second), h.data.size() * 8, st);
-        out[o.first] = std::move(h);
-      } else {
-        out[o.first] = std::make_shared<ConstantValue>(program.getVecSize(), ex.rawValue(o.second->index));
+    for (int b = 0; b < B; b++)
+      for (auto &o : program.getOutputs()) {
+        const ValueInfo &vi = ex.info(o.second);
+        if (vi.kind == Kind::Cipher) {
+          HostCipher h; h.size = vi.size; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.size * vi.ell * N);
+          s_->dev->download(h.data.data(), ex.valuePtr(o.second, b), h.data.size() * 8, st);
+          outs[b][o.first] = std::move(h);
+        } else if (vi.kind == Kind::Plain) {
+          HostPlain h; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.ell * N);
+          s_->dev->download(h.data.data(), ex.valuePtr(o.second, b), h.data.size() * 8, st);
+          outs[b][o.first] = std::move(h);
+        } else {
+          outs[b][o.first] = std::make_shared<ConstantValue>(program.getVecSize(), ex.rawValue(o.second->index, b));
+        }
       }
-    }
     s_->dev->sync(st);
-    return out;
+    return outs;
   }
   std::shared_ptr<Shared> shared() const { return s_; }
   ExecOptions options;

@@ -48,6 +48,13 @@ struct ExecOptions {
   int numStreams = 8;
   bool useGraph = true;
   bool cacheConstants = true;  // encode plan-time-constant plaintexts once per plan instead of on every run
+  int batch = 1;               // independent program instances executed by every (fat) kernel launch
+};
+
+// scoped evab_set_batch: ops issued by this thread act on `batch` instances
+struct BatchGuard {
+  BatchGuard(int batch, std::size_t stride, std::size_t vstride) { check(evab_set_batch(batch, stride, vstride)); }
+  ~BatchGuard() { evab_set_batch(1, 0, 0); }
 };
 
 class Executor {
@@ -71,10 +78,11 @@ public:
     return mainStream_;
   }
   const ValueInfo &info(const Term::Ptr &t) const { return vals_.at(t->index); }
-  u64 *valuePtr(const Term::Ptr &t) const { return arena_.get() + vals_.at(t->index).off; }
-  u64 *valuePtr(std::uint64_t index) const { return arena_.get() + vals_.at(index).off; }
+  int batch() const { return opt_.batch; }
+  u64 *valuePtr(const Term::Ptr &t, int b = 0) const { return arena_.get() + (std::size_t)b * stride_ + vals_.at(t->index).off; }
+  u64 *valuePtr(std::uint64_t index, int b = 0) const { return arena_.get() + (std::size_t)b * stride_ + vals_.at(index).off; }
   const ValueInfo &info(std::uint64_t index) const { return vals_.at(index); }
-  const std::vector<double> &rawValue(std::uint64_t index) const { return raws_.at(index); }
+  const std::vector<double> &rawValue(std::uint64_t index, int b = 0) const { return rawsB_.at(b).at(index); }
 
   // device-resident run: inputs must already be in valuePtr(input term); raw
   // inputs set through setRawInput.  Enqueues the whole program on `stream`
@@ -88,12 +96,12 @@ public:
       replay(stream);
     }
   }
-  void setRawInput(const std::string &name, const std::vector<double> &v) {
+  void setRawInput(const std::string &name, const std::vector<double> &v, int b = 0) {
     auto t = prog_.getInput(name);
     if (vals_.at(t->index).kind != Kind::Raw) throw std::runtime_error("input " + name + " is not a raw input");
     std::vector<double> x;
     ConstantValue(prog_.getVecSize(), v).expandTo(x, prog_.getVecSize());
-    raws_[t->index] = x;
+    rawsB_.at(b)[t->index] = x;
     rawDirty_ = true;
   }
 
@@ -102,7 +110,8 @@ private:
   void buildPlan() {
     for (auto &t : prog_.toposort()) order_.push_back(t.get());  // raw: the plan lives inside the Program (attachment)
     vals_.assign(prog_.termCount(), ValueInfo{});
-    raws_.resize(prog_.termCount());
+    if (opt_.batch < 1) throw std::invalid_argument("batch must be >= 1");
+    rawsB_.assign(opt_.batch, std::vector<std::vector<double>>(prog_.termCount()));
     std::size_t arenaWords = 0;
     auto place = [&](ValueInfo &v) { v.off = arenaWords; arenaWords += (std::size_t)(v.kind == Kind::Cipher ? v.size : 1) * v.ell * N_; };
     for (auto &t : order_) {
@@ -119,7 +128,7 @@ private:
         } break;
         case Op::Constant:
           v.kind = Kind::Raw;
-          t->constant->expandTo(raws_[t->index], prog_.getVecSize());
+          for (auto &r : rawsB_) t->constant->expandTo(r[t->index], prog_.getVecSize());
           break;
         case Op::Encode:
           if (a(0).kind != Kind::Raw) throw std::runtime_error("Encode expects a raw operand");
@@ -260,8 +269,10 @@ private:
     for (auto &st : steps_) usedStreams_ = std::max(usedStreams_, st.stream + 1);
     workOff_.assign(usedStreams_, 0);
     for (int s = 0; s < usedStreams_; s++) { workOff_[s] = arenaWords; arenaWords += workWords[s]; }
-    arena_ = DBuf(dev_, arenaWords + 8);
-    rawArena_ = DBuf(dev_, rawWords_ + 8);
+    stride_ = (arenaWords + 63) & ~std::size_t(63);
+    rawStride_ = (rawWords_ + 7) & ~std::size_t(7);
+    arena_ = DBuf(dev_, stride_ * opt_.batch + 8);
+    rawArena_ = DBuf(dev_, rawStride_ * opt_.batch + 8);
     dev_->sync();  // stream-ordered allocation made on the null stream: publish it to the plan's streams
     for (int s = 0; s < usedStreams_; s++) { void *h; check(evab_stream_create(dev_->ctx(), &h)); streams_.push_back(h); }
     for (int e = 0; e < numEvents_ + usedStreams_ + 1; e++) { void *h; check(evab_event_create(dev_->ctx(), &h)); events_.push_back(h); }
@@ -293,43 +304,48 @@ private:
   void evalRawAndEncodes(void *stream) {
     hasDynamicEncodes_ = false;
     std::vector<char> dyn(prog_.termCount(), 0);
-    for (auto &t : order_) {
-      const ValueInfo &v = vals_[t->index];
-      bool d = (t->op == Op::Input && v.kind == Kind::Raw);
-      for (auto &o : t->getOperands()) d = d || dyn[o->index];
-      dyn[t->index] = d;
-      if (v.kind == Kind::Raw && t->op != Op::Input && t->op != Op::Constant) {
-        auto &out = raws_[t->index];
-        auto &x = raws_[t->operandAt(0)->index];
-        if (t->op == Op::Output) { out = x; continue; }
-        if (x.empty()) { out.clear(); continue; }  // raw input not provided yet
-        const std::size_t n = x.size();
-        out.resize(n);
-        if (t->op == Op::Negate) for (std::size_t i = 0; i < n; i++) out[i] = -x[i];
-        else if (t->op == Op::RotateLeftConst || t->op == Op::RotateRightConst) {
-          long long sh = *t->rotation;
-          if (t->op == Op::RotateRightConst) sh = -sh;
-          sh %= (long long)n; if (sh < 0) sh += n;
-          for (std::size_t i = 0; i < n; i++) out[i] = x[(i + sh) % n];
-        } else {
-          auto &y = raws_[t->operandAt(1)->index];
-          if (y.empty()) { out.clear(); continue; }
-          for (std::size_t i = 0; i < n; i++) out[i] = t->op == Op::Add ? x[i] + y[i] : t->op == Op::Sub ? x[i] - y[i] : x[i] * y[i];
+    for (int b = 0; b < opt_.batch; b++) {
+      auto &raws = rawsB_[b];
+      for (auto &t : order_) {
+        const ValueInfo &v = vals_[t->index];
+        bool d = (t->op == Op::Input && v.kind == Kind::Raw);
+        for (auto &o : t->getOperands()) d = d || dyn[o->index];
+        dyn[t->index] = d;
+        if (v.kind == Kind::Raw && t->op != Op::Input && t->op != Op::Constant) {
+          auto &out = raws[t->index];
+          auto &x = raws[t->operandAt(0)->index];
+          if (t->op == Op::Output) { out = x; continue; }
+          if (x.empty()) { out.clear(); continue; }  // raw input not provided yet
+          const std::size_t n = x.size();
+          out.resize(n);
+          if (t->op == Op::Negate) for (std::size_t i = 0; i < n; i++) out[i] = -x[i];
+          else if (t->op == Op::RotateLeftConst || t->op == Op::RotateRightConst) {
+            long long sh = *t->rotation;
+            if (t->op == Op::RotateRightConst) sh = -sh;
+            sh %= (long long)n; if (sh < 0) sh += n;
+            for (std::size_t i = 0; i < n; i++) out[i] = x[(i + sh) % n];
+          } else {
+            auto &y = raws[t->operandAt(1)->index];
+            if (y.empty()) { out.clear(); continue; }
+            for (std::size_t i = 0; i < n; i++) out[i] = t->op == Op::Add ? x[i] + y[i] : t->op == Op::Sub ? x[i] - y[i] : x[i] * y[i];
+          }
         }
-      }
-      if (t->op == Op::Encode) {
-        auto &x = raws_[t->operandAt(0)->index];
-        if (x.empty()) continue;
-        if (dyn[t->index]) hasDynamicEncodes_ = true;
-        if (!rawUploaded_.count(t->index) || dyn[t->index]) {
-          if ((N_ / 2) % x.size()) throw std::runtime_error("Vector size must exactly divide the slot count");
-          dev_->upload(rawArena_.get() + rawOff_.at(t->index), x.data(), x.size() * 8, stream);
-          rawUploaded_.insert(t->index);
+        if (t->op == Op::Encode) {
+          auto &x = raws[t->operandAt(0)->index];
+          if (x.empty()) continue;
+          if (dyn[t->index]) hasDynamicEncodes_ = true;
+          const std::uint64_t key = t->index * 65536ull + (std::uint64_t)b;
+          if (!rawUploaded_.count(key) || dyn[t->index]) {
+            if ((N_ / 2) % x.size()) throw std::runtime_error("Vector size must exactly divide the slot count");
+            dev_->upload(rawArena_.get() + (std::size_t)b * rawStride_ + rawOff_.at(t->index), x.data(), x.size() * 8, stream);
+            rawUploaded_.insert(key);
+          }
         }
       }
     }
-    dev_->sync(stream);  // the staged host vectors are temporaries of this call
+    dev_->sync(stream);  // the staged host vectors must outlive the copies
     if (opt_.cacheConstants && !staticEncoded_) {
+      BatchGuard bg(opt_.batch, stride_, rawStride_);
       for (auto &g : groups_) if (!g.dynamic) issueEncodeGroup(g, stream);
       dev_->sync(stream);
       staticEncoded_ = true;
@@ -340,7 +356,7 @@ private:
     std::vector<const double *> ptrs; std::vector<std::uint32_t> vec; std::vector<double> sc;
     for (Term *t : g.members) {
       ptrs.push_back(reinterpret_cast<const double *>(rawArena_.get() + rawOff_.at(t->index)));
-      vec.push_back((std::uint32_t)raws_[t->operandAt(0)->index].size());
+      vec.push_back((std::uint32_t)rawsB_[0][t->operandAt(0)->index].size());
       sc.push_back(vals_[t->index].scale);
     }
     check(evab_encode(dev_->ctx(), (int)g.members.size(), ptrs.data(), vec.data(), sc.data(), g.ell, arena_.get() + g.outOff,
@@ -375,7 +391,7 @@ private:
       } break;
       case Op::Negate: check(evab_negate(c, o.ell, out, P(0), V(0).size, stream)); break;
       case Op::RotateLeftConst: case Op::RotateRightConst:
-        if (*t.rotation == 0) check(evab_add_plain(c, o.ell, out, P(0), 2, enc_.zeroPlain(o.ell), stream));  // rotate_vector(0): copy
+        if (*t.rotation == 0) check(evab_copy(c, o.ell, out, P(0), 2, stream));  // rotate_vector(0): copy
         else { const u64 elt = galoisElt(t); check(evab_rotate(c, o.ell, out, P(0), elt, keys_.galois.at(elt).get(), work, stream)); }
         break;
       case Op::Relinearize: check(evab_relinearize(c, o.ell, out, P(0), keys_.relin.get(), work, stream)); break;
@@ -387,6 +403,7 @@ private:
   // fork from `stream` into the plan's streams, issue every step, join back
   void replay(void *stream) {
     evab_ctx *c = dev_->ctx();
+    BatchGuard bg(opt_.batch, stride_, rawStride_);
     void *forkEv = events_[numEvents_ + usedStreams_];
     check(evab_event_record(c, forkEv, stream));
     for (int s = 0; s < usedStreams_; s++) check(evab_stream_wait_event(c, streams_[s], forkEv));
@@ -405,7 +422,6 @@ private:
     evab_ctx *c = dev_->ctx();
     if (graph_) { evab_graph_destroy(c, graph_); graph_ = nullptr; }
     if (!capStream_) { check(evab_stream_create(c, &capStream_)); streams_.push_back(capStream_); }
-    enc_.zeroPlain(k_);  // make sure lazily-created helpers exist before capture
     check(evab_graph_begin(c, capStream_));
     try { replay(capStream_); } catch (...) { void *g = nullptr; evab_graph_end(c, capStream_, &g); throw; }
     check(evab_graph_end(c, capStream_, &graph_));
@@ -421,7 +437,8 @@ private:
   int k_;
   std::vector<Term *> order_;
   std::vector<ValueInfo> vals_;
-  std::vector<std::vector<double>> raws_;
+  std::vector<std::vector<std::vector<double>>> rawsB_;   // [instance][term]
+  std::size_t stride_ = 0, rawStride_ = 0;
   std::vector<EncodeGroup> groups_;
   std::vector<Term *> encodeTerms_;
   std::unordered_map<std::uint64_t, int> groupIndex_;

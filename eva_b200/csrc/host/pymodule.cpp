@@ -133,31 +133,36 @@ PYBIND11_MODULE(_eva_b200, m) {
   py::class_<B200Public>(mb, "B200Public", "The public part of the context: encryption and execution on the GPU")
       .def("encrypt", &B200Public::encrypt, py::arg("inputs"), py::arg("signature"))
       .def("execute", &B200Public::execute, py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>())
+      .def("execute_batch", &B200Public::executeBatch, py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>(),
+           "Execute one compiled program on a list of valuations with batched kernels; returns a list of valuations")
       .def("set_options", [](B200Public &p, int streams, bool graph, bool cache) { p.options.numStreams = streams; p.options.useGraph = graph; p.options.cacheConstants = cache; },
            py::arg("num_streams") = 8, py::arg("use_graph") = true, py::arg("cache_constants") = true)
-      .def("drop_plan", &B200Public::dropExecutor)
+      .def("drop_plan", &B200Public::dropExecutor, py::arg("program"), py::arg("batch") = 1)
       .def("cipher_op_count", [](B200Public &p, Program &prog) { return p.executorFor(prog).cipherOpCount(); })
       .def("launch_count", [](B200Public &p) { return evab_launch_count(p.shared()->dev->ctx()); })
       .def("primes", [](B200Public &p) { return p.shared()->dev->primes(); })
       // ---- benchmark hooks: device-resident execution on a caller-provided stream
-      .def("stage_inputs", [](B200Public &p, Program &prog, const B200Valuation &in, std::uintptr_t stream) { p.stageInputs(p.executorFor(prog), prog, in, (void *)stream); })
-      .def("run_resident", [](B200Public &p, Program &prog, std::uintptr_t stream) { p.executorFor(prog).run((void *)stream); },
-           py::call_guard<py::gil_scoped_release>())
+      .def("stage_inputs", [](B200Public &p, Program &prog, const std::vector<B200Valuation> &in, std::uintptr_t stream) {
+        Executor &ex = p.executorFor(prog, (int)in.size());
+        for (std::size_t b = 0; b < in.size(); b++) p.stageInputs(ex, prog, in[b], (void *)stream, (int)b);
+      })
+      .def("run_resident", [](B200Public &p, Program &prog, std::uintptr_t stream, int batch) { p.executorFor(prog, batch).run((void *)stream); },
+           py::arg("program"), py::arg("stream"), py::arg("batch") = 1, py::call_guard<py::gil_scoped_release>())
       .def("sync", [](B200Public &p, std::uintptr_t stream) { p.shared()->dev->sync((void *)stream); }, py::call_guard<py::gil_scoped_release>())
       // ---- test hooks
-      .def("debug_value", [](B200Public &p, Program &prog, std::uint64_t index) -> py::object {
-        Executor &ex = p.executorFor(prog);
+      .def("debug_value", [](B200Public &p, Program &prog, std::uint64_t index, int batch, int b) -> py::object {
+        Executor &ex = p.executorFor(prog, batch);
         const ValueInfo &vi = ex.info(index);
         auto dev = p.shared()->dev;
-        if (vi.kind == Kind::Raw) return py::cast(ex.rawValue(index));
+        if (vi.kind == Kind::Raw) return py::cast(ex.rawValue(index, b));
         if (vi.kind == Kind::None) return py::none();
         const std::size_t polys = vi.kind == Kind::Cipher ? vi.size : 1;
         u64arr a({polys, (std::size_t)vi.ell, (std::size_t)dev->N()});
         dev->sync();
-        dev->download(a.mutable_data(), ex.valuePtr(index), a.size() * 8);
+        dev->download(a.mutable_data(), ex.valuePtr(index, b), a.size() * 8);
         dev->sync();
         return py::make_tuple(a, vi.scale);
-      })
+      }, py::arg("program"), py::arg("index"), py::arg("batch") = 1, py::arg("instance") = 0)
       .def("encode", [](B200Public &p, const std::vector<double> &values, double scale, int ell, bool host) {
         auto dev = p.shared()->dev;
         DBuf pt(dev, (std::size_t)ell * dev->N());

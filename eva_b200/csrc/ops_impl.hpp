@@ -57,9 +57,20 @@ int dyadic_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, int s
   if (sa < 1 || sa > 3 || (b && !plain && (sb < 1 || sb > 3))) return be.error("ciphertext size must be 1..3");
   DyArgs A;
   A.out = out; A.a = a; A.b = b; A.primes = c.primes; A.ell = ell; A.N = (int)c.N;
-  A.sa = sa; A.sb = sb; A.b_is_plain = plain;
+  A.sa = sa; A.sb = sb; A.b_is_plain = plain; A.a_ell = ell;
   A.sout = (plain || !b) ? sa : (sa > sb ? sa : sb);
   return be.dyadic(OP, A);
+}
+// copy the first `ell_out` residues of every polynomial: ell_out == ell_in is a plain
+// ciphertext copy (rotate_vector by 0), ell_out == ell_in - 1 is
+// Evaluator::mod_switch_to_next (reference eva/seal/seal_executor.h:206; Appendix A.7)
+template <class BE> int copy_impl(BE &be, const CtxView &c, int ell_in, int ell_out, u64 *out, const u64 *a, int sa) {
+  if (ell_out < 1 || ell_out > ell_in || ell_in > c.k) return be.error("copy: bad residue counts");
+  if (sa < 1 || sa > 3) return be.error("ciphertext size must be 1..3");
+  DyArgs A;
+  A.out = out; A.a = a; A.b = nullptr; A.primes = c.primes; A.ell = ell_out; A.N = (int)c.N;
+  A.sa = sa; A.sb = 0; A.b_is_plain = 0; A.a_ell = ell_in; A.sout = sa;
+  return be.dyadic(DY_COPY, A);
 }
 
 template <class BE> int mulct_impl(BE &be, const CtxView &c, bool square, int ell, u64 *out, const u64 *a, const u64 *b) {

@@ -5,7 +5,7 @@
 #pragma once
 #include "ntt_core.cuh"
 
-enum { DY_ADD = 0, DY_SUB = 1, DY_NEG = 2, DY_MULPT = 3 };
+enum { DY_ADD = 0, DY_SUB = 1, DY_NEG = 2, DY_MULPT = 3, DY_COPY = 4 };
 
 struct DyArgs {
   u64 *out; const u64 *a; const u64 *b;
@@ -13,6 +13,7 @@ struct DyArgs {
   int ell, N;
   int sa, sb, sout;  // polys in a / b / out
   int b_is_plain;    // b = plaintext [ell][N]: add/sub touch poly 0 only, mulpt every poly
+  int a_ell;         // residues per polynomial of `a` (>= ell; DY_COPY with a_ell = ell+1 drops the last residue)
 };
 
 EVAB_HD u64x2 ld2(const u64 *p) { return *reinterpret_cast<const u64x2 *>(p); }
@@ -24,15 +25,17 @@ template <int OP> EVAB_HD void dyadic_elem(const DyArgs &A, int res, int j) {
   const PrimeDev P = A.primes[i];
   const u64 p = P.p;
   const size_t off = (size_t)res * A.N;
+  const size_t aoff = ((size_t)s * A.a_ell + i) * A.N;
   const bool has_a = s < A.sa;
   const bool has_b = A.b_is_plain ? (OP == DY_MULPT || s == 0) : (s < A.sb);
   const size_t boff = A.b_is_plain ? (size_t)i * A.N : off;
   u64x2 va = u64x2{0, 0}, vb = u64x2{0, 0}, r;
-  if (has_a) va = ld2(A.a + off + j);
-  if (OP != DY_NEG && has_b) vb = ld2(A.b + boff + j);
+  if (has_a) va = ld2(A.a + aoff + j);
+  if (OP != DY_NEG && OP != DY_COPY && has_b) vb = ld2(A.b + boff + j);
   if (OP == DY_ADD) { r.x = addmod(va.x, vb.x, p); r.y = addmod(va.y, vb.y, p); }
   else if (OP == DY_SUB) { r.x = submod(va.x, vb.x, p); r.y = submod(va.y, vb.y, p); }
   else if (OP == DY_NEG) { r.x = negmod(va.x, p); r.y = negmod(va.y, p); }
+  else if (OP == DY_COPY) { r = va; }
   else { r.x = mulmod(va.x, vb.x, p, P.ratio_lo, P.ratio_hi); r.y = mulmod(va.y, vb.y, p, P.ratio_lo, P.ratio_hi); }
   st2(A.out + off + j, r);
 }

@@ -69,6 +69,13 @@ int evab_graph_begin(evab_ctx *ctx, void *stream);
 int evab_graph_end(evab_ctx *ctx, void *stream, void **graph_exec);
 int evab_graph_launch(evab_ctx *ctx, void *graph_exec, void *stream);
 int evab_graph_destroy(evab_ctx *ctx, void *graph_exec);
+/* Batched issue (thread-local): until reset with batch = 1, every op enqueued by this
+ * thread is applied to `batch` independent instances laid out at a fixed distance:
+ * instance b uses every ciphertext / plaintext / workspace device pointer shifted by
+ * b * stride_words (u64 words) and every evab_encode value pointer shifted by
+ * b * value_stride (doubles); keys and tables are shared.  One fat launch replaces
+ * `batch` launches (horizontal fusion across program instances). */
+int evab_set_batch(int batch, size_t stride_words, size_t value_stride);
 /* number of kernel launches issued through this context so far */
 uint64_t evab_launch_count(const evab_ctx *ctx);
 
@@ -108,6 +115,8 @@ int evab_square(evab_ctx *ctx, int ell, uint64_t *d_out3, const uint64_t *d_a2, 
  * d_work: evab_rescale_work_bytes(ctx, sa) bytes of scratch. */
 size_t evab_rescale_work_bytes(const evab_ctx *ctx, int sa);
 int evab_rescale(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, void *d_work, void *stream);
+/* plain copy of a ciphertext (rotate_vector by 0 steps) */
+int evab_copy(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, void *stream);
 /* Evaluator::mod_switch_to_next :206 -- drop the last residue */
 int evab_mod_switch(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, void *stream);
 /* Evaluator::relinearize :200 (size 3 -> 2) and rotate_vector :181,188.

@@ -105,6 +105,7 @@ struct EmuBE {
           case DY_ADD: dyadic_elem<DY_ADD>(A, res, j); break;
           case DY_SUB: dyadic_elem<DY_SUB>(A, res, j); break;
           case DY_NEG: dyadic_elem<DY_NEG>(A, res, j); break;
+          case DY_COPY: dyadic_elem<DY_COPY>(A, res, j); break;
           default: dyadic_elem<DY_MULPT>(A, res, j); break;
         }
     return 0;
