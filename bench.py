@@ -113,18 +113,27 @@ def run_ours(args):
     relin, galois, cts = synthetic_inputs(d, primes, seed=1234 + rank)
     pub = b200.context_from_raw_keys(N, primes, relin, galois, local)
     pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache)
-    # B independent program instances (different input ciphertexts, same keys) executed by ONE
-    # batched plan: every kernel launch covers all B instances (execute_batch / evab_set_batch)
-    prog, params, sig, terms = program_io.build_program(d)
-    vals = []
-    for i in range(B):
-        _, _, cts_i = synthetic_inputs({**d, "terms": []}, primes, seed=77 * (rank + 1) + i)
-        val = b200.B200Valuation()
-        for name, (ct, scale) in cts_i.items():
-            val.set_cipher(name, ct, scale)
-        vals.append(val)
-    nops = pub.cipher_op_count(prog)
+    # B independent program instances (different input ciphertexts, same keys), organised as
+    # G concurrent plan replays (one CUDA graph each, on its own stream) x F instances fused
+    # into every kernel launch of a plan (execute_batch / evab_set_batch):  B = G * F
+    from concurrent.futures import ThreadPoolExecutor
+    F = max(1, min(args.fuse, B))
+    G = B // F
+    assert G * F == B, "--instances must be a multiple of --fuse"
+    groups = []
+    for g in range(G):
+        prog, params, sig, terms = program_io.build_program(d)
+        vals = []
+        for i in range(F):
+            _, _, cts_i = synthetic_inputs({**d, "terms": []}, primes, seed=77 * (rank + 1) + g * F + i)
+            val = b200.B200Valuation()
+            for name, (ct, scale) in cts_i.items():
+                val.set_cipher(name, ct, scale)
+            vals.append(val)
+        groups.append((prog, vals))
+    nops = pub.cipher_op_count(groups[0][0])
     main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(G)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -132,23 +141,35 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- launches per step: one un-graphed replay of the batched plan
+    def step_resident():
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for g in range(G):
+            streams[g].wait_event(fork)
+            pub.run_resident(groups[g][0], streams[g].cuda_stream, F)
+            ev_ = torch.cuda.Event()
+            ev_.record(streams[g])
+            main.wait_event(ev_)
+
+    # ---- launches per step: one un-graphed replay of one group's plan, times G
     pub.set_options(num_streams=args.streams, use_graph=False, cache_constants=not args.no_const_cache)
-    pub.stage_inputs(prog, vals, main.cuda_stream)
-    pub.run_resident(prog, main.cuda_stream, B)
+    pub.stage_inputs(groups[0][0], groups[0][1], main.cuda_stream)
+    pub.run_resident(groups[0][0], main.cuda_stream, F)
     torch.cuda.synchronize()
     l0 = pub.launch_count()
-    pub.run_resident(prog, main.cuda_stream, B)
+    pub.run_resident(groups[0][0], main.cuda_stream, F)
     torch.cuda.synchronize()
-    launches_per_step = pub.launch_count() - l0
+    launches_per_step = (pub.launch_count() - l0) * G
     pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache)
-    pub.drop_plan(prog, B)
-    pub.stage_inputs(prog, vals, main.cuda_stream)
+    pub.drop_plan(groups[0][0], F)
+    for prog, vals in groups:
+        pub.stage_inputs(prog, vals, main.cuda_stream)
     torch.cuda.synchronize()
     for _ in range(max(3, args.warmup)):
-        pub.run_resident(prog, main.cuda_stream, B)
+        step_resident()
     torch.cuda.synchronize()
-    outs = pub.execute_batch(prog, vals)   # warm the e2e path
+    pool = ThreadPoolExecutor(max_workers=G)
+    outs = list(pool.map(lambda g: pub.execute_batch(groups[g][0], groups[g][1]), range(G)))   # warm the e2e path
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -158,33 +179,36 @@ def run_ours(args):
     for i in range(args.steps):
         flush.zero_()
         ev[i][0].record(main)
-        pub.run_resident(prog, main.cuda_stream, B)
+        step_resident()
         ev[i][1].record(main)
     barrier()
     t_res = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
     # ---- single-instance latency (batch-1 plan, one graph launch, nothing else on the GPU)
-    pub.stage_inputs(prog, vals[:1], main.cuda_stream)
+    prog0, vals0 = groups[0]
+    pub.stage_inputs(prog0, vals0[:1], main.cuda_stream)
     for _ in range(3):
-        pub.run_resident(prog, main.cuda_stream, 1)
+        pub.run_resident(prog0, main.cuda_stream, 1)
     torch.cuda.synchronize()
     lat = []
     for i in range(10):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(main); pub.run_resident(prog, main.cuda_stream, 1); b.record(main)
+        a.record(main); pub.run_resident(prog0, main.cuda_stream, 1); b.record(main)
         torch.cuda.synchronize()
         lat.append(a.elapsed_time(b))
     lat.sort()
-    # ---- e2e through the public API: host buffers in/out (H2D + D2H inside the timed region)
+    # ---- e2e through the public API: host buffers in/out (H2D + D2H inside the timed region);
+    #      G concurrent execute_batch() calls of F valuations each per step
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        outs = pub.execute_batch(prog, vals)
+        outs = list(pool.map(lambda g: pub.execute_batch(groups[g][0], groups[g][1]), range(G)))
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    vals = groups[0][1]
     clocks = sampler.finish()
     h2d = sum(ct.nbytes for ct, _ in cts.values()) * B
-    okind, oarr, _ = outs[0].get(list(d["outputs"].keys())[0])
+    okind, oarr, _ = outs[0][0].get(list(d["outputs"].keys())[0])
     d2h = int(oarr.nbytes) * B
     # ---- final gather of the outputs on rank 0 (north_star: NCCL only for the final gather)
     if world > 1:
@@ -202,10 +226,10 @@ def run_ours(args):
         "config": {"workload": "sobel_64x64 (examples/image_processing.py) compiled by the reference compiler: N=16384, prime_bits=[60]*5, 61 ciphertext ops per instance; one step = batch of %d independent program instances (images) per GPU" % B,
                    "instances_per_gpu": B,
                    "parallelism": "replicas x%d GPUs (independent program instances, no data-path collective; NCCL gather of outputs)" % world,
-                   "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("one cuda-graph per step" if not args.no_graph else "streams") + ", %d streams, kernels batched over the %d instances" % (args.streams, B),
+                   "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("%d concurrent cuda-graphs" % G if not args.no_graph else "streams") + " x %d instances fused per kernel launch, %d streams inside a plan" % (F, args.streams),
                    "const_encode": "cached per plan" if not args.no_const_cache else "23 Encode terms run on the GPU inside every execute (FP64 FFT + NTT), as in the reference"},
         "e2e": {"value": total_ops / t_e2e, "unit": "ops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,
-                "note": "B200Public.execute_batch() on %d host-resident valuations per step (host wall clock incl. H2D/D2H)" % B},
+                "note": "%d concurrent B200Public.execute_batch() calls of %d host-resident valuations each per step (host wall clock incl. H2D/D2H)" % (G, F)},
         "single_instance": {"latency_ms": lat[len(lat) // 2], "ops_per_s": nops / (lat[len(lat) // 2] * 1e-3)},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
@@ -311,7 +335,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--streams", type=int, default=8)
-    ap.add_argument("--instances", type=int, default=16, help="independent Sobel program instances per GPU per step")
+    ap.add_argument("--instances", type=int, default=32, help="independent Sobel program instances per GPU per step")
+    ap.add_argument("--fuse", type=int, default=1, help="instances fused into each kernel launch (instances/fuse concurrent graphs)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--const-cache", dest="no_const_cache", action="store_false",
                     help="encode constant plaintexts once per plan instead of inside every execute (default: every execute, like the reference)")

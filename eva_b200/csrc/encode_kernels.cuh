@@ -39,10 +39,11 @@ struct EncBatch {
 };
 
 // scatter: slot i (and its conjugate slot) <- values[i mod vec]
-EVAB_HD void enc_scatter(const EncBatch &B, u32 e, u32 i) {
+// off / voff: per-instance element offsets (u64 words / doubles) of a batched launch
+EVAB_HD void enc_scatter(const EncBatch &B, u32 e, u32 i, long long off = 0, long long voff = 0) {
   const u32 slots = B.N >> 1;
-  const double v = B.vals[e][i % B.vec[e]];
-  cplx *w = B.work + (size_t)e * B.N;
+  const double v = (B.vals[e] + voff)[i % B.vec[e]];
+  cplx *w = B.work + off / 2 + (size_t)e * B.N;
   cplx c; c.re = v; c.im = 0.0;
   w[B.slot_index[i]] = c;
   w[B.slot_index[slots + i]] = c;
@@ -59,9 +60,9 @@ EVAB_HD void enc_bfly(cplx &x, cplx &y, const cplx r) {
 }
 // NS consecutive inverse-FFT stages (gaps g, 2g, .. 2^(NS-1) g) on one closed set of
 // 2^NS elements spaced g apart; set u of N / 2^NS
-template <int NS> EVAB_HD void enc_fft_set(const EncBatch &B, u32 e, u32 u, u32 g) {
+template <int NS> EVAB_HD void enc_fft_set(const EncBatch &B, u32 e, u32 u, u32 g, long long off) {
   constexpr int M = 1 << NS;
-  cplx *w = B.work + (size_t)e * B.N;
+  cplx *w = B.work + off / 2 + (size_t)e * B.N;
   const u32 low = u % g, high = u / g;
   const u32 base = high * (M * g) + low;
   cplx x[M];
@@ -80,17 +81,17 @@ template <int NS> EVAB_HD void enc_fft_set(const EncBatch &B, u32 e, u32 u, u32 
   for (int j = 0; j < M; j++) w[base + j * g] = x[j];
 }
 // thread t of N/8 handles 8 elements = 8 / 2^nstages closed sets
-EVAB_HD void enc_fft8(const EncBatch &B, u32 e, u32 t, u32 g, int nstages) {
-  if (nstages == 3) enc_fft_set<3>(B, e, t, g);
-  else if (nstages == 2) { enc_fft_set<2>(B, e, 2 * t, g); enc_fft_set<2>(B, e, 2 * t + 1, g); }
-  else { for (u32 s = 0; s < 4; s++) enc_fft_set<1>(B, e, 4 * t + s, g); }
+EVAB_HD void enc_fft8(const EncBatch &B, u32 e, u32 t, u32 g, int nstages, long long off = 0) {
+  if (nstages == 3) enc_fft_set<3>(B, e, t, g, off);
+  else if (nstages == 2) { enc_fft_set<2>(B, e, 2 * t, g, off); enc_fft_set<2>(B, e, 2 * t + 1, g, off); }
+  else { for (u32 s = 0; s < 4; s++) enc_fft_set<1>(B, e, 4 * t + s, g, off); }
 }
 
 // coefficient j: round(re * scale / N) -> residue mod prime i (sign-aware; exact for
 // magnitudes beyond 2^64 through mantissa * 2^shift)
-EVAB_HD void enc_round(const EncBatch &B, u32 e, u32 j, int k) {
+EVAB_HD void enc_round(const EncBatch &B, u32 e, u32 j, long long off = 0) {
   const double fix = B.scale[e] / (double)B.N;
-  const double c = round(D_MUL(B.work[(size_t)e * B.N + j].re, fix));
+  const double c = round(D_MUL((B.work + off / 2)[(size_t)e * B.N + j].re, fix));
   const bool neg = signbit(c);
   const double mag = fabs(c);
   u64 mant; int sh = 0;
@@ -100,7 +101,6 @@ EVAB_HD void enc_round(const EncBatch &B, u32 e, u32 j, int k) {
     const PrimeDev P = B.primes[i];
     u64 v = barrett64(mant, P.p, P.ratio64);
     if (sh) v = mulmod(v, B.pow2[(size_t)i * 128 + (sh > 127 ? 127 : sh)], P.p, P.ratio_lo, P.ratio_hi);
-    B.out[((size_t)e * B.ell + i) * B.N + j] = (neg && v) ? P.p - v : v;
+    (B.out + off)[((size_t)e * B.ell + i) * B.N + j] = (neg && v) ? P.p - v : v;
   }
-  (void)k;
 }

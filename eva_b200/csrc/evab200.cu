@@ -50,11 +50,7 @@ extern "C" int evab_set_batch(int batch, size_t stride_words, size_t value_strid
   g_batch.batch = batch; g_batch.stride = (long long)stride_words; g_batch.vstride = (long long)value_stride;
   return 0;
 }
-__device__ __forceinline__ void shift(NttLaunch &L, long long off) {
-  L.src += off; L.dst += off;
-  if (L.aux0) L.aux0 += off;
-  if (L.aux1) L.aux1 += off;
-}
+
 
 // ---------------------------------------------------------------------------
 // kernels
@@ -68,11 +64,10 @@ struct BlockSync {
 };
 // one CTA = one residue (or one half of a 2^15 residue); T = N/16 threads, 64 registers
 template <int LOGN, bool SPLIT, int PRO, int EPI>
-__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_fwd(NttLaunch L, const long long bstride) {
+__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_fwd(const NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
-  shift(L, (long long)blockIdx.y * bstride);
   typedef FwdBody<LOGN, SPLIT, PRO, EPI> B;
-  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1);
+  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1, (long long)blockIdx.y * bstride);
   if (J.skip) return;
   NttState S;
   const u32 tid = threadIdx.x;
@@ -84,18 +79,16 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_n
   B::phE(S, L, J, tid);
 }
 template <int LOGN, bool SPLIT, int PRO, int EPI>
-__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_inv(NttLaunch L, const long long bstride) {
+__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_inv(const NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
-  shift(L, (long long)blockIdx.y * bstride);
   typedef InvBody<LOGN, SPLIT, PRO, EPI> B;
-  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1);
+  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1, (long long)blockIdx.y * bstride);
   if (J.skip) return;
   NttState S;
   PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, sm, BlockSync());
 }
-__global__ void __launch_bounds__(256) k_inv_last_stage(NttLaunch L, u32 half_n, const long long bstride) {
-  shift(L, (long long)blockIdx.z * bstride);
-  const NttJob J = ntt_job(L, blockIdx.y, 1);
+__global__ void __launch_bounds__(256) k_inv_last_stage(const NttLaunch L, u32 half_n, const long long bstride) {
+  const NttJob J = ntt_job(L, blockIdx.y, 1, (long long)blockIdx.z * bstride);
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < half_n) inv_last_stage_elem(L, J, i, half_n);
 }
@@ -114,21 +107,17 @@ __global__ void __launch_bounds__(256) k_ks_inner(IpArgs A, const long long bstr
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
     ks_inner_elem(A, blockIdx.y, j);
 }
-__device__ __forceinline__ void shift(EncBatch &B, long long off, long long voff) {
-  B.work += off / 2; B.out += off;   // work is addressed in 16-byte complex elements
-  for (u32 e = 0; e < B.count; e++) B.vals[e] += voff;
+__global__ void __launch_bounds__(256) k_enc_scatter(const EncBatch B, const long long bstride, const long long vstride) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B.N / 2; i += gridDim.x * blockDim.x)
+    enc_scatter(B, blockIdx.y, i, (long long)blockIdx.z * bstride, (long long)blockIdx.z * vstride);
 }
-__global__ void __launch_bounds__(256) k_enc_scatter(EncBatch B, const long long bstride, const long long vstride) {
-  shift(B, (long long)blockIdx.z * bstride, (long long)blockIdx.z * vstride);
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B.N / 2; i += gridDim.x * blockDim.x) enc_scatter(B, blockIdx.y, i);
+__global__ void __launch_bounds__(256) k_enc_fft(const EncBatch B, u32 g, int nstages, const long long bstride) {
+  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < B.N / 8; t += gridDim.x * blockDim.x)
+    enc_fft8(B, blockIdx.y, t, g, nstages, (long long)blockIdx.z * bstride);
 }
-__global__ void __launch_bounds__(256) k_enc_fft(EncBatch B, u32 g, int nstages, const long long bstride) {
-  B.work += (long long)blockIdx.z * bstride / 2;
-  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < B.N / 8; t += gridDim.x * blockDim.x) enc_fft8(B, blockIdx.y, t, g, nstages);
-}
-__global__ void __launch_bounds__(256) k_enc_round(EncBatch B, const long long bstride) {
-  { const long long off = (long long)blockIdx.z * bstride; B.work += off / 2; B.out += off; }
-  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < B.N; j += gridDim.x * blockDim.x) enc_round(B, blockIdx.y, j, 0);
+__global__ void __launch_bounds__(256) k_enc_round(const EncBatch B, const long long bstride) {
+  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < B.N; j += gridDim.x * blockDim.x)
+    enc_round(B, blockIdx.y, j, (long long)blockIdx.z * bstride);
 }
 __global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, const u32 *perm, int N, const long long bstride) {
   out += (long long)blockIdx.z * bstride; in += (long long)blockIdx.z * bstride;

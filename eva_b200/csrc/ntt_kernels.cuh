@@ -41,26 +41,34 @@ struct NttState { u64 x[NTT_E]; int b; };
 struct NttJob {
   const u64 *src; u64 *dst; const u64 *aux0; const u64 *aux1;
   u32 pi; u32 h; bool skip;
+  u32 spi;   // prime index of the values stored in src (PRO_MODRED)
 };
 
-EVAB_HD NttJob ntt_job(const NttLaunch &L, u32 cta, int ctas_per_job) {
+// boff: element offset of this batch instance (evab_set_batch), applied to every data pointer
+EVAB_HD NttJob ntt_job(const NttLaunch &L, u32 cta, int ctas_per_job, long long boff = 0) {
   NttJob J;
   u32 job = cta / ctas_per_job;
   J.h = cta % ctas_per_job;
   u32 q = job / L.inner, r = job % L.inner;
   J.pi = L.prime_on_q ? L.pmap[q] : L.pmap[r];
   J.skip = L.skip_diag && (L.pmap[q] == L.pmap2[r]);
-  J.src = L.src + q * L.src_sq + r * L.src_sr;
-  J.dst = L.dst + q * L.dst_sq + r * L.dst_sr;
-  J.aux0 = L.aux0 ? L.aux0 + q * L.aux0_sq + r * L.aux0_sr : nullptr;
-  J.aux1 = L.aux1 ? L.aux1 + q * L.aux1_sq + r * L.aux1_sr : nullptr;
+  J.spi = L.pmap2[r];
+  J.src = L.src + q * L.src_sq + r * L.src_sr + boff;
+  J.dst = L.dst + q * L.dst_sq + r * L.dst_sr + boff;
+  J.aux0 = L.aux0 ? L.aux0 + q * L.aux0_sq + r * L.aux0_sr + boff : nullptr;
+  J.aux1 = L.aux1 ? L.aux1 + q * L.aux1_sq + r * L.aux1_sr + boff : nullptr;
   return J;
 }
 
-template <int PRO> EVAB_HD u64 pro_load(const NttLaunch &L, const NttJob &J, const PrimeDev &P, u32 idx, u64 sub) {
+// PRO_MODRED: the source holds canonical residues of prime `srcp`; when srcp <= 2p one
+// conditional subtraction reduces them mod p, otherwise a 64-bit Barrett reduction
+template <int PRO, bool CHEAP> EVAB_HD u64 pro_load(const NttLaunch &L, const NttJob &J, const PrimeDev &P, u32 idx, u64 sub) {
   if (PRO == PRO_GATHER) return EVAB_LDG(J.src + EVAB_LDG(L.perm + idx));
   u64 v = EVAB_LDG(J.src + idx);
-  if (PRO == PRO_MODRED) v = submod(barrett64(v, P.p, P.ratio64), sub, P.p);
+  if (PRO == PRO_MODRED) {
+    v = CHEAP ? csub(v, P.p) : barrett64(v, P.p, P.ratio64);
+    v = submod(v, sub, P.p);
+  }
   return v;
 }
 
@@ -97,29 +105,34 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct
   typedef NttGeom<LOGN> G;
   static constexpr int NPH = G::NPH;
 
+  // load of pass 0 (strided, coalesced) with the fused prologue [+ first stage of a split transform]
+  template <bool CHEAP> static EVAB_HD void load0(NttState &S, const NttLaunch &L, const NttJob &J, const PrimeDev &P, u32 tid, u64 sub) {
+    if (!SPLIT) {
+#pragma unroll
+      for (int k = 0; k < NTT_E; k++) S.x[k] = pro_load<PRO, CHEAP>(L, J, P, idx_s<LOGN, 0>(tid, k), sub);
+      S.b = 1;
+    } else {
+      // first stage of the 2N transform: pairs (i, i + N) with twiddle tw[1];
+      // this CTA keeps the h-th output half and continues with root prefix 2+h
+      const u64x2 w = ldg_tw(P.tw + 1);
+      const u64 two_p = 2 * P.p;
+#pragma unroll
+      for (int k = 0; k < NTT_E; k++) {
+        const u32 i = idx_s<LOGN, 0>(tid, k);
+        const u64 X = pro_load<PRO, CHEAP>(L, J, P, i, sub), Y = pro_load<PRO, CHEAP>(L, J, P, i + G::N, sub);
+        const u64 t = shoup_lazy(Y, w.x, w.y, P.p);
+        S.x[k] = J.h ? X - t + two_p : X + t;
+      }
+      S.b = 3;
+    }
+  }
   template <int PH> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
     const PrimeDev P = L.primes[J.pi];
     const u32 root = SPLIT ? 2 + J.h : 1;
     if constexpr (PH == 0) {
       const u64 sub = (PRO == PRO_MODRED) ? EVAB_LDG(L.subtab + J.pi) : 0;
-      if (!SPLIT) {
-#pragma unroll
-        for (int k = 0; k < NTT_E; k++) S.x[k] = pro_load<PRO>(L, J, P, idx_s<LOGN, 0>(tid, k), sub);
-        S.b = 1;
-      } else {
-        // first stage of the 2N transform: pairs (i, i + N) with twiddle tw[1];
-        // this CTA keeps the h-th output half and continues with root prefix 2+h
-        const u64x2 w = ldg_tw(P.tw + 1);
-        const u64 two_p = 2 * P.p;
-#pragma unroll
-        for (int k = 0; k < NTT_E; k++) {
-          const u32 i = idx_s<LOGN, 0>(tid, k);
-          const u64 X = pro_load<PRO>(L, J, P, i, sub), Y = pro_load<PRO>(L, J, P, i + G::N, sub);
-          const u64 t = shoup_lazy(Y, w.x, w.y, P.p);
-          S.x[k] = J.h ? X - t + two_p : X + t;
-        }
-        S.b = 3;
-      }
+      const bool cheap = (PRO == PRO_MODRED) && (L.primes[J.spi].p <= 2 * P.p);   // CTA-uniform
+      if (cheap) load0<true>(S, L, J, P, tid, sub); else load0<false>(S, L, J, P, tid, sub);
       fwd_pass_s<LOGN, 0>(S.x, P.tw, root, P.p, tid, S.b);
       xchg_write_s<LOGN, 0, 1>(S.x, sm, tid);
     } else if constexpr (PH == NPH - 1) {
@@ -140,19 +153,32 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct
   // transforms the caller must barrier the CTA pair (cluster) before this phase.
   static EVAB_HD void phE(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid) {
     const PrimeDev P = L.primes[J.pi];
-    canon(S.x, P.p, S.b);
     const size_t base = (size_t)(SPLIT ? J.h * G::N : 0) + ((size_t)tid << NTT_EL);
     if (EPI == EPI_DIVROUND) {
+      // (aux0 - x) * c [+ aux1] without canonicalising x first: x < b*p, so
+      // aux0 + b*p - x is positive and < 16p; the Shoup product lands in [0,2p)
       const u64x2 c = ldg_tw(L.consts + J.pi);
+      int b = S.b;
+      if (b > 14) {
+#pragma unroll
+        for (int k = 0; k < NTT_E; k++) S.x[k] = csub(S.x[k], 8 * P.p);
+        b = 8;
+      }
+      const u64 bias = (u64)b * P.p;
       u64 a[NTT_E];
       load16(a, J.aux0 + base);
 #pragma unroll
-      for (int k = 0; k < NTT_E; k++) S.x[k] = shoup_mul(submod(a[k], S.x[k], P.p), c.x, c.y, P.p);
+      for (int k = 0; k < NTT_E; k++) S.x[k] = shoup_lazy(a[k] + bias - S.x[k], c.x, c.y, P.p);
       if (J.aux1) {
         load16(a, J.aux1 + base);
 #pragma unroll
-        for (int k = 0; k < NTT_E; k++) S.x[k] = addmod(S.x[k], a[k], P.p);
+        for (int k = 0; k < NTT_E; k++) S.x[k] = csub(csub(S.x[k] + a[k], 2 * P.p), P.p);
+      } else {
+#pragma unroll
+        for (int k = 0; k < NTT_E; k++) S.x[k] = csub(S.x[k], P.p);
       }
+    } else {
+      canon(S.x, P.p, S.b);
     }
     store16(J.dst + base, S.x);
   }

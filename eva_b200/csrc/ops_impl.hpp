@@ -101,7 +101,7 @@ int divround_impl(BE &be, const CtxView &c, const u64 *in, long long in_poly_str
   B.aux1 = add; B.aux1_sq = add_poly_stride; B.aux1_sr = N;
   B.dst = out; B.dst_sq = out_poly_stride; B.dst_sr = N;
   B.inner = nres - 1; B.prime_on_q = 0;
-  for (int r = 0; r < nres - 1; r++) B.pmap[r] = pm[r];
+  for (int r = 0; r < nres - 1; r++) { B.pmap[r] = pm[r]; B.pmap2[r] = (unsigned char)last; }   // src holds residues mod q_last
   B.pro = PRO_MODRED; B.epi = EPI_DIVROUND;
   B.subtab = c.halfmod + (size_t)last * c.k;
   B.consts = c.qinv + (size_t)last * c.k;

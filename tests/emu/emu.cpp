@@ -129,7 +129,7 @@ struct EmuBE {
     return 0;
   }
   int enc_round(const EncBatch &B) {
-    for (u32 e = 0; e < B.count; e++) for (u32 j = 0; j < B.N; j++) ::enc_round(B, e, j, 0);
+    for (u32 e = 0; e < B.count; e++) for (u32 j = 0; j < B.N; j++) ::enc_round(B, e, j);
     return 0;
   }
   int perm(u64 *out, const u64 *in, const u32 *p, int N, int rows) {
