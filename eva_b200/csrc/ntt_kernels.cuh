@@ -72,6 +72,21 @@ template <int PRO, bool CHEAP> EVAB_HD u64 pro_load(const NttLaunch &L, const Nt
   return v;
 }
 
+// 4 contiguous coefficients = one 256-bit access
+EVAB_HD void load4(u64 (&a)[4], const u64 *p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a[0]), "=l"(a[1]), "=l"(a[2]), "=l"(a[3]) : "l"(p));
+#else
+  for (int k = 0; k < 4; k++) a[k] = p[k];
+#endif
+}
+EVAB_HD void store4(u64 *p, const u64 (&a)[4]) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]) : "memory");
+#else
+  for (int k = 0; k < 4; k++) p[k] = a[k];
+#endif
+}
 // 16 contiguous coefficients with 256-bit accesses (full 32-byte sectors per lane)
 EVAB_HD void load16(u64 (&a)[NTT_E], const u64 *p) {
 #if defined(__CUDA_ARCH__)
@@ -156,30 +171,36 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct
     const size_t base = (size_t)(SPLIT ? J.h * G::N : 0) + ((size_t)tid << NTT_EL);
     if (EPI == EPI_DIVROUND) {
       // (aux0 - x) * c [+ aux1] without canonicalising x first: x < b*p, so
-      // aux0 + b*p - x is positive and < 16p; the Shoup product lands in [0,2p)
+      // aux0 + b*p - x is positive and < 16p; the Shoup product lands in [0,2p).
+      // Processed four coefficients at a time (one 256-bit access per operand) to
+      // keep the register footprint at 64.
       const u64x2 c = ldg_tw(L.consts + J.pi);
-      int b = S.b;
-      if (b > 14) {
+      const bool fix = S.b > 14;
+      const u64 bias = (u64)(fix ? 8 : S.b) * P.p, eight_p = 8 * P.p, two_p = 2 * P.p;
 #pragma unroll
-        for (int k = 0; k < NTT_E; k++) S.x[k] = csub(S.x[k], 8 * P.p);
-        b = 8;
+      for (int q = 0; q < NTT_E / 4; q++) {
+        u64 a[4];
+        load4(a, J.aux0 + base + 4 * q);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          u64 x = S.x[4 * q + k];
+          if (fix) x = csub(x, eight_p);
+          a[k] = shoup_lazy(a[k] + bias - x, c.x, c.y, P.p);
+        }
+        if (J.aux1) {
+          u64 d[4];
+          load4(d, J.aux1 + base + 4 * q);
+#pragma unroll
+          for (int k = 0; k < 4; k++) a[k] = csub(csub(a[k] + d[k], two_p), P.p);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) a[k] = csub(a[k], P.p);
+        }
+        store4(J.dst + base + 4 * q, a);
       }
-      const u64 bias = (u64)b * P.p;
-      u64 a[NTT_E];
-      load16(a, J.aux0 + base);
-#pragma unroll
-      for (int k = 0; k < NTT_E; k++) S.x[k] = shoup_lazy(a[k] + bias - S.x[k], c.x, c.y, P.p);
-      if (J.aux1) {
-        load16(a, J.aux1 + base);
-#pragma unroll
-        for (int k = 0; k < NTT_E; k++) S.x[k] = csub(csub(S.x[k] + a[k], 2 * P.p), P.p);
-      } else {
-#pragma unroll
-        for (int k = 0; k < NTT_E; k++) S.x[k] = csub(S.x[k], P.p);
-      }
-    } else {
-      canon(S.x, P.p, S.b);
+      return;
     }
+    canon(S.x, P.p, S.b);
     store16(J.dst + base, S.x);
   }
 };
@@ -216,11 +237,10 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct
         for (int k = 0; k < NTT_E; k++) J.dst[(size_t)J.h * G::N + idx_s<LOGN, 0>(tid, k)] = S.x[k];
         return;
       }
-      scale_canon(S.x, P.ninv, P.ninv_s, P.p);
       const u64 half = P.p >> 1;
 #pragma unroll
       for (int k = 0; k < NTT_E; k++) {
-        u64 v = S.x[k];
+        u64 v = csub(shoup_lazy(S.x[k], P.ninv, P.ninv_s, P.p), P.p);   // * N^-1, canonical
         if (EPI == EPI_ADDHALF) v = addmod(v, half, P.p);
         J.dst[idx_s<LOGN, 0>(tid, k)] = v;
       }
