@@ -127,3 +127,71 @@ def test_security_levels_and_error_paths():
             check(prog, {'x': [0.5] * 64}, {"security_level": s, "quantum_safe": q, "warn_vec_size": "false"})
     with pytest.raises(RuntimeError):
         CKKSCompiler({"security_level": "1024"}).compile(prog)
+
+
+def test_regressions_like_reference_large_programs():
+    """linear (63 inputs), polynomial and multivariate regression: reference tests/large_programs.py:55-146"""
+    from eva import EvaProgram, Input, Output
+    lin = EvaProgram('linear_regression', vec_size=2048)
+    with lin:
+        p = 63
+        x = [Input('x%d' % i) for i in range(p)]
+        y = Input('e') + 6.56
+        for i in range(p):
+            y += x[i] * (i * 0.732)
+        Output('y', y)
+    lin.set_input_scales(40); lin.set_output_ranges(30)
+    ins = {'e': [(2048 - i) * 0.001 for i in range(2048)]}
+    for i in range(63):
+        ins['x%d' % i] = [i * j * 0.01 for j in range(2048)]
+    check(lin, ins, {'warn_vec_size': 'false'})
+
+    pol = EvaProgram('polynomial_regression', vec_size=4096)
+    with pol:
+        x, y = Input('x'), Input('e') + 6.56
+        for i in range(4):
+            xi = x
+            for _ in range(i):
+                xi = xi * x
+            y += xi * (i * 0.732)
+        Output('y', y)
+    pol.set_input_scales(40); pol.set_output_ranges(30)
+    check(pol, {'x': [i * 0.0001 for i in range(4096)], 'e': [(4096 - i) * 0.001 for i in range(4096)]}, {'warn_vec_size': 'false'})
+
+
+def test_high_inner_term_scale_and_transparent():
+    """reference tests/bug_fixes.py:10-26 and tests/features.py:135-152"""
+    from eva import EvaProgram, Input, Output
+    prog = EvaProgram('HighInnerTermScale', vec_size=4)
+    with prog:
+        x1, x2 = Input('x1'), Input('x2')
+        Output('y', x1 * x1 * x2)
+    prog.set_output_ranges(20); prog.set_input_scales(60)
+    check(prog, {'x1': [0.5, -1.0, 1.5, 2.0], 'x2': [1.0, 0.25, -0.5, 1.25]}, {'rescaler': 'lazy_waterline', 'warn_vec_size': 'false'})
+    tr = EvaProgram('Transparent', vec_size=4096)
+    with tr:
+        x = Input('x')
+        Output('y', x - x + x * 0)
+    tr.set_output_ranges(20); tr.set_input_scales(30)
+    check(tr, {'x': [0.001 * i for i in range(4096)]}, {'warn_vec_size': 'false'})
+
+
+def test_harris_and_large_sobel():
+    """Harris corner detector (examples/image_processing.py:65-100) and the 90x90 Sobel of
+    tests/large_programs.py:10-53 (vec 8192, scale 45, range 20) with balance on/off"""
+    import math
+    from tests_programs import harris
+    img = [0.5 + 0.25 * math.sin(0.1 * (k % 64)) * math.cos(0.07 * (k // 64)) for k in range(4096)]
+    check(harris(), {'image': img}, {'warn_vec_size': 'false'})
+    from eva import EvaProgram, Input, Output
+    from tests_programs import _conv_xy, SOBEL_FILTER
+    sob = EvaProgram('sobel', vec_size=8192)
+    with sob:
+        image = Input('image')
+        ix, iy = _conv_xy(image, 90, SOBEL_FILTER)
+        x = ix ** 2 + iy ** 2
+        Output('image', x * 2.2137874823876622 + x ** 2 * -1.0984324107372518 + x ** 3 * 0.17254603006834726)
+    sob.set_input_scales(45); sob.set_output_ranges(20)
+    img = [0.5 + 0.25 * math.sin(0.05 * (k % 90)) for k in range(8192)]
+    for bal in ('true', 'false'):
+        check(sob, {'image': img}, {'balance_reductions': bal, 'warn_vec_size': 'false'})
