@@ -152,6 +152,7 @@ template <int LOGN, bool SPLIT, int PRO, int EPI> static int launch_fwd_m(const 
 template <int LOGN, bool SPLIT> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_PLAIN, EPI_STORE>(L, jobs, st);
   if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE_LAZY>(L, jobs, st);
   if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_DIVROUND>(L, jobs, st);
   return fail("unsupported forward NTT prologue/epilogue combination");
 }

@@ -81,6 +81,20 @@ EVAB_HD u64 barrett128(u64 lo, u64 hi, u64 p, u64 rlo, u64 rhi) {
   return csub(lo - q * p, p);
 }
 
+// same for any 128-bit input (e.g. sums of products of lazily reduced operands): the
+// quotient estimate is short by at most 3, two conditional subtractions finish
+EVAB_HD u64 barrett128_wide(u64 lo, u64 hi, u64 p, u64 rlo, u64 rhi) {
+  u64 carry = mulhi64(lo, rlo);
+  u64 t0 = lo * rhi, t1 = mulhi64(lo, rhi);
+  u64 tmp1 = t0 + carry;
+  u64 tmp3 = t1 + (tmp1 < carry);
+  u64 u0 = hi * rlo, u1 = mulhi64(hi, rlo);
+  u64 tmp1b = tmp1 + u0;
+  carry = u1 + (tmp1b < tmp1);
+  u64 q = hi * rhi + tmp3 + carry;
+  return csub(csub(lo - q * p, 2 * p), p);
+}
+
 // canonical product of two values in [0,p)
 EVAB_HD u64 mulmod(u64 a, u64 b, u64 p, u64 rlo, u64 rhi) {
   return barrett128(a * b, mulhi64(a, b), p, rlo, rhi);

@@ -19,6 +19,7 @@ enum : int {
   EPI_STORE = 0,     // dst[idx] = x
   EPI_ADDHALF = 1,   // dst[idx] = (x + half) mod p        (half = floor(p/2))
   EPI_DIVROUND = 2,  // dst[idx] = (aux0[idx] - x) * c mod p  [+ aux1[idx] mod p]
+  EPI_STORE_LAZY = 3,  // dst[idx] = x without canonicalisation (x < 16p; consumer reduces)
 };
 
 struct NttLaunch {
@@ -200,7 +201,7 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct
       }
       return;
     }
-    canon(S.x, P.p, S.b);
+    if (EPI != EPI_STORE_LAZY) canon(S.x, P.p, S.b);
     store16(J.dst + base, S.x);
   }
 };

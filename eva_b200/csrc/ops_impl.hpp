@@ -148,6 +148,9 @@ int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, co
   B.src = that; B.src_sq = 0; B.src_sr = N;
   B.dst = ext; B.dst_sq = (long long)ell * N; B.dst_sr = N;
   B.inner = ell; B.prime_on_q = 1; B.skip_diag = 1; B.pro = PRO_MODRED;
+  // the extended digits only feed the 128-bit inner product, which reduces lazily:
+  // skip their canonicalisation while the accumulated sum stays below 2^128
+  B.epi = (ell <= 15) ? EPI_STORE_LAZY : EPI_STORE;
   B.subtab = c.zeros;
   for (int mi = 0; mi <= ell; mi++) B.pmap[mi] = (unsigned char)(mi == ell ? sp : mi);
   for (int J = 0; J < ell; J++) B.pmap2[J] = (unsigned char)J;

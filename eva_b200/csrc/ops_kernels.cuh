@@ -88,8 +88,9 @@ EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j) {
     mac128(l1x, h1x, v.x, k1.x); mac128(l1y, h1y, v.y, k1.y);
   }
   u64x2 r0, r1;
-  r0.x = barrett128(l0x, h0x, P.p, P.ratio_lo, P.ratio_hi); r0.y = barrett128(l0y, h0y, P.p, P.ratio_lo, P.ratio_hi);
-  r1.x = barrett128(l1x, h1x, P.p, P.ratio_lo, P.ratio_hi); r1.y = barrett128(l1y, h1y, P.p, P.ratio_lo, P.ratio_hi);
+  // ext operands may be lazily reduced (< 16p, see EPI_STORE_LAZY): wide reduction
+  r0.x = barrett128_wide(l0x, h0x, P.p, P.ratio_lo, P.ratio_hi); r0.y = barrett128_wide(l0y, h0y, P.p, P.ratio_lo, P.ratio_hi);
+  r1.x = barrett128_wide(l1x, h1x, P.p, P.ratio_lo, P.ratio_hi); r1.y = barrett128_wide(l1y, h1y, P.p, P.ratio_lo, P.ratio_hi);
   st2(A.acc + ((size_t)0 * (A.ell + 1) + mi) * N + j, r0);
   st2(A.acc + ((size_t)1 * (A.ell + 1) + mi) * N + j, r1);
 }

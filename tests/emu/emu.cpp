@@ -64,6 +64,7 @@ template <int LOGN, bool SPLIT, bool INV> static void run_ntt(const NttLaunch &L
   if (!INV) {
     if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_PLAIN, EPI_STORE>(L, jobs);
     if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE_LAZY>(L, jobs);
     if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_DIVROUND>(L, jobs);
   } else {
     if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_STORE>(L, jobs);
