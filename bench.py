@@ -112,7 +112,7 @@ def run_ours(args):
     primes = b200.create_coeff_modulus(N, d["prime_bits"])
     relin, galois, cts = synthetic_inputs(d, primes, seed=1234 + rank)
     pub = b200.context_from_raw_keys(N, primes, relin, galois, local)
-    pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache)
+    pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache, dedup_constants=not args.no_dedup)
     # B independent program instances (different input ciphertexts, same keys), organised as
     # G concurrent plan replays (one CUDA graph each, on its own stream) x F instances fused
     # into every kernel launch of a plan (execute_batch / evab_set_batch):  B = G * F
@@ -152,7 +152,7 @@ def run_ours(args):
             main.wait_event(ev_)
 
     # ---- launches per step: one un-graphed replay of one group's plan, times G
-    pub.set_options(num_streams=args.streams, use_graph=False, cache_constants=not args.no_const_cache)
+    pub.set_options(num_streams=args.streams, use_graph=False, cache_constants=not args.no_const_cache, dedup_constants=not args.no_dedup)
     pub.drop_plan(groups[0][0], F)   # (cipher_op_count above may have built a graph-mode plan)
     pub.stage_inputs(groups[0][0], groups[0][1], main.cuda_stream)
     pub.run_resident(groups[0][0], main.cuda_stream, F)
@@ -161,7 +161,7 @@ def run_ours(args):
     pub.run_resident(groups[0][0], main.cuda_stream, F)
     torch.cuda.synchronize()
     launches_per_step = (pub.launch_count() - l0) * G
-    pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache)
+    pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache, dedup_constants=not args.no_dedup)
     pub.drop_plan(groups[0][0], F)
     for prog, vals in groups:
         pub.stage_inputs(prog, vals, main.cuda_stream)
@@ -228,7 +228,8 @@ def run_ours(args):
                    "instances_per_gpu": B,
                    "parallelism": "replicas x%d GPUs (independent program instances, no data-path collective; NCCL gather of outputs)" % world,
                    "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("%d concurrent cuda-graphs" % G if not args.no_graph else "streams") + " x %d instances fused per kernel launch, %d streams inside a plan" % (F, args.streams),
-                   "const_encode": "cached per plan" if not args.no_const_cache else "23 Encode terms run on the GPU inside every execute (FP64 FFT + NTT), as in the reference"},
+                   "const_encode": "cached per plan" if not args.no_const_cache else ("23 Encode terms evaluated on the GPU inside every execute (FP64 FFT + NTT), as in the reference"
+                                    + ("; identical constants share one plaintext (same bits), constant polynomials skip the NTT butterflies" if not args.no_dedup else ""))},
         "e2e": {"value": total_ops / t_e2e, "unit": "ops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,
                 "note": "%d concurrent B200Public.execute_batch() calls of %d host-resident valuations each per step (host wall clock incl. H2D/D2H)" % (G, F)},
         "single_instance": {"latency_ms": lat[len(lat) // 2], "ops_per_s": nops / (lat[len(lat) // 2] * 1e-3)},
@@ -342,6 +343,7 @@ def main():
     ap.add_argument("--const-cache", dest="no_const_cache", action="store_false",
                     help="encode constant plaintexts once per plan instead of inside every execute (default: every execute, like the reference)")
     ap.set_defaults(no_const_cache=True)
+    ap.add_argument("--no-dedup", action="store_true", help="encode every Encode term separately even when constants repeat")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -30,6 +30,7 @@ struct EncBatch {
   u32 vec[ENC_MAX_BATCH];
   double scale[ENC_MAX_BATCH];
   cplx *work;                         // [count][N]
+  u64 *flags;                         // [count]: 1 when vector e encodes to a non-constant polynomial
   u64 *out;                           // [count][ell][N] coefficient-form residues
   const cplx *roots;                  // [N] zeta^bitrev(i)
   const u32 *slot_index;              // [N]
@@ -45,6 +46,7 @@ EVAB_HD void enc_scatter(const EncBatch &B, u32 e, u32 i, long long off = 0, lon
   const double v = (B.vals[e] + voff)[i % B.vec[e]];
   cplx *w = B.work + off / 2 + (size_t)e * B.N;
   cplx c; c.re = v; c.im = 0.0;
+  if (i == 0) (B.flags + off)[e] = 0;   // set again by enc_round when a coefficient j > 0 is non-zero
   w[B.slot_index[i]] = c;
   w[B.slot_index[slots + i]] = c;
 }
@@ -94,6 +96,7 @@ EVAB_HD void enc_round(const EncBatch &B, u32 e, u32 j, long long off = 0) {
   const double c = round(D_MUL((B.work + off / 2)[(size_t)e * B.N + j].re, fix));
   const bool neg = signbit(c);
   const double mag = fabs(c);
+  if (j > 0 && mag != 0.0) (B.flags + off)[e] = 1;
   u64 mant; int sh = 0;
   if (mag < 18446744073709551616.0) mant = (u64)mag;
   else { int ex; const double fr = frexp(mag, &ex); mant = (u64)ldexp(fr, 64); sh = ex - 64; }

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_n
   if (J.skip) return;
   NttState S;
   const u32 tid = threadIdx.x;
+  if (PRO == PRO_PLAIN && EPI == EPI_STORE && J.bcast) { fwd_const_poly<LOGN, SPLIT>(J, tid); return; }
   PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, sm, BlockSync());
   if (SPLIT) {  // CTA pair (cluster of 2): both halves have consumed the input
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
@@ -429,6 +430,7 @@ extern "C" int evab_ntt_fwd(evab_ctx *c, uint64_t *d, size_t count, const int *p
 extern "C" int evab_ntt_inv(evab_ctx *c, uint64_t *d, size_t count, const int *pidx, int np, void *stream) {
   BE_BEGIN return ntt_batch_impl(be, c->v, true, d, count, pidx, np);
 }
+extern "C" size_t evab_encode_work_bytes(const evab_ctx *c, int count) { return encode_work_bytes(c->v, count); }
 extern "C" int evab_encode(evab_ctx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell,
                            uint64_t *out, void *work, void *stream) {
   BE_BEGIN return encode_impl(be, c->v, count, vals, vec, scales, ell, out, (cplx *)work);

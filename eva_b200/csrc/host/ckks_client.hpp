@@ -77,7 +77,7 @@ public:
   // device path: the batched encoder kernels behind evab_encode (FP64 FFT + NTT on the GPU)
   void encode(const std::vector<double> &values, double scale, int ell, u64 *d_pt, void *stream = nullptr) const {
     if (values.empty() || (N_ / 2) % values.size()) throw std::invalid_argument("values size must divide the slot count");
-    DBuf vals(dev_, values.size()), work(dev_, (std::size_t)N_ * 2);
+    DBuf vals(dev_, values.size()), work(dev_, evab_encode_work_bytes(dev_->ctx(), 1) / 8);
     dev_->upload(vals.get(), values.data(), values.size() * 8, stream);
     const double *ptr = reinterpret_cast<const double *>(vals.get());
     const std::uint32_t vec = (std::uint32_t)values.size();

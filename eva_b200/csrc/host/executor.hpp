@@ -15,7 +15,9 @@
 #include "ir.hpp"
 #include <cmath>
 #include <functional>
+#include <map>
 #include <set>
+#include <tuple>
 #include <unordered_set>
 #include <unordered_map>
 
@@ -49,6 +51,7 @@ struct ExecOptions {
   bool useGraph = true;
   bool cacheConstants = true;  // encode plan-time-constant plaintexts once per plan instead of on every run
   int batch = 1;               // independent program instances executed by every (fat) kernel launch
+  bool dedupConstants = true;  // Encode terms of identical constants at the same (level, scale) share one plaintext
 };
 
 // scoped evab_set_batch: ops issued by this thread act on `batch` instances
@@ -195,7 +198,19 @@ private:
         dyn[t->index] = d;
       }
       std::map<std::pair<int, int>, int> groupOf;
+      // identical constant vectors encoded at the same level and scale give identical plaintexts:
+      // later occurrences alias the first one (same bits as encoding each, seal_executor.h:217-248)
+      std::map<std::tuple<int, double, std::vector<double>>, Term *> firstOf;
       for (Term *t : encodeTerms_) {
+        if (opt_.dedupConstants && !dyn[t->index] && t->operandAt(0)->op == Op::Constant) {
+          auto ck = std::make_tuple(vals_[t->index].ell, vals_[t->index].scale, rawsB_[0][t->operandAt(0)->index]);
+          auto ins = firstOf.emplace(std::move(ck), t);
+          if (!ins.second) {
+            encodeAlias_[t->index] = ins.first->second;
+            groupIndex_[t->index] = groupIndex_.at(ins.first->second->index);
+            continue;
+          }
+        }
         auto key = std::make_pair(vals_[t->index].ell, (int)dyn[t->index]);
         auto it = groupOf.find(key);
         if (it == groupOf.end()) { it = groupOf.emplace(key, (int)groups_.size()).first; groups_.push_back(EncodeGroup{key.first, key.second != 0, {}, 0, 0, 0}); }
@@ -205,10 +220,11 @@ private:
       for (auto &g : groups_) {
         g.outOff = arenaWords;
         for (Term *t : g.members) { vals_[t->index].off = arenaWords; arenaWords += (std::size_t)g.ell * N_; }
-        g.workOff = arenaWords; arenaWords += g.members.size() * N_ * 2;
+        g.workOff = arenaWords; arenaWords += evab_encode_work_bytes(dev_->ctx(), (int)g.members.size()) / 8;
         g.rawOff = rawWords_;
         for (Term *t : g.members) { rawOff_[t->index] = rawWords_; rawWords_ += prog_.getVecSize(); }
       }
+      for (auto &kv : encodeAlias_) vals_[kv.first].off = vals_[kv.second->index].off;
     }
     // ---- stream assignment + event edges
     const int S = std::max(1, opt_.numStreams);
@@ -331,6 +347,7 @@ private:
           }
         }
         if (t->op == Op::Encode) {
+          if (encodeAlias_.count(t->index)) continue;
           auto &x = raws[t->operandAt(0)->index];
           if (x.empty()) continue;
           if (dyn[t->index]) hasDynamicEncodes_ = true;
@@ -443,6 +460,7 @@ private:
   std::vector<Term *> encodeTerms_;
   std::unordered_map<std::uint64_t, int> groupIndex_;
   std::unordered_map<std::uint64_t, std::size_t> rawOff_;
+  std::unordered_map<std::uint64_t, Term *> encodeAlias_;  // Encode term -> identical earlier Encode term
   std::unordered_set<std::uint64_t> rawUploaded_;
   std::size_t rawWords_ = 0;
   bool staticEncoded_ = false;

@@ -135,8 +135,10 @@ PYBIND11_MODULE(_eva_b200, m) {
       .def("execute", &B200Public::execute, py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>())
       .def("execute_batch", &B200Public::executeBatch, py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>(),
            "Execute one compiled program on a list of valuations with batched kernels; returns a list of valuations")
-      .def("set_options", [](B200Public &p, int streams, bool graph, bool cache) { p.options.numStreams = streams; p.options.useGraph = graph; p.options.cacheConstants = cache; },
-           py::arg("num_streams") = 8, py::arg("use_graph") = true, py::arg("cache_constants") = true)
+      .def("set_options", [](B200Public &p, int streams, bool graph, bool cache, bool dedup) {
+             p.options.numStreams = streams; p.options.useGraph = graph; p.options.cacheConstants = cache; p.options.dedupConstants = dedup;
+           },
+           py::arg("num_streams") = 8, py::arg("use_graph") = true, py::arg("cache_constants") = true, py::arg("dedup_constants") = true)
       .def("drop_plan", &B200Public::dropExecutor, py::arg("program"), py::arg("batch") = 1)
       .def("cipher_op_count", [](B200Public &p, Program &prog) { return p.executorFor(prog).cipherOpCount(); })
       .def("launch_count", [](B200Public &p) { return evab_launch_count(p.shared()->dev->ctx()); })

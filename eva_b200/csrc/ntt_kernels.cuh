@@ -25,6 +25,8 @@ enum : int {
 struct NttLaunch {
   const u64 *src; u64 *dst; const u64 *aux0; const u64 *aux1;
   const u32 *perm;             // PRO_GATHER
+  const u64 *cflags;           // optional [q]: 0 = polynomial q is constant (only coefficient 0 set): its
+                               // transform is that value everywhere, written without running the NTT
   const PrimeDev *primes;
   const u64x2 *consts;         // EPI_DIVROUND: {c, shoup(c)} per prime index; PRO_MODRED: .x of subtab
   const u64 *subtab;           // PRO_MODRED: value to subtract per prime index (canonical mod that prime)
@@ -33,6 +35,7 @@ struct NttLaunch {
   int prime_on_q;              // 1: prime = pmap[q], 0: prime = pmap[r]
   int pro, epi;
   int skip_diag;               // key-switch mod-up: CTA exits when pmap[q] == pmap2[r]
+  int aux1_polys;              // aux1 applies to q < aux1_polys only (rotate: c0 has a base, c1 none)
   unsigned char pmap[32];
   unsigned char pmap2[32];
 };
@@ -42,6 +45,7 @@ struct NttState { u64 x[NTT_E]; int b; };
 struct NttJob {
   const u64 *src; u64 *dst; const u64 *aux0; const u64 *aux1;
   u32 pi; u32 h; bool skip;
+  bool bcast;  // constant polynomial (cflags)
   u32 spi;   // prime index of the values stored in src (PRO_MODRED)
 };
 
@@ -54,10 +58,11 @@ EVAB_HD NttJob ntt_job(const NttLaunch &L, u32 cta, int ctas_per_job, long long 
   J.pi = L.prime_on_q ? L.pmap[q] : L.pmap[r];
   J.skip = L.skip_diag && (L.pmap[q] == L.pmap2[r]);
   J.spi = L.pmap2[r];
+  J.bcast = L.cflags && (L.cflags + boff)[q] == 0;
   J.src = L.src + q * L.src_sq + r * L.src_sr + boff;
   J.dst = L.dst + q * L.dst_sq + r * L.dst_sr + boff;
   J.aux0 = L.aux0 ? L.aux0 + q * L.aux0_sq + r * L.aux0_sr + boff : nullptr;
-  J.aux1 = L.aux1 ? L.aux1 + q * L.aux1_sq + r * L.aux1_sr + boff : nullptr;
+  J.aux1 = (L.aux1 && (int)q < L.aux1_polys) ? L.aux1 + q * L.aux1_sq + r * L.aux1_sr + boff : nullptr;
   return J;
 }
 
@@ -110,6 +115,16 @@ EVAB_HD void store16(u64 *p, const u64 (&a)[NTT_E]) {
   for (int k = 0; k < NTT_E; k++) p[k] = a[k];
 #endif
 }
+// forward transform of a constant polynomial c (canonical): c at every evaluation point.
+// Thread tid of CTA half h writes its 16 contiguous outputs (in place: dst[0] keeps its value).
+template <int LOGN, bool SPLIT> EVAB_HD void fwd_const_poly(const NttJob &J, u32 tid) {
+  const u64 v = EVAB_LDG(J.src);
+  u64 x[NTT_E];
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) x[k] = v;
+  store16(J.dst + ((size_t)(SPLIT ? J.h : 0) * NttGeom<LOGN>::T + tid) * NTT_E, x);
+}
+
 
 // ------------------------------ forward ------------------------------------
 // Phases (separated by block barriers), P = NttGeom::P register passes:

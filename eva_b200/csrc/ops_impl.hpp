@@ -32,6 +32,7 @@ inline NttLaunch base_launch(const CtxView &c) {
   memset(&L, 0, sizeof(L));
   L.primes = c.primes;
   L.inner = 1;
+  L.aux1_polys = 1 << 30;
   return L;
 }
 
@@ -87,7 +88,8 @@ template <class BE> int mulct_impl(BE &be, const CtxView &c, bool square, int el
 //   out[q][r] = (in[q][r] - NTT((iNTT(in[q][last]) + h) mod q_last mod q_r - h mod q_r)) * q_last^-1  (+ add[q][r])
 template <class BE>
 int divround_impl(BE &be, const CtxView &c, const u64 *in, long long in_poly_stride, int npoly, int nres, const unsigned char *pm,
-                  int last, u64 *out, long long out_poly_stride, const u64 *add, long long add_poly_stride, u64 *tmp) {
+                  int last, u64 *out, long long out_poly_stride, const u64 *add, long long add_poly_stride, u64 *tmp,
+                  int add_polys = 1 << 30) {
   const long long N = (long long)c.N;
   NttLaunch A = base_launch(c);
   A.src = in + (long long)(nres - 1) * N; A.dst = tmp;
@@ -98,7 +100,7 @@ int divround_impl(BE &be, const CtxView &c, const u64 *in, long long in_poly_str
   NttLaunch B = base_launch(c);
   B.src = tmp; B.src_sq = N; B.src_sr = 0;
   B.aux0 = in; B.aux0_sq = in_poly_stride; B.aux0_sr = N;
-  B.aux1 = add; B.aux1_sq = add_poly_stride; B.aux1_sr = N;
+  B.aux1 = add; B.aux1_sq = add_poly_stride; B.aux1_sr = N; B.aux1_polys = add_polys;
   B.dst = out; B.dst_sq = out_poly_stride; B.dst_sr = N;
   B.inner = nres - 1; B.prime_on_q = 0;
   for (int r = 0; r < nres - 1; r++) { B.pmap[r] = pm[r]; B.pmap2[r] = (unsigned char)last; }   // src holds residues mod q_last
@@ -162,10 +164,9 @@ int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, co
   // 4. mod-down by P with rounding, fused with the accumulation into base
   unsigned char pm[32];
   for (int i = 0; i < ell; i++) pm[i] = (unsigned char)i;
-  if (base_polys == 2)
-    return divround_impl(be, c, acc, (long long)(ell + 1) * N, 2, ell + 1, pm, sp, out, (long long)ell * N, base, (long long)ell * N, tmp);
-  if (int rc = divround_impl(be, c, acc, 0, 1, ell + 1, pm, sp, out, 0, base, 0, tmp)) return rc;
-  return divround_impl(be, c, acc + (size_t)(ell + 1) * N, 0, 1, ell + 1, pm, sp, out + (size_t)ell * N, 0, (const u64 *)nullptr, 0, tmp + N);
+  // base holds c0 and c1 (relinearize) or c0 only (rotate: the switched c1 has no base)
+  return divround_impl(be, c, acc, (long long)(ell + 1) * N, 2, ell + 1, pm, sp, out, (long long)ell * N, base, (long long)ell * N, tmp,
+                       base_polys);
 }
 
 // Evaluator::relinearize (3 -> 2) -- reference eva/seal/seal_executor.h:200
@@ -183,6 +184,10 @@ int rotate_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, const
 }
 
 
+// encoder workspace: count*N complex values followed by count u64 flags
+inline size_t encode_work_bytes(const CtxView &c, int count) { return (size_t)count * c.N * sizeof(cplx) + (size_t)((count + 7) & ~7) * sizeof(u64); }
+inline u64 *encode_flags(const CtxView &c, int count, cplx *work) { return reinterpret_cast<u64 *>(work + (size_t)count * c.N); }
+
 // seal::CKKSEncoder::encode (vector overload) for a batch of vectors -- reference
 // eva/seal/seal_executor.h:242.  d_values/vec/scale are host arrays of `count` entries.
 template <class BE>
@@ -199,6 +204,7 @@ int encode_impl(BE &be, const CtxView &c, int count, const double *const *d_valu
       B.vals[e] = d_values[e0 + e]; B.vec[e] = vec[e0 + e]; B.scale[e] = scale[e0 + e];
     }
     B.work = work + (size_t)e0 * c.N; B.out = out + (size_t)e0 * ell * c.N;
+    B.flags = encode_flags(c, count, work) + e0;
     B.roots = c.roots; B.slot_index = c.slot_index; B.primes = c.primes; B.pow2 = c.pow2;
     B.N = (u32)c.N; B.ell = (u32)ell;
     if (int rc = be.enc_scatter(B)) return rc;
@@ -215,5 +221,7 @@ int encode_impl(BE &be, const CtxView &c, int count, const double *const *d_valu
   L.src = out; L.dst = out; L.inner = ell;
   L.src_sq = L.dst_sq = (long long)ell * c.N; L.src_sr = L.dst_sr = (long long)c.N;
   for (int i = 0; i < ell; i++) L.pmap[i] = (unsigned char)i;
+  // scalar constants (the common case in EVA programs) encode to constant polynomials
+  L.cflags = encode_flags(c, count, work);
   return be.fwd(L, (size_t)count * ell);
 }

@@ -91,7 +91,11 @@ int evab_ntt_inv(evab_ctx *ctx, uint64_t *d_data, size_t count, const int *prime
  * (and seal.cpp:68,80).  Encodes `count` vectors in one batch: vector e has
  * vec_sizes[e] doubles at d_values[e] (device), is replicated over the N/2 slots
  * and encoded at absolute scale scales[e] into d_out[e][ell][N] (NTT form).
- * h_* arguments are host arrays read during the call.  d_work: count*N*16 bytes. ---- */
+ * h_* arguments are host arrays read during the call.  d_work:
+ * evab_encode_work_bytes(ctx, count) bytes (FP64 FFT buffer + one flag word per vector:
+ * vectors that encode to a constant polynomial -- scalar constants -- skip the NTT,
+ * their transform is the constant itself). ---- */
+size_t evab_encode_work_bytes(const evab_ctx *ctx, int count);
 int evab_encode(evab_ctx *ctx, int count, const double *const *h_d_values, const uint32_t *h_vec_sizes, const double *h_scales,
                 int ell, uint64_t *d_out, void *d_work, void *stream);
 

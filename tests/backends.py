@@ -42,7 +42,7 @@ class EmuBackend:
         self.lib = C.CDLL(so)
         self.lib.emu_ctx_create.restype = C.c_void_p
         self.lib.emu_last_error.restype = C.c_char_p
-        for n in ("emu_rescale_work_bytes", "emu_keyswitch_work_bytes"):
+        for n in ("emu_rescale_work_bytes", "emu_keyswitch_work_bytes", "emu_encode_work_bytes"):
             getattr(self.lib, n).restype = C.c_size_t
         pa = np.array(primes, dtype=np.uint64)
         self.h = C.c_void_p(self.lib.emu_ctx_create(C.c_uint64(N), _p(pa), len(primes)))
@@ -114,6 +114,19 @@ class EmuBackend:
         work = np.zeros(self.lib.emu_keyswitch_work_bytes(self.h, a.shape[1]) // 8, dtype=np.uint64)
         self._chk(self.lib.emu_rotate(self.h, a.shape[1], _p(out), _p(a), C.c_uint64(_elt(self.N, steps)), _p(gk), _p(work)))
         return out
+
+    def encode(self, values, scale, ell):
+        """Batched-encoder kernel bodies on the CPU: list of vectors (or one vector) -> [count][ell][N]."""
+        single = np.ndim(values[0]) == 0
+        vecs = [np.ascontiguousarray(values, dtype=np.float64)] if single else [np.ascontiguousarray(v, dtype=np.float64) for v in values]
+        n = len(vecs)
+        ptrs = (C.c_void_p * n)(*[v.ctypes.data for v in vecs])
+        sizes = (C.c_uint32 * n)(*[len(v) for v in vecs])
+        scales = (C.c_double * n)(*([float(scale)] * n))
+        out = np.empty((n, ell, self.N), dtype=np.uint64)
+        work = np.zeros(self.lib.emu_encode_work_bytes(self.h, n) // 8, dtype=np.uint64)
+        self._chk(self.lib.emu_encode(self.h, n, ptrs, sizes, scales, ell, _p(out), _p(work)))
+        return out[0] if single else out
 
 
 class GpuBackend:

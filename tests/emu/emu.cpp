@@ -39,6 +39,11 @@ template <int LOGN, bool SPLIT, bool INV, int PRO, int EPI> static void run_ntt_
     NttJob J[CPJ];
     for (int h = 0; h < CPJ; h++) J[h] = ntt_job(L, (u32)(job * CPJ + h), CPJ);
     if (J[0].skip) continue;
+    if (!INV && PRO == PRO_PLAIN && EPI == EPI_STORE && J[0].bcast) {
+      for (int h = 0; h < CPJ; h++)
+        for (u32 t = 0; t < (u32)G::T; t++) fwd_const_poly<LOGN, SPLIT>(J[h], t);
+      continue;
+    }
     if (!INV) {
       // forward: the CTAs of one job (a cluster when SPLIT) run all compute phases,
       // then the cluster barrier, then the store phase
@@ -170,6 +175,7 @@ int emu_negate(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa) { Emu
 int emu_mul_plain(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt) { EmuBE be{c}; return dyadic_impl<DY_MULPT>(be, c->v, ell, o, a, sa, pt, 1, 1); }
 int emu_mul(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *b) { EmuBE be{c}; return mulct_impl(be, c->v, false, ell, o, a, b); }
 int emu_square(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a) { EmuBE be{c}; return mulct_impl(be, c->v, true, ell, o, a, (const u64 *)nullptr); }
+size_t emu_encode_work_bytes(EmuCtx *c, int count) { return encode_work_bytes(c->v, count); }
 int emu_encode(EmuCtx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell, uint64_t *out, void *work) {
   EmuBE be{c};
   return encode_impl(be, c->v, count, vals, vec, scales, ell, out, (cplx *)work);

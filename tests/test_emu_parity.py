@@ -40,3 +40,20 @@ def test_emu_ops_n32768():
     be = EmuBackend(32768, orc.primes)
     pc.case_rescale(be, orc, 3)
     pc.case_keyswitch(be, orc, 3, steps=(-1,))
+
+
+@pytest.mark.parametrize("N,bits", [(1024, [40, 50, 60, 60]), (4096, [60, 20, 60, 60]), (32768, [60, 20, 60, 60])])
+def test_emu_encode(N, bits):
+    """Device encoder bodies (FP64 FFT, rounding, residues, NTT) vs the oracle, including scalar
+    constants, which take the constant-polynomial path of the forward NTT."""
+    import numpy as np
+    orc = pc.get_oracle(N, bits)
+    be = EmuBackend(N, orc.primes)
+    rng = np.random.default_rng(N)
+    vecs = [np.array([1.0]), np.array([-2.0]), np.array([0.0]), rng.uniform(-3, 3, 8), np.array([0.17254603006834726]),
+            rng.uniform(-1, 1, N // 2), np.array([2.5, 2.5]), np.array([1.0, -1.0])]
+    for scale_bits, ell in ((25, 2), (40, len(bits) - 1), (60, 1), (90, len(bits))):
+        got = be.encode(vecs, 2.0 ** scale_bits, ell)
+        for e, v in enumerate(vecs):
+            want = orc.encode(v, 2.0 ** scale_bits, ell)
+            assert np.array_equal(got[e], want), (scale_bits, ell, e)

@@ -13,11 +13,43 @@ __device__ __forceinline__ u64 mulhi_4wide(u64 a, u64 b) {  // schoolbook, no ca
   asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t3) : "r"(a1), "r"(b1), "l"(t1 >> 32));
   return t3 + (t2 >> 32);
 }
+__device__ __forceinline__ u64 mulhi_approx(u64 a, u64 b) {  // >= true - 2: drops a0*b0 and the low halves of the cross terms
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  u32 c0, c1; u64 t;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(c0) : "r"(a1), "r"(b0));
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(c1) : "r"(a0), "r"(b1));
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t) : "r"(a1), "r"(b1), "l"((u64)c0));
+  return t + c1;
+}
+// hand-scheduled forward butterfly: s = xa + w*y + q*np with q = mulhi_approx(ws, y); returns s,
+// xb = 2*xa + bias - s.  3 mad.wide + 2 mul.hi + 4 mad.lo on the fma pipe.
+__device__ __forceinline__ void bfly_ptx(u64 &xa, u64 &xb, u64 w, u64 ws, u64 np, u64 bias) {
+  u32 y0 = (u32)xb, y1 = (u32)(xb >> 32), w0 = (u32)w, w1 = (u32)(w >> 32);
+  u32 s0 = (u32)ws, s1 = (u32)(ws >> 32), n0 = (u32)np, n1 = (u32)(np >> 32);
+  u32 c0, c1; u64 q, m;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(c0) : "r"(s1), "r"(y0));
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(c1) : "r"(s0), "r"(y1));
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(q) : "r"(s1), "r"(y1), "l"((u64)c0));
+  q += c1;
+  u32 q0 = (u32)q, q1 = (u32)(q >> 32);
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(m) : "r"(w0), "r"(y0), "l"(xa));
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(m) : "r"(q0), "r"(n0), "l"(m));
+  u32 h = (u32)(m >> 32);
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(w0), "r"(y1));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(w1), "r"(y0));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(q0), "r"(n1));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(q1), "r"(n0));
+  u64 s = ((u64)h << 32) | (u32)m;
+  xb = xa + xa + bias - s;
+  xa = s;
+}
 template <int V> __device__ __forceinline__ u64 mulw(u64 y, u64 w, u64 ws, u64 p, u64 np) {
   if (V == 0 || V == 1) { u64 q = __umul64hi(ws, y); return w * y + q * np; }
   if (V == 2) { u64 q = __umul64hi(ws, y); u64 a = w * y, b = q * p; asm volatile("" : "+l"(a), "+l"(b)); return a - b; }
   if (V == 3) { u64 q = mulhi_4wide(ws, y); return w * y + q * np; }
   if (V == 4) { u64 q = mulhi_4wide(ws, y); u64 a = w * y, b = q * p; asm volatile("" : "+l"(a), "+l"(b)); return a - b; }
+  if (V == 5 || V == 7) { u64 q = mulhi_approx(ws, y); return w * y + q * np; }
+  if (V == 6) { u64 q = __umul64hi(ws, y); return w * y + q * np; }
   return 0;
 }
 template <int V, int E> __global__ void __launch_bounds__(1024, 1) k(u64 *out, u64 p, u64 w0, u64 ws0) {
@@ -34,9 +66,15 @@ template <int V, int E> __global__ void __launch_bounds__(1024, 1) k(u64 *out, u
 #pragma unroll
         for (int j = 0; j < d; j++) {
           const int a = g * 2 * d + j, b = a + d;
-          u64 t = mulw<V>(x[b], w, ws, p, np);
           u64 xa = x[a];
-          x[a] = xa + t; x[b] = xa - t + two_p;
+          if (V == 8) { bfly_ptx(x[a], x[b], w, ws, np, 2 * two_p); }
+          else if (V >= 6) {
+            u64 s = xa + mulw<V>(x[b], w, ws, p, np);
+            x[b] = (xa + xa + (V == 7 ? 2 * two_p : two_p)) - s; x[a] = s;
+          } else {
+          u64 t = mulw<V>(x[b], w, ws, p, np);
+          x[a] = xa + t; x[b] = xa - t + (V == 5 ? 2 * two_p : two_p);
+          }
         }
     }
     if (V != 1) {
@@ -72,5 +110,9 @@ int main() {
   run<3, 16>("V3 4x mad.wide mulhi (no .X), fused low", 1024);
   run<4, 16>("V4 4x mad.wide mulhi, separate low", 1024);
   run<3, 8>("V3 E=8", 1024);
+  run<6, 16>("V6 exact mulhi, add folded into the mad chain", 1024);
+  run<7, 16>("V7 approx mulhi, add folded", 1024);
+  run<8, 16>("V8 hand-written PTX butterfly (approx mulhi, folded)", 1024);
+  run<5, 16>("V5 approx mulhi (2 mul.hi + 1 mad.wide), fused low", 1024);
   return 0;
 }
