@@ -276,8 +276,16 @@ def ntt_roofline(pub, primes, N, stream):
     ach = algo / (ms * 1e-3) / 1e9
     del data
     lib.evab_ctx_destroy(h)
+    # DRAM traffic of the same launch from the committed ncu --set full capture (profiles/)
+    traffic, traffic_src = None, None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_ntt_fwd_v4.json")))
+        if prof.get("residues_per_launch") == cnt:
+            traffic, traffic_src = prof["traffic_bytes_per_launch"], prof["source"]
+    except Exception:
+        pass
     return {"bound": "hbm", "kernel": "k_ntt_fwd<14> (batched, %d residues/launch)" % cnt, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback 6650",
+            "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback 6650",
             "algorithmic_bytes_per_launch": algo, "launch_ms": ms}
 
 

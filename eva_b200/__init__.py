@@ -101,3 +101,14 @@ def Input(name, is_encrypted=True):
 def Output(name, expr):
     program = _curr()
     program._make_output(name, _py_to_term(expr, program))
+
+
+def save(obj, path):
+    """reference python/eva/__init__.py `save`: protobuf serialization (eva/serialization/*).
+    Out of scope for this backend (no protobuf runtime in the image)."""
+    raise NotImplementedError("eva_b200: protobuf serialization (save/load) is not part of the B200 execution path")
+
+
+def load(path):
+    """reference python/eva/__init__.py `load` -- see save()."""
+    raise NotImplementedError("eva_b200: protobuf serialization (save/load) is not part of the B200 execution path")
