@@ -98,6 +98,11 @@ def synthetic_inputs(d, primes, seed):
     return relin, galois, cts
 
 
+def multi_seed(rank, index):
+    from eva_b200 import multi
+    return multi.instance_seed(rank, index)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -125,7 +130,7 @@ def run_ours(args):
         prog, params, sig, terms = program_io.build_program(d)
         vals = []
         for i in range(F):
-            _, _, cts_i = synthetic_inputs({**d, "terms": []}, primes, seed=77 * (rank + 1) + g * F + i)
+            _, _, cts_i = synthetic_inputs({**d, "terms": []}, primes, seed=multi_seed(rank, g * F + i))
             val = b200.B200Valuation()
             for name, (ct, scale) in cts_i.items():
                 val.set_cipher(name, ct, scale)
@@ -212,14 +217,12 @@ def run_ours(args):
     okind, oarr, _ = outs[0][0].get(list(d["outputs"].keys())[0])
     d2h = int(oarr.nbytes) * B
     # ---- final gather of the outputs on rank 0 (north_star: NCCL only for the final gather)
+    from eva_b200 import multi
     if world > 1:
-        o_dev = torch.from_numpy(oarr.view(np.int64)).cuda()
-        gathered = [torch.empty_like(o_dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(o_dev, gathered, dst=0)
-        tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_res, t_e2e = tt.tolist()
-    total_ops = nops * B * args.steps * world
+        gathered = multi.gather_outputs(oarr, rank, world, device="cuda")
+        assert rank != 0 or len(gathered) == world
+        t_res, t_e2e = multi.max_over_ranks([t_res, t_e2e], world, device="cuda")
+    total_ops = multi.aggregate_ops(nops, B, args.steps, world)
     result = {
         "metric": METRIC, "value": total_ops / t_res, "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
