@@ -104,6 +104,9 @@ def multi_seed(rank, index):
 
 
 def run_ours(args):
+    if args.ntt_cluster is not None:
+        from eva_b200 import cabi
+        assert cabi.load().evab_set_ntt_cluster(args.ntt_cluster) == 0
     import torch
     import torch.distributed as dist
     from eva_b200 import b200, program_io
@@ -356,6 +359,7 @@ def main():
     ap.set_defaults(no_const_cache=True)
     ap.add_argument("--no-dedup", action="store_true", help="encode every Encode term separately even when constants repeat")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ntt-cluster", type=int, default=None, help="CTAs per residue transform (1, 2, 4); default: library default")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -38,6 +38,7 @@ _SIGS = {
     "evab_launch_count": (u64, [vp]),
     "evab_ntt_fwd": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
     "evab_ntt_inv": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
+    "evab_set_ntt_cluster": (ci, [ci]),
     "evab_encode_work_bytes": (szt, [vp, ci]),
     "evab_encode": (ci, [vp, ci, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_double), ci, vp, vp, vp]),
     "evab_add": (ci, [vp, ci, vp, vp, ci, vp, ci, vp]),

@@ -45,6 +45,7 @@ static cudaStream_t S(void *s) { return (cudaStream_t)s; }
 // thread-local batched-issue state (evab_set_batch)
 struct BatchState { int batch = 1; long long stride = 0, vstride = 0; };
 static thread_local BatchState g_batch;
+extern "C" int evab_set_ntt_cluster(int ctas_per_residue);
 extern "C" int evab_set_batch(int batch, size_t stride_words, size_t value_stride) {
   if (batch < 1 || batch > 65535) return fail("evab_set_batch: batch must be in [1, 65535]");
   g_batch.batch = batch; g_batch.stride = (long long)stride_words; g_batch.vstride = (long long)value_stride;
@@ -55,38 +56,67 @@ extern "C" int evab_set_batch(int batch, size_t stride_words, size_t value_strid
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-struct BlockSync {
-  EVAB_HD void operator()() const {
-#if defined(__CUDA_ARCH__)
-    __syncthreads();
-#endif
+// barrier after a phase: 0 = block, 1 = cluster (release / acquire: the exchange just written lives
+// partly in the peers' shared memory), 2 = none
+template <int CL> struct DevSync {
+  __device__ __forceinline__ void operator()(int kind) const {
+    if (CL > 1 && kind == 1) {
+      asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    } else if (kind != 2) {
+      __syncthreads();
+    }
   }
 };
-// one CTA = one residue (or one half of a 2^15 residue); T = N/16 threads, 64 registers
-template <int LOGN, bool SPLIT, int PRO, int EPI>
-__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_fwd(const NttLaunch L, const long long bstride) {
+// split cluster barrier ordering the distributed-shared-memory stores after the peers' last reads
+template <int CL> struct DevHooks {
+  __device__ __forceinline__ void arrive() const { if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+  __device__ __forceinline__ void wait() const { if (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+};
+template <int CL> __device__ __forceinline__ SmemView<CL> smem_view(u64 *sm) {
+  SmemView<CL> v;
+  v.local = sm;
+#pragma unroll
+  for (int r = 0; r < CL; r++) {
+    if (CL > 1) {
+      // generic address of the same shared-memory offset in CTA r of this cluster
+      u64 *p;
+      asm volatile("mapa.u64 %0, %1, %2;\n" : "=l"(p) : "l"(sm), "r"(r));
+      v.peer[r] = p;
+    } else {
+      v.peer[r] = sm;
+    }
+  }
+  return v;
+}
+// CL = 1: one CTA = one residue (or one half of a 2^15 residue), T = N/16 threads, 64 registers.
+// CL = 2, 4: one residue over a cluster of CL CTAs of T/CL threads (ntt_core.cuh), CL CTAs per SM more.
+template <int LOGN, bool SPLIT, int PRO, int EPI, int CL>
+__global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::T / CL)) k_ntt_fwd(const NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
-  typedef FwdBody<LOGN, SPLIT, PRO, EPI> B;
-  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1, (long long)blockIdx.y * bstride);
+  typedef FwdBody<LOGN, SPLIT, PRO, EPI, CL> B;
+  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : CL, (long long)blockIdx.y * bstride);
   if (J.skip) return;
   NttState S;
   const u32 tid = threadIdx.x;
-  if (PRO == PRO_PLAIN && EPI == EPI_STORE && J.bcast) { fwd_const_poly<LOGN, SPLIT>(J, tid); return; }
-  PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, sm, BlockSync());
+  if (PRO == PRO_PLAIN && EPI == EPI_STORE && J.bcast) { fwd_const_poly<LOGN, SPLIT>(J, B::vtid(J, tid)); return; }
+  const DevHooks<CL> hk;
+  hk.arrive();   // this CTA is resident: peers may store into its shared memory (waited on in phase 0)
+  PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, smem_view<CL>(sm), DevSync<CL>(), hk);
   if (SPLIT) {  // CTA pair (cluster of 2): both halves have consumed the input
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
   }
   B::phE(S, L, J, tid);
 }
-template <int LOGN, bool SPLIT, int PRO, int EPI>
-__global__ void __launch_bounds__(NttGeom<LOGN>::T, 1024 / NttGeom<LOGN>::T) k_ntt_inv(const NttLaunch L, const long long bstride) {
+template <int LOGN, bool SPLIT, int PRO, int EPI, int CL>
+__global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::T / CL)) k_ntt_inv(const NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
-  typedef InvBody<LOGN, SPLIT, PRO, EPI> B;
-  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : 1, (long long)blockIdx.y * bstride);
+  typedef InvBody<LOGN, SPLIT, PRO, EPI, CL> B;
+  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : CL, (long long)blockIdx.y * bstride);
   if (J.skip) return;
   NttState S;
-  PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, sm, BlockSync());
+  PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, smem_view<CL>(sm), DevSync<CL>(), DevHooks<CL>());
 }
 __global__ void __launch_bounds__(256) k_inv_last_stage(const NttLaunch L, u32 half_n, const long long bstride) {
   const NttJob J = ntt_job(L, blockIdx.y, 1, (long long)blockIdx.z * bstride);
@@ -129,45 +159,50 @@ __global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, co
 // ---------------------------------------------------------------------------
 // CUDA backend
 // ---------------------------------------------------------------------------
-template <int LOGN, bool SPLIT, int PRO, int EPI> static int launch_fwd_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  const size_t smem = (size_t)NttGeom<LOGN>::N * sizeof(u64);
-  static std::atomic<bool> done[64];
+static int g_ntt_cluster = 4;   // CTAs per residue for 2^13 <= N <= 2^14 (evab_set_ntt_cluster); 4: +15% Sobel throughput, -48% latency vs 1
+
+template <class K> static int launch_ntt(K kernel, const NttLaunch &L, size_t ctas, int threads, size_t smem, int cluster, cudaStream_t st, std::atomic<bool> *done) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!done[dev & 63].load()) {
-    CUDA_OK(cudaFuncSetAttribute(k_ntt_fwd<LOGN, SPLIT, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done[dev & 63].store(true);
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(jobs * (SPLIT ? 2 : 1)), (unsigned)g_batch.batch);
-  cfg.blockDim = dim3(NttGeom<LOGN>::T);
+  cfg.gridDim = dim3((unsigned)ctas, (unsigned)g_batch.batch);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = SPLIT ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  CUDA_OK(cudaLaunchKernelEx(&cfg, k_ntt_fwd<LOGN, SPLIT, PRO, EPI>, L, g_batch.stride));
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, L, g_batch.stride));
   return 0;
 }
-template <int LOGN, bool SPLIT> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_PLAIN, EPI_STORE>(L, jobs, st);
-  if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE>(L, jobs, st);
-  if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE_LAZY>(L, jobs, st);
-  if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_DIVROUND>(L, jobs, st);
+template <int LOGN, bool SPLIT, int PRO, int EPI, int CL> static int launch_fwd_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  static std::atomic<bool> done[64];
+  constexpr int CPJ = SPLIT ? 2 : CL;
+  return launch_ntt(k_ntt_fwd<LOGN, SPLIT, PRO, EPI, CL>, L, jobs * CPJ, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CPJ, st, done);
+}
+template <int LOGN, bool SPLIT, int CL> static int launch_fwd_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_PLAIN, EPI_STORE, CL>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE, CL>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE_LAZY, CL>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_DIVROUND, CL>(L, jobs, st);
   return fail("unsupported forward NTT prologue/epilogue combination");
 }
-template <int LOGN, bool SPLIT, int EPI> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  const size_t smem = (size_t)NttGeom<LOGN>::N * sizeof(u64);
-  static std::atomic<bool> done[64];
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!done[dev & 63].load()) {
-    CUDA_OK(cudaFuncSetAttribute(k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done[dev & 63].store(true);
+template <int LOGN, bool SPLIT> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  if constexpr (LOGN >= 13 && !SPLIT) {
+    if (g_ntt_cluster == 2) return launch_fwd_c<LOGN, SPLIT, 2>(L, jobs, st);
+    if (g_ntt_cluster == 4) return launch_fwd_c<LOGN, SPLIT, 4>(L, jobs, st);
   }
-  k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI><<<dim3((unsigned)(jobs * (SPLIT ? 2 : 1)), (unsigned)g_batch.batch), NttGeom<LOGN>::T, smem, st>>>(L, g_batch.stride);
-  CUDA_OK(cudaGetLastError());
+  return launch_fwd_c<LOGN, SPLIT, 1>(L, jobs, st);
+}
+template <int LOGN, bool SPLIT, int EPI, int CL> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  static std::atomic<bool> done[64];
+  constexpr int CPJ = SPLIT ? 2 : CL;
+  if (int rc = launch_ntt(k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI, CL>, L, jobs * CPJ, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), SPLIT ? 1 : CL, st, done)) return rc;
   if (SPLIT) {
     const u32 half = NttGeom<LOGN>::N;
     dim3 g((half + 255) / 256, (unsigned)jobs, (unsigned)g_batch.batch);
@@ -176,11 +211,18 @@ template <int LOGN, bool SPLIT, int EPI> static int launch_inv_m(const NttLaunch
   }
   return 0;
 }
-template <int LOGN, bool SPLIT> static int launch_inv_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+template <int LOGN, bool SPLIT, int CL> static int launch_inv_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   if (L.pro != PRO_PLAIN) return fail("unsupported inverse NTT prologue");
-  if (L.epi == EPI_STORE) return launch_inv_m<LOGN, SPLIT, EPI_STORE>(L, jobs, st);
-  if (L.epi == EPI_ADDHALF) return launch_inv_m<LOGN, SPLIT, EPI_ADDHALF>(L, jobs, st);
+  if (L.epi == EPI_STORE) return launch_inv_m<LOGN, SPLIT, EPI_STORE, CL>(L, jobs, st);
+  if (L.epi == EPI_ADDHALF) return launch_inv_m<LOGN, SPLIT, EPI_ADDHALF, CL>(L, jobs, st);
   return fail("unsupported inverse NTT epilogue");
+}
+template <int LOGN, bool SPLIT> static int launch_inv_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  if constexpr (LOGN >= 13 && !SPLIT) {
+    if (g_ntt_cluster == 2) return launch_inv_c<LOGN, SPLIT, 2>(L, jobs, st);
+    if (g_ntt_cluster == 4) return launch_inv_c<LOGN, SPLIT, 4>(L, jobs, st);
+  }
+  return launch_inv_c<LOGN, SPLIT, 1>(L, jobs, st);
 }
 
 struct CudaBE {
@@ -429,6 +471,11 @@ extern "C" int evab_ntt_fwd(evab_ctx *c, uint64_t *d, size_t count, const int *p
 }
 extern "C" int evab_ntt_inv(evab_ctx *c, uint64_t *d, size_t count, const int *pidx, int np, void *stream) {
   BE_BEGIN return ntt_batch_impl(be, c->v, true, d, count, pidx, np);
+}
+extern "C" int evab_set_ntt_cluster(int cl) {
+  if (cl != 1 && cl != 2 && cl != 4) return fail("evab_set_ntt_cluster: 1, 2 or 4 CTAs per residue");
+  g_ntt_cluster = cl;
+  return 0;
 }
 extern "C" size_t evab_encode_work_bytes(const evab_ctx *c, int count) { return encode_work_bytes(c->v, count); }
 extern "C" int evab_encode(evab_ctx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell,

@@ -135,6 +135,89 @@ template <int LOGN> EVAB_HD void xchg_write_c(const u64 (&x)[NTT_E], u64 *sm, u3
 }
 
 // ---------------------------------------------------------------------------
+// One residue spread over a cluster of CL CTAs (CL = 2 or 4, LOGN >= 12): CTA `rank` runs the
+// virtual threads v = rank*Tc + tid, Tc = T/CL, and keeps the slice [rank*N/CL, (rank+1)*N/CL) of the
+// exchange index space in its own shared memory (N/CL * 8 bytes), so several smaller CTAs share an SM
+// and overlap each other's load / exchange / store phases.  After pass 0 (forward) the transform
+// splits into 16 independent sub-transforms of N/16 points, CL-aligned: only the exchange between
+// pass 0 and pass 1 crosses CTAs.  It is written straight into the consumer's shared memory
+// (distributed shared memory stores) and followed by a cluster barrier; every other exchange is
+// CTA-local with indices taken modulo N/CL.
+// ---------------------------------------------------------------------------
+template <int CL> struct SmemView {
+  u64 *local;        // this CTA's slice
+  u64 *peer[CL];     // generic pointers to every rank's slice (peer[rank] == local)
+};
+template <int LOGN, int CL> struct ClGeom {
+  static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size 1, 2 or 4");
+  static_assert(CL == 1 || LOGN >= 12, "cluster-distributed transform needs N >= 4096");
+  static constexpr int LGC = CL == 1 ? 0 : (CL == 2 ? 1 : 2);
+  static constexpr int Tc = NttGeom<LOGN>::T / CL;
+  static constexpr int LGT = LOGN - NTT_EL - LGC;   // log2(Tc)
+  static constexpr u32 NC = (u32)NttGeom<LOGN>::N / CL;
+  static constexpr u32 mask = NC - 1u;
+};
+// local (masked) variants of the exchanges above; v = virtual thread id
+template <int LOGN, int J, int JR, int CL> EVAB_HD void xchg_write_sl(const u64 (&x)[NTT_E], u64 *sm, u32 v) {
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) sm[swz_s<LOGN, JR>(idx_s<LOGN, J>(v, k)) & ClGeom<LOGN, CL>::mask] = x[k];
+}
+template <int LOGN, int J, int JR, int CL> EVAB_HD void xchg_read_sl(u64 (&x)[NTT_E], const u64 *sm, u32 v) {
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) x[k] = sm[swz_s<LOGN, JR>(idx_s<LOGN, J>(v, k)) & ClGeom<LOGN, CL>::mask];
+}
+template <int LOGN, int J, int CL> EVAB_HD void xchg_write_scl(const u64 (&x)[NTT_E], u64 *sm, u32 v) {
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) sm[swz_c<LOGN>(idx_s<LOGN, J>(v, k)) & ClGeom<LOGN, CL>::mask] = x[k];
+}
+template <int LOGN, int J, int CL> EVAB_HD void xchg_read_scl(u64 (&x)[NTT_E], const u64 *sm, u32 v) {
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) x[k] = sm[swz_c<LOGN>(idx_s<LOGN, J>(v, k)) & ClGeom<LOGN, CL>::mask];
+}
+template <int LOGN, int CL> EVAB_HD void xchg_read_cl(u64 (&x)[NTT_E], const u64 *sm, u32 v) {
+  const u64x2 *row = reinterpret_cast<const u64x2 *>(sm + (((size_t)v << NTT_EL) & ClGeom<LOGN, CL>::mask));
+  const u32 f = swz_rowf<LOGN>(v);
+#pragma unroll
+  for (int c = 0; c < NTT_E / 2; c++) {
+    u64x2 t = row[c ^ f];
+    x[2 * c] = t.x; x[2 * c + 1] = t.y;
+  }
+}
+template <int LOGN, int CL> EVAB_HD void xchg_write_cl(const u64 (&x)[NTT_E], u64 *sm, u32 v) {
+  u64x2 *row = reinterpret_cast<u64x2 *>(sm + (((size_t)v << NTT_EL) & ClGeom<LOGN, CL>::mask));
+  const u32 f = swz_rowf<LOGN>(v);
+#pragma unroll
+  for (int c = 0; c < NTT_E / 2; c++) {
+    u64x2 t; t.x = x[2 * c]; t.y = x[2 * c + 1];
+    row[c ^ f] = t;
+  }
+}
+// forward, pass 0 -> pass 1: element k of virtual thread v has natural index (k << (n-4)) | v; its
+// reader is a pass-1 thread of rank k >> (4 - LGC) (compile-time per k)
+template <int LOGN, int CL> EVAB_HD void xchg_write_dist_fwd(const u64 (&x)[NTT_E], const SmemView<CL> &sm, u32 v) {
+  typedef ClGeom<LOGN, CL> C;
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) sm.peer[k >> (NTT_EL - C::LGC)][idx_s<LOGN, 0>(v, (u32)k) & C::mask] = x[k];
+}
+// inverse, pass 1 -> pass 0: the reader of natural index i is the pass-0 virtual thread
+// v0 = i mod T, element k0 = i / T; it is stored in v0's CTA at (k0 << log2 Tc) | (v0 mod Tc).
+// For a pass-1 writer (v, k1): k0 = v >> (n-8), v0 = (k1 << (n-8)) | (v mod 2^(n-8)), rank = k1 >> (4-LGC).
+template <int LOGN, int CL> EVAB_HD void xchg_write_dist_inv(const u64 (&x)[NTT_E], const SmemView<CL> &sm, u32 v) {
+  typedef ClGeom<LOGN, CL> C;
+  constexpr int lb = NttGeom<LOGN>::lowbits(1);
+  const u32 k0 = v >> lb, L = v & ((1u << lb) - 1u);
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) {
+    const u32 v0 = ((u32)k << lb) | L;
+    sm.peer[k >> (NTT_EL - C::LGC)][(k0 << C::LGT) | (v0 & (u32)(C::Tc - 1))] = x[k];
+  }
+}
+template <int LOGN, int CL> EVAB_HD void xchg_read_dist_inv(u64 (&x)[NTT_E], const u64 *sm, u32 tid) {
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) x[k] = sm[((u32)k << ClGeom<LOGN, CL>::LGT) | tid];
+}
+
+// ---------------------------------------------------------------------------
 // forward (Cooley-Tukey) register passes.  `b` is the compile-time tracked
 // upper bound of every live value in units of p (values < b*p <= 16p < 2^64).
 // `root` is the twiddle root prefix: 1 for a full transform; 2+h for the h-th

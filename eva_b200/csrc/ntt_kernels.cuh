@@ -132,9 +132,15 @@ template <int LOGN, bool SPLIT> EVAB_HD void fwd_const_poly(const NttJob &J, u32
 //   2j-1, 2j   : exchange read + pass j   |   exchange write        (1 <= j <= P-2)
 //   2(P-1)-1   : exchange read + last (contiguous) pass
 //   phE        : fused epilogue + store
-template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct FwdBody {
+template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct FwdBody {
   typedef NttGeom<LOGN> G;
+  typedef ClGeom<LOGN, CL> C;
+  static_assert(!(SPLIT && CL > 1), "split and cluster-distributed transforms are exclusive");
   static constexpr int NPH = G::NPH;
+  // barrier after phase PH: 0 = block, 1 = cluster (the exchange written in phase 0 crosses CTAs)
+  static EVAB_HD constexpr int sync_kind(int ph) { return (CL > 1 && ph == 0) ? 1 : 0; }
+  // virtual thread id: rank * Tc + tid
+  static EVAB_HD u32 vtid(const NttJob &J, u32 tid) { return CL > 1 ? J.h * (u32)C::Tc + tid : tid; }
 
   // load of pass 0 (strided, coalesced) with the fused prologue [+ first stage of a split transform]
   template <bool CHEAP> static EVAB_HD void load0(NttState &S, const NttLaunch &L, const NttJob &J, const PrimeDev &P, u32 tid, u64 sub) {
@@ -157,33 +163,43 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct
       S.b = 3;
     }
   }
-  template <int PH> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
+  // ltid: thread index inside the CTA; the passes run on the virtual thread id
+  template <int PH, class Hooks> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid, const SmemView<CL> &smv, Hooks hk) {
     const PrimeDev P = L.primes[J.pi];
     const u32 root = SPLIT ? 2 + J.h : 1;
+    const u32 tid = vtid(J, ltid);
+    u64 *sm = smv.local;
     if constexpr (PH == 0) {
       const u64 sub = (PRO == PRO_MODRED) ? EVAB_LDG(L.subtab + J.pi) : 0;
       const bool cheap = (PRO == PRO_MODRED) && (L.primes[J.spi].p <= 2 * P.p);   // CTA-uniform
       if (cheap) load0<true>(S, L, J, P, tid, sub); else load0<false>(S, L, J, P, tid, sub);
       fwd_pass_s<LOGN, 0>(S.x, P.tw, root, P.p, tid, S.b);
-      xchg_write_s<LOGN, 0, 1>(S.x, sm, tid);
+      if constexpr (CL > 1) { hk.wait(); xchg_write_dist_fwd<LOGN, CL>(S.x, smv, tid); }   // peers are resident (arrive at kernel start)
+      else xchg_write_s<LOGN, 0, 1>(S.x, sm, tid);
     } else if constexpr (PH == NPH - 1) {
-      xchg_read_c<LOGN>(S.x, sm, tid);
+      if constexpr (CL > 1) xchg_read_cl<LOGN, CL>(S.x, sm, tid); else xchg_read_c<LOGN>(S.x, sm, tid);
       fwd_pass_c<LOGN>(S.x, P.tw, root, P.p, tid, S.b);
     } else if constexpr (PH % 2 == 1) {
       constexpr int j = (PH + 1) / 2;
-      xchg_read_s<LOGN, j, j>(S.x, sm, tid);
+      if constexpr (CL > 1) xchg_read_sl<LOGN, j, j, CL>(S.x, sm, tid); else xchg_read_s<LOGN, j, j>(S.x, sm, tid);
       fwd_pass_s<LOGN, j>(S.x, P.tw, root, P.p, tid, S.b);
     } else {
       constexpr int j = PH / 2;
-      if constexpr (j + 1 == G::P - 1) xchg_write_sc<LOGN, j>(S.x, sm, tid);
-      else xchg_write_s<LOGN, j, j + 1>(S.x, sm, tid);
+      if constexpr (CL > 1) {
+        if constexpr (j + 1 == G::P - 1) xchg_write_scl<LOGN, j, CL>(S.x, sm, tid);
+        else xchg_write_sl<LOGN, j, j + 1, CL>(S.x, sm, tid);
+      } else {
+        if constexpr (j + 1 == G::P - 1) xchg_write_sc<LOGN, j>(S.x, sm, tid);
+        else xchg_write_s<LOGN, j, j + 1>(S.x, sm, tid);
+      }
     }
   }
   // final phase: fused epilogue + store of 16 contiguous coefficients.
   // SPLIT: the two CTAs of a job both read the whole input, so for in-place
   // transforms the caller must barrier the CTA pair (cluster) before this phase.
-  static EVAB_HD void phE(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid) {
+  static EVAB_HD void phE(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid) {
     const PrimeDev P = L.primes[J.pi];
+    const u32 tid = vtid(J, ltid);
     const size_t base = (size_t)(SPLIT ? J.h * G::N : 0) + ((size_t)tid << NTT_EL);
     if (EPI == EPI_DIVROUND) {
       // (aux0 - x) * c [+ aux1] without canonicalising x first: x < b*p, so
@@ -227,13 +243,23 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct
 //         last: exchange read + pass 0 + scale by N^-1 + epilogue store (strided, coalesced).
 // SPLIT: each CTA runs the LOGN-stage inverse on one half (root prefix 2+h) and
 // stores lazily-reduced values; inv_last_stage_elem then finishes the transform.
-template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct InvBody {
+template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct InvBody {
   typedef NttGeom<LOGN> G;
+  typedef ClGeom<LOGN, CL> C;
+  static_assert(!(SPLIT && CL > 1), "split and cluster-distributed transforms are exclusive");
   static constexpr int NPH = G::NPH;
+  // barrier after phase PH: 0 = block, 1 = cluster, 2 = none.  CL > 1: the exchange into pass 0
+  // (written in phase NPH-2) crosses CTAs; every CTA signals "done reading my slice" right after the
+  // exchange read of phase NPH-3 (hk.arrive) and waits for all peers before writing (hk.wait), so the
+  // barrier latency hides behind the butterflies of that pass.
+  static EVAB_HD constexpr int sync_kind(int ph) { return CL == 1 ? 0 : (ph == NPH - 2 ? 1 : (ph == NPH - 3 ? 2 : 0)); }
+  static EVAB_HD u32 vtid(const NttJob &J, u32 tid) { return CL > 1 ? J.h * (u32)C::Tc + tid : tid; }
 
-  template <int PH> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm) {
+  template <int PH, class Hooks> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid, const SmemView<CL> &smv, Hooks hk) {
     const PrimeDev P = L.primes[J.pi];
     const u32 root = SPLIT ? 2 + J.h : 1;
+    const u32 tid = vtid(J, ltid);
+    u64 *sm = smv.local;
     if constexpr (PH == 0) {
       const size_t base = (size_t)(SPLIT ? J.h * G::N : 0) + ((size_t)tid << NTT_EL);
       if (PRO == PRO_GATHER) {
@@ -244,9 +270,9 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct
       }
       S.b = 1;
       inv_pass_c<LOGN>(S.x, P.itw, root, P.p, tid, S.b);
-      xchg_write_c<LOGN>(S.x, sm, tid);
+      if constexpr (CL > 1) xchg_write_cl<LOGN, CL>(S.x, sm, tid); else xchg_write_c<LOGN>(S.x, sm, tid);
     } else if constexpr (PH == NPH - 1) {
-      xchg_read_s<LOGN, 0, 1>(S.x, sm, tid);
+      if constexpr (CL > 1) xchg_read_dist_inv<LOGN, CL>(S.x, sm, ltid); else xchg_read_s<LOGN, 0, 1>(S.x, sm, tid);
       inv_pass_s<LOGN, 0>(S.x, P.itw, root, P.p, tid, S.b);
       if (SPLIT) {  // leave < 8p values for the last-stage kernel
 #pragma unroll
@@ -262,12 +288,23 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE> struct
       }
     } else if constexpr (PH % 2 == 1) {
       constexpr int j = G::P - 2 - (PH - 1) / 2;
-      if constexpr (j == G::P - 2) xchg_read_sc<LOGN, j>(S.x, sm, tid);
-      else xchg_read_s<LOGN, j, j + 1>(S.x, sm, tid);
+      if constexpr (CL > 1) {
+        if constexpr (j == G::P - 2) xchg_read_scl<LOGN, j, CL>(S.x, sm, tid);
+        else xchg_read_sl<LOGN, j, j + 1, CL>(S.x, sm, tid);
+        if constexpr (j == 1) hk.arrive();
+      } else {
+        if constexpr (j == G::P - 2) xchg_read_sc<LOGN, j>(S.x, sm, tid);
+        else xchg_read_s<LOGN, j, j + 1>(S.x, sm, tid);
+      }
       inv_pass_s<LOGN, j>(S.x, P.itw, root, P.p, tid, S.b);
     } else {
       constexpr int j = G::P - 2 - (PH - 2) / 2;   // pass that just ran
-      xchg_write_s<LOGN, j, j>(S.x, sm, tid);
+      if constexpr (CL > 1) {
+        if constexpr (j == 1) { hk.wait(); xchg_write_dist_inv<LOGN, CL>(S.x, smv, tid); }
+        else xchg_write_sl<LOGN, j, j, CL>(S.x, sm, tid);
+      } else {
+        xchg_write_s<LOGN, j, j>(S.x, sm, tid);
+      }
     }
   }
 };
@@ -287,13 +324,16 @@ EVAB_HD void inv_last_stage_elem(const NttLaunch &L, const NttJob &J, u32 i, u32
 }
 
 // compile-time loop over the barrier-separated phases
+// sync(kind): barrier after a phase (B::sync_kind); hk: split cluster barrier (arrive / wait) used to
+// order the stores into a peer's shared memory after that peer's last reads of it
+struct NoHooks { EVAB_HD void arrive() const {} EVAB_HD void wait() const {} };
 template <class B, int PH, int NPH> struct PhaseLoop {
-  template <class Sync> static EVAB_HD void run(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, u64 *sm, Sync sync) {
-    B::template phase<PH>(S, L, J, tid, sm);
-    if (PH + 1 < NPH) sync();
-    PhaseLoop<B, PH + 1, NPH>::run(S, L, J, tid, sm, sync);
+  template <class SM, class Sync, class Hooks> static EVAB_HD void run(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, const SM &sm, Sync sync, Hooks hk) {
+    B::template phase<PH>(S, L, J, tid, sm, hk);
+    if (PH + 1 < NPH) sync(B::sync_kind(PH));
+    PhaseLoop<B, PH + 1, NPH>::run(S, L, J, tid, sm, sync, hk);
   }
 };
 template <class B, int NPH> struct PhaseLoop<B, NPH, NPH> {
-  template <class Sync> static EVAB_HD void run(NttState &, const NttLaunch &, const NttJob &, u32, u64 *, Sync) {}
+  template <class SM, class Sync, class Hooks> static EVAB_HD void run(NttState &, const NttLaunch &, const NttJob &, u32, const SM &, Sync, Hooks) {}
 };

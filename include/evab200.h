@@ -87,6 +87,10 @@ uint64_t evab_launch_count(const evab_ctx *ctx);
 int evab_ntt_fwd(evab_ctx *ctx, uint64_t *d_data, size_t count, const int *prime_idx, int nprimes, void *stream);
 int evab_ntt_inv(evab_ctx *ctx, uint64_t *d_data, size_t count, const int *prime_idx, int nprimes, void *stream);
 
+/* Tuning knob (process-wide): spread every residue transform of 8192 <= N <= 16384 over a thread-block
+ * cluster of 1, 2 or 4 CTAs (distributed shared memory exchange).  Results are identical. */
+int evab_set_ntt_cluster(int ctas_per_residue);
+
 /* ---- CKKS encoder on the device: seal::CKKSEncoder::encode at seal_executor.h:242
  * (and seal.cpp:68,80).  Encodes `count` vectors in one batch: vector e has
  * vec_sizes[e] doubles at d_values[e] (device), is replicated over the N/2 slots

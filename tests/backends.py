@@ -33,7 +33,7 @@ def _elt(N, steps):
 class EmuBackend:
     name = "emu"
 
-    def __init__(self, N, primes):
+    def __init__(self, N, primes, cluster=1):
         so = os.path.join(ROOT, "tests", "emu", "libevab_emu.so")
         src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
         deps = [src] + [os.path.join(ROOT, "eva_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "eva_b200", "csrc"))]
@@ -49,10 +49,17 @@ class EmuBackend:
         if not self.h:
             raise RuntimeError(self.lib.emu_last_error().decode())
         self.N, self.k = N, len(primes)
+        self.cluster = cluster
 
     def _chk(self, rc):
         if rc:
             raise RuntimeError(self.lib.emu_last_error().decode())
+
+    def __getattribute__(self, name):
+        # the emulator's cluster setting is process-global: select this backend's value before every op
+        if name in ("ntt", "rescale", "relinearize", "rotate", "encode"):
+            object.__getattribute__(self, "lib").emu_set_cluster(object.__getattribute__(self, "cluster"))
+        return object.__getattribute__(self, name)
 
     def ntt(self, data, prime_idx, inverse=False):
         d = np.ascontiguousarray(data, dtype=np.uint64).copy()

@@ -19,43 +19,51 @@ struct EmuCtx {
   std::map<u64, std::vector<u32>> perms;
 };
 
-// run phase PH of body B for every thread of one CTA, then recurse to PH+1
-template <class B, int PH, int NPH> struct EmuPhases {
-  static void run(NttState *st, int T, const NttLaunch &L, const NttJob &J, u64 *sm) {
-    for (u32 t = 0; t < (u32)T; t++) B::template phase<PH>(st[t], L, J, t, sm);
-    EmuPhases<B, PH + 1, NPH>::run(st, T, L, J, sm);
+// run phase PH of body B for every thread of every CTA of one job (the CTAs of a cluster advance in
+// lockstep, phase by phase -- what the block / cluster barriers guarantee on the device), then PH+1
+template <class B, int CL, int PH, int NPH> struct EmuPhases {
+  static void run(NttState *st, int Tc, int nctas, const NttLaunch &L, const NttJob *J, const SmemView<CL> *sm) {
+    for (int h = 0; h < nctas; h++)
+      for (u32 t = 0; t < (u32)Tc; t++) B::template phase<PH>(st[(size_t)h * Tc + t], L, J[h], t, sm[h], NoHooks());
+    EmuPhases<B, CL, PH + 1, NPH>::run(st, Tc, nctas, L, J, sm);
   }
 };
-template <class B, int NPH> struct EmuPhases<B, NPH, NPH> {
-  static void run(NttState *, int, const NttLaunch &, const NttJob &, u64 *) {}
+template <class B, int CL, int NPH> struct EmuPhases<B, CL, NPH, NPH> {
+  static void run(NttState *, int, int, const NttLaunch &, const NttJob *, const SmemView<CL> *) {}
 };
 
-template <int LOGN, bool SPLIT, bool INV, int PRO, int EPI> static void run_ntt_m(const NttLaunch &L, size_t jobs) {
+// CL > 1: one residue over a cluster of CL CTAs (distributed shared memory exchange);
+// SPLIT: the two independent half transforms of a 2^15 residue (each with its own shared memory)
+template <int LOGN, bool SPLIT, bool INV, int PRO, int EPI, int CL> static void run_ntt_m(const NttLaunch &L, size_t jobs) {
   typedef NttGeom<LOGN> G;
-  constexpr int CPJ = SPLIT ? 2 : 1;
-  std::vector<u64> smc((size_t)CPJ * G::N);
-  std::vector<NttState> stc((size_t)CPJ * G::T);
+  constexpr int CPJ = SPLIT ? 2 : CL;         // CTAs per job
+  constexpr int Tc = G::T / CL;                // threads per CTA
+  constexpr size_t SMC = (size_t)G::N / CL;    // shared-memory words per CTA
+  std::vector<u64> smc((size_t)CPJ * SMC);
+  std::vector<NttState> stc((size_t)CPJ * Tc);
   for (size_t job = 0; job < jobs; job++) {
     NttJob J[CPJ];
-    for (int h = 0; h < CPJ; h++) J[h] = ntt_job(L, (u32)(job * CPJ + h), CPJ);
+    SmemView<CL> sm[CPJ];
+    for (int h = 0; h < CPJ; h++) {
+      J[h] = ntt_job(L, (u32)(job * CPJ + h), CPJ);
+      sm[h].local = smc.data() + (size_t)h * SMC;
+      for (int r = 0; r < CL; r++) sm[h].peer[r] = CL > 1 ? smc.data() + (size_t)r * SMC : sm[h].local;
+    }
     if (J[0].skip) continue;
     if (!INV && PRO == PRO_PLAIN && EPI == EPI_STORE && J[0].bcast) {
       for (int h = 0; h < CPJ; h++)
-        for (u32 t = 0; t < (u32)G::T; t++) fwd_const_poly<LOGN, SPLIT>(J[h], t);
+        for (u32 t = 0; t < (u32)Tc; t++) fwd_const_poly<LOGN, SPLIT>(J[h], (CL > 1 ? (u32)h * Tc : 0u) + t);
       continue;
     }
     if (!INV) {
-      // forward: the CTAs of one job (a cluster when SPLIT) run all compute phases,
-      // then the cluster barrier, then the store phase
-      typedef FwdBody<LOGN, SPLIT, PRO, EPI> B;
+      // forward: all compute phases, then (SPLIT: cluster barrier, then) the store phase
+      typedef FwdBody<LOGN, SPLIT, PRO, EPI, CL> B;
+      EmuPhases<B, CL, 0, B::NPH>::run(stc.data(), Tc, CPJ, L, J, sm);
       for (int h = 0; h < CPJ; h++)
-        EmuPhases<B, 0, B::NPH>::run(stc.data() + (size_t)h * G::T, G::T, L, J[h], smc.data() + (size_t)h * G::N);
-      for (int h = 0; h < CPJ; h++)
-        for (u32 t = 0; t < (u32)G::T; t++) B::phE(stc[(size_t)h * G::T + t], L, J[h], t);
+        for (u32 t = 0; t < (u32)Tc; t++) B::phE(stc[(size_t)h * Tc + t], L, J[h], t);
     } else {
-      typedef InvBody<LOGN, SPLIT, PRO, EPI> B;
-      for (int h = 0; h < CPJ; h++)
-        EmuPhases<B, 0, B::NPH>::run(stc.data() + (size_t)h * G::T, G::T, L, J[h], smc.data() + (size_t)h * G::N);
+      typedef InvBody<LOGN, SPLIT, PRO, EPI, CL> B;
+      EmuPhases<B, CL, 0, B::NPH>::run(stc.data(), Tc, CPJ, L, J, sm);
     }
   }
   if (INV && SPLIT)
@@ -65,17 +73,26 @@ template <int LOGN, bool SPLIT, bool INV, int PRO, int EPI> static void run_ntt_
     }
 }
 
-template <int LOGN, bool SPLIT, bool INV> static void run_ntt(const NttLaunch &L, size_t jobs) {
+static int g_cl = 1;   // emu_set_cluster: CTAs per residue for N >= 4096 (1, 2, 4)
+
+template <int LOGN, bool SPLIT, bool INV, int CL> static void run_ntt_c(const NttLaunch &L, size_t jobs) {
   if (!INV) {
-    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_PLAIN, EPI_STORE>(L, jobs);
-    if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE>(L, jobs);
-    if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE_LAZY>(L, jobs);
-    if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_DIVROUND>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_PLAIN, EPI_STORE, CL>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE, CL>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE_LAZY, CL>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_DIVROUND, CL>(L, jobs);
   } else {
-    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_STORE>(L, jobs);
-    if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_ADDHALF>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_STORE, CL>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_ADDHALF, CL>(L, jobs);
   }
   abort();
+}
+template <int LOGN, bool SPLIT, bool INV> static void run_ntt(const NttLaunch &L, size_t jobs) {
+  if constexpr (LOGN >= 12 && !SPLIT) {
+    if (g_cl == 2) return run_ntt_c<LOGN, SPLIT, INV, 2>(L, jobs);
+    if (g_cl == 4) return run_ntt_c<LOGN, SPLIT, INV, 4>(L, jobs);
+  }
+  return run_ntt_c<LOGN, SPLIT, INV, 1>(L, jobs);
 }
 
 struct EmuBE {
@@ -175,6 +192,7 @@ int emu_negate(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa) { Emu
 int emu_mul_plain(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt) { EmuBE be{c}; return dyadic_impl<DY_MULPT>(be, c->v, ell, o, a, sa, pt, 1, 1); }
 int emu_mul(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *b) { EmuBE be{c}; return mulct_impl(be, c->v, false, ell, o, a, b); }
 int emu_square(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a) { EmuBE be{c}; return mulct_impl(be, c->v, true, ell, o, a, (const u64 *)nullptr); }
+int emu_set_cluster(int cl) { if (cl != 1 && cl != 2 && cl != 4) return 1; g_cl = cl; return 0; }
 size_t emu_encode_work_bytes(EmuCtx *c, int count) { return encode_work_bytes(c->v, count); }
 int emu_encode(EmuCtx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell, uint64_t *out, void *work) {
   EmuBE be{c};

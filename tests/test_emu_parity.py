@@ -57,3 +57,18 @@ def test_emu_encode(N, bits):
         for e, v in enumerate(vecs):
             want = orc.encode(v, 2.0 ** scale_bits, ell)
             assert np.array_equal(got[e], want), (scale_bits, ell, e)
+
+
+@pytest.mark.parametrize("N,bits,cl", [(4096, [60, 20, 60, 60], 2), (4096, [60, 20, 60, 60], 4), (8192, [60, 60, 60], 4),
+                                        (16384, [60, 60, 60, 60, 60], 2), (16384, [60, 60, 60, 60, 60], 4)])
+def test_emu_cluster_distributed(N, bits, cl):
+    """one residue spread over a cluster of 2 / 4 CTAs (distributed shared-memory exchange)"""
+    import numpy as np
+    orc = pc.get_oracle(N, bits)
+    be = EmuBackend(N, orc.primes, cluster=cl)
+    pc.case_ntt(be, orc)
+    ell = len(bits) - 1
+    pc.case_rescale(be, orc, ell)
+    pc.case_keyswitch(be, orc, ell, steps=(3,))
+    v = np.array([0.5, -1.25, 3.0, 2.0])
+    assert np.array_equal(be.encode(v, 2.0 ** 30, ell), orc.encode(v, 2.0 ** 30, ell))

@@ -101,3 +101,25 @@ def test_gpu_encoder_bit_exact(N, bits):
     x = rng.uniform(-2, 2, N // 2)
     dec = np.array(pub.decode(pub.encode(list(x), 2.0 ** 40, k - 1), 2.0 ** 40))
     assert np.abs(dec - x).max() < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,bits,cl", [(8192, [60, 60, 60], 1), (8192, [60, 60, 60], 2), (16384, [60] * 5, 1), (16384, [60] * 5, 2)])
+def test_gpu_cluster_distributed_ntt(N, bits, cl):
+    """evab_set_ntt_cluster: one residue over a cluster of 2 / 4 CTAs (distributed shared memory) --
+    identical results for the transforms and every fused variant (key switch, rescale, encoder)."""
+    import numpy as np
+    from eva_b200 import cabi
+    lib = cabi.load()
+    orc = pc.get_oracle(N, bits)
+    be = _be(N, orc.primes)
+    assert lib.evab_set_ntt_cluster(cl) == 0
+    try:
+        pc.case_ntt(be, orc)
+        for ell in range(len(bits) - 1, 0, -1):
+            pc.case_keyswitch(be, orc, ell, steps=(1, -3))
+            if ell >= 2:
+                pc.case_rescale(be, orc, ell)
+    finally:
+        assert lib.evab_set_ntt_cluster(4) == 0   # library default
+    assert lib.evab_set_ntt_cluster(3) != 0
