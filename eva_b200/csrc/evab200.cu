@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, co
 // ---------------------------------------------------------------------------
 // CUDA backend
 // ---------------------------------------------------------------------------
-static int g_ntt_cluster = 4;   // CTAs per residue for 2^13 <= N <= 2^14 (evab_set_ntt_cluster); 4: +15% Sobel throughput, -48% latency vs 1
+static int g_ntt_cluster = 8;   // CTAs per residue for 2^13 <= N <= 2^14 (evab_set_ntt_cluster).  Sobel ops/s and single-instance latency: 1: 414k 1.11 ms, 2: 444k 0.76, 4: 477k 0.57, 8: 494k 0.49
 
 template <class K> static int launch_ntt(K kernel, const NttLaunch &L, size_t ctas, int threads, size_t smem, int cluster, cudaStream_t st, std::atomic<bool> *done) {
   int dev = 0;
@@ -196,6 +196,7 @@ template <int LOGN, bool SPLIT> static int launch_fwd_t(const NttLaunch &L, size
   if constexpr (LOGN >= 13 && !SPLIT) {
     if (g_ntt_cluster == 2) return launch_fwd_c<LOGN, SPLIT, 2>(L, jobs, st);
     if (g_ntt_cluster == 4) return launch_fwd_c<LOGN, SPLIT, 4>(L, jobs, st);
+    if (g_ntt_cluster == 8) return launch_fwd_c<LOGN, SPLIT, 8>(L, jobs, st);
   }
   return launch_fwd_c<LOGN, SPLIT, 1>(L, jobs, st);
 }
@@ -221,6 +222,7 @@ template <int LOGN, bool SPLIT> static int launch_inv_t(const NttLaunch &L, size
   if constexpr (LOGN >= 13 && !SPLIT) {
     if (g_ntt_cluster == 2) return launch_inv_c<LOGN, SPLIT, 2>(L, jobs, st);
     if (g_ntt_cluster == 4) return launch_inv_c<LOGN, SPLIT, 4>(L, jobs, st);
+    if (g_ntt_cluster == 8) return launch_inv_c<LOGN, SPLIT, 8>(L, jobs, st);
   }
   return launch_inv_c<LOGN, SPLIT, 1>(L, jobs, st);
 }
@@ -473,7 +475,7 @@ extern "C" int evab_ntt_inv(evab_ctx *c, uint64_t *d, size_t count, const int *p
   BE_BEGIN return ntt_batch_impl(be, c->v, true, d, count, pidx, np);
 }
 extern "C" int evab_set_ntt_cluster(int cl) {
-  if (cl != 1 && cl != 2 && cl != 4) return fail("evab_set_ntt_cluster: 1, 2 or 4 CTAs per residue");
+  if (cl != 1 && cl != 2 && cl != 4 && cl != 8) return fail("evab_set_ntt_cluster: 1, 2, 4 or 8 CTAs per residue");
   g_ntt_cluster = cl;
   return 0;
 }

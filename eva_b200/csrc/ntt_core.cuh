@@ -149,9 +149,9 @@ template <int CL> struct SmemView {
   u64 *peer[CL];     // generic pointers to every rank's slice (peer[rank] == local)
 };
 template <int LOGN, int CL> struct ClGeom {
-  static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size 1, 2 or 4");
+  static_assert(CL == 1 || CL == 2 || CL == 4 || CL == 8, "cluster size 1, 2, 4 or 8");
   static_assert(CL == 1 || LOGN >= 12, "cluster-distributed transform needs N >= 4096");
-  static constexpr int LGC = CL == 1 ? 0 : (CL == 2 ? 1 : 2);
+  static constexpr int LGC = CL == 1 ? 0 : (CL == 2 ? 1 : (CL == 4 ? 2 : 3));
   static constexpr int Tc = NttGeom<LOGN>::T / CL;
   static constexpr int LGT = LOGN - NTT_EL - LGC;   // log2(Tc)
   static constexpr u32 NC = (u32)NttGeom<LOGN>::N / CL;

@@ -91,6 +91,7 @@ template <int LOGN, bool SPLIT, bool INV> static void run_ntt(const NttLaunch &L
   if constexpr (LOGN >= 12 && !SPLIT) {
     if (g_cl == 2) return run_ntt_c<LOGN, SPLIT, INV, 2>(L, jobs);
     if (g_cl == 4) return run_ntt_c<LOGN, SPLIT, INV, 4>(L, jobs);
+    if (g_cl == 8) return run_ntt_c<LOGN, SPLIT, INV, 8>(L, jobs);
   }
   return run_ntt_c<LOGN, SPLIT, INV, 1>(L, jobs);
 }
@@ -192,7 +193,7 @@ int emu_negate(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa) { Emu
 int emu_mul_plain(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt) { EmuBE be{c}; return dyadic_impl<DY_MULPT>(be, c->v, ell, o, a, sa, pt, 1, 1); }
 int emu_mul(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *b) { EmuBE be{c}; return mulct_impl(be, c->v, false, ell, o, a, b); }
 int emu_square(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a) { EmuBE be{c}; return mulct_impl(be, c->v, true, ell, o, a, (const u64 *)nullptr); }
-int emu_set_cluster(int cl) { if (cl != 1 && cl != 2 && cl != 4) return 1; g_cl = cl; return 0; }
+int emu_set_cluster(int cl) { if (cl != 1 && cl != 2 && cl != 4 && cl != 8) return 1; g_cl = cl; return 0; }
 size_t emu_encode_work_bytes(EmuCtx *c, int count) { return encode_work_bytes(c->v, count); }
 int emu_encode(EmuCtx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell, uint64_t *out, void *work) {
   EmuBE be{c};
