@@ -39,6 +39,8 @@ _SIGS = {
     "evab_ntt_fwd": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
     "evab_ntt_inv": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
     "evab_set_ntt_cluster": (ci, [ci]),
+    "evab_host_alloc": (ci, [szt, C.POINTER(vp)]),
+    "evab_host_free": (ci, [vp]),
     "evab_encode_work_bytes": (szt, [vp, ci]),
     "evab_encode": (ci, [vp, ci, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_double), ci, vp, vp, vp]),
     "evab_add": (ci, [vp, ci, vp, vp, ci, vp, ci, vp]),

@@ -399,6 +399,14 @@ extern "C" int evab_download(evab_ctx *c, void *h, const void *d, size_t bytes, 
   CUDA_OK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, S(stream)));
   return 0;
 }
+extern "C" int evab_host_alloc(size_t bytes, void **p) {
+  CUDA_OK(cudaHostAlloc(p, bytes ? bytes : 8, cudaHostAllocPortable));
+  return 0;
+}
+extern "C" int evab_host_free(void *p) {
+  CUDA_OK(cudaFreeHost(p));
+  return 0;
+}
 extern "C" int evab_sync(evab_ctx *c, void *stream) {
   CUDA_OK(cudaSetDevice(c->device));
   CUDA_OK(cudaStreamSynchronize(S(stream)));

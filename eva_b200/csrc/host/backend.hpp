@@ -30,8 +30,9 @@ using Valuation = std::map<std::string, std::vector<double>>;
 
 // host-resident encrypted values (the reference keeps seal::Ciphertext objects
 // in host memory inside SEALValuation, eva/seal/seal.h:21-41)
-struct HostCipher { std::vector<u64> data; int size = 0, ell = 0; double scale = 0; };
-struct HostPlain { std::vector<u64> data; int ell = 0; double scale = 0; };
+// host images of ciphertexts / plaintexts live in page-locked memory (asynchronous, full-rate H2D / D2H)
+struct HostCipher { HostBuf data; int size = 0, ell = 0; double scale = 0; };
+struct HostPlain { HostBuf data; int ell = 0; double scale = 0; };
 using SchemeValue = std::variant<HostCipher, HostPlain, std::shared_ptr<ConstantValue>>;
 
 class B200Valuation {

@@ -16,6 +16,7 @@ using namespace evab;
 typedef py::array_t<std::uint64_t, py::array::c_style | py::array::forcecast> u64arr;
 
 static std::vector<u64> toVec(const u64arr &a) { return std::vector<u64>(a.data(), a.data() + a.size()); }
+static HostBuf toHostBuf(const u64arr &a) { HostBuf b(a.size()); std::memcpy(b.data(), a.data(), a.size() * 8); return b; }
 
 PYBIND11_MODULE(_eva_b200, m) {
   m.doc() = "B200-native EVA backend";
@@ -106,11 +107,11 @@ PYBIND11_MODULE(_eva_b200, m) {
       .def("names", [](const B200Valuation &v) { std::vector<std::string> n; for (auto &e : v) n.push_back(e.first); return n; })
       .def("set_cipher", [](B200Valuation &v, const std::string &name, const u64arr &data, double scale) {
         if (data.ndim() != 3) throw std::runtime_error("ciphertext array must be [size][ell][N]");
-        HostCipher h; h.data = toVec(data); h.size = (int)data.shape(0); h.ell = (int)data.shape(1); h.scale = scale;
+        HostCipher h; h.data = toHostBuf(data); h.size = (int)data.shape(0); h.ell = (int)data.shape(1); h.scale = scale;
         v[name] = std::move(h);
       }, "test/benchmark hook: inject a raw ciphertext [size][ell][N]")
       .def("set_plain", [](B200Valuation &v, const std::string &name, const u64arr &data, double scale) {
-        HostPlain h; h.data = toVec(data); h.ell = (int)data.shape(0); h.scale = scale; v[name] = std::move(h);
+        HostPlain h; h.data = toHostBuf(data); h.ell = (int)data.shape(0); h.scale = scale; v[name] = std::move(h);
       })
       .def("set_raw", [](B200Valuation &v, const std::string &name, const std::vector<double> &x) { v[name] = std::make_shared<ConstantValue>(x.size(), x); })
       .def("get", [](const B200Valuation &v, const std::string &name) -> py::object {

@@ -90,6 +90,45 @@ private:
 };
 
 // owning device buffer of u64 words
+// Page-locked host memory for the buffers that cross the boundary (HostCipher / HostPlain):
+// size-class free lists so that steady-state execute() calls never hit cudaHostAlloc.
+class PinnedPool {
+public:
+  static PinnedPool &get() { static PinnedPool p; return p; }
+  void *alloc(std::size_t bytes) {
+    const std::size_t cls = sizeClass(bytes);
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto &fl = free_[cls];
+      if (!fl.empty()) { void *p = fl.back(); fl.pop_back(); return p; }
+    }
+    void *p = nullptr;
+    check(evab_host_alloc((std::size_t)1 << cls, &p));
+    return p;
+  }
+  void release(void *p, std::size_t bytes) {
+    std::lock_guard<std::mutex> g(mu_);
+    free_[sizeClass(bytes)].push_back(p);
+  }
+private:
+  static std::size_t sizeClass(std::size_t bytes) { std::size_t c = 12; while (((std::size_t)1 << c) < bytes) c++; return c; }
+  std::mutex mu_;
+  std::map<std::size_t, std::vector<void *>> free_;   // blocks stay pinned for the life of the process
+};
+template <class T> struct PinnedAlloc {
+  typedef T value_type;
+  PinnedAlloc() {}
+  template <class U> PinnedAlloc(const PinnedAlloc<U> &) {}
+  T *allocate(std::size_t n) { return static_cast<T *>(PinnedPool::get().alloc(n * sizeof(T))); }
+  void deallocate(T *p, std::size_t n) { PinnedPool::get().release(p, n * sizeof(T)); }
+  // resize() of a buffer that is about to be overwritten by a download: no zero fill
+  template <class U> void construct(U *) {}
+  template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+  template <class U> bool operator==(const PinnedAlloc<U> &) const { return true; }
+  template <class U> bool operator!=(const PinnedAlloc<U> &) const { return false; }
+};
+typedef std::vector<u64, PinnedAlloc<u64>> HostBuf;
+
 class DBuf {
 public:
   DBuf() {}

@@ -51,6 +51,11 @@ int evab_free(evab_ctx *ctx, void *d_ptr, void *stream);
 int evab_upload(evab_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
 int evab_download(evab_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
 int evab_sync(evab_ctx *ctx, void *stream); /* blocks the calling thread */
+/* page-locked host memory for ciphertext / plaintext buffers that cross the boundary: uploads and
+ * downloads from it are truly asynchronous and run at full PCIe rate (replaces the seal::Ciphertext
+ * heap buffers copied at reference seal.cpp:104-122) */
+int evab_host_alloc(size_t bytes, void **h_ptr);
+int evab_host_free(void *h_ptr);
 
 /* ---- scheduler glue: streams, events and CUDA-graph capture.  These replace
  * the Galois worklist + atomics of MulticoreProgramTraversal::forwardPass
