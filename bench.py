@@ -124,22 +124,19 @@ def run_ours(args):
     # B independent program instances (different input ciphertexts, same keys), organised as
     # G concurrent plan replays (one CUDA graph each, on its own stream) x F instances fused
     # into every kernel launch of a plan (execute_batch / evab_set_batch):  B = G * F
-    from concurrent.futures import ThreadPoolExecutor
     F = max(1, min(args.fuse, B))
     G = B // F
     assert G * F == B, "--instances must be a multiple of --fuse"
-    groups = []
-    for g in range(G):
-        prog, params, sig, terms = program_io.build_program(d)
-        vals = []
-        for i in range(F):
-            _, _, cts_i = synthetic_inputs({**d, "terms": []}, primes, seed=multi_seed(rank, g * F + i))
-            val = b200.B200Valuation()
-            for name, (ct, scale) in cts_i.items():
-                val.set_cipher(name, ct, scale)
-            vals.append(val)
-        groups.append((prog, vals))
-    nops = pub.cipher_op_count(groups[0][0])
+    prog, params, sig, terms = program_io.build_program(d)
+    all_vals = []
+    for i in range(B):
+        _, _, cts_i = synthetic_inputs({**d, "terms": []}, primes, seed=multi_seed(rank, i))
+        val = b200.B200Valuation()
+        for name, (ct, scale) in cts_i.items():
+            val.set_cipher(name, ct, scale)   # host image in page-locked memory
+        all_vals.append(val)
+    groups = [all_vals[g * F:(g + 1) * F] for g in range(G)]   # plan replica g executes instances gF .. gF+F-1
+    nops = pub.cipher_op_count(prog)
     main = torch.cuda.current_stream()
     streams = [torch.cuda.Stream() for _ in range(G)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -154,31 +151,32 @@ def run_ours(args):
         fork.record(main)
         for g in range(G):
             streams[g].wait_event(fork)
-            pub.run_resident(groups[g][0], streams[g].cuda_stream, F)
+            pub.run_resident(prog, streams[g].cuda_stream, F, g)
             ev_ = torch.cuda.Event()
             ev_.record(streams[g])
             main.wait_event(ev_)
 
     # ---- launches per step: one un-graphed replay of one group's plan, times G
-    pub.set_options(num_streams=args.streams, use_graph=False, cache_constants=not args.no_const_cache, dedup_constants=not args.no_dedup)
-    pub.drop_plan(groups[0][0], F)   # (cipher_op_count above may have built a graph-mode plan)
-    pub.stage_inputs(groups[0][0], groups[0][1], main.cuda_stream)
-    pub.run_resident(groups[0][0], main.cuda_stream, F)
+    opts = dict(num_streams=args.streams, cache_constants=not args.no_const_cache, dedup_constants=not args.no_dedup, fuse=F)
+    pub.set_options(use_graph=False, **opts)
+    pub.drop_plan(prog, 1)   # (cipher_op_count above built a batch-1 plan)
+    pub.drop_plan(prog, F)
+    pub.stage_inputs(prog, groups[0], main.cuda_stream)
+    pub.run_resident(prog, main.cuda_stream, F)
     torch.cuda.synchronize()
     l0 = pub.launch_count()
-    pub.run_resident(groups[0][0], main.cuda_stream, F)
+    pub.run_resident(prog, main.cuda_stream, F)
     torch.cuda.synchronize()
     launches_per_step = (pub.launch_count() - l0) * G
-    pub.set_options(num_streams=args.streams, use_graph=not args.no_graph, cache_constants=not args.no_const_cache, dedup_constants=not args.no_dedup)
-    pub.drop_plan(groups[0][0], F)
-    for prog, vals in groups:
-        pub.stage_inputs(prog, vals, main.cuda_stream)
+    pub.set_options(use_graph=not args.no_graph, **opts)
+    pub.drop_plan(prog, F)
+    for g in range(G):
+        pub.stage_inputs(prog, groups[g], main.cuda_stream, g)
     torch.cuda.synchronize()
     for _ in range(max(3, args.warmup)):
         step_resident()
     torch.cuda.synchronize()
-    pool = ThreadPoolExecutor(max_workers=G)
-    outs = list(pool.map(lambda g: pub.execute_batch(groups[g][0], groups[g][1]), range(G)))   # warm the e2e path
+    outs = pub.execute_batch(prog, all_vals)   # warm the e2e path (same plan replicas)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -193,8 +191,8 @@ def run_ours(args):
     barrier()
     t_res = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
     # ---- single-instance latency (batch-1 plan, one graph launch, nothing else on the GPU)
-    prog0, vals0 = groups[0]
-    pub.stage_inputs(prog0, vals0[:1], main.cuda_stream)
+    prog0 = prog
+    pub.stage_inputs(prog0, all_vals[:1], main.cuda_stream)
     for _ in range(3):
         pub.run_resident(prog0, main.cuda_stream, 1)
     torch.cuda.synchronize()
@@ -210,14 +208,13 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        outs = list(pool.map(lambda g: pub.execute_batch(groups[g][0], groups[g][1]), range(G)))
+        outs = pub.execute_batch(prog, all_vals)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
-    vals = groups[0][1]
     clocks = sampler.finish()
     h2d = sum(ct.nbytes for ct, _ in cts.values()) * B
-    okind, oarr, _ = outs[0][0].get(list(d["outputs"].keys())[0])
+    okind, oarr, _ = outs[0].get(list(d["outputs"].keys())[0])
     d2h = int(oarr.nbytes) * B
     # ---- final gather of the outputs on rank 0 (north_star: NCCL only for the final gather)
     from eva_b200 import multi
@@ -237,7 +234,7 @@ def run_ours(args):
                    "const_encode": "cached per plan" if not args.no_const_cache else ("23 Encode terms evaluated on the GPU inside every execute (FP64 FFT + NTT), as in the reference"
                                     + ("; identical constants share one plaintext (same bits), constant polynomials skip the NTT butterflies" if not args.no_dedup else ""))},
         "e2e": {"value": total_ops / t_e2e, "unit": "ops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,
-                "note": "%d concurrent B200Public.execute_batch() calls of %d host-resident valuations each per step (host wall clock incl. H2D/D2H)" % (G, F)},
+                "note": "one B200Public.execute_batch(program, %d host-resident valuations) call per step: %d concurrent plan replicas x %d fused instances, page-locked host buffers, H2D + graph + D2H per replica stream (host wall clock)" % (B, G, F)},
         "single_instance": {"latency_ms": lat[len(lat) // 2], "ops_per_s": nops / (lat[len(lat) // 2] * 1e-3)},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,

@@ -3,6 +3,9 @@
 // execute}, B200Secret::decrypt, B200Valuation.  Same argument meaning, ownership
 // and error behaviour (C++ exceptions -> Python exceptions through pybind11).
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "executor.hpp"
 #include <atomic>
 #include <tuple>
@@ -101,8 +104,12 @@ public:
     return out;
   }
 
-  Executor &executorFor(Program &program, int batch = 1) {
-    const std::uint64_t key = id_ * 65536ull + (std::uint64_t)batch;
+  // one plan (arena, streams, captured graph) per (context, batch, replica); replicas of the same
+  // batch size run concurrently in executeMany
+  std::uint64_t planKey(int batch, int replica) const { return (id_ << 32) | ((std::uint64_t)replica << 16) | (std::uint64_t)batch; }
+  Executor &executorFor(Program &program, int batch = 1, int replica = 0) {
+    if (batch < 1 || batch > 65535 || replica < 0 || replica > 65535) throw std::invalid_argument("batch / replica out of range");
+    const std::uint64_t key = planKey(batch, replica);
     auto h = std::static_pointer_cast<PlanHolder>(program.attachment(key));
     if (!h || h->termCount != program.termCount()) {
       h = std::make_shared<PlanHolder>();
@@ -115,7 +122,7 @@ public:
     }
     return *h->exec;
   }
-  void dropExecutor(Program &program, int batch = 1) { program.attach(id_ * 65536ull + (std::uint64_t)batch, nullptr); }
+  void dropExecutor(Program &program, int batch = 1, int replica = 0) { program.attach(planKey(batch, replica), nullptr); }
 
   // upload host inputs into the executor's arena (H2D on `stream`)
   void stageInputs(Executor &ex, Program &program, const B200Valuation &inputs, void *stream, int b = 0) {
@@ -151,31 +158,58 @@ public:
     for (auto &v : inputs) in.push_back(&v);
     return executeMany(program, in);
   }
+  // B valuations are split into chunks of options.fuse instances; every chunk has its own plan
+  // replica (arena + captured graph) and all replicas are in flight at once: H2D, graph and D2H of
+  // different chunks overlap, and 148 SMs are filled by concurrency rather than by launch width.
   std::vector<B200Valuation> executeMany(Program &program, const std::vector<const B200Valuation *> &inputs) {
     const int B = (int)inputs.size();
     if (B < 1) throw std::invalid_argument("execute needs at least one valuation");
-    Executor &ex = executorFor(program, B);
-    void *st = ex.mainStream();
-    for (int b = 0; b < B; b++) stageInputs(ex, program, *inputs[b], st, b);
-    ex.run(st);
+    const int F = std::max(1, std::min(options.fuse, B));
     std::vector<B200Valuation> outs(B);
+    std::vector<void *> streams;
     const u64 N = s_->dev->N();
-    for (int b = 0; b < B; b++)
-      for (auto &o : program.getOutputs()) {
-        const ValueInfo &vi = ex.info(o.second);
-        if (vi.kind == Kind::Cipher) {
-          HostCipher h; h.size = vi.size; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.size * vi.ell * N);
-          s_->dev->download(h.data.data(), ex.valuePtr(o.second, b), h.data.size() * 8, st);
-          outs[b][o.first] = std::move(h);
-        } else if (vi.kind == Kind::Plain) {
-          HostPlain h; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.ell * N);
-          s_->dev->download(h.data.data(), ex.valuePtr(o.second, b), h.data.size() * 8, st);
-          outs[b][o.first] = std::move(h);
-        } else {
-          outs[b][o.first] = std::make_shared<ConstantValue>(program.getVecSize(), ex.rawValue(o.second->index, b));
+    static const bool trace = std::getenv("EVAB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    double tPlan = 0, tStage = 0, tRun = 0, tDown = 0;
+    auto t00 = now();
+    for (int b0 = 0, g = 0; b0 < B; b0 += F, g++) {
+      const int nb = std::min(F, B - b0);
+      auto t0 = now();
+      Executor &ex = executorFor(program, nb, g);
+      void *st = ex.mainStream();
+      streams.push_back(st);
+      auto t1 = now();
+      for (int b = 0; b < nb; b++) stageInputs(ex, program, *inputs[b0 + b], st, b);
+      auto t2 = now();
+      ex.run(st);
+      auto t3 = now();
+      tPlan += std::chrono::duration<double>(t1 - t0).count(); tStage += std::chrono::duration<double>(t2 - t1).count();
+      tRun += std::chrono::duration<double>(t3 - t2).count();
+      for (int b = 0; b < nb; b++)
+        for (auto &o : program.getOutputs()) {
+          const ValueInfo &vi = ex.info(o.second);
+          B200Valuation &out = outs[b0 + b];
+          if (vi.kind == Kind::Cipher) {
+            HostCipher h; h.size = vi.size; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.size * vi.ell * N);
+            s_->dev->download(h.data.data(), ex.valuePtr(o.second, b), h.data.size() * 8, st);
+            out[o.first] = std::move(h);
+          } else if (vi.kind == Kind::Plain) {
+            HostPlain h; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.ell * N);
+            s_->dev->download(h.data.data(), ex.valuePtr(o.second, b), h.data.size() * 8, st);
+            out[o.first] = std::move(h);
+          } else {
+            out[o.first] = std::make_shared<ConstantValue>(program.getVecSize(), ex.rawValue(o.second->index, b));
+          }
         }
-      }
-    s_->dev->sync(st);
+    }
+    auto t4 = now();
+    for (void *st : streams) s_->dev->sync(st);
+    if (trace) {
+      auto t5 = now();
+      std::fprintf(stderr, "[evab] executeMany B=%d F=%d: plan %.3f stage %.3f run %.3f enqueue-total %.3f sync %.3f ms\n", B, F, tPlan * 1e3, tStage * 1e3, tRun * 1e3,
+                   std::chrono::duration<double>(t4 - t00).count() * 1e3, std::chrono::duration<double>(t5 - t4).count() * 1e3);
+    }
+    (void)tDown;
     return outs;
   }
   std::shared_ptr<Shared> shared() const { return s_; }

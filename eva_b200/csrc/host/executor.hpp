@@ -51,6 +51,7 @@ struct ExecOptions {
   bool useGraph = true;
   bool cacheConstants = true;  // encode plan-time-constant plaintexts once per plan instead of on every run
   int batch = 1;               // independent program instances executed by every (fat) kernel launch
+  int fuse = 1;                // executeBatch: instances per plan replica (replicas run concurrently)
   bool dedupConstants = true;  // Encode terms of identical constants at the same (level, scale) share one plaintext
 };
 

@@ -134,23 +134,27 @@ PYBIND11_MODULE(_eva_b200, m) {
   py::class_<B200Public>(mb, "B200Public", "The public part of the context: encryption and execution on the GPU")
       .def("encrypt", &B200Public::encrypt, py::arg("inputs"), py::arg("signature"))
       .def("execute", &B200Public::execute, py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>())
-      .def("execute_batch", &B200Public::executeBatch, py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>(),
+      // the list is converted to pointers to the caller's valuations: no copy of the host ciphertexts
+      .def("execute_batch", [](B200Public &p, Program &prog, const std::vector<const B200Valuation *> &in) { return p.executeMany(prog, in); },
+           py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>(),
            "Execute one compiled program on a list of valuations with batched kernels; returns a list of valuations")
-      .def("set_options", [](B200Public &p, int streams, bool graph, bool cache, bool dedup) {
+      .def("set_options", [](B200Public &p, int streams, bool graph, bool cache, bool dedup, int fuse) {
              p.options.numStreams = streams; p.options.useGraph = graph; p.options.cacheConstants = cache; p.options.dedupConstants = dedup;
+             p.options.fuse = fuse;
            },
-           py::arg("num_streams") = 8, py::arg("use_graph") = true, py::arg("cache_constants") = true, py::arg("dedup_constants") = true)
-      .def("drop_plan", &B200Public::dropExecutor, py::arg("program"), py::arg("batch") = 1)
+           py::arg("num_streams") = 8, py::arg("use_graph") = true, py::arg("cache_constants") = true, py::arg("dedup_constants") = true,
+           py::arg("fuse") = 1)
+      .def("drop_plan", &B200Public::dropExecutor, py::arg("program"), py::arg("batch") = 1, py::arg("replica") = 0)
       .def("cipher_op_count", [](B200Public &p, Program &prog) { return p.executorFor(prog).cipherOpCount(); })
       .def("launch_count", [](B200Public &p) { return evab_launch_count(p.shared()->dev->ctx()); })
       .def("primes", [](B200Public &p) { return p.shared()->dev->primes(); })
       // ---- benchmark hooks: device-resident execution on a caller-provided stream
-      .def("stage_inputs", [](B200Public &p, Program &prog, const std::vector<B200Valuation> &in, std::uintptr_t stream) {
-        Executor &ex = p.executorFor(prog, (int)in.size());
-        for (std::size_t b = 0; b < in.size(); b++) p.stageInputs(ex, prog, in[b], (void *)stream, (int)b);
-      })
-      .def("run_resident", [](B200Public &p, Program &prog, std::uintptr_t stream, int batch) { p.executorFor(prog, batch).run((void *)stream); },
-           py::arg("program"), py::arg("stream"), py::arg("batch") = 1, py::call_guard<py::gil_scoped_release>())
+      .def("stage_inputs", [](B200Public &p, Program &prog, const std::vector<const B200Valuation *> &in, std::uintptr_t stream, int replica) {
+        Executor &ex = p.executorFor(prog, (int)in.size(), replica);
+        for (std::size_t b = 0; b < in.size(); b++) p.stageInputs(ex, prog, *in[b], (void *)stream, (int)b);
+      }, py::arg("program"), py::arg("inputs"), py::arg("stream"), py::arg("replica") = 0)
+      .def("run_resident", [](B200Public &p, Program &prog, std::uintptr_t stream, int batch, int replica) { p.executorFor(prog, batch, replica).run((void *)stream); },
+           py::arg("program"), py::arg("stream"), py::arg("batch") = 1, py::arg("replica") = 0, py::call_guard<py::gil_scoped_release>())
       .def("sync", [](B200Public &p, std::uintptr_t stream) { p.shared()->dev->sync((void *)stream); }, py::call_guard<py::gil_scoped_release>())
       // ---- test hooks
       .def("debug_value", [](B200Public &p, Program &prog, std::uint64_t index, int batch, int b) -> py::object {

@@ -122,7 +122,7 @@ def test_batched_execute_matches_single():
         op = OracleProgram(d, orc)
         op.prepare_keys()
         pub = b200.context_from_raw_keys(N, orc.primes, op.rk, {int(e): k for e, k in op.gks.items()})
-        pub.set_options(num_streams=4, use_graph=True, cache_constants=False)
+        pub.set_options(num_streams=4, use_graph=True, cache_constants=False, fuse=3)   # one plan, 3 instances per launch
         rng = np.random.default_rng(5)
         vals, inputs_o = [], []
         for b in range(3):
@@ -151,3 +151,10 @@ def test_batched_execute_matches_single():
                 arr, scale = pub.debug_value(prog, terms[t["id"]].index, 3, b)
                 w = want[1] if want[0] == "cipher" else want[1][None]
                 assert np.array_equal(arr, w), (name, b, t)
+        # concurrent plan replicas: chunks of 2 + 1 instances (fuse=2) and 3 x 1 (fuse=1)
+        for fuse in (2, 1):
+            pub.set_options(num_streams=4, use_graph=True, cache_constants=False, fuse=fuse)
+            outs3 = pub.execute_batch(prog, vals)
+            for b in range(3):
+                for oname in d["outputs"]:
+                    assert np.array_equal(outs3[b].get(oname)[1], outs[b].get(oname)[1])
