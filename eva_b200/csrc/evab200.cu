@@ -133,6 +133,11 @@ template <bool SQ> __global__ void __launch_bounds__(256) k_mul_ct(MulArgs A, co
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
     mulct_elem<SQ>(A, blockIdx.y, j);
 }
+__global__ void __launch_bounds__(256) k_sum_terms(const SumArgs A, const long long bstride) {
+  const long long off = (long long)blockIdx.z * bstride;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
+    sum_terms_elem(A, blockIdx.y, j, off);
+}
 __global__ void __launch_bounds__(256) k_ks_inner(IpArgs A, const long long bstride) {
   { const long long off = (long long)blockIdx.z * bstride; A.t += off; A.ext += off; A.acc += off; }
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
@@ -271,6 +276,12 @@ struct CudaBE {
       case DY_COPY: k_dyadic<DY_COPY><<<g, 256, 0, st>>>(A, g_batch.stride); break;
       default: k_dyadic<DY_MULPT><<<g, 256, 0, st>>>(A, g_batch.stride); break;
     }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int sum(const SumArgs &A) {
+    count();
+    k_sum_terms<<<grid(A.sout * A.ell), 256, 0, st>>>(A, g_batch.stride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -509,6 +520,9 @@ extern "C" int evab_negate(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a,
 }
 extern "C" int evab_mul_plain(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *pt, void *stream) {
   BE_BEGIN return dyadic_impl<DY_MULPT>(be, c->v, ell, o, a, sa, pt, 1, 1);
+}
+extern "C" int evab_sum_terms(evab_ctx *c, int ell, uint64_t *o, int n, const uint64_t *const *cts, const int *sizes, const uint64_t *const *pts, void *stream) {
+  BE_BEGIN return sum_terms_impl(be, c->v, ell, o, n, cts, sizes, pts);
 }
 extern "C" int evab_mul(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *b, void *stream) {
   BE_BEGIN return mulct_impl(be, c->v, false, ell, o, a, b);

@@ -32,6 +32,7 @@ struct ValueInfo {
   double scale = 0.0;  // absolute scale (always an exact power of two in EVA)
   std::size_t off = 0; // word offset into the arena (Cipher / Plain)
   bool alias = false;  // shares its operand's storage (Output, step-0 rotation)
+  bool fused = false;  // absorbed into a fused sum: the value is never materialised
 };
 
 struct Step {
@@ -41,6 +42,8 @@ struct Step {
   std::vector<int> waits;  // event ids to wait for before issuing
   int record = -1;         // event id recorded after issuing
   std::size_t work = 0;    // scratch word offset in the stream's workspace (0 = none)
+  // fused sum (root Add of a tree of cipher+cipher Adds): out = sum of ct (* pt when pt != null)
+  std::vector<std::pair<const Term *, const Term *>> sum;
 };
 
 // Encode terms of one level that are encoded by a single batched device launch sequence
@@ -52,6 +55,7 @@ struct ExecOptions {
   bool cacheConstants = true;  // encode plan-time-constant plaintexts once per plan instead of on every run
   int batch = 1;               // independent program instances executed by every (fat) kernel launch
   int fuse = 1;                // executeBatch: instances per plan replica (replicas run concurrently)
+  bool fuseSums = true;        // trees of Add over multiply_plain results / ciphertexts run as one kernel
   bool dedupConstants = true;  // Encode terms of identical constants at the same (level, scale) share one plaintext
 };
 
@@ -227,6 +231,56 @@ private:
       }
       for (auto &kv : encodeAlias_) vals_[kv.first].off = vals_[kv.second->index].off;
     }
+    // ---- fused sums: a tree of cipher+cipher Adds whose inner nodes have a single use collapses into
+    // one kernel; leaves that are single-use multiply_plain results are multiplied on the fly
+    // (Sobel / Harris filter taps: sum_i rot_i(x) * w_i).  Same canonical result, see evab_sum_terms.
+    std::unordered_map<std::uint64_t, std::vector<std::pair<const Term *, const Term *>>> sumOf;
+    if (opt_.fuseSums) {
+      std::vector<int> uses(prog_.termCount(), 0);
+      for (auto &t : order_) for (auto &o : t->getOperands()) uses[o->index]++;
+      auto isCipherAdd = [&](const Term *t) {
+        return t->op == Op::Add && vals_[t->operandAt(0)->index].kind == Kind::Cipher && vals_[t->operandAt(1)->index].kind == Kind::Cipher;
+      };
+      auto plainMul = [&](const Term *t, const Term *&ct, const Term *&pt) {
+        if (t->op != Op::Mul) return false;
+        const Term *a = t->operandAt(0).get(), *b = t->operandAt(1).get();
+        if (vals_[a->index].kind == Kind::Cipher && vals_[b->index].kind == Kind::Plain) { ct = a; pt = b; return true; }
+        if (vals_[b->index].kind == Kind::Cipher && vals_[a->index].kind == Kind::Plain) { ct = b; pt = a; return true; }
+        return false;
+      };
+      for (auto it = order_.rbegin(); it != order_.rend(); ++it) {
+        Term *root = *it;
+        if (!isCipherAdd(root) || vals_[root->index].fused) continue;
+        std::vector<std::pair<const Term *, const Term *>> leaves;
+        std::vector<const Term *> absorbed;
+        std::function<void(const Term *)> expand = [&](const Term *t) {
+          const Term *ct = nullptr, *pt = nullptr;
+          const bool inner = t != root;
+          if ((!inner || uses[t->index] == 1) && isCipherAdd(t) && leaves.size() + 2 <= 30) {
+            if (inner) absorbed.push_back(t);
+            expand(t->operandAt(0).get());
+            expand(t->operandAt(1).get());
+          } else if (inner && uses[t->index] == 1 && plainMul(t, ct, pt)) {
+            absorbed.push_back(t);
+            leaves.emplace_back(ct, pt);
+          } else {
+            leaves.emplace_back(t, nullptr);
+          }
+        };
+        expand(root);
+        if (absorbed.empty() || leaves.size() > 32) continue;   // a plain two-operand add
+        for (const Term *t : absorbed) vals_[t->index].fused = true;
+        sumOf[root->index] = std::move(leaves);
+      }
+    }
+    // operands a step really reads (fused sums read their leaves)
+    auto stepOperands = [&](const Term *t) {
+      std::vector<const Term *> ops;
+      auto f = sumOf.find(t->index);
+      if (f == sumOf.end()) { for (auto &o : t->getOperands()) ops.push_back(o.get()); return ops; }
+      for (auto &l : f->second) { ops.push_back(l.first); if (l.second) ops.push_back(l.second); }
+      return ops;
+    };
     // ---- stream assignment + event edges
     const int S = std::max(1, opt_.numStreams);
     std::vector<int> streamOf(prog_.termCount(), -1), eventOf(prog_.termCount(), -1);
@@ -235,13 +289,15 @@ private:
     int rr = 0;
     for (auto &t : order_) {
       const ValueInfo &v = vals_[t->index];
-      const bool device = (v.kind == Kind::Cipher || v.kind == Kind::Plain) && t->op != Op::Input && !v.alias;
+      const bool device = (v.kind == Kind::Cipher || v.kind == Kind::Plain) && t->op != Op::Input && !v.alias && !v.fused;
       if (!device) {
         if (v.alias) streamOf[t->index] = streamOf[t->operandAt(0)->index];
         continue;
       }
       Step st;
       st.term = t; st.op = t->op;
+      { auto f = sumOf.find(t->index); if (f != sumOf.end()) st.sum = f->second; }
+      const std::vector<const Term *> operands = stepOperands(t);
       // continue the chain of a device operand nobody continued yet, else take a new stream round-robin
       int chosen = -1;
       if (t->op == Op::Encode) {
@@ -249,13 +305,13 @@ private:
         if (g.stream < 0) g.stream = (rr++) % S;
         chosen = g.stream;
       }
-      for (auto &o : t->getOperands()) {
+      for (const Term *o : operands) {
         const int so = streamOf[o->index];
         if (so >= 0 && !chainTaken[o->index] && o->op != Op::Input) { chosen = so; chainTaken[o->index] = 1; break; }
       }
       if (chosen < 0) chosen = (rr++) % S;
       st.stream = chosen;
-      for (auto &o : t->getOperands()) {
+      for (const Term *o : operands) {
         const int so = streamOf[o->index];
         if (so >= 0 && so != chosen && o->op != Op::Input) {
           std::uint64_t src = o->index;
@@ -386,6 +442,16 @@ private:
     evab_ctx *c = dev_->ctx();
     const ValueInfo &o = vals_[t.index];
     u64 *out = arena_.get() + o.off;
+    if (!st.sum.empty()) {   // fused multiply_plain / add tree
+      std::vector<const u64 *> cts, pts; std::vector<int> sizes;
+      for (auto &l : st.sum) {
+        cts.push_back(arena_.get() + vals_[l.first->index].off);
+        sizes.push_back(vals_[l.first->index].size);
+        pts.push_back(l.second ? arena_.get() + vals_[l.second->index].off : nullptr);
+      }
+      check(evab_sum_terms(c, o.ell, out, (int)cts.size(), cts.data(), sizes.data(), pts.data(), stream));
+      return;
+    }
     auto V = [&](int i) -> const ValueInfo & { return vals_[t.operandAt(i)->index]; };
     auto P = [&](int i) -> const u64 * { return arena_.get() + vals_[t.operandAt(i)->index].off; };
     u64 *work = arena_.get() + workOff_[st.stream];

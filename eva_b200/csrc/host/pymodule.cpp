@@ -138,12 +138,12 @@ PYBIND11_MODULE(_eva_b200, m) {
       .def("execute_batch", [](B200Public &p, Program &prog, const std::vector<const B200Valuation *> &in) { return p.executeMany(prog, in); },
            py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>(),
            "Execute one compiled program on a list of valuations with batched kernels; returns a list of valuations")
-      .def("set_options", [](B200Public &p, int streams, bool graph, bool cache, bool dedup, int fuse) {
+      .def("set_options", [](B200Public &p, int streams, bool graph, bool cache, bool dedup, int fuse, bool fuseSums) {
              p.options.numStreams = streams; p.options.useGraph = graph; p.options.cacheConstants = cache; p.options.dedupConstants = dedup;
-             p.options.fuse = fuse;
+             p.options.fuse = fuse; p.options.fuseSums = fuseSums;
            },
            py::arg("num_streams") = 8, py::arg("use_graph") = true, py::arg("cache_constants") = true, py::arg("dedup_constants") = true,
-           py::arg("fuse") = 1)
+           py::arg("fuse") = 1, py::arg("fuse_sums") = true)
       .def("drop_plan", &B200Public::dropExecutor, py::arg("program"), py::arg("batch") = 1, py::arg("replica") = 0)
       .def("cipher_op_count", [](B200Public &p, Program &prog) { return p.executorFor(prog).cipherOpCount(); })
       .def("launch_count", [](B200Public &p) { return evab_launch_count(p.shared()->dev->ctx()); })
@@ -162,7 +162,7 @@ PYBIND11_MODULE(_eva_b200, m) {
         const ValueInfo &vi = ex.info(index);
         auto dev = p.shared()->dev;
         if (vi.kind == Kind::Raw) return py::cast(ex.rawValue(index, b));
-        if (vi.kind == Kind::None) return py::none();
+        if (vi.kind == Kind::None || vi.fused) return py::none();   // fused away: never materialised
         const std::size_t polys = vi.kind == Kind::Cipher ? vi.size : 1;
         u64arr a({polys, (std::size_t)vi.ell, (std::size_t)dev->N()});
         dev->sync();

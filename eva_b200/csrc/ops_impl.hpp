@@ -74,6 +74,24 @@ template <class BE> int copy_impl(BE &be, const CtxView &c, int ell_in, int ell_
   return be.dyadic(DY_COPY, A);
 }
 
+// out = sum_t (pts[t] ? cts[t] * pts[t] : cts[t]); out size = max ciphertext size.  out may alias
+// none of the inputs (every input is read after other outputs coefficients are written only at
+// the same index, so aliasing a ct of full size is in fact safe, but callers do not rely on it).
+template <class BE>
+int sum_terms_impl(BE &be, const CtxView &c, int ell, u64 *out, int nterms, const u64 *const *cts, const int *sizes, const u64 *const *pts) {
+  if (ell < 1 || ell > c.k) return be.error("ell out of range");
+  if (nterms < 1 || nterms > SUM_MAX_TERMS) return be.error("evab_sum_terms: 1..32 terms");
+  SumArgs A;
+  memset(&A, 0, sizeof(A));
+  A.out = out; A.primes = c.primes; A.n = nterms; A.ell = ell; A.N = (int)c.N; A.sout = 0;
+  for (int t = 0; t < nterms; t++) {
+    if (sizes[t] < 1 || sizes[t] > 3) return be.error("ciphertext size must be 1..3");
+    A.ct[t] = cts[t]; A.pt[t] = pts ? pts[t] : nullptr; A.size[t] = (unsigned char)sizes[t];
+    if (sizes[t] > A.sout) A.sout = sizes[t];
+  }
+  return be.sum(A);
+}
+
 template <class BE> int mulct_impl(BE &be, const CtxView &c, bool square, int ell, u64 *out, const u64 *a, const u64 *b) {
   if (ell < 1 || ell > c.k) return be.error("ell out of range");
   MulArgs A;

@@ -40,6 +40,42 @@ template <int OP> EVAB_HD void dyadic_elem(const DyArgs &A, int res, int j) {
   st2(A.out + off + j, r);
 }
 
+// fused sum of terms, term t = ct[t] * pt[t] (multiply_plain) or ct[t] (pt[t] == null):
+// a chain of Evaluator::multiply_plain / Evaluator::add calls (reference seal_executor.h:124,168)
+// evaluated in one pass.  Products are accumulated in 128 bits and reduced once; the canonical
+// result equals the sequence of canonical mul_plain / add results (exact modular arithmetic).
+#define SUM_MAX_TERMS 32
+struct SumArgs {
+  u64 *out;
+  const u64 *ct[SUM_MAX_TERMS];
+  const u64 *pt[SUM_MAX_TERMS];
+  unsigned char size[SUM_MAX_TERMS];   // polynomials of ct[t]
+  const PrimeDev *primes;
+  int n, ell, N, sout;
+};
+// coefficients j, j+1 of output residue `res` (= s*ell + i); off = batch instance offset (words)
+EVAB_HD void sum_terms_elem(const SumArgs &A, int res, int j, long long off) {
+  const int s = res / A.ell, i = res % A.ell;
+  const PrimeDev P = A.primes[i];
+  const size_t coff = (size_t)res * A.N + j, poff = (size_t)i * A.N + j;
+  u64 lx = 0, hx = 0, ly = 0, hy = 0;
+  for (int t = 0; t < A.n; t++) {
+    if (s >= (int)A.size[t]) continue;
+    const u64x2 v = ld2(A.ct[t] + off + coff);
+    if (A.pt[t]) {
+      const u64x2 w = ld2(A.pt[t] + off + poff);
+      mac128(lx, hx, v.x, w.x); mac128(ly, hy, v.y, w.y);
+    } else {
+      lx += v.x; hx += (lx < v.x);
+      ly += v.y; hy += (ly < v.y);
+    }
+  }
+  u64x2 r;
+  r.x = barrett128_wide(lx, hx, P.p, P.ratio_lo, P.ratio_hi);
+  r.y = barrett128_wide(ly, hy, P.p, P.ratio_lo, P.ratio_hi);
+  st2(A.out + off + coff, r);
+}
+
 struct MulArgs { u64 *out; const u64 *a; const u64 *b; const PrimeDev *primes; int ell, N; };
 
 // 2x2 -> 3 tensor product (Evaluator::multiply) or square, residue i, coeffs j,j+1

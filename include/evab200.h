@@ -121,6 +121,12 @@ int evab_sub_plain(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a,
 int evab_negate(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, void *stream);
 /* Evaluator::multiply_plain :168 -- may alias a */
 int evab_mul_plain(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, int sa, const uint64_t *d_pt, void *stream);
+/* A chain of Evaluator::multiply_plain :168 and Evaluator::add :124 calls in one pass:
+ * out = sum_t (h_d_pts[t] ? cts[t] * pts[t] : cts[t]), 1 <= nterms <= 32, out size = max size.
+ * Products are accumulated in 128 bits and reduced once: the canonical result is identical to
+ * performing the calls one by one.  h_* are host arrays of device pointers read during the call. */
+int evab_sum_terms(evab_ctx *ctx, int ell, uint64_t *d_out, int nterms, const uint64_t *const *h_d_cts, const int *h_sizes,
+                   const uint64_t *const *h_d_pts, void *stream);
 /* Evaluator::multiply :164 (2x2 -> 3) and square :162 */
 int evab_mul(evab_ctx *ctx, int ell, uint64_t *d_out3, const uint64_t *d_a2, const uint64_t *d_b2, void *stream);
 int evab_square(evab_ctx *ctx, int ell, uint64_t *d_out3, const uint64_t *d_a2, void *stream);

@@ -86,6 +86,17 @@ class EmuBackend:
     def sub_plain(self, a, pt): return self._plain("emu_sub_plain", a, pt)
     def mul_plain(self, a, pt): return self._plain("emu_mul_plain", a, pt)
 
+    def sum_terms(self, cts, pts):
+        """out = sum_t (pts[t] is None ? cts[t] : cts[t] * pts[t])"""
+        n = len(cts)
+        ell = cts[0].shape[1]
+        out = np.empty((max(c.shape[0] for c in cts), ell, self.N), dtype=np.uint64)
+        cp = (C.c_void_p * n)(*[c.ctypes.data for c in cts])
+        pp = (C.c_void_p * n)(*[(p.ctypes.data if p is not None else None) for p in pts])
+        sz = (C.c_int * n)(*[c.shape[0] for c in cts])
+        self._chk(self.lib.emu_sum_terms(self.h, ell, _p(out), n, cp, sz, pp))
+        return out
+
     def negate(self, a):
         out = np.empty_like(a)
         self._chk(self.lib.emu_negate(self.h, a.shape[1], _p(out), _p(a), a.shape[0]))
@@ -215,6 +226,21 @@ class GpuBackend:
     def add_plain(self, a, pt): return self._plain("evab_add_plain", a, pt)
     def sub_plain(self, a, pt): return self._plain("evab_sub_plain", a, pt)
     def mul_plain(self, a, pt): return self._plain("evab_mul_plain", a, pt)
+
+    def sum_terms(self, cts, pts):
+        n = len(cts)
+        ell = cts[0].shape[1]
+        shape = (max(c.shape[0] for c in cts), ell, self.N)
+        dc = [self._up(c) for c in cts]
+        dp = [self._up(p) if p is not None else None for p in pts]
+        do = self._alloc(int(np.prod(shape)) * 8)
+        cp = (C.c_void_p * n)(*[d.value for d in dc])
+        pp = (C.c_void_p * n)(*[(d.value if d is not None else None) for d in dp])
+        sz = (C.c_int * n)(*[c.shape[0] for c in cts])
+        self._chk(self.lib.evab_sum_terms(self.h, ell, do, n, cp, sz, pp, None))
+        out = self._down(do, shape)
+        self._free(do, *dc, *[d for d in dp if d is not None])
+        return out
 
     def negate(self, a):
         da, do = self._up(a), self._alloc(a.nbytes)

@@ -134,6 +134,11 @@ struct EmuBE {
         }
     return 0;
   }
+  int sum(const SumArgs &A) {
+    for (int res = 0; res < A.sout * A.ell; res++)
+      for (int j = 0; j < A.N; j += 2) sum_terms_elem(A, res, j, 0);
+    return 0;
+  }
   int mulct(bool sq, const MulArgs &A) {
     for (int i = 0; i < A.ell; i++)
       for (int j = 0; j < A.N; j += 2) { if (sq) mulct_elem<true>(A, i, j); else mulct_elem<false>(A, i, j); }
@@ -194,6 +199,10 @@ int emu_mul_plain(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, co
 int emu_mul(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *b) { EmuBE be{c}; return mulct_impl(be, c->v, false, ell, o, a, b); }
 int emu_square(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a) { EmuBE be{c}; return mulct_impl(be, c->v, true, ell, o, a, (const u64 *)nullptr); }
 int emu_set_cluster(int cl) { if (cl != 1 && cl != 2 && cl != 4 && cl != 8) return 1; g_cl = cl; return 0; }
+int emu_sum_terms(EmuCtx *c, int ell, uint64_t *o, int n, const uint64_t *const *cts, const int *sizes, const uint64_t *const *pts) {
+  EmuBE be{c};
+  return sum_terms_impl(be, c->v, ell, o, n, cts, sizes, pts);
+}
 size_t emu_encode_work_bytes(EmuCtx *c, int count) { return encode_work_bytes(c->v, count); }
 int emu_encode(EmuCtx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell, uint64_t *out, void *work) {
   EmuBE be{c};

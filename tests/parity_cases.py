@@ -75,6 +75,26 @@ def case_dyadic(be, orc, ell):
         eq(be.mod_switch(a3), orc.mod_switch(a3))
 
 
+def case_sum_terms(be, orc, ell, nterms=(2, 9, 32)):
+    """fused multiply_plain / add chains == the same calls one by one on the oracle"""
+    for n in nterms:
+        cts = [rand_ct(orc, 3 if (t % 5 == 4) else 2, ell, 300 + t) for t in range(n)]
+        pts = [None if (t % 3 == 2) else rand_ct(orc, 1, ell, 400 + t)[0] for t in range(n)]
+        want = None
+        for c, p in zip(cts, pts):
+            term = c if p is None else orc.mul_plain(c, p)
+            want = term if want is None else orc.add(want, term)
+        eq(be.sum_terms(cts, pts), want)
+    # worst-case magnitudes: every residue p-1
+    c = np.stack([np.stack([np.full(orc.N, orc.primes[i] - 1, dtype=np.uint64) for i in range(ell)])] * 2)
+    cts, pts = [c] * 32, [c[0]] * 32
+    want = None
+    for t in range(32):
+        term = orc.mul_plain(cts[t], pts[t])
+        want = term if want is None else orc.add(want, term)
+    eq(be.sum_terms(cts, pts), want)
+
+
 def case_rescale(be, orc, ell):
     for size in (2, 3):
         a = rand_ct(orc, size, ell, 10 + size)

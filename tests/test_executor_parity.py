@@ -13,7 +13,9 @@ from oracle_exec import OracleProgram
 pytestmark = pytest.mark.gpu
 
 
-def run_both(name, seed=1, use_graph=True, streams=8, lo=-1.0, hi=1.0, cache=True):
+def run_both(name, seed=1, use_graph=True, streams=8, lo=-1.0, hi=1.0, cache=True, fuse_sums=False):
+    """fuse_sums=False materialises every term (all intermediates are compared); with fuse_sums=True the
+    inner nodes of fused multiply_plain / add trees do not exist and are skipped (debug_value -> None)"""
     from eva_b200 import b200
     d = gl.load_json(name)
     prog, params, sig, terms = gl.build_program(d)
@@ -23,7 +25,7 @@ def run_both(name, seed=1, use_graph=True, streams=8, lo=-1.0, hi=1.0, cache=Tru
     op.prepare_keys()
     assert b200.create_coeff_modulus(N, d["prime_bits"]) == orc.primes
     pub = b200.context_from_raw_keys(N, orc.primes, op.rk, {int(e): k for e, k in op.gks.items()})
-    pub.set_options(num_streams=streams, use_graph=use_graph, cache_constants=cache)
+    pub.set_options(num_streams=streams, use_graph=use_graph, cache_constants=cache, fuse_sums=fuse_sums)
     rng = np.random.default_rng(seed)
     inputs_o, val, plain_inputs = {}, b200.B200Valuation(), {}
     for name_, info in d["signature"].items():
@@ -44,10 +46,13 @@ def run_both(name, seed=1, use_graph=True, streams=8, lo=-1.0, hi=1.0, cache=Tru
     V = op.run(inputs_o)
     out = pub.execute(prog, val)
     out2 = pub.execute(prog, val)   # second run replays the captured graph
-    n_checked = 0
+    n_checked = n_fused = 0
     for t in d["terms"]:
         want = V[t["id"]]
         got = pub.debug_value(prog, terms[t["id"]].index)
+        if got is None and fuse_sums and want[0] == "cipher":
+            n_fused += 1
+            continue
         if want[0] == "raw":
             assert np.allclose(np.asarray(got), want[1])
             continue
@@ -64,6 +69,8 @@ def run_both(name, seed=1, use_graph=True, streams=8, lo=-1.0, hi=1.0, cache=Tru
             if kind == "cipher":
                 assert np.array_equal(arr, want[1]) and scale == want[2]
     assert pub.cipher_op_count(prog) == op.cipher_op_count()
+    if fuse_sums:
+        return d, orc, V, plain_inputs, n_checked, n_fused
     return d, orc, V, plain_inputs, n_checked
 
 
@@ -110,6 +117,14 @@ def test_wide_dag():
     run_both("wide64")
 
 
+@pytest.mark.parametrize("name,min_fused", [("sobel", 30), ("harris", 40), ("polynomial", 0), ("feat_hsum", 0), ("feat_mixed", 0), ("wide64", 1)])
+def test_fused_sums_bit_exact(name, min_fused):
+    """default executor mode: trees of multiply_plain / add evaluated by one kernel (evab_sum_terms);
+    every materialised term and every output still matches the oracle bit for bit"""
+    r = run_both(name, lo=0.0, hi=0.2, fuse_sums=True)
+    assert r[5] >= min_fused, r[5]
+
+
 def test_batched_execute_matches_single():
     """execute_batch (one plan, kernels batched over instances) == separate execute() calls, bit for bit,
     with raw inputs differing per instance (feat_mixed) and with rotations / key switching (sobel)."""
@@ -122,7 +137,7 @@ def test_batched_execute_matches_single():
         op = OracleProgram(d, orc)
         op.prepare_keys()
         pub = b200.context_from_raw_keys(N, orc.primes, op.rk, {int(e): k for e, k in op.gks.items()})
-        pub.set_options(num_streams=4, use_graph=True, cache_constants=False, fuse=3)   # one plan, 3 instances per launch
+        pub.set_options(num_streams=4, use_graph=True, cache_constants=False, fuse=3, fuse_sums=False)   # one plan, 3 instances per launch; every term materialised
         rng = np.random.default_rng(5)
         vals, inputs_o = [], []
         for b in range(3):

@@ -29,6 +29,7 @@ def test_gpu_ops_small(N, bits):
     be = _be(N, orc.primes)
     for ell in range(1, orc.k):
         pc.case_dyadic(be, orc, ell)
+        pc.case_sum_terms(be, orc, ell)
         pc.case_keyswitch(be, orc, ell)
         if ell >= 2:
             pc.case_rescale(be, orc, ell)
@@ -40,6 +41,7 @@ def test_gpu_ops_sobel_shape():
     be = _be(16384, orc.primes)
     for ell in (4, 3, 2, 1):
         pc.case_dyadic(be, orc, ell)
+        pc.case_sum_terms(be, orc, ell, nterms=(9,))
         pc.case_keyswitch(be, orc, ell, steps=(1, 64, 130))
         if ell >= 2:
             pc.case_rescale(be, orc, ell)
