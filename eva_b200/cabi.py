@@ -62,6 +62,8 @@ _SIGS = {
     "evab_galois_elt_from_step": (u64, [u64, ci]),
     "evab_galois_prepare": (ci, [vp, u64]),
     "evab_rotate": (ci, [vp, ci, vp, vp, u64, vp, vp, vp]),
+    "evab_rotate_prepare": (ci, [vp, ci, vp, vp, vp]),
+    "evab_rotate_prepared": (ci, [vp, ci, vp, vp, vp, u64, vp, vp, vp]),
 }
 
 

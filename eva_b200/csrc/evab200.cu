@@ -36,7 +36,8 @@ struct evab_ctx {
   cplx *d_roots = nullptr;
   u32 *d_slot = nullptr;
   u64 *d_pow2 = nullptr;
-  std::map<u64, u32 *> perms;  // galois elt -> device permutation table
+  std::map<u64, u32 *> perms;  // galois elt -> device permutation table (NTT domain)
+  std::map<u64, u32 *> cperms; // galois elt -> device signed gather table (coefficient domain)
   std::mutex mu;
   mutable std::atomic<unsigned long long> launches{0};
 };
@@ -195,6 +196,7 @@ template <int LOGN, bool SPLIT, int CL> static int launch_fwd_c(const NttLaunch 
   if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE, CL>(L, jobs, st);
   if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE_LAZY, CL>(L, jobs, st);
   if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_DIVROUND, CL>(L, jobs, st);
+  if (L.pro == PRO_MODRED_SG && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED_SG, EPI_STORE_LAZY, CL>(L, jobs, st);
   return fail("unsupported forward NTT prologue/epilogue combination");
 }
 template <int LOGN, bool SPLIT> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
@@ -381,6 +383,7 @@ extern "C" void evab_ctx_destroy(evab_ctx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (auto &kv : c->perms) cudaFree(kv.second);
+  for (auto &kv : c->cperms) cudaFree(kv.second);
   cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_qinv); cudaFree(c->d_halfmod); cudaFree(c->d_zeros);
   cudaFree(c->d_roots); cudaFree(c->d_slot); cudaFree(c->d_pow2);
   delete c;
@@ -557,7 +560,26 @@ extern "C" int evab_galois_prepare(evab_ctx *c, uint64_t elt) {
   CUDA_OK(cudaMalloc(&d, tab.size() * sizeof(u32)));
   CUDA_OK(cudaMemcpy(d, tab.data(), tab.size() * sizeof(u32), cudaMemcpyHostToDevice));
   c->perms[elt] = d;
+  evab_host::galois_coeff_table(c->v.N, elt, tab);
+  u32 *dc = nullptr;
+  CUDA_OK(cudaMalloc(&dc, tab.size() * sizeof(u32)));
+  CUDA_OK(cudaMemcpy(dc, tab.data(), tab.size() * sizeof(u32), cudaMemcpyHostToDevice));
+  c->cperms[elt] = dc;
   return 0;
+}
+extern "C" int evab_rotate_prepare(evab_ctx *c, int ell, uint64_t *hoist, const uint64_t *a, void *stream) {
+  BE_BEGIN return rotate_prepare_impl(be, c->v, ell, hoist, a);
+}
+extern "C" int evab_rotate_prepared(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *hoist, uint64_t elt, const uint64_t *key, void *work,
+                                    void *stream) {
+  u32 *perm = nullptr, *ctab = nullptr;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->perms.find(elt);
+    if (it == c->perms.end()) return fail("evab_rotate_prepared: call evab_galois_prepare(elt) first");
+    perm = it->second; ctab = c->cperms.at(elt);
+  }
+  BE_BEGIN return rotate_prepared_impl(be, c->v, ell, o, a, hoist, perm, ctab, key, (u64 *)work);
 }
 extern "C" int evab_rotate(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, uint64_t elt, const uint64_t *key, void *work, void *stream) {
   u32 *perm = nullptr;

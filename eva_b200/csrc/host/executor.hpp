@@ -44,6 +44,8 @@ struct Step {
   std::size_t work = 0;    // scratch word offset in the stream's workspace (0 = none)
   // fused sum (root Add of a tree of cipher+cipher Adds): out = sum of ct (* pt when pt != null)
   std::vector<std::pair<const Term *, const Term *>> sum;
+  int hoist = -1;              // rotation group sharing one inverse NTT (op == Undef: the step computing it)
+  std::uint64_t producer = 0;  // term index, or termCount + group for a hoist step
 };
 
 // Encode terms of one level that are encoded by a single batched device launch sequence
@@ -55,6 +57,7 @@ struct ExecOptions {
   bool cacheConstants = true;  // encode plan-time-constant plaintexts once per plan instead of on every run
   int batch = 1;               // independent program instances executed by every (fat) kernel launch
   int fuse = 1;                // executeBatch: instances per plan replica (replicas run concurrently)
+  bool hoistRotations = true;  // rotations of one ciphertext share the inverse NTT of its c1 (exact)
   bool fuseSums = true;        // trees of Add over multiply_plain results / ciphertexts run as one kernel
   bool dedupConstants = true;  // Encode terms of identical constants at the same (level, scale) share one plaintext
 };
@@ -281,12 +284,58 @@ private:
       for (auto &l : f->second) { ops.push_back(l.first); if (l.second) ops.push_back(l.second); }
       return ops;
     };
-    // ---- stream assignment + event edges
+    // ---- hoisted rotations: two or more rotations of the same ciphertext share the inverse NTT of
+    // its c1 (evab_rotate_prepare); the shared buffer is produced by a pseudo step of its own
+    const std::uint64_t TC = prog_.termCount();
+    std::unordered_map<std::uint64_t, int> hoistOf;       // rotation term -> group
+    std::vector<const Term *> hoistSrc;
+    if (opt_.hoistRotations) {
+      std::map<std::uint64_t, std::vector<const Term *>> bySrc;
+      for (auto &t : order_)
+        if ((t->op == Op::RotateLeftConst || t->op == Op::RotateRightConst) && *t->rotation != 0 && vals_[t->index].kind == Kind::Cipher &&
+            vals_[t->index].ell <= 15)
+          bySrc[t->operandAt(0)->index].push_back(t);
+      for (auto &kv : bySrc) {
+        if (kv.second.size() < 2) continue;
+        const int gid = (int)hoistSrc.size();
+        hoistSrc.push_back(kv.second.front()->operandAt(0).get());
+        hoistOff_.push_back(arenaWords);
+        arenaWords += (std::size_t)vals_[kv.first].ell * N_;
+        for (const Term *r : kv.second) hoistOf[r->index] = gid;
+      }
+    }
+    // ---- stream assignment + event edges.  Producers are identified by term index, or TC + group
+    // for the hoist pseudo steps.
     const int S = std::max(1, opt_.numStreams);
-    std::vector<int> streamOf(prog_.termCount(), -1), eventOf(prog_.termCount(), -1);
-    std::vector<char> chainTaken(prog_.termCount(), 0);
+    const std::size_t NP = TC + hoistSrc.size();
+    std::vector<int> streamOf(NP, -1), eventOf(NP, -1);
+    std::vector<char> chainTaken(NP, 0), hoistDone(hoistSrc.size(), 0);
     std::vector<std::size_t> workWords(S, 0);
     int rr = 0;
+    std::vector<char> inputTerm(NP, 0);
+    for (auto &t : order_) if (t->op == Op::Input) inputTerm[t->index] = 1;
+    auto isInput = [&](std::uint64_t id) { return inputTerm[id] != 0; };
+    // place one step: continue the chain of a device operand nobody continued yet, else take a new
+    // stream round-robin; cross-stream operands become event waits
+    auto emit = [&](Step st, const std::vector<std::uint64_t> &operands, int forced, std::size_t w) {
+      int chosen = forced;
+      for (std::uint64_t o : operands) {
+        const int so = streamOf[o];
+        if (so >= 0 && !chainTaken[o] && !isInput(o)) { chosen = so; chainTaken[o] = 1; break; }
+      }
+      if (chosen < 0) chosen = (rr++) % S;
+      st.stream = chosen;
+      for (std::uint64_t o : operands) {
+        const int so = streamOf[o];
+        if (so >= 0 && so != chosen && !isInput(o)) {
+          if (eventOf[o] < 0) { eventOf[o] = numEvents_++; recordAfter_[o] = eventOf[o]; }
+          if (std::find(st.waits.begin(), st.waits.end(), eventOf[o]) == st.waits.end()) st.waits.push_back(eventOf[o]);
+        }
+      }
+      workWords[chosen] = std::max(workWords[chosen], w);
+      streamOf[st.producer] = chosen;
+      steps_.push_back(st);
+    };
     for (auto &t : order_) {
       const ValueInfo &v = vals_[t->index];
       const bool device = (v.kind == Kind::Cipher || v.kind == Kind::Plain) && t->op != Op::Input && !v.alias && !v.fused;
@@ -295,38 +344,34 @@ private:
         continue;
       }
       Step st;
-      st.term = t; st.op = t->op;
+      st.term = t; st.op = t->op; st.producer = t->index;
       { auto f = sumOf.find(t->index); if (f != sumOf.end()) st.sum = f->second; }
-      const std::vector<const Term *> operands = stepOperands(t);
-      // continue the chain of a device operand nobody continued yet, else take a new stream round-robin
-      int chosen = -1;
+      std::vector<std::uint64_t> operands;
+      for (const Term *o : stepOperands(t)) operands.push_back(o->index);
+      int forced = -1;
       if (t->op == Op::Encode) {
         EncodeGroup &g = groups_[groupIndex_.at(t->index)];
         if (g.stream < 0) g.stream = (rr++) % S;
-        chosen = g.stream;
-      }
-      for (const Term *o : operands) {
-        const int so = streamOf[o->index];
-        if (so >= 0 && !chainTaken[o->index] && o->op != Op::Input) { chosen = so; chainTaken[o->index] = 1; break; }
-      }
-      if (chosen < 0) chosen = (rr++) % S;
-      st.stream = chosen;
-      for (const Term *o : operands) {
-        const int so = streamOf[o->index];
-        if (so >= 0 && so != chosen && o->op != Op::Input) {
-          std::uint64_t src = o->index;
-          if (eventOf[src] < 0) { eventOf[src] = numEvents_++; recordAfter_[src] = eventOf[src]; }
-          if (std::find(st.waits.begin(), st.waits.end(), eventOf[src]) == st.waits.end()) st.waits.push_back(eventOf[src]);
-        }
+        forced = g.stream;
       }
       std::size_t w = 0;
       if (t->op == Op::Relinearize || ((t->op == Op::RotateLeftConst || t->op == Op::RotateRightConst) && *t->rotation != 0))
         w = evab_keyswitch_work_bytes(dev_->ctx(), vals_[t->operandAt(0)->index].ell) / 8;
       else if (t->op == Op::Rescale)
         w = evab_rescale_work_bytes(dev_->ctx(), vals_[t->operandAt(0)->index].size) / 8;
-      workWords[chosen] = std::max(workWords[chosen], w);
-      streamOf[t->index] = chosen;
-      steps_.push_back(st);
+      auto h = hoistOf.find(t->index);
+      if (h != hoistOf.end()) {
+        const int gid = h->second;
+        if (!hoistDone[gid]) {   // first rotation of the group in program order: the shared inverse NTT goes first
+          Step hs;
+          hs.term = hoistSrc[gid]; hs.op = Op::Undef; hs.hoist = gid; hs.producer = TC + gid;
+          emit(hs, {hoistSrc[gid]->index}, -1, 0);
+          hoistDone[gid] = 1;
+        }
+        st.hoist = gid;
+        operands.push_back(TC + gid);
+      }
+      emit(st, operands, forced, w);
     }
     // resolve alias chains (Output of X shares X's storage; Output(Output) never occurs)
     for (auto &t : order_) {
@@ -334,7 +379,7 @@ private:
       if (v.alias) { const ValueInfo &src = vals_[t->operandAt(0)->index]; v.off = src.off; }
     }
     for (auto &st : steps_) {
-      auto it = recordAfter_.find(st.term->index);
+      auto it = recordAfter_.find(st.producer);
       if (it != recordAfter_.end()) st.record = it->second;
     }
     // last step of every stream must be joined back into the caller's stream
@@ -442,6 +487,10 @@ private:
     evab_ctx *c = dev_->ctx();
     const ValueInfo &o = vals_[t.index];
     u64 *out = arena_.get() + o.off;
+    if (st.op == Op::Undef) {   // shared inverse NTT of a rotation group's input
+      check(evab_rotate_prepare(c, o.ell, arena_.get() + hoistOff_[st.hoist], arena_.get() + o.off, stream));
+      return;
+    }
     if (!st.sum.empty()) {   // fused multiply_plain / add tree
       std::vector<const u64 *> cts, pts; std::vector<int> sizes;
       for (auto &l : st.sum) {
@@ -476,7 +525,11 @@ private:
       case Op::Negate: check(evab_negate(c, o.ell, out, P(0), V(0).size, stream)); break;
       case Op::RotateLeftConst: case Op::RotateRightConst:
         if (*t.rotation == 0) check(evab_copy(c, o.ell, out, P(0), 2, stream));  // rotate_vector(0): copy
-        else { const u64 elt = galoisElt(t); check(evab_rotate(c, o.ell, out, P(0), elt, keys_.galois.at(elt).get(), work, stream)); }
+        else {
+          const u64 elt = galoisElt(t);
+          if (st.hoist >= 0) check(evab_rotate_prepared(c, o.ell, out, P(0), arena_.get() + hoistOff_[st.hoist], elt, keys_.galois.at(elt).get(), work, stream));
+          else check(evab_rotate(c, o.ell, out, P(0), elt, keys_.galois.at(elt).get(), work, stream));
+        }
         break;
       case Op::Relinearize: check(evab_relinearize(c, o.ell, out, P(0), keys_.relin.get(), work, stream)); break;
       case Op::ModSwitch: check(evab_mod_switch(c, V(0).ell, out, P(0), V(0).size, stream)); break;
@@ -527,6 +580,7 @@ private:
   std::vector<Term *> encodeTerms_;
   std::unordered_map<std::uint64_t, int> groupIndex_;
   std::unordered_map<std::uint64_t, std::size_t> rawOff_;
+  std::vector<std::size_t> hoistOff_;   // arena word offset of every hoist buffer
   std::unordered_map<std::uint64_t, Term *> encodeAlias_;  // Encode term -> identical earlier Encode term
   std::unordered_set<std::uint64_t> rawUploaded_;
   std::size_t rawWords_ = 0;

@@ -119,4 +119,16 @@ inline void galois_table(u64 N, int logN, u64 elt, std::vector<u32> &tab) {
     tab[i] = bitrev((u32)raw, logN);
   }
 }
+// coefficient-domain form of the same automorphism a(X) -> a(X^elt): output coefficient j is
+// +-a_i with i = j * elt^-1 mod N; entry = (i << 1) | negate.  inverse_ntt(galois_table(x)) ==
+// this signed gather applied to inverse_ntt(x) (with canonical negation p - v, 0 -> 0).
+inline void galois_coeff_table(u64 N, u64 elt, std::vector<u32> &tab) {
+  tab.assign(N, 0);
+  const u64 m = 2 * N;
+  for (u64 i = 0; i < N; i++) {
+    const u64 pos = (i * elt) & (m - 1);
+    if (pos < N) tab[pos] = (u32)(i << 1);
+    else tab[pos - N] = (u32)((i << 1) | 1u);
+  }
+}
 }  // namespace evab_host

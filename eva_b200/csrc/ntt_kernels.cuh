@@ -14,6 +14,8 @@ enum : int {
   PRO_PLAIN = 0,   // x = src[idx]
   PRO_MODRED = 1,  // x = (src[idx] mod p) - sub_r   (sub_r = subtab[pmap]: e.g. floor(q_last/2) mod p)
   PRO_GATHER = 2,  // x = src[perm[idx]]              (Galois automorphism, NTT domain)
+  PRO_MODRED_SG = 3,  // PRO_MODRED on the signed gather +-src[perm[idx] >> 1] (negate when perm[idx] & 1):
+                      // Galois automorphism in the coefficient domain, values canonical mod the source prime
 };
 enum : int {
   EPI_STORE = 0,     // dst[idx] = x
@@ -24,7 +26,8 @@ enum : int {
 
 struct NttLaunch {
   const u64 *src; u64 *dst; const u64 *aux0; const u64 *aux1;
-  const u32 *perm;             // PRO_GATHER
+  const u32 *perm;             // PRO_GATHER / PRO_MODRED_SG
+  const u32 *aux1_perm;        // EPI_DIVROUND: aux1 is read through this permutation (NTT-domain automorphism)
   const u64 *cflags;           // optional [q]: 0 = polynomial q is constant (only coefficient 0 set): its
                                // transform is that value everywhere, written without running the NTT
   const PrimeDev *primes;
@@ -70,8 +73,15 @@ EVAB_HD NttJob ntt_job(const NttLaunch &L, u32 cta, int ctas_per_job, long long 
 // conditional subtraction reduces them mod p, otherwise a 64-bit Barrett reduction
 template <int PRO, bool CHEAP> EVAB_HD u64 pro_load(const NttLaunch &L, const NttJob &J, const PrimeDev &P, u32 idx, u64 sub) {
   if (PRO == PRO_GATHER) return EVAB_LDG(J.src + EVAB_LDG(L.perm + idx));
-  u64 v = EVAB_LDG(J.src + idx);
-  if (PRO == PRO_MODRED) {
+  u64 v;
+  if (PRO == PRO_MODRED_SG) {
+    const u32 e = EVAB_LDG(L.perm + idx);
+    v = EVAB_LDG(J.src + (e >> 1));
+    if ((e & 1u) && v) v = L.primes[J.spi].p - v;   // canonical negation mod the source prime
+  } else {
+    v = EVAB_LDG(J.src + idx);
+  }
+  if (PRO == PRO_MODRED || PRO == PRO_MODRED_SG) {
     v = CHEAP ? csub(v, P.p) : barrett64(v, P.p, P.ratio64);
     v = submod(v, sub, P.p);
   }
@@ -170,8 +180,9 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL
     const u32 tid = vtid(J, ltid);
     u64 *sm = smv.local;
     if constexpr (PH == 0) {
-      const u64 sub = (PRO == PRO_MODRED) ? EVAB_LDG(L.subtab + J.pi) : 0;
-      const bool cheap = (PRO == PRO_MODRED) && (L.primes[J.spi].p <= 2 * P.p);   // CTA-uniform
+      constexpr bool MR = (PRO == PRO_MODRED || PRO == PRO_MODRED_SG);
+      const u64 sub = MR ? EVAB_LDG(L.subtab + J.pi) : 0;
+      const bool cheap = MR && (L.primes[J.spi].p <= 2 * P.p);   // CTA-uniform
       if (cheap) load0<true>(S, L, J, P, tid, sub); else load0<false>(S, L, J, P, tid, sub);
       fwd_pass_s<LOGN, 0>(S.x, P.tw, root, P.p, tid, S.b);
       if constexpr (CL > 1) { hk.wait(); xchg_write_dist_fwd<LOGN, CL>(S.x, smv, tid); }   // peers are resident (arrive at kernel start)
@@ -221,7 +232,12 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL
         }
         if (J.aux1) {
           u64 d[4];
-          load4(d, J.aux1 + base + 4 * q);
+          if (L.aux1_perm) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) d[k] = EVAB_LDG(J.aux1 + EVAB_LDG(L.aux1_perm + base + 4 * q + k));
+          } else {
+            load4(d, J.aux1 + base + 4 * q);
+          }
 #pragma unroll
           for (int k = 0; k < 4; k++) a[k] = csub(csub(a[k] + d[k], two_p), P.p);
         } else {

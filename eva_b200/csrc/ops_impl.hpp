@@ -107,7 +107,7 @@ template <class BE> int mulct_impl(BE &be, const CtxView &c, bool square, int el
 template <class BE>
 int divround_impl(BE &be, const CtxView &c, const u64 *in, long long in_poly_stride, int npoly, int nres, const unsigned char *pm,
                   int last, u64 *out, long long out_poly_stride, const u64 *add, long long add_poly_stride, u64 *tmp,
-                  int add_polys = 1 << 30) {
+                  int add_polys = 1 << 30, const u32 *add_perm = nullptr) {
   const long long N = (long long)c.N;
   NttLaunch A = base_launch(c);
   A.src = in + (long long)(nres - 1) * N; A.dst = tmp;
@@ -118,7 +118,7 @@ int divround_impl(BE &be, const CtxView &c, const u64 *in, long long in_poly_str
   NttLaunch B = base_launch(c);
   B.src = tmp; B.src_sq = N; B.src_sr = 0;
   B.aux0 = in; B.aux0_sq = in_poly_stride; B.aux0_sr = N;
-  B.aux1 = add; B.aux1_sq = add_poly_stride; B.aux1_sr = N; B.aux1_polys = add_polys;
+  B.aux1 = add; B.aux1_sq = add_poly_stride; B.aux1_sr = N; B.aux1_polys = add_polys; B.aux1_perm = add_perm;
   B.dst = out; B.dst_sq = out_poly_stride; B.dst_sr = N;
   B.inner = nres - 1; B.prime_on_q = 0;
   for (int r = 0; r < nres - 1; r++) { B.pmap[r] = pm[r]; B.pmap2[r] = (unsigned char)last; }   // src holds residues mod q_last
@@ -149,8 +149,12 @@ inline size_t keyswitch_work_elems(const CtxView &c, int ell) { return ks_off_pc
 
 // Evaluator::switch_key_inplace (Appendix A.5): out[c][J] = base[c][J] + ks_c[J];
 // base holds `base_polys` (1 or 2) polynomials.
+// Hoisted form (rotations sharing the inverse NTT of their input, exact): `that_in` = iNTT of the
+// UNrotated digits, `ctab` the coefficient-domain signed gather of the automorphism, `nperm` its
+// NTT-domain permutation; t and base are then the unrotated c1 / c0 and are read through nperm.
 template <class BE>
-int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, const u64 *key, const u64 *base, int base_polys, u64 *work) {
+int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, const u64 *key, const u64 *base, int base_polys, u64 *work,
+                   const u64 *that_in = nullptr, const u32 *ctab = nullptr, const u32 *nperm = nullptr) {
   const long long N = (long long)c.N;
   const int k = c.k, sp = k - 1;
   if (ell < 1 || ell > k - 1) return be.error("key switching needs 1 <= ell <= k-1");
@@ -159,15 +163,20 @@ int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, co
   u64 *acc = work + ks_off_acc(c, ell);
   u64 *tmp = work + ks_off_tmp(c, ell);
   // 1. digits to coefficient form: that[J] = iNTT_{q_J}(t[J])
-  NttLaunch A = base_launch(c);
-  A.src = t; A.dst = that; A.inner = ell; A.src_sr = A.dst_sr = N;
-  for (int J = 0; J < ell; J++) A.pmap[J] = (unsigned char)J;
-  if (int rc = be.inv(A, ell)) return rc;
+  if (!that_in) {
+    NttLaunch A = base_launch(c);
+    A.src = t; A.dst = that; A.inner = ell; A.src_sr = A.dst_sr = N;
+    for (int J = 0; J < ell; J++) A.pmap[J] = (unsigned char)J;
+    if (int rc = be.inv(A, ell)) return rc;
+  } else if (ell > 15) {
+    return be.error("hoisted key switching supports ell <= 15");
+  }
   // 2. ext[m][J] = NTT_m(that[J] mod m) for every output modulus m != q_J
   NttLaunch B = base_launch(c);
-  B.src = that; B.src_sq = 0; B.src_sr = N;
+  B.src = that_in ? that_in : that; B.src_sq = 0; B.src_sr = N;
   B.dst = ext; B.dst_sq = (long long)ell * N; B.dst_sr = N;
-  B.inner = ell; B.prime_on_q = 1; B.skip_diag = 1; B.pro = PRO_MODRED;
+  B.inner = ell; B.prime_on_q = 1; B.skip_diag = 1; B.pro = that_in ? PRO_MODRED_SG : PRO_MODRED;
+  B.perm = ctab;
   // the extended digits only feed the 128-bit inner product, which reduces lazily:
   // skip their canonicalisation while the accumulated sum stays below 2^128
   B.epi = (ell <= 15) ? EPI_STORE_LAZY : EPI_STORE;
@@ -178,13 +187,14 @@ int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, co
   // 3. inner product with the key rows of the live primes and P
   IpArgs I;
   I.t = t; I.ext = ext; I.key = key; I.acc = acc; I.primes = c.primes; I.ell = ell; I.k = k; I.N = (int)N;
+  I.tperm = that_in ? nperm : nullptr;
   if (int rc = be.inner(I)) return rc;
   // 4. mod-down by P with rounding, fused with the accumulation into base
   unsigned char pm[32];
   for (int i = 0; i < ell; i++) pm[i] = (unsigned char)i;
   // base holds c0 and c1 (relinearize) or c0 only (rotate: the switched c1 has no base)
   return divround_impl(be, c, acc, (long long)(ell + 1) * N, 2, ell + 1, pm, sp, out, (long long)ell * N, base, (long long)ell * N, tmp,
-                       base_polys);
+                       base_polys, that_in ? nperm : nullptr);
 }
 
 // Evaluator::relinearize (3 -> 2) -- reference eva/seal/seal_executor.h:200
@@ -205,6 +215,23 @@ int rotate_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, const
 // encoder workspace: count*N complex values followed by count u64 flags
 inline size_t encode_work_bytes(const CtxView &c, int count) { return (size_t)count * c.N * sizeof(cplx) + (size_t)((count + 7) & ~7) * sizeof(u64); }
 inline u64 *encode_flags(const CtxView &c, int count, cplx *work) { return reinterpret_cast<u64 *>(work + (size_t)count * c.N); }
+
+// Rotations of one ciphertext share the inverse NTT of its c1 (the automorphism commutes with the
+// transform): rotate_prepare_impl computes it once, rotate_prepared_impl is rotate_impl without the
+// permuted copy and without the per-rotation inverse NTTs.  Results are identical to rotate_impl.
+template <class BE> int rotate_prepare_impl(BE &be, const CtxView &c, int ell, u64 *hoist, const u64 *a) {
+  if (ell < 1 || ell > c.k - 1) return be.error("rotate needs 1 <= ell <= k-1");
+  NttLaunch A = base_launch(c);
+  A.src = a + (size_t)ell * c.N; A.dst = hoist; A.inner = ell; A.src_sr = A.dst_sr = (long long)c.N;
+  for (int J = 0; J < ell; J++) A.pmap[J] = (unsigned char)J;
+  return be.inv(A, ell);
+}
+template <class BE>
+int rotate_prepared_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, const u64 *hoist, const u32 *nperm, const u32 *ctab, const u64 *key,
+                         u64 *work) {
+  if (ell < 1 || ell > c.k - 1) return be.error("rotate needs 1 <= ell <= k-1");
+  return keyswitch_impl(be, c, ell, out, a + (size_t)ell * c.N, key, a, 1, work, hoist, ctab, nperm);
+}
 
 // seal::CKKSEncoder::encode (vector overload) for a batch of vectors -- reference
 // eva/seal/seal_executor.h:242.  d_values/vec/scale are host arrays of `count` entries.

@@ -108,6 +108,7 @@ template <bool SQUARE> EVAB_HD void mulct_elem(const MulArgs &A, int i, int j) {
 // opnd(m,J) = t[J] when row(m)==J (the digit's own modulus) else ext[m][J].
 struct IpArgs {
   const u64 *t, *ext, *key; u64 *acc; const PrimeDev *primes;
+  const u32 *tperm;   // optional: t is read through this NTT-domain permutation (rotation without a permuted copy)
   int ell, k, N;
 };
 EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j) {
@@ -116,8 +117,14 @@ EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j) {
   const size_t N = A.N;
   u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
   for (int J = 0; J < A.ell; J++) {
-    const u64 *op = (row == J) ? A.t + (size_t)J * N : A.ext + ((size_t)mi * A.ell + J) * N;
-    const u64x2 v = ld2(op + j);
+    u64x2 v;
+    if (row == J) {
+      const u64 *tp = A.t + (size_t)J * N;
+      if (A.tperm) { v.x = EVAB_LDG(tp + EVAB_LDG(A.tperm + j)); v.y = EVAB_LDG(tp + EVAB_LDG(A.tperm + j + 1)); }
+      else v = ld2(tp + j);
+    } else {
+      v = ld2(A.ext + ((size_t)mi * A.ell + J) * N + j);
+    }
     const u64x2 k0 = ld2(A.key + (((size_t)J * 2 + 0) * A.k + row) * N + j);
     const u64x2 k1 = ld2(A.key + (((size_t)J * 2 + 1) * A.k + row) * N + j);
     mac128(l0x, h0x, v.x, k0.x); mac128(l0y, h0y, v.y, k0.y);

@@ -149,6 +149,13 @@ uint64_t evab_galois_elt_from_step(uint64_t N, int steps);
  * device (blocking); must be called once before evab_rotate uses that element */
 int evab_galois_prepare(evab_ctx *ctx, uint64_t galois_elt);
 int evab_rotate(evab_ctx *ctx, int ell, uint64_t *d_out2, const uint64_t *d_a2, uint64_t galois_elt, const uint64_t *d_key, void *d_work, void *stream);
+/* Rotations of the SAME ciphertext share the inverse NTT of its c1 (the automorphism commutes with
+ * the transform; SEAL recomputes it inside every rotate_vector :181,:188).  evab_rotate_prepare
+ * writes it to d_hoist [ell][N]; evab_rotate_prepared(…, d_hoist, …) then equals evab_rotate bit
+ * for bit with fewer transforms and no permuted copy.  Same workspace as evab_rotate; ell <= 15. */
+int evab_rotate_prepare(evab_ctx *ctx, int ell, uint64_t *d_hoist, const uint64_t *d_a, void *stream);
+int evab_rotate_prepared(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, const uint64_t *d_hoist, uint64_t galois_elt,
+                         const uint64_t *d_key, void *d_work, void *stream);
 
 #ifdef __cplusplus
 }

@@ -57,7 +57,7 @@ class EmuBackend:
 
     def __getattribute__(self, name):
         # the emulator's cluster setting is process-global: select this backend's value before every op
-        if name in ("ntt", "rescale", "relinearize", "rotate", "encode"):
+        if name in ("ntt", "rescale", "relinearize", "rotate", "rotate_many", "encode"):
             object.__getattribute__(self, "lib").emu_set_cluster(object.__getattribute__(self, "cluster"))
         return object.__getattribute__(self, name)
 
@@ -145,6 +145,19 @@ class EmuBackend:
         work = np.zeros(self.lib.emu_encode_work_bytes(self.h, n) // 8, dtype=np.uint64)
         self._chk(self.lib.emu_encode(self.h, n, ptrs, sizes, scales, ell, _p(out), _p(work)))
         return out[0] if single else out
+
+    def rotate_many(self, a, steps_list, gks):
+        """rotations of one ciphertext sharing the inverse NTT of c1 (evab_rotate_prepare / _prepared)"""
+        ell = a.shape[1]
+        hoist = np.empty((ell, self.N), dtype=np.uint64)
+        self._chk(self.lib.emu_rotate_prepare(self.h, ell, _p(hoist), _p(a)))
+        outs = []
+        for s_, gk in zip(steps_list, gks):
+            out = np.empty((2, ell, self.N), dtype=np.uint64)
+            work = np.zeros(self.lib.emu_keyswitch_work_bytes(self.h, ell) // 8, dtype=np.uint64)
+            self._chk(self.lib.emu_rotate_prepared(self.h, ell, _p(out), _p(a), _p(hoist), C.c_uint64(_elt(self.N, s_)), _p(gk), _p(work)))
+            outs.append(out)
+        return outs
 
 
 class GpuBackend:
@@ -290,6 +303,25 @@ class GpuBackend:
         out = self._down(do, shape)
         self._free(da, dk, do, dw)
         return out
+
+    def rotate_many(self, a, steps_list, gks):
+        ell = a.shape[1]
+        da = self._up(a)
+        dh = self._alloc(ell * self.N * 8)
+        self._chk(self.lib.evab_rotate_prepare(self.h, ell, dh, da, None))
+        outs = []
+        for s_, gk in zip(steps_list, gks):
+            elt = _elt(self.N, s_)
+            if elt not in self._prepared:
+                self._chk(self.lib.evab_galois_prepare(self.h, C.c_uint64(elt)))
+                self._prepared.add(elt)
+            dk, do = self._up(gk), self._alloc(2 * ell * self.N * 8)
+            dw = self._alloc(self.lib.evab_keyswitch_work_bytes(self.h, ell))
+            self._chk(self.lib.evab_rotate_prepared(self.h, ell, do, da, dh, C.c_uint64(elt), dk, dw, None))
+            outs.append(self._down(do, (2, ell, self.N)))
+            self._free(dk, do, dw)
+        self._free(da, dh)
+        return outs
 
     def rotate(self, a, steps, gk):
         elt = int(self.lib.evab_galois_elt_from_step(C.c_uint64(self.N), steps))

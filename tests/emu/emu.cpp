@@ -16,7 +16,7 @@ struct EmuCtx {
   CtxView v;
   evab_host::Tables T;
   std::vector<u64> zeros;
-  std::map<u64, std::vector<u32>> perms;
+  std::map<u64, std::vector<u32>> perms, cperms;
 };
 
 // run phase PH of body B for every thread of every CTA of one job (the CTAs of a cluster advance in
@@ -81,6 +81,7 @@ template <int LOGN, bool SPLIT, bool INV, int CL> static void run_ntt_c(const Nt
     if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE, CL>(L, jobs);
     if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE_LAZY, CL>(L, jobs);
     if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_DIVROUND, CL>(L, jobs);
+    if (L.pro == PRO_MODRED_SG && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED_SG, EPI_STORE_LAZY, CL>(L, jobs);
   } else {
     if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_STORE, CL>(L, jobs);
     if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_ADDHALF, CL>(L, jobs);
@@ -216,5 +217,15 @@ int emu_rotate(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, uint64_t elt,
   if (!c->perms.count(elt)) evab_host::galois_table(c->v.N, c->v.logN, elt, c->perms[elt]);
   EmuBE be{c};
   return rotate_impl(be, c->v, ell, o, a, c->perms[elt].data(), key, (u64 *)work);
+}
+int emu_rotate_prepare(EmuCtx *c, int ell, uint64_t *hoist, const uint64_t *a) {
+  EmuBE be{c};
+  return rotate_prepare_impl(be, c->v, ell, hoist, a);
+}
+int emu_rotate_prepared(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *hoist, uint64_t elt, const uint64_t *key, void *work) {
+  if (!c->perms.count(elt)) evab_host::galois_table(c->v.N, c->v.logN, elt, c->perms[elt]);
+  if (!c->cperms.count(elt)) evab_host::galois_coeff_table(c->v.N, elt, c->cperms[elt]);
+  EmuBE be{c};
+  return rotate_prepared_impl(be, c->v, ell, o, a, hoist, c->perms[elt].data(), c->cperms[elt].data(), key, (u64 *)work);
 }
 }

@@ -106,6 +106,12 @@ def case_keyswitch(be, orc, ell, steps=(1, -2)):
     rk = orc.relin_key()
     eq(be.relinearize(a3, rk), orc.relinearize(a3, rk))
     a2 = rand_ct(orc, 2, ell, 22)
+    gks = []
     for s in steps:
         gk = orc.galois_key(o.galois_elt_from_step(orc.N, s))
+        gks.append(gk)
         eq(be.rotate(a2, s, gk), orc.rotate(a2, s, gk))
+    # rotations sharing the inverse NTT of the input (hoisted, exact)
+    if hasattr(be, "rotate_many"):
+        for s, gk, got in zip(steps, gks, be.rotate_many(a2, list(steps), gks)):
+            eq(got, orc.rotate(a2, s, gk))

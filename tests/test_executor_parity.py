@@ -117,6 +117,17 @@ def test_wide_dag():
     run_both("wide64")
 
 
+def test_without_hoisted_rotations():
+    """hoist_rotations=False: every rotation runs the plain evab_rotate path (default shares the inverse NTT)"""
+    from eva_b200 import b200
+    orig = b200.B200Public.set_options
+    try:
+        b200.B200Public.set_options = lambda self, **kw: orig(self, **{**kw, "hoist_rotations": False})
+        run_both("sobel", lo=0.0, hi=0.2)
+    finally:
+        b200.B200Public.set_options = orig
+
+
 @pytest.mark.parametrize("name,min_fused", [("sobel", 30), ("harris", 40), ("polynomial", 0), ("feat_hsum", 0), ("feat_mixed", 0), ("wide64", 1)])
 def test_fused_sums_bit_exact(name, min_fused):
     """default executor mode: trees of multiply_plain / add evaluated by one kernel (evab_sum_terms);
