@@ -19,7 +19,12 @@ for ell in (4, 3):
     stride = (3 * ell * N * 3 + ws + 64 + 63) // 64 * 64          # a3 | a2 | out | work per instance
     buf = torch.randint(0, 1 << 59, (B, stride), dtype=torch.int64, device="cuda")
     a3, a2, out, work = buf[0, :3*ell*N], buf[0, 3*ell*N:5*ell*N], buf[0, 6*ell*N:9*ell*N], buf[0, 9*ell*N:9*ell*N+ws]
-    ops = {"relinearize": (lambda: lib.evab_relinearize(h, ell, P(out), P(a3), P(key), P(work), st), ell + ell*ell + 2 + 2*ell),
+    hoist = torch.randint(0, 1 << 59, (B, stride), dtype=torch.int64, device="cuda")   # same stride: instance b at b*stride
+    def rot_prepared():
+        return lib.evab_rotate_prepared(h, ell, P(out), P(a2), P(buf[0, 5*ell*N:6*ell*N]), 3, P(key), P(work), st)
+    ops = {"rotate_prepared": (rot_prepared, ell*ell + 2 + 2*ell),
+           "rotate_prepare": (lambda: lib.evab_rotate_prepare(h, ell, P(buf[0, 5*ell*N:6*ell*N]), P(a2), st), ell),
+           "relinearize": (lambda: lib.evab_relinearize(h, ell, P(out), P(a3), P(key), P(work), st), ell + ell*ell + 2 + 2*ell),
            "rotate": (lambda: lib.evab_rotate(h, ell, P(out), P(a2), 3, P(key), P(work), st), ell + ell*ell + 2 + 2*ell),
            "rescale3": (lambda: lib.evab_rescale(h, ell, P(out), P(a3), 3, P(work), st), 3 + 3*(ell-1)),
            "mul_plain": (lambda: lib.evab_mul_plain(h, ell, P(out), P(a2), 2, P(a3), st), 0),
