@@ -165,7 +165,16 @@ __global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, co
 // ---------------------------------------------------------------------------
 // CUDA backend
 // ---------------------------------------------------------------------------
-static int g_ntt_cluster = 8;   // CTAs per residue for 2^13 <= N <= 2^14 (evab_set_ntt_cluster).  Sobel ops/s and single-instance latency: 1: 414k 1.11 ms, 2: 444k 0.76, 4: 477k 0.57, 8: 494k 0.49
+// CTAs per residue (evab_set_ntt_cluster); 0 = automatic: 128-thread CTAs, i.e. N/2048 CTAs per residue
+// (N=16384: 8, 8192: 4, 4096: 2).  Sobel ops/s and single-instance latency at N=16384:
+// 1: 414k 1.11 ms, 2: 444k 0.76, 4: 477k 0.57, 8: 494k 0.49; N=8192 is fastest at 4 (64-thread CTAs lose).
+static int g_ntt_cluster = 0;
+template <int LOGN> static int ntt_cluster_for() {
+  const int most = NttGeom<LOGN>::T / 128 < 1 ? 1 : NttGeom<LOGN>::T / 128;   // keep CTAs at >= 128 threads
+  int cl = g_ntt_cluster ? g_ntt_cluster : most;
+  if (cl > most) cl = most;
+  return cl;
+}
 
 template <class K> static int launch_ntt(K kernel, const NttLaunch &L, size_t ctas, int threads, size_t smem, int cluster, cudaStream_t st, std::atomic<bool> *done) {
   int dev = 0;
@@ -200,10 +209,13 @@ template <int LOGN, bool SPLIT, int CL> static int launch_fwd_c(const NttLaunch 
   return fail("unsupported forward NTT prologue/epilogue combination");
 }
 template <int LOGN, bool SPLIT> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  if constexpr (LOGN >= 13 && !SPLIT) {
-    if (g_ntt_cluster == 2) return launch_fwd_c<LOGN, SPLIT, 2>(L, jobs, st);
-    if (g_ntt_cluster == 4) return launch_fwd_c<LOGN, SPLIT, 4>(L, jobs, st);
-    if (g_ntt_cluster == 8) return launch_fwd_c<LOGN, SPLIT, 8>(L, jobs, st);
+  if constexpr (LOGN >= 12 && !SPLIT) {
+    const int cl = ntt_cluster_for<LOGN>();
+    if (cl == 2) return launch_fwd_c<LOGN, SPLIT, 2>(L, jobs, st);
+    if constexpr (LOGN >= 13) {
+      if (cl == 4) return launch_fwd_c<LOGN, SPLIT, 4>(L, jobs, st);
+      if (cl == 8) return launch_fwd_c<LOGN, SPLIT, 8>(L, jobs, st);
+    }
   }
   return launch_fwd_c<LOGN, SPLIT, 1>(L, jobs, st);
 }
@@ -226,10 +238,13 @@ template <int LOGN, bool SPLIT, int CL> static int launch_inv_c(const NttLaunch 
   return fail("unsupported inverse NTT epilogue");
 }
 template <int LOGN, bool SPLIT> static int launch_inv_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  if constexpr (LOGN >= 13 && !SPLIT) {
-    if (g_ntt_cluster == 2) return launch_inv_c<LOGN, SPLIT, 2>(L, jobs, st);
-    if (g_ntt_cluster == 4) return launch_inv_c<LOGN, SPLIT, 4>(L, jobs, st);
-    if (g_ntt_cluster == 8) return launch_inv_c<LOGN, SPLIT, 8>(L, jobs, st);
+  if constexpr (LOGN >= 12 && !SPLIT) {
+    const int cl = ntt_cluster_for<LOGN>();
+    if (cl == 2) return launch_inv_c<LOGN, SPLIT, 2>(L, jobs, st);
+    if constexpr (LOGN >= 13) {
+      if (cl == 4) return launch_inv_c<LOGN, SPLIT, 4>(L, jobs, st);
+      if (cl == 8) return launch_inv_c<LOGN, SPLIT, 8>(L, jobs, st);
+    }
   }
   return launch_inv_c<LOGN, SPLIT, 1>(L, jobs, st);
 }
@@ -497,7 +512,7 @@ extern "C" int evab_ntt_inv(evab_ctx *c, uint64_t *d, size_t count, const int *p
   BE_BEGIN return ntt_batch_impl(be, c->v, true, d, count, pidx, np);
 }
 extern "C" int evab_set_ntt_cluster(int cl) {
-  if (cl != 1 && cl != 2 && cl != 4 && cl != 8) return fail("evab_set_ntt_cluster: 1, 2, 4 or 8 CTAs per residue");
+  if (cl != 0 && cl != 1 && cl != 2 && cl != 4 && cl != 8) return fail("evab_set_ntt_cluster: 0 (automatic), 1, 2, 4 or 8 CTAs per residue");
   g_ntt_cluster = cl;
   return 0;
 }

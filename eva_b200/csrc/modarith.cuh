@@ -56,6 +56,38 @@ EVAB_HD u64 shoup_lazy_n(u64 y, u64 w, u64 ws, u64 np) {
   return w * y + q * np;
 }
 
+// ---- hand-scheduled lazy Shoup product for the NTT butterflies --------------------------------
+// B200 has no 64x64 multiplier; IMAD.WIDE.U32 / IMAD.HI.U32 hold the fma pipe for two cycles and
+// that pipe bounds the transforms.  The quotient estimate therefore uses THREE partial products:
+// q~ = a1*b1 + hi32(a1*b0) + hi32(a0*b1) drops a0*b0 and the low halves of the cross terms, so
+// q - 2 <= q~ <= q = floor(ws*y / 2^64), and  w*y - q~*p  is congruent to w*y and lies in [0, 4p)
+// for ANY u64 y (primes < 2^60 leave room for 16p).  shoup_mad4 returns  c + w*y + q~*np  (mod 2^64,
+// np = 2^64 - p) with the addend c riding in the multiply-add chain: 3 wide + 2 high + 4 low
+// multiplies and one 64-bit add.  Host and device evaluate the same integers.
+EVAB_HD u64 shoup_mad4(u64 y, u64 w, u64 ws, u64 np, u64 c) {
+  const u32 y0 = (u32)y, y1 = (u32)(y >> 32), w0 = (u32)w, w1 = (u32)(w >> 32);
+  const u32 s0 = (u32)ws, s1 = (u32)(ws >> 32), n0 = (u32)np, n1 = (u32)(np >> 32);
+#if defined(__CUDA_ARCH__)
+  u32 c0, c1; u64 q, m;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(c0) : "r"(s1), "r"(y0));
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(c1) : "r"(s0), "r"(y1));
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(q) : "r"(s1), "r"(y1), "l"((u64)c0));
+  q += c1;
+  const u32 q0 = (u32)q, q1 = (u32)(q >> 32);
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(m) : "r"(w0), "r"(y0), "l"(c));
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(m) : "r"(q0), "r"(n0), "l"(m));
+  u32 h = (u32)(m >> 32);
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(w0), "r"(y1));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(w1), "r"(y0));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(q0), "r"(n1));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(q1), "r"(n0));
+  return ((u64)h << 32) | (u32)m;
+#else
+  const u64 q = (u64)s1 * y1 + (((u64)s1 * y0) >> 32) + (((u64)s0 * y1) >> 32);
+  return c + w * y + q * np;
+#endif
+}
+
 // canonical add / sub / neg for operands already in [0,p)
 EVAB_HD u64 addmod(u64 a, u64 b, u64 p) { return csub(a + b, p); }
 EVAB_HD u64 submod(u64 a, u64 b, u64 p) { return a >= b ? a - b : a + p - b; }

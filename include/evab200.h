@@ -92,8 +92,9 @@ uint64_t evab_launch_count(const evab_ctx *ctx);
 int evab_ntt_fwd(evab_ctx *ctx, uint64_t *d_data, size_t count, const int *prime_idx, int nprimes, void *stream);
 int evab_ntt_inv(evab_ctx *ctx, uint64_t *d_data, size_t count, const int *prime_idx, int nprimes, void *stream);
 
-/* Tuning knob (process-wide): spread every residue transform of 8192 <= N <= 16384 over a thread-block
- * cluster of 1, 2, 4 or 8 (default) CTAs (distributed shared memory exchange).  Results are identical. */
+/* Tuning knob (process-wide): spread every residue transform of 4096 <= N <= 16384 over a thread-block
+ * cluster of 1, 2, 4 or 8 CTAs (distributed shared memory exchange), capped so that a CTA keeps at least
+ * 128 threads; 0 (default) = that cap.  Results are identical. */
 int evab_set_ntt_cluster(int ctas_per_residue);
 
 /* ---- CKKS encoder on the device: seal::CKKSEncoder::encode at seal_executor.h:242

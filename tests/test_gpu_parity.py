@@ -106,7 +106,7 @@ def test_gpu_encoder_bit_exact(N, bits):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,bits,cl", [(8192, [60, 60, 60], 1), (8192, [60, 60, 60], 2), (16384, [60] * 5, 1), (16384, [60] * 5, 4)])
+@pytest.mark.parametrize("N,bits,cl", [(4096, [60, 20, 60, 60], 1), (8192, [60, 60, 60], 1), (8192, [60, 60, 60], 2), (16384, [60] * 5, 1), (16384, [60] * 5, 4)])
 def test_gpu_cluster_distributed_ntt(N, bits, cl):
     """evab_set_ntt_cluster: one residue over a cluster of 2 / 4 CTAs (distributed shared memory) --
     identical results for the transforms and every fused variant (key switch, rescale, encoder)."""
@@ -123,5 +123,5 @@ def test_gpu_cluster_distributed_ntt(N, bits, cl):
             if ell >= 2:
                 pc.case_rescale(be, orc, ell)
     finally:
-        assert lib.evab_set_ntt_cluster(8) == 0   # library default
+        assert lib.evab_set_ntt_cluster(0) == 0   # library default (automatic)
     assert lib.evab_set_ntt_cluster(3) != 0
