@@ -98,6 +98,12 @@ def synthetic_inputs(d, primes, seed):
     return relin, galois, cts
 
 
+def workload_desc(name, d, nops):
+    head = "sobel_64x64 (examples/image_processing.py)" if name == "sobel" else name
+    return "%s compiled by the reference compiler: N=%d, prime_bits=%s, %d ciphertext ops per instance" % (
+        head, d["poly_modulus_degree"], "[60]*5" if d["prime_bits"] == [60] * 5 else str(d["prime_bits"]), nops)
+
+
 def multi_seed(rank, index):
     from eva_b200 import multi
     return multi.instance_seed(rank, index)
@@ -114,7 +120,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    d = program_io.load_json(WORKLOAD)
+    d = program_io.load_json(args.workload)
     B = args.instances
     N = d["poly_modulus_degree"]
     primes = b200.create_coeff_modulus(N, d["prime_bits"])
@@ -227,7 +233,7 @@ def run_ours(args):
         "metric": METRIC, "value": total_ops / t_res, "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "sobel_64x64 (examples/image_processing.py) compiled by the reference compiler: N=16384, prime_bits=[60]*5, 61 ciphertext ops per instance; one step = batch of %d independent program instances (images) per GPU" % B,
+        "config": {"workload": workload_desc(args.workload, d, nops) + "; one step = batch of %d independent program instances (images) per GPU" % B,
                    "instances_per_gpu": B,
                    "parallelism": "replicas x%d GPUs (independent program instances, no data-path collective; NCCL gather of outputs)" % world,
                    "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("%d concurrent cuda-graphs" % G if not args.no_graph else "streams") + " x %d instances fused per kernel launch, %d streams inside a plan" % (F, args.streams),
@@ -317,8 +323,8 @@ def cpu_baseline(d, B, sample_steps=1, threads=None):
     for _ in range(sample_steps):
         run_many(op, batch, threads)
     dt = time.perf_counter() - t0
-    return {"value": nops * B * sample_steps / dt, "unit": "ops/s", "cores": threads, "kind": "port",
-            "sample": "%d step(s) of %d Sobel instances (61 ops each) on the oracle port (not SEAL), one dependency-counting thread pool over %d threads" % (sample_steps, B, threads),
+    return {"value": nops * B * sample_steps / dt, "unit": "ops/s", "cores": threads, "kind": "port", "ops_per_instance": nops,
+            "sample": "%d step(s) of %d program instances (%d ops each) on the oracle port (not SEAL), one dependency-counting thread pool over %d threads" % (sample_steps, B, nops, threads),
             "ms_per_step": dt / sample_steps * 1e3}
 
 
@@ -327,15 +333,20 @@ def run_reference(args):
     if rank != 0:
         return
     from eva_b200 import program_io  # JSON loader only (no GPU work on this arm)
-    d = program_io.load_json(WORKLOAD)
+    d = program_io.load_json(args.workload)
     cb = None
     t0 = time.perf_counter()
-    cb = cpu_baseline(d, args.instances, sample_steps=max(1, args.steps))
+    # each step is a bounded sample of the workload: as many program instances of the batch as the host
+    # cores can run concurrently (4 threads each), so K steps end within a few minutes on any host
+    threads = len(os.sched_getaffinity(0))
+    Bs = max(1, min(args.instances, threads // 4))
+    cb = cpu_baseline(d, Bs, sample_steps=max(1, args.steps))
+    nops = cb["ops_per_instance"]
     dt = time.perf_counter() - t0
     res = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": "sobel_64x64 (examples/image_processing.py) compiled by the reference compiler: N=16384, prime_bits=[60]*5, 61 ciphertext ops per instance; one step = batch of %d independent program instances" % args.instances,
-                      "instances_per_gpu": args.instances,
+           "config": {"workload": workload_desc(args.workload, d, nops) + "; one step = batch of %d independent program instances" % args.instances,
+                      "instances_per_gpu": args.instances, "cpu_sample_instances_per_step": Bs,
                       "note": "reference SEAL+Galois path cannot be built (SEAL absent); CPU oracle port of the same path, all host threads"},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": dt}
     print(json.dumps(res))
@@ -356,6 +367,7 @@ def main():
     ap.set_defaults(no_const_cache=True)
     ap.add_argument("--no-dedup", action="store_true", help="encode every Encode term separately even when constants repeat")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default=WORKLOAD, help="fixture under tests/golden/programs (default: the BASELINE workload, sobel); e.g. harris")
     ap.add_argument("--ntt-cluster", type=int, default=None, help="CTAs per residue transform (1, 2, 4); default: library default")
     args = ap.parse_args()
     if args.impl == "reference":
