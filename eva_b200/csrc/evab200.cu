@@ -90,39 +90,30 @@ template <int CL> __device__ __forceinline__ SmemView<CL> smem_view(u64 *sm) {
   }
   return v;
 }
-// CL = 1: one CTA = one residue (or one half of a 2^15 residue), T = N/16 threads, 64 registers.
+// CL = 1: one CTA = one residue, T = N/16 threads, 64 registers.
 // CL = 2, 4: one residue over a cluster of CL CTAs of T/CL threads (ntt_core.cuh), CL CTAs per SM more.
-template <int LOGN, bool SPLIT, int PRO, int EPI, int CL>
+template <int LOGN, int PRO, int EPI, int CL>
 __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::T / CL)) k_ntt_fwd(const NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
-  typedef FwdBody<LOGN, SPLIT, PRO, EPI, CL> B;
-  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : CL, (long long)blockIdx.y * bstride);
+  typedef FwdBody<LOGN, PRO, EPI, CL> B;
+  const NttJob J = ntt_job(L, blockIdx.x, CL, (long long)blockIdx.y * bstride);
   if (J.skip) return;
   NttState S;
   const u32 tid = threadIdx.x;
-  if (PRO == PRO_PLAIN && EPI == EPI_STORE && J.bcast) { fwd_const_poly<LOGN, SPLIT>(J, B::vtid(J, tid)); return; }
+  if (PRO == PRO_PLAIN && EPI == EPI_STORE && J.bcast) { fwd_const_poly<LOGN>(J, B::vtid(J, tid)); return; }
   const DevHooks<CL> hk;
   hk.arrive();   // this CTA is resident: peers may store into its shared memory (waited on in phase 0)
   PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, smem_view<CL>(sm), DevSync<CL>(), hk);
-  if (SPLIT) {  // CTA pair (cluster of 2): both halves have consumed the input
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-  }
   B::phE(S, L, J, tid);
 }
-template <int LOGN, bool SPLIT, int PRO, int EPI, int CL>
+template <int LOGN, int PRO, int EPI, int CL>
 __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::T / CL)) k_ntt_inv(const NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
-  typedef InvBody<LOGN, SPLIT, PRO, EPI, CL> B;
-  const NttJob J = ntt_job(L, blockIdx.x, SPLIT ? 2 : CL, (long long)blockIdx.y * bstride);
+  typedef InvBody<LOGN, PRO, EPI, CL> B;
+  const NttJob J = ntt_job(L, blockIdx.x, CL, (long long)blockIdx.y * bstride);
   if (J.skip) return;
   NttState S;
   PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, smem_view<CL>(sm), DevSync<CL>(), DevHooks<CL>());
-}
-__global__ void __launch_bounds__(256) k_inv_last_stage(const NttLaunch L, u32 half_n, const long long bstride) {
-  const NttJob J = ntt_job(L, blockIdx.y, 1, (long long)blockIdx.z * bstride);
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < half_n) inv_last_stage_elem(L, J, i, half_n);
 }
 template <int OP> __global__ void __launch_bounds__(256) k_dyadic(DyArgs A, const long long bstride) {
   { const long long off = (long long)blockIdx.z * bstride; A.out += off; if (A.a) A.a += off; if (A.b) A.b += off; }
@@ -170,9 +161,11 @@ __global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, co
 // 1: 414k 1.11 ms, 2: 444k 0.76, 4: 477k 0.57, 8: 494k 0.49; N=8192 is fastest at 4 (64-thread CTAs lose).
 static int g_ntt_cluster = 0;
 template <int LOGN> static int ntt_cluster_for() {
-  const int most = NttGeom<LOGN>::T / 128 < 1 ? 1 : NttGeom<LOGN>::T / 128;   // keep CTAs at >= 128 threads
+  int most = NttGeom<LOGN>::T / 128 < 1 ? 1 : NttGeom<LOGN>::T / 128;   // keep CTAs at >= 128 threads
+  if (most > 8) most = 8;                                                 // portable cluster size
   int cl = g_ntt_cluster ? g_ntt_cluster : most;
   if (cl > most) cl = most;
+  if (LOGN == 15 && cl < 2) cl = 2;                                       // 2048 threads never fit one CTA
   return cl;
 }
 
@@ -195,58 +188,51 @@ template <class K> static int launch_ntt(K kernel, const NttLaunch &L, size_t ct
   CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, L, g_batch.stride));
   return 0;
 }
-template <int LOGN, bool SPLIT, int PRO, int EPI, int CL> static int launch_fwd_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+template <int LOGN, int PRO, int EPI, int CL> static int launch_fwd_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   static std::atomic<bool> done[64];
-  constexpr int CPJ = SPLIT ? 2 : CL;
-  return launch_ntt(k_ntt_fwd<LOGN, SPLIT, PRO, EPI, CL>, L, jobs * CPJ, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CPJ, st, done);
+  return launch_ntt(k_ntt_fwd<LOGN, PRO, EPI, CL>, L, jobs * CL, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CL, st, done);
 }
-template <int LOGN, bool SPLIT, int CL> static int launch_fwd_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_PLAIN, EPI_STORE, CL>(L, jobs, st);
-  if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE, CL>(L, jobs, st);
-  if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_STORE_LAZY, CL>(L, jobs, st);
-  if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED, EPI_DIVROUND, CL>(L, jobs, st);
-  if (L.pro == PRO_MODRED_SG && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, SPLIT, PRO_MODRED_SG, EPI_STORE_LAZY, CL>(L, jobs, st);
+template <int LOGN, int CL> static int launch_fwd_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_fwd_m<LOGN, PRO_PLAIN, EPI_STORE, CL>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return launch_fwd_m<LOGN, PRO_MODRED, EPI_STORE, CL>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, PRO_MODRED, EPI_STORE_LAZY, CL>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return launch_fwd_m<LOGN, PRO_MODRED, EPI_DIVROUND, CL>(L, jobs, st);
+  if (L.pro == PRO_MODRED_SG && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, PRO_MODRED_SG, EPI_STORE_LAZY, CL>(L, jobs, st);
   return fail("unsupported forward NTT prologue/epilogue combination");
 }
-template <int LOGN, bool SPLIT> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  if constexpr (LOGN >= 12 && !SPLIT) {
+template <int LOGN> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  if constexpr (LOGN >= 12) {
     const int cl = ntt_cluster_for<LOGN>();
-    if (cl == 2) return launch_fwd_c<LOGN, SPLIT, 2>(L, jobs, st);
     if constexpr (LOGN >= 13) {
-      if (cl == 4) return launch_fwd_c<LOGN, SPLIT, 4>(L, jobs, st);
-      if (cl == 8) return launch_fwd_c<LOGN, SPLIT, 8>(L, jobs, st);
+      if (cl == 4) return launch_fwd_c<LOGN, 4>(L, jobs, st);
+      if (cl == 8) return launch_fwd_c<LOGN, 8>(L, jobs, st);
     }
+    if (cl == 2 || LOGN == 15) return launch_fwd_c<LOGN, 2>(L, jobs, st);
   }
-  return launch_fwd_c<LOGN, SPLIT, 1>(L, jobs, st);
+  if constexpr (LOGN <= 14) return launch_fwd_c<LOGN, 1>(L, jobs, st);
+  return fail("unsupported cluster size");
 }
-template <int LOGN, bool SPLIT, int EPI, int CL> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+template <int LOGN, int EPI, int CL> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   static std::atomic<bool> done[64];
-  constexpr int CPJ = SPLIT ? 2 : CL;
-  if (int rc = launch_ntt(k_ntt_inv<LOGN, SPLIT, PRO_PLAIN, EPI, CL>, L, jobs * CPJ, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), SPLIT ? 1 : CL, st, done)) return rc;
-  if (SPLIT) {
-    const u32 half = NttGeom<LOGN>::N;
-    dim3 g((half + 255) / 256, (unsigned)jobs, (unsigned)g_batch.batch);
-    k_inv_last_stage<<<g, 256, 0, st>>>(L, half, g_batch.stride);
-    CUDA_OK(cudaGetLastError());
-  }
-  return 0;
+  return launch_ntt(k_ntt_inv<LOGN, PRO_PLAIN, EPI, CL>, L, jobs * CL, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CL, st, done);
 }
-template <int LOGN, bool SPLIT, int CL> static int launch_inv_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+template <int LOGN, int CL> static int launch_inv_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   if (L.pro != PRO_PLAIN) return fail("unsupported inverse NTT prologue");
-  if (L.epi == EPI_STORE) return launch_inv_m<LOGN, SPLIT, EPI_STORE, CL>(L, jobs, st);
-  if (L.epi == EPI_ADDHALF) return launch_inv_m<LOGN, SPLIT, EPI_ADDHALF, CL>(L, jobs, st);
+  if (L.epi == EPI_STORE) return launch_inv_m<LOGN, EPI_STORE, CL>(L, jobs, st);
+  if (L.epi == EPI_ADDHALF) return launch_inv_m<LOGN, EPI_ADDHALF, CL>(L, jobs, st);
   return fail("unsupported inverse NTT epilogue");
 }
-template <int LOGN, bool SPLIT> static int launch_inv_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  if constexpr (LOGN >= 12 && !SPLIT) {
+template <int LOGN> static int launch_inv_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  if constexpr (LOGN >= 12) {
     const int cl = ntt_cluster_for<LOGN>();
-    if (cl == 2) return launch_inv_c<LOGN, SPLIT, 2>(L, jobs, st);
     if constexpr (LOGN >= 13) {
-      if (cl == 4) return launch_inv_c<LOGN, SPLIT, 4>(L, jobs, st);
-      if (cl == 8) return launch_inv_c<LOGN, SPLIT, 8>(L, jobs, st);
+      if (cl == 4) return launch_inv_c<LOGN, 4>(L, jobs, st);
+      if (cl == 8) return launch_inv_c<LOGN, 8>(L, jobs, st);
     }
+    if (cl == 2 || LOGN == 15) return launch_inv_c<LOGN, 2>(L, jobs, st);
   }
-  return launch_inv_c<LOGN, SPLIT, 1>(L, jobs, st);
+  if constexpr (LOGN <= 14) return launch_inv_c<LOGN, 1>(L, jobs, st);
+  return fail("unsupported cluster size");
 }
 
 struct CudaBE {
@@ -262,24 +248,24 @@ struct CudaBE {
   int fwd(const NttLaunch &L, size_t jobs) {
     count();
     switch (c->v.logN) {
-      case 10: return launch_fwd_t<10, false>(L, jobs, st);
-      case 11: return launch_fwd_t<11, false>(L, jobs, st);
-      case 12: return launch_fwd_t<12, false>(L, jobs, st);
-      case 13: return launch_fwd_t<13, false>(L, jobs, st);
-      case 14: return launch_fwd_t<14, false>(L, jobs, st);
-      case 15: return launch_fwd_t<14, true>(L, jobs, st);
+      case 10: return launch_fwd_t<10>(L, jobs, st);
+      case 11: return launch_fwd_t<11>(L, jobs, st);
+      case 12: return launch_fwd_t<12>(L, jobs, st);
+      case 13: return launch_fwd_t<13>(L, jobs, st);
+      case 14: return launch_fwd_t<14>(L, jobs, st);
+      case 15: return launch_fwd_t<15>(L, jobs, st);
     }
     return fail("unsupported N");
   }
   int inv(const NttLaunch &L, size_t jobs) {
-    count(c->v.logN == 15 ? 2 : 1);
+    count();
     switch (c->v.logN) {
-      case 10: return launch_inv_t<10, false>(L, jobs, st);
-      case 11: return launch_inv_t<11, false>(L, jobs, st);
-      case 12: return launch_inv_t<12, false>(L, jobs, st);
-      case 13: return launch_inv_t<13, false>(L, jobs, st);
-      case 14: return launch_inv_t<14, false>(L, jobs, st);
-      case 15: return launch_inv_t<14, true>(L, jobs, st);
+      case 10: return launch_inv_t<10>(L, jobs, st);
+      case 11: return launch_inv_t<11>(L, jobs, st);
+      case 12: return launch_inv_t<12>(L, jobs, st);
+      case 13: return launch_inv_t<13>(L, jobs, st);
+      case 14: return launch_inv_t<14>(L, jobs, st);
+      case 15: return launch_inv_t<15>(L, jobs, st);
     }
     return fail("unsupported N");
   }

@@ -1,11 +1,11 @@
 // ntt_core.cuh -- register-resident negacyclic NTT / iNTT over one RNS residue.
 //
-// One CTA of T = N/16 threads transforms one residue polynomial (N = 2^n,
-// 10 <= n <= 14; n = 15 is handled by the callers as two n = 14 sub-transforms
-// with a twiddle "root prefix").  Every thread keeps E = 16 coefficients in
-// registers for the whole transform (64 registers/thread: a full SM holds one
-// N = 16384 residue in 32 warps) -- the residue never lives in shared memory,
-// which is only the exchange medium between P = ceil(n/4) register passes:
+// T = N/16 threads transform one residue polynomial (N = 2^n, 10 <= n <= 15), as one
+// CTA or spread over a thread-block cluster of 2/4/8 CTAs (see SmemView below; n = 15
+// needs a cluster: 2048 threads).  Every thread keeps E = 16 coefficients in registers
+// for the whole transform (64 registers/thread: the register file of one SM holds one
+// N = 16384 residue) -- the residue never lives in shared memory, which is only the
+// exchange medium between P = ceil(n/4) register passes:
 //
 //   pass j < P-1   stages 4j..4j+3   thread owns idx = (H << (lb+4)) | (k << lb) | L,
 //                                    lb = n - 4(j+1), tid = (H << lb) | L        (strided)
@@ -47,7 +47,7 @@ constexpr int NTT_EL = 4;            // log2(coefficients per thread)
 constexpr int NTT_E = 1 << NTT_EL;   // coefficients per thread
 
 template <int LOGN> struct NttGeom {
-  static_assert(LOGN >= 10 && LOGN <= 14, "register NTT core supports 2^10..2^14");
+  static_assert(LOGN >= 10 && LOGN <= 15, "register NTT core supports 2^10..2^15 (2^15 only across a cluster: 2048 threads)");
   static constexpr int N = 1 << LOGN;
   static constexpr int T = N / NTT_E;                          // threads per residue
   static constexpr int P = (LOGN + NTT_EL - 1) / NTT_EL;       // register passes
@@ -220,8 +220,7 @@ template <int LOGN, int CL> EVAB_HD void xchg_read_dist_inv(u64 (&x)[NTT_E], con
 // ---------------------------------------------------------------------------
 // forward (Cooley-Tukey) register passes.  `b` is the compile-time tracked
 // upper bound of every live value in units of p (values < b*p <= 16p < 2^64).
-// `root` is the twiddle root prefix: 1 for a full transform; 2+h for the h-th
-// half of an n+1 transform (twiddle index = (root << s) + group).
+// `root` is the twiddle root prefix (twiddle index = (root << s) + group): 1 for a full transform.
 // ---------------------------------------------------------------------------
 // one forward stage over the registers: pair distance D (in k), E/2/D groups of
 // twiddles starting at table index tw0 (consecutive).

@@ -126,57 +126,41 @@ EVAB_HD void store16(u64 *p, const u64 (&a)[NTT_E]) {
 #endif
 }
 // forward transform of a constant polynomial c (canonical): c at every evaluation point.
-// Thread tid of CTA half h writes its 16 contiguous outputs (in place: dst[0] keeps its value).
-template <int LOGN, bool SPLIT> EVAB_HD void fwd_const_poly(const NttJob &J, u32 tid) {
+// Virtual thread tid writes its 16 contiguous outputs (in place: dst[0] keeps its value).
+template <int LOGN> EVAB_HD void fwd_const_poly(const NttJob &J, u32 tid) {
   const u64 v = EVAB_LDG(J.src);
   u64 x[NTT_E];
 #pragma unroll
   for (int k = 0; k < NTT_E; k++) x[k] = v;
-  store16(J.dst + ((size_t)(SPLIT ? J.h : 0) * NttGeom<LOGN>::T + tid) * NTT_E, x);
+  store16(J.dst + (size_t)tid * NTT_E, x);
 }
 
 
 // ------------------------------ forward ------------------------------------
 // Phases (separated by block barriers), P = NttGeom::P register passes:
-//   0          : load (layout of pass 0) [+ split stage] + pass 0 + exchange write
+//   0          : load (layout of pass 0) + pass 0 + exchange write
 //   2j-1, 2j   : exchange read + pass j   |   exchange write        (1 <= j <= P-2)
 //   2(P-1)-1   : exchange read + last (contiguous) pass
 //   phE        : fused epilogue + store
-template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct FwdBody {
+template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct FwdBody {
   typedef NttGeom<LOGN> G;
   typedef ClGeom<LOGN, CL> C;
-  static_assert(!(SPLIT && CL > 1), "split and cluster-distributed transforms are exclusive");
   static constexpr int NPH = G::NPH;
   // barrier after phase PH: 0 = block, 1 = cluster (the exchange written in phase 0 crosses CTAs)
   static EVAB_HD constexpr int sync_kind(int ph) { return (CL > 1 && ph == 0) ? 1 : 0; }
   // virtual thread id: rank * Tc + tid
   static EVAB_HD u32 vtid(const NttJob &J, u32 tid) { return CL > 1 ? J.h * (u32)C::Tc + tid : tid; }
 
-  // load of pass 0 (strided, coalesced) with the fused prologue [+ first stage of a split transform]
+  // load of pass 0 (strided, coalesced) with the fused prologue
   template <bool CHEAP> static EVAB_HD void load0(NttState &S, const NttLaunch &L, const NttJob &J, const PrimeDev &P, u32 tid, u64 sub) {
-    if (!SPLIT) {
 #pragma unroll
-      for (int k = 0; k < NTT_E; k++) S.x[k] = pro_load<PRO, CHEAP>(L, J, P, idx_s<LOGN, 0>(tid, k), sub);
-      S.b = 1;
-    } else {
-      // first stage of the 2N transform: pairs (i, i + N) with twiddle tw[1];
-      // this CTA keeps the h-th output half and continues with root prefix 2+h
-      const u64x2 w = ldg_tw(P.tw + 1);
-      const u64 two_p = 2 * P.p;
-#pragma unroll
-      for (int k = 0; k < NTT_E; k++) {
-        const u32 i = idx_s<LOGN, 0>(tid, k);
-        const u64 X = pro_load<PRO, CHEAP>(L, J, P, i, sub), Y = pro_load<PRO, CHEAP>(L, J, P, i + G::N, sub);
-        const u64 t = shoup_lazy(Y, w.x, w.y, P.p);
-        S.x[k] = J.h ? X - t + two_p : X + t;
-      }
-      S.b = 3;
-    }
+    for (int k = 0; k < NTT_E; k++) S.x[k] = pro_load<PRO, CHEAP>(L, J, P, idx_s<LOGN, 0>(tid, k), sub);
+    S.b = 1;
   }
   // ltid: thread index inside the CTA; the passes run on the virtual thread id
   template <int PH, class Hooks> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid, const SmemView<CL> &smv, Hooks hk) {
     const PrimeDev P = L.primes[J.pi];
-    const u32 root = SPLIT ? 2 + J.h : 1;
+    const u32 root = 1;   // twiddle root prefix of a full transform
     const u32 tid = vtid(J, ltid);
     u64 *sm = smv.local;
     if constexpr (PH == 0) {
@@ -206,12 +190,10 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL
     }
   }
   // final phase: fused epilogue + store of 16 contiguous coefficients.
-  // SPLIT: the two CTAs of a job both read the whole input, so for in-place
-  // transforms the caller must barrier the CTA pair (cluster) before this phase.
   static EVAB_HD void phE(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid) {
     const PrimeDev P = L.primes[J.pi];
     const u32 tid = vtid(J, ltid);
-    const size_t base = (size_t)(SPLIT ? J.h * G::N : 0) + ((size_t)tid << NTT_EL);
+    const size_t base = (size_t)tid << NTT_EL;
     if (EPI == EPI_DIVROUND) {
       // (aux0 - x) * c [+ aux1] without canonicalising x first: x < b*p, so
       // aux0 + b*p - x is positive and < 16p; the Shoup product lands in [0,2p).
@@ -257,12 +239,9 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL
 // Phases: 0: contiguous load + last-pass stages + exchange write;
 //         then for j = P-2 .. 1: exchange read + pass j | exchange write;
 //         last: exchange read + pass 0 + scale by N^-1 + epilogue store (strided, coalesced).
-// SPLIT: each CTA runs the LOGN-stage inverse on one half (root prefix 2+h) and
-// stores lazily-reduced values; inv_last_stage_elem then finishes the transform.
-template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct InvBody {
+template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct InvBody {
   typedef NttGeom<LOGN> G;
   typedef ClGeom<LOGN, CL> C;
-  static_assert(!(SPLIT && CL > 1), "split and cluster-distributed transforms are exclusive");
   static constexpr int NPH = G::NPH;
   // barrier after phase PH: 0 = block, 1 = cluster, 2 = none.  CL > 1: the exchange into pass 0
   // (written in phase NPH-2) crosses CTAs; every CTA signals "done reading my slice" right after the
@@ -273,11 +252,11 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL
 
   template <int PH, class Hooks> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid, const SmemView<CL> &smv, Hooks hk) {
     const PrimeDev P = L.primes[J.pi];
-    const u32 root = SPLIT ? 2 + J.h : 1;
+    const u32 root = 1;   // twiddle root prefix of a full transform
     const u32 tid = vtid(J, ltid);
     u64 *sm = smv.local;
     if constexpr (PH == 0) {
-      const size_t base = (size_t)(SPLIT ? J.h * G::N : 0) + ((size_t)tid << NTT_EL);
+      const size_t base = (size_t)tid << NTT_EL;
       if (PRO == PRO_GATHER) {
 #pragma unroll
         for (int k = 0; k < NTT_E; k++) S.x[k] = EVAB_LDG(J.src + EVAB_LDG(L.perm + base + k));
@@ -290,11 +269,6 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL
     } else if constexpr (PH == NPH - 1) {
       if constexpr (CL > 1) xchg_read_dist_inv<LOGN, CL>(S.x, sm, ltid); else xchg_read_s<LOGN, 0, 1>(S.x, sm, tid);
       inv_pass_s<LOGN, 0>(S.x, P.itw, root, P.p, tid, S.b);
-      if (SPLIT) {  // leave < 8p values for the last-stage kernel
-#pragma unroll
-        for (int k = 0; k < NTT_E; k++) J.dst[(size_t)J.h * G::N + idx_s<LOGN, 0>(tid, k)] = S.x[k];
-        return;
-      }
       const u64 half = P.p >> 1;
 #pragma unroll
       for (int k = 0; k < NTT_E; k++) {
@@ -325,21 +299,6 @@ template <int LOGN, bool SPLIT, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL
   }
 };
 
-// last stage of a split inverse transform of length 2N2 = 2^(LOGN+1):
-// X' = (X + Y) * ninv, Y' = (X - Y) * itw[1] * ninv, inputs < 8p.
-EVAB_HD void inv_last_stage_elem(const NttLaunch &L, const NttJob &J, u32 i, u32 half_n) {
-  const PrimeDev P = L.primes[J.pi];
-  const u64x2 w = ldg_tw(P.itw + 1);
-  u64 X = J.dst[i], Y = J.dst[i + half_n];
-  u64 s = X + Y;                 // < 16p
-  u64 d = X - Y + 8 * P.p;       // < 16p
-  u64 a = shoup_mul(s, P.ninv, P.ninv_s, P.p);
-  u64 b = shoup_mul(shoup_lazy(d, w.x, w.y, P.p), P.ninv, P.ninv_s, P.p);
-  if (L.epi == EPI_ADDHALF) { const u64 h = P.p >> 1; a = addmod(a, h, P.p); b = addmod(b, h, P.p); }
-  J.dst[i] = a; J.dst[i + half_n] = b;
-}
-
-// compile-time loop over the barrier-separated phases
 // sync(kind): barrier after a phase (B::sync_kind); hk: split cluster barrier (arrive / wait) used to
 // order the stores into a peer's shared memory after that peer's last reads of it
 struct NoHooks { EVAB_HD void arrive() const {} EVAB_HD void wait() const {} };

@@ -32,69 +32,62 @@ template <class B, int CL, int NPH> struct EmuPhases<B, CL, NPH, NPH> {
   static void run(NttState *, int, int, const NttLaunch &, const NttJob *, const SmemView<CL> *) {}
 };
 
-// CL > 1: one residue over a cluster of CL CTAs (distributed shared memory exchange);
-// SPLIT: the two independent half transforms of a 2^15 residue (each with its own shared memory)
-template <int LOGN, bool SPLIT, bool INV, int PRO, int EPI, int CL> static void run_ntt_m(const NttLaunch &L, size_t jobs) {
+// one residue over a cluster of CL CTAs (CL = 1: a single CTA); distributed shared memory = the
+// SmemView's peer pointers
+template <int LOGN, bool INV, int PRO, int EPI, int CL> static void run_ntt_m(const NttLaunch &L, size_t jobs) {
   typedef NttGeom<LOGN> G;
-  constexpr int CPJ = SPLIT ? 2 : CL;         // CTAs per job
   constexpr int Tc = G::T / CL;                // threads per CTA
   constexpr size_t SMC = (size_t)G::N / CL;    // shared-memory words per CTA
-  std::vector<u64> smc((size_t)CPJ * SMC);
-  std::vector<NttState> stc((size_t)CPJ * Tc);
+  std::vector<u64> smc((size_t)CL * SMC);
+  std::vector<NttState> stc((size_t)CL * Tc);
   for (size_t job = 0; job < jobs; job++) {
-    NttJob J[CPJ];
-    SmemView<CL> sm[CPJ];
-    for (int h = 0; h < CPJ; h++) {
-      J[h] = ntt_job(L, (u32)(job * CPJ + h), CPJ);
+    NttJob J[CL];
+    SmemView<CL> sm[CL];
+    for (int h = 0; h < CL; h++) {
+      J[h] = ntt_job(L, (u32)(job * CL + h), CL);
       sm[h].local = smc.data() + (size_t)h * SMC;
-      for (int r = 0; r < CL; r++) sm[h].peer[r] = CL > 1 ? smc.data() + (size_t)r * SMC : sm[h].local;
+      for (int r = 0; r < CL; r++) sm[h].peer[r] = smc.data() + (size_t)r * SMC;
     }
     if (J[0].skip) continue;
     if (!INV && PRO == PRO_PLAIN && EPI == EPI_STORE && J[0].bcast) {
-      for (int h = 0; h < CPJ; h++)
-        for (u32 t = 0; t < (u32)Tc; t++) fwd_const_poly<LOGN, SPLIT>(J[h], (CL > 1 ? (u32)h * Tc : 0u) + t);
+      for (int h = 0; h < CL; h++)
+        for (u32 t = 0; t < (u32)Tc; t++) fwd_const_poly<LOGN>(J[h], (u32)h * Tc + t);
       continue;
     }
     if (!INV) {
-      // forward: all compute phases, then (SPLIT: cluster barrier, then) the store phase
-      typedef FwdBody<LOGN, SPLIT, PRO, EPI, CL> B;
-      EmuPhases<B, CL, 0, B::NPH>::run(stc.data(), Tc, CPJ, L, J, sm);
-      for (int h = 0; h < CPJ; h++)
+      typedef FwdBody<LOGN, PRO, EPI, CL> B;
+      EmuPhases<B, CL, 0, B::NPH>::run(stc.data(), Tc, CL, L, J, sm);
+      for (int h = 0; h < CL; h++)
         for (u32 t = 0; t < (u32)Tc; t++) B::phE(stc[(size_t)h * Tc + t], L, J[h], t);
     } else {
-      typedef InvBody<LOGN, SPLIT, PRO, EPI, CL> B;
-      EmuPhases<B, CL, 0, B::NPH>::run(stc.data(), Tc, CPJ, L, J, sm);
+      typedef InvBody<LOGN, PRO, EPI, CL> B;
+      EmuPhases<B, CL, 0, B::NPH>::run(stc.data(), Tc, CL, L, J, sm);
     }
   }
-  if (INV && SPLIT)
-    for (size_t job = 0; job < jobs; job++) {
-      const NttJob J = ntt_job(L, (u32)job, 1);
-      for (u32 i = 0; i < (u32)G::N; i++) inv_last_stage_elem(L, J, i, G::N);
-    }
 }
 
 static int g_cl = 1;   // emu_set_cluster: CTAs per residue for N >= 4096 (1, 2, 4)
 
-template <int LOGN, bool SPLIT, bool INV, int CL> static void run_ntt_c(const NttLaunch &L, size_t jobs) {
+template <int LOGN, bool INV, int CL> static void run_ntt_c(const NttLaunch &L, size_t jobs) {
   if (!INV) {
-    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_PLAIN, EPI_STORE, CL>(L, jobs);
-    if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE, CL>(L, jobs);
-    if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_STORE_LAZY, CL>(L, jobs);
-    if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED, EPI_DIVROUND, CL>(L, jobs);
-    if (L.pro == PRO_MODRED_SG && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, SPLIT, false, PRO_MODRED_SG, EPI_STORE_LAZY, CL>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, false, PRO_PLAIN, EPI_STORE, CL>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return run_ntt_m<LOGN, false, PRO_MODRED, EPI_STORE, CL>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, false, PRO_MODRED, EPI_STORE_LAZY, CL>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return run_ntt_m<LOGN, false, PRO_MODRED, EPI_DIVROUND, CL>(L, jobs);
+    if (L.pro == PRO_MODRED_SG && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, false, PRO_MODRED_SG, EPI_STORE_LAZY, CL>(L, jobs);
   } else {
-    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_STORE, CL>(L, jobs);
-    if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return run_ntt_m<LOGN, SPLIT, true, PRO_PLAIN, EPI_ADDHALF, CL>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_STORE, CL>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_ADDHALF, CL>(L, jobs);
   }
   abort();
 }
-template <int LOGN, bool SPLIT, bool INV> static void run_ntt(const NttLaunch &L, size_t jobs) {
-  if constexpr (LOGN >= 12 && !SPLIT) {
-    if (g_cl == 2) return run_ntt_c<LOGN, SPLIT, INV, 2>(L, jobs);
-    if (g_cl == 4) return run_ntt_c<LOGN, SPLIT, INV, 4>(L, jobs);
-    if (g_cl == 8) return run_ntt_c<LOGN, SPLIT, INV, 8>(L, jobs);
+template <int LOGN, bool INV> static void run_ntt(const NttLaunch &L, size_t jobs) {
+  if constexpr (LOGN >= 12) {
+    if (g_cl == 4) return run_ntt_c<LOGN, INV, 4>(L, jobs);
+    if (g_cl == 8) return run_ntt_c<LOGN, INV, 8>(L, jobs);
+    if (g_cl == 2 || LOGN == 15) return run_ntt_c<LOGN, INV, 2>(L, jobs);   // 2^15: at least 2 CTAs
   }
-  return run_ntt_c<LOGN, SPLIT, INV, 1>(L, jobs);
+  if constexpr (LOGN <= 14) return run_ntt_c<LOGN, INV, 1>(L, jobs);
 }
 
 struct EmuBE {
@@ -102,24 +95,24 @@ struct EmuBE {
   int error(const char *m) { g_err = m; return 1; }
   int fwd(const NttLaunch &L, size_t jobs) {
     switch (c->v.logN) {
-      case 10: run_ntt<10, false, false>(L, jobs); break;
-      case 11: run_ntt<11, false, false>(L, jobs); break;
-      case 12: run_ntt<12, false, false>(L, jobs); break;
-      case 13: run_ntt<13, false, false>(L, jobs); break;
-      case 14: run_ntt<14, false, false>(L, jobs); break;
-      case 15: run_ntt<14, true, false>(L, jobs); break;
+      case 10: run_ntt<10, false>(L, jobs); break;
+      case 11: run_ntt<11, false>(L, jobs); break;
+      case 12: run_ntt<12, false>(L, jobs); break;
+      case 13: run_ntt<13, false>(L, jobs); break;
+      case 14: run_ntt<14, false>(L, jobs); break;
+      case 15: run_ntt<15, false>(L, jobs); break;
       default: return error("unsupported N");
     }
     return 0;
   }
   int inv(const NttLaunch &L, size_t jobs) {
     switch (c->v.logN) {
-      case 10: run_ntt<10, false, true>(L, jobs); break;
-      case 11: run_ntt<11, false, true>(L, jobs); break;
-      case 12: run_ntt<12, false, true>(L, jobs); break;
-      case 13: run_ntt<13, false, true>(L, jobs); break;
-      case 14: run_ntt<14, false, true>(L, jobs); break;
-      case 15: run_ntt<14, true, true>(L, jobs); break;
+      case 10: run_ntt<10, true>(L, jobs); break;
+      case 11: run_ntt<11, true>(L, jobs); break;
+      case 12: run_ntt<12, true>(L, jobs); break;
+      case 13: run_ntt<13, true>(L, jobs); break;
+      case 14: run_ntt<14, true>(L, jobs); break;
+      case 15: run_ntt<15, true>(L, jobs); break;
       default: return error("unsupported N");
     }
     return 0;

@@ -61,7 +61,8 @@ def test_emu_encode(N, bits):
 
 
 @pytest.mark.parametrize("N,bits,cl", [(4096, [60, 20, 60, 60], 2), (4096, [60, 20, 60, 60], 4), (8192, [60, 60, 60], 4),
-                                        (16384, [60, 60, 60, 60, 60], 2), (16384, [60, 60, 60, 60, 60], 4), (8192, [60, 60, 60], 8), (16384, [60, 60, 60, 60, 60], 8)])
+                                        (16384, [60, 60, 60, 60, 60], 2), (16384, [60, 60, 60, 60, 60], 4), (8192, [60, 60, 60], 8), (16384, [60, 60, 60, 60, 60], 8),
+                                        (32768, [60, 20, 60, 60], 4), (32768, [60, 20, 60, 60], 8)])
 def test_emu_cluster_distributed(N, bits, cl):
     """one residue spread over a cluster of 2 / 4 CTAs (distributed shared-memory exchange)"""
     import numpy as np
