@@ -182,7 +182,8 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         step_resident()
     torch.cuda.synchronize()
-    outs = pub.execute_batch(prog, all_vals)   # warm the e2e path (same plan replicas)
+    for _ in range(max(3, args.warmup)):       # warm the e2e path (same plan replicas; fills the pinned-buffer pool)
+        outs = pub.execute_batch(prog, all_vals)
 
     sampler = ClockSampler(local)
     sampler.start()
