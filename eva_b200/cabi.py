@@ -43,6 +43,7 @@ _SIGS = {
     "evab_host_alloc": (ci, [szt, C.POINTER(vp)]),
     "evab_host_free": (ci, [vp]),
     "evab_encode_work_bytes": (szt, [vp, ci]),
+    "evab_encode_uniform": (ci, [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double), ci, vp, vp]),
     "evab_encode": (ci, [vp, ci, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_double), ci, vp, vp, vp]),
     "evab_add": (ci, [vp, ci, vp, vp, ci, vp, ci, vp]),
     "evab_sub": (ci, [vp, ci, vp, vp, ci, vp, ci, vp]),

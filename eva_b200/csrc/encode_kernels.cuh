@@ -89,21 +89,44 @@ EVAB_HD void enc_fft8(const EncBatch &B, u32 e, u32 t, u32 g, int nstages, long 
   else { for (u32 s = 0; s < 4; s++) enc_fft_set<1>(B, e, 4 * t + s, g, off); }
 }
 
-// coefficient j: round(re * scale / N) -> residue mod prime i (sign-aware; exact for
-// magnitudes beyond 2^64 through mantissa * 2^shift)
-EVAB_HD void enc_round(const EncBatch &B, u32 e, u32 j, long long off = 0) {
-  const double fix = B.scale[e] / (double)B.N;
-  const double c = round(D_MUL((B.work + off / 2)[(size_t)e * B.N + j].re, fix));
+// rounded coefficient c (an integer-valued double of any magnitude) -> residue mod prime i
+// (sign-aware; exact beyond 2^64 through mantissa * 2^shift)
+EVAB_HD u64 enc_residue(double c, const PrimeDev &P, const u64 *pow2_row) {
   const bool neg = signbit(c);
   const double mag = fabs(c);
-  if (j > 0 && mag != 0.0) (B.flags + off)[e] = 1;
   u64 mant; int sh = 0;
   if (mag < 18446744073709551616.0) mant = (u64)mag;
   else { int ex; const double fr = frexp(mag, &ex); mant = (u64)ldexp(fr, 64); sh = ex - 64; }
-  for (u32 i = 0; i < B.ell; i++) {
-    const PrimeDev P = B.primes[i];
-    u64 v = barrett64(mant, P.p, P.ratio64);
-    if (sh) v = mulmod(v, B.pow2[(size_t)i * 128 + (sh > 127 ? 127 : sh)], P.p, P.ratio_lo, P.ratio_hi);
-    (B.out + off)[((size_t)e * B.ell + i) * B.N + j] = (neg && v) ? P.p - v : v;
-  }
+  u64 v = barrett64(mant, P.p, P.ratio64);
+  if (sh) v = mulmod(v, pow2_row[sh > 127 ? 127 : sh], P.p, P.ratio_lo, P.ratio_hi);
+  return (neg && v) ? P.p - v : v;
+}
+// coefficient j: round(re * scale / N) -> residue mod every prime
+EVAB_HD void enc_round(const EncBatch &B, u32 e, u32 j, long long off = 0) {
+  const double fix = B.scale[e] / (double)B.N;
+  const double c = round(D_MUL((B.work + off / 2)[(size_t)e * B.N + j].re, fix));
+  if (j > 0 && c != 0.0) (B.flags + off)[e] = 1;
+  for (u32 i = 0; i < B.ell; i++)
+    (B.out + off)[((size_t)e * B.ell + i) * B.N + j] = enc_residue(c, B.primes[i], B.pow2 + (size_t)i * 128);
+}
+
+// ---- uniform vectors (every scalar constant of an EVA program, constant_value.h:64-71): all N
+// inputs of the inverse FFT are equal, so every butterfly difference is exactly zero and every sum
+// an exact doubling: the FFT output is value * N at index 0 and zero elsewhere, the plaintext is the
+// constant polynomial round((value * N) * (scale / N)) and its NTT is that constant at every point.
+// enc_uniform writes exactly what scatter -> FFT -> enc_round -> NTT produce, in one pass.
+struct EncUniform {
+  double value[ENC_MAX_BATCH], scale[ENC_MAX_BATCH];
+  u64 *out;                 // [count][ell][N]
+  const PrimeDev *primes;
+  const u64 *pow2;
+  u32 N, ell, count;
+};
+// coefficients j, j+1 of residue row (e, i)
+EVAB_HD void enc_uniform_elem(const EncUniform &B, u32 e, u32 i, u32 j, long long off = 0) {
+  const double re = D_MUL(B.value[e], (double)B.N);            // log2(N) exact doublings of the FFT
+  const double c = round(D_MUL(re, B.scale[e] / (double)B.N));
+  const u64 r = enc_residue(c, B.primes[i], B.pow2 + (size_t)i * 128);
+  u64x2 v; v.x = r; v.y = r;
+  *reinterpret_cast<u64x2 *>(B.out + off + ((size_t)e * B.ell + i) * B.N + j) = v;
 }

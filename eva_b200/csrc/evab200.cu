@@ -147,6 +147,11 @@ __global__ void __launch_bounds__(256) k_enc_round(const EncBatch B, const long 
   for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < B.N; j += gridDim.x * blockDim.x)
     enc_round(B, blockIdx.y, j, (long long)blockIdx.z * bstride);
 }
+__global__ void __launch_bounds__(256) k_enc_uniform(const EncUniform B, const long long bstride) {
+  const u32 e = blockIdx.y / B.ell, i = blockIdx.y % B.ell;
+  for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < B.N; j += gridDim.x * blockDim.x * 2)
+    enc_uniform_elem(B, e, i, j, (long long)blockIdx.z * bstride);
+}
 __global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, const u32 *perm, int N, const long long bstride) {
   out += (long long)blockIdx.z * bstride; in += (long long)blockIdx.z * bstride;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
@@ -310,6 +315,12 @@ struct CudaBE {
   int enc_fft(const EncBatch &B, u32 g, int ns) {
     count();
     k_enc_fft<<<dim3((B.N / 8 + 255) / 256, B.count, g_batch.batch), 256, 0, st>>>(B, g, ns, g_batch.stride);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int enc_uniform(const EncUniform &B) {
+    count();
+    k_enc_uniform<<<dim3((B.N / 2 + 255) / 256, B.count * B.ell, g_batch.batch), 256, 0, st>>>(B, g_batch.stride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -501,6 +512,9 @@ extern "C" int evab_set_ntt_cluster(int cl) {
   if (cl != 0 && cl != 1 && cl != 2 && cl != 4 && cl != 8) return fail("evab_set_ntt_cluster: 0 (automatic), 1, 2, 4 or 8 CTAs per residue");
   g_ntt_cluster = cl;
   return 0;
+}
+extern "C" int evab_encode_uniform(evab_ctx *c, int count, const double *values, const double *scales, int ell, uint64_t *out, void *stream) {
+  BE_BEGIN return encode_uniform_impl(be, c->v, count, values, scales, ell, out);
 }
 extern "C" size_t evab_encode_work_bytes(const evab_ctx *c, int count) { return encode_work_bytes(c->v, count); }
 extern "C" int evab_encode(evab_ctx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell,

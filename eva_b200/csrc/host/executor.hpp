@@ -13,7 +13,9 @@
 #pragma once
 #include "ckks_client.hpp"
 #include "ir.hpp"
+#include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <functional>
 #include <map>
 #include <set>
@@ -49,7 +51,11 @@ struct Step {
 };
 
 // Encode terms of one level that are encoded by a single batched device launch sequence
-struct EncodeGroup { int ell; bool dynamic; std::vector<Term *> members; std::size_t outOff, workOff, rawOff; int stream = -1; };
+struct EncodeGroup {
+  int ell; bool dynamic; std::vector<Term *> members; std::size_t outOff, workOff, rawOff; int stream = -1;
+  Term *first = nullptr;   // earliest member in program order: its step issues the whole group
+  int nUniform = 0;        // leading members whose vector is a replicated scalar: one-pass encoder
+};
 
 struct ExecOptions {
   int numStreams = 8;
@@ -57,6 +63,7 @@ struct ExecOptions {
   bool cacheConstants = true;  // encode plan-time-constant plaintexts once per plan instead of on every run
   int batch = 1;               // independent program instances executed by every (fat) kernel launch
   int fuse = 1;                // executeBatch: instances per plan replica (replicas run concurrently)
+  bool uniformEncode = true;   // replicated scalars are encoded by the one-pass encoder (evab_encode_uniform)
   bool hoistRotations = true;  // rotations of one ciphertext share the inverse NTT of its c1 (exact)
   bool fuseSums = true;        // trees of Add over multiply_plain results / ciphertexts run as one kernel
   bool dedupConstants = true;  // Encode terms of identical constants at the same (level, scale) share one plaintext
@@ -226,9 +233,18 @@ private:
         groupIndex_[t->index] = it->second;
       }
       for (auto &g : groups_) {
+        g.first = g.members.front();
+        if (!g.dynamic && opt_.uniformEncode) {   // scalar constants first: they go through evab_encode_uniform
+          auto uniform = [&](Term *t) {
+            const auto &x = rawsB_[0][t->operandAt(0)->index];
+            return !x.empty() && std::all_of(x.begin(), x.end(), [&](double v) { return std::memcmp(&v, &x[0], sizeof(double)) == 0; });
+          };
+          auto mid = std::stable_partition(g.members.begin(), g.members.end(), uniform);
+          g.nUniform = (int)(mid - g.members.begin());
+        }
         g.outOff = arenaWords;
         for (Term *t : g.members) { vals_[t->index].off = arenaWords; arenaWords += (std::size_t)g.ell * N_; }
-        g.workOff = arenaWords; arenaWords += evab_encode_work_bytes(dev_->ctx(), (int)g.members.size()) / 8;
+        g.workOff = arenaWords; arenaWords += evab_encode_work_bytes(dev_->ctx(), (int)g.members.size() - g.nUniform) / 8;
         g.rawOff = rawWords_;
         for (Term *t : g.members) { rawOff_[t->index] = rawWords_; rawWords_ += prog_.getVecSize(); }
       }
@@ -472,13 +488,21 @@ private:
   }
   // one batched device encode (scatter -> inverse FFT -> round/reduce -> NTT) for a group
   void issueEncodeGroup(const EncodeGroup &g, void *stream) {
+    if (g.nUniform) {   // replicated scalars: constant polynomials, no FFT / NTT needed (bit-identical)
+      std::vector<double> v, sc;
+      for (int i = 0; i < g.nUniform; i++) { v.push_back(rawsB_[0][g.members[i]->operandAt(0)->index][0]); sc.push_back(vals_[g.members[i]->index].scale); }
+      check(evab_encode_uniform(dev_->ctx(), g.nUniform, v.data(), sc.data(), g.ell, arena_.get() + g.outOff, stream));
+    }
+    const int rest = (int)g.members.size() - g.nUniform;
+    if (!rest) return;
     std::vector<const double *> ptrs; std::vector<std::uint32_t> vec; std::vector<double> sc;
-    for (Term *t : g.members) {
+    for (int i = g.nUniform; i < (int)g.members.size(); i++) {
+      Term *t = g.members[i];
       ptrs.push_back(reinterpret_cast<const double *>(rawArena_.get() + rawOff_.at(t->index)));
       vec.push_back((std::uint32_t)rawsB_[0][t->operandAt(0)->index].size());
       sc.push_back(vals_[t->index].scale);
     }
-    check(evab_encode(dev_->ctx(), (int)g.members.size(), ptrs.data(), vec.data(), sc.data(), g.ell, arena_.get() + g.outOff,
+    check(evab_encode(dev_->ctx(), rest, ptrs.data(), vec.data(), sc.data(), g.ell, arena_.get() + g.outOff + (std::size_t)g.nUniform * g.ell * N_,
                       arena_.get() + g.workOff, stream));
   }
   // ---------------------------------------------------------------- execution
@@ -507,7 +531,7 @@ private:
     switch (t.op) {
       case Op::Encode: {
         const EncodeGroup &g = groups_[groupIndex_.at(t.index)];
-        if (g.members.front() == &t && (g.dynamic || !opt_.cacheConstants)) issueEncodeGroup(g, stream);
+        if (g.first == &t && (g.dynamic || !opt_.cacheConstants)) issueEncodeGroup(g, stream);
       } break;
       case Op::Add: case Op::Sub: case Op::Mul: {
         int ci = V(0).kind == Kind::Cipher ? 0 : 1, oi = 1 - ci;

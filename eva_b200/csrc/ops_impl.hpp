@@ -212,6 +212,20 @@ int rotate_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, const
 }
 
 
+// seal::CKKSEncoder::encode of vectors whose elements are all equal (scalar constants): see enc_uniform_elem
+template <class BE> int encode_uniform_impl(BE &be, const CtxView &c, int count, const double *values, const double *scales, int ell, u64 *out) {
+  if (ell < 1 || ell > c.k) return be.error("encode: ell out of range");
+  for (int e0 = 0; e0 < count; e0 += ENC_MAX_BATCH) {
+    EncUniform B;
+    memset(&B, 0, sizeof(B));
+    B.count = (u32)((count - e0) < ENC_MAX_BATCH ? (count - e0) : ENC_MAX_BATCH);
+    for (u32 e = 0; e < B.count; e++) { B.value[e] = values[e0 + e]; B.scale[e] = scales[e0 + e]; }
+    B.out = out + (size_t)e0 * ell * c.N; B.primes = c.primes; B.pow2 = c.pow2; B.N = (u32)c.N; B.ell = (u32)ell;
+    if (int rc = be.enc_uniform(B)) return rc;
+  }
+  return 0;
+}
+
 // encoder workspace: count*N complex values followed by count u64 flags
 inline size_t encode_work_bytes(const CtxView &c, int count) { return (size_t)count * c.N * sizeof(cplx) + (size_t)((count + 7) & ~7) * sizeof(u64); }
 inline u64 *encode_flags(const CtxView &c, int count, cplx *work) { return reinterpret_cast<u64 *>(work + (size_t)count * c.N); }

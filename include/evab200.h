@@ -108,6 +108,12 @@ int evab_set_ntt_cluster(int ctas_per_residue);
 size_t evab_encode_work_bytes(const evab_ctx *ctx, int count);
 int evab_encode(evab_ctx *ctx, int count, const double *const *h_d_values, const uint32_t *h_vec_sizes, const double *h_scales,
                 int ell, uint64_t *d_out, void *d_work, void *stream);
+/* The same encoder for vectors whose elements are all equal (every scalar constant of an EVA program,
+ * constant_value.h:64-71): encodes h_values[e] replicated over all slots at scale h_scales[e] into
+ * d_out[e][ell][N].  All FFT butterflies are exact for equal inputs, so the result -- the constant
+ * polynomial round(value * scale), whose NTT is that constant -- is bit-identical to evab_encode of the
+ * replicated vector, in one launch and without workspace. */
+int evab_encode_uniform(evab_ctx *ctx, int count, const double *h_values, const double *h_scales, int ell, uint64_t *d_out, void *stream);
 
 /* ---- evaluator ops; one per SEAL call site of eva/seal/seal_executor.h ----
  * `ell` = residues of the inputs' level.  Outputs must not alias inputs unless

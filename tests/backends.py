@@ -146,6 +146,15 @@ class EmuBackend:
         self._chk(self.lib.emu_encode(self.h, n, ptrs, sizes, scales, ell, _p(out), _p(work)))
         return out[0] if single else out
 
+    def encode_uniform(self, values, scale, ell):
+        """scalar constants: [count] values -> [count][ell][N] (evab_encode_uniform)"""
+        n = len(values)
+        vals = (C.c_double * n)(*[float(v) for v in values])
+        scales = (C.c_double * n)(*([float(scale)] * n))
+        out = np.empty((n, ell, self.N), dtype=np.uint64)
+        self._chk(self.lib.emu_encode_uniform(self.h, n, vals, scales, ell, _p(out)))
+        return out
+
     def rotate_many(self, a, steps_list, gks):
         """rotations of one ciphertext sharing the inverse NTT of c1 (evab_rotate_prepare / _prepared)"""
         ell = a.shape[1]
@@ -302,6 +311,16 @@ class GpuBackend:
         self._chk(self.lib.evab_relinearize(self.h, a.shape[1], do, da, dk, dw, None))
         out = self._down(do, shape)
         self._free(da, dk, do, dw)
+        return out
+
+    def encode_uniform(self, values, scale, ell):
+        n = len(values)
+        vals = (C.c_double * n)(*[float(v) for v in values])
+        scales = (C.c_double * n)(*([float(scale)] * n))
+        do = self._alloc(n * ell * self.N * 8)
+        self._chk(self.lib.evab_encode_uniform(self.h, n, vals, scales, ell, do, None))
+        out = self._down(do, (n, ell, self.N))
+        self._free(do)
         return out
 
     def rotate_many(self, a, steps_list, gks):

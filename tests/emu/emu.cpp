@@ -151,6 +151,12 @@ struct EmuBE {
     for (u32 e = 0; e < B.count; e++) for (u32 t = 0; t < B.N / 8; t++) enc_fft8(B, e, t, g, ns);
     return 0;
   }
+  int enc_uniform(const EncUniform &B) {
+    for (u32 e = 0; e < B.count; e++)
+      for (u32 i = 0; i < B.ell; i++)
+        for (u32 j = 0; j < B.N; j += 2) enc_uniform_elem(B, e, i, j);
+    return 0;
+  }
   int enc_round(const EncBatch &B) {
     for (u32 e = 0; e < B.count; e++) for (u32 j = 0; j < B.N; j++) ::enc_round(B, e, j);
     return 0;
@@ -196,6 +202,10 @@ int emu_set_cluster(int cl) { if (cl != 1 && cl != 2 && cl != 4 && cl != 8) retu
 int emu_sum_terms(EmuCtx *c, int ell, uint64_t *o, int n, const uint64_t *const *cts, const int *sizes, const uint64_t *const *pts) {
   EmuBE be{c};
   return sum_terms_impl(be, c->v, ell, o, n, cts, sizes, pts);
+}
+int emu_encode_uniform(EmuCtx *c, int count, const double *values, const double *scales, int ell, uint64_t *out) {
+  EmuBE be{c};
+  return encode_uniform_impl(be, c->v, count, values, scales, ell, out);
 }
 size_t emu_encode_work_bytes(EmuCtx *c, int count) { return encode_work_bytes(c->v, count); }
 int emu_encode(EmuCtx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell, uint64_t *out, void *work) {

@@ -95,6 +95,17 @@ def case_sum_terms(be, orc, ell, nterms=(2, 9, 32)):
     eq(be.sum_terms(cts, pts), want)
 
 
+def case_encode_uniform(be, orc):
+    """scalar constants through the one-pass encoder == the full FFT encoder of the oracle on the replicated vector"""
+    vals = [0.0, -0.0, 1.0, -1.0, 2.0, -2.0, 0.5, 0.17254603006834726, -1.0984324107372518, 2.213787482387662, 1e-9, -3e-7, 123456.789, 1e12, -7e15]
+    for scale_bits, ell in ((25, min(2, orc.k)), (40, orc.k - 1), (60, 1), (90, orc.k), (120, orc.k)):
+        got = be.encode_uniform(vals, 2.0 ** scale_bits, ell)
+        for e, v in enumerate(vals):
+            eq(got[e], orc.encode(np.array([v]), 2.0 ** scale_bits, ell))
+            if e % 5 == 0:   # replicated explicitly over more than one element
+                eq(got[e], orc.encode(np.full(8, v), 2.0 ** scale_bits, ell))
+
+
 def case_rescale(be, orc, ell):
     for size in (2, 3):
         a = rand_ct(orc, size, ell, 10 + size)

@@ -53,6 +53,7 @@ def test_emu_encode(N, bits):
     rng = np.random.default_rng(N)
     vecs = [np.array([1.0]), np.array([-2.0]), np.array([0.0]), rng.uniform(-3, 3, 8), np.array([0.17254603006834726]),
             rng.uniform(-1, 1, N // 2), np.array([2.5, 2.5]), np.array([1.0, -1.0])]
+    pc.case_encode_uniform(be, orc)
     for scale_bits, ell in ((25, 2), (40, len(bits) - 1), (60, 1), (90, len(bits))):
         got = be.encode(vecs, 2.0 ** scale_bits, ell)
         for e, v in enumerate(vecs):

@@ -118,12 +118,13 @@ def test_wide_dag():
 
 
 def test_without_hoisted_rotations():
-    """hoist_rotations=False: every rotation runs the plain evab_rotate path (default shares the inverse NTT)"""
+    """hoist_rotations=False: every rotation runs the plain evab_rotate path (default shares the inverse NTT);
+    uniform_encode=False: scalar constants go through the full FFT encoder (default: one-pass encoder)"""
     from eva_b200 import b200
     orig = b200.B200Public.set_options
     try:
-        b200.B200Public.set_options = lambda self, **kw: orig(self, **{**kw, "hoist_rotations": False})
-        run_both("sobel", lo=0.0, hi=0.2)
+        b200.B200Public.set_options = lambda self, **kw: orig(self, **{**kw, "hoist_rotations": False, "uniform_encode": False})
+        run_both("sobel", lo=0.0, hi=0.2, cache=False)
     finally:
         b200.B200Public.set_options = orig
 

@@ -84,6 +84,7 @@ def test_gpu_error_paths():
 
 @pytest.mark.parametrize("N,bits", [(4096, [60, 40, 60]), (16384, [60] * 5), (32768, [60, 20, 60, 60])])
 def test_gpu_encoder_bit_exact(N, bits):
+    pc.case_encode_uniform(_be(N, pc.get_oracle(N, bits).primes), pc.get_oracle(N, bits))
     """SURVEY 8a row E: device encoder (FP64 FFT + rounding + NTT) == host encoder == oracle, bit for bit;
     decode(encode(x)) ~ x."""
     from eva_b200 import b200
