@@ -238,8 +238,8 @@ def run_ours(args):
                    "instances_per_gpu": B,
                    "parallelism": "replicas x%d GPUs (independent program instances, no data-path collective; NCCL gather of outputs)" % world,
                    "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("%d concurrent cuda-graphs" % G if not args.no_graph else "streams") + " x %d instances fused per kernel launch, %d streams inside a plan" % (F, args.streams),
-                   "const_encode": "cached per plan" if not args.no_const_cache else ("23 Encode terms evaluated on the GPU inside every execute (FP64 FFT + NTT), as in the reference"
-                                    + ("; identical constants share one plaintext (same bits), constant polynomials skip the NTT butterflies" if not args.no_dedup else ""))},
+                   "const_encode": "cached per plan" if not args.no_const_cache else ("every Encode term is evaluated on the GPU inside every execute, as in the reference"
+                                    + ("; identical constants share one plaintext and replicated scalars use the one-pass encoder (bit-identical to the FP64 FFT + NTT path)" if not args.no_dedup else ""))},
         "e2e": {"value": total_ops / t_e2e, "unit": "ops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,
                 "note": "one B200Public.execute_batch(program, %d host-resident valuations) call per step: %d concurrent plan replicas x %d fused instances, page-locked host buffers, H2D + graph + D2H per replica stream (host wall clock)" % (B, G, F)},
         "single_instance": {"latency_ms": lat[len(lat) // 2], "ops_per_s": nops / (lat[len(lat) // 2] * 1e-3)},
