@@ -103,12 +103,14 @@ def Output(name, expr):
     program._make_output(name, _py_to_term(expr, program))
 
 
+
 def save(obj, path):
-    """reference python/eva/__init__.py `save`: protobuf serialization (eva/serialization/*).
-    Out of scope for this backend (no protobuf runtime in the image)."""
-    raise NotImplementedError("eva_b200: protobuf serialization (save/load) is not part of the B200 execution path")
+    """reference python/eva/__init__.py `save`: protobuf files of eva/serialization (see serialization.py)"""
+    from . import serialization
+    serialization.save(obj, path)
 
 
 def load(path):
-    """reference python/eva/__init__.py `load` -- see save()."""
-    raise NotImplementedError("eva_b200: protobuf serialization (save/load) is not part of the B200 execution path")
+    """reference python/eva/__init__.py `load`"""
+    from . import serialization
+    return serialization.load(path)

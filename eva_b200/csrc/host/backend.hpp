@@ -245,6 +245,7 @@ public:
     }
     return out;
   }
+  std::shared_ptr<Shared> shared() const { return s_; }
 private:
   std::shared_ptr<Shared> s_;
 };

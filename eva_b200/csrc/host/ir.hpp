@@ -78,6 +78,9 @@ public:
   const Op op;
   Program &program;
   std::uint64_t index;
+  // false once the owning Program is gone (a Python-held Term may outlive it): the destructor then
+  // must not touch the program's source / sink sets
+  std::shared_ptr<bool> programAlive;
 
   // attributes (reference eva/ir/attributes.h:11-18)
   std::optional<std::uint32_t> rescaleDivisor, range, encodeAtScale, encodeAtLevel;
@@ -134,6 +137,7 @@ public:
     // release the roots first; Terms deregister themselves from sources_/sinks_
     outputs_.clear();
     inputs_.clear();
+    *alive_ = false;   // terms still referenced from outside are orphaned
   }
   // opaque per-backend state (e.g. a cached execution plan) that must not outlive the program
   std::shared_ptr<void> attachment(std::uint64_t key) const { auto it = attachments_.find(key); return it == attachments_.end() ? nullptr : it->second; }
@@ -198,6 +202,7 @@ private:
   std::uint32_t vecSize_;
   std::uint64_t nextIndex_ = 0;
   std::unordered_set<Term *> sources_, sinks_;
+  std::shared_ptr<bool> alive_ = std::make_shared<bool>(true);
   std::vector<TermMapBase *> maps_;
   std::map<std::uint64_t, std::shared_ptr<void>> attachments_;
   // roots last: their destruction tears the graph down while the sets above are alive
@@ -231,11 +236,12 @@ private:
 };
 
 // ---------------------------------------------------------------------------
-inline Term::Term(Op o, Program &p) : op(o), program(p), index(p.allocateIndex()) {
+inline Term::Term(Op o, Program &p) : op(o), program(p), index(p.allocateIndex()), programAlive(p.alive_) {
   p.sources_.insert(this);
   p.sinks_.insert(this);
 }
 inline Term::~Term() {
+  if (!*programAlive) return;   // operands outlive or die with this term; nothing to deregister from
   for (auto &d : operands_) d->eraseUse(this);
   if (operands_.empty()) program.sources_.erase(this);
   if (uses_.empty()) program.sinks_.erase(this);

@@ -146,6 +146,26 @@ PYBIND11_MODULE(_eva_b200, m) {
            py::arg("fuse") = 1, py::arg("fuse_sums") = true, py::arg("hoist_rotations") = true, py::arg("uniform_encode") = true)
       .def("drop_plan", &B200Public::dropExecutor, py::arg("program"), py::arg("batch") = 1, py::arg("replica") = 0)
       .def("cipher_op_count", [](B200Public &p, Program &prog) { return p.executorFor(prog).cipherOpCount(); })
+      // serialization (eva_b200/serialization.py): public key material only (never the secret key)
+      .def("_export", [](B200Public &x) {
+        auto s = x.shared();
+        const std::size_t N = s->dev->N(), k = s->dev->k();
+        py::dict d;
+        d["N"] = N; d["primes"] = s->dev->primes();
+        s->dev->sync();
+        auto down = [&](const DBuf &b, std::vector<std::size_t> shape) {
+          u64arr a(shape);
+          s->dev->download(a.mutable_data(), b.get(), a.size() * 8);
+          s->dev->sync();
+          return a;
+        };
+        if (s->keys.pk) d["public_key"] = down(s->keys.pk, {2, k, N});
+        if (s->keys.relin) d["relin_key"] = down(s->keys.relin, {k - 1, 2, k, N});
+        py::dict g;
+        for (auto &kv : s->keys.galois) g[py::int_(kv.first)] = down(kv.second, {k - 1, 2, k, N});
+        d["galois_keys"] = g;
+        return d;
+      })
       .def("launch_count", [](B200Public &p) { return evab_launch_count(p.shared()->dev->ctx()); })
       .def("primes", [](B200Public &p) { return p.shared()->dev->primes(); })
       // ---- benchmark hooks: device-resident execution on a caller-provided stream
@@ -190,7 +210,19 @@ PYBIND11_MODULE(_eva_b200, m) {
         return p.shared()->client->encoder().decode(d.get(), (int)pt.shape(0), scale);
       });
   py::class_<B200Secret>(mb, "B200Secret", "The secret part of the context: decryption")
-      .def("decrypt", &B200Secret::decrypt, py::arg("enc_outputs"), py::arg("signature"));
+      .def("decrypt", &B200Secret::decrypt, py::arg("enc_outputs"), py::arg("signature"))
+      // serialization (eva_b200/serialization.py): secret key image [k][N] + the modulus chain
+      .def("_export", [](B200Secret &x) {
+        auto s = x.shared();
+        py::dict d;
+        d["N"] = s->dev->N(); d["primes"] = s->dev->primes();
+        u64arr a({(std::size_t)s->dev->k(), (std::size_t)s->dev->N()});
+        s->dev->sync();
+        s->dev->download(a.mutable_data(), s->keys.sk.get(), a.size() * 8);
+        s->dev->sync();
+        d["secret_key"] = a;
+        return d;
+      });
 
   mb.def("generate_keys", [](const CKKSParameters &p, int device, std::uint64_t seed) { return generateKeys(p, device, seed); },
          py::arg("abstract_params"), py::arg("device") = 0, py::arg("seed") = 0);
@@ -210,5 +242,31 @@ PYBIND11_MODULE(_eva_b200, m) {
     s->dev->sync();
     return std::make_unique<B200Public>(s);
   }, py::arg("N"), py::arg("primes"), py::arg("relin_key"), py::arg("galois_keys"), py::arg("device") = 0);
+  // serialization: contexts rebuilt from saved key material
+  mb.def("public_from_raw", [](std::uint64_t N, const std::vector<u64> &primes, py::object pk, py::object relin, const std::map<u64, u64arr> &galois, int device) {
+    auto s = std::make_shared<Shared>();
+    s->dev = std::make_shared<Device>(N, primes, device);
+    std::random_device rd;
+    s->client = std::make_unique<CkksClient>(s->dev, ((std::uint64_t)rd() << 32) ^ rd());
+    auto up = [&](DBuf &dst, const u64arr &a) { dst = DBuf(s->dev, a.size()); s->dev->upload(dst.get(), a.data(), a.size() * 8); s->dev->sync(); };
+    if (!pk.is_none()) up(s->keys.pk, py::cast<u64arr>(pk));
+    if (!relin.is_none()) up(s->keys.relin, py::cast<u64arr>(relin));
+    for (auto &g : galois) {
+      check(evab_galois_prepare(s->dev->ctx(), g.first));
+      DBuf d;
+      up(d, g.second);
+      s->keys.galois.emplace(g.first, std::move(d));
+    }
+    return std::make_unique<B200Public>(s);
+  }, py::arg("N"), py::arg("primes"), py::arg("public_key"), py::arg("relin_key"), py::arg("galois_keys"), py::arg("device") = 0);
+  mb.def("secret_from_raw", [](std::uint64_t N, const std::vector<u64> &primes, const u64arr &sk, int device) {
+    auto s = std::make_shared<Shared>();
+    s->dev = std::make_shared<Device>(N, primes, device);
+    s->client = std::make_unique<CkksClient>(s->dev, 1);
+    s->keys.sk = DBuf(s->dev, sk.size());
+    s->dev->upload(s->keys.sk.get(), sk.data(), sk.size() * 8);
+    s->dev->sync();
+    return std::make_unique<B200Secret>(s);
+  }, py::arg("N"), py::arg("primes"), py::arg("secret_key"), py::arg("device") = 0);
   mb.def("create_coeff_modulus", [](std::uint64_t N, const std::vector<int> &bits) { return hmod::createCoeffModulus(N, bits); });
 }
