@@ -152,11 +152,6 @@ __global__ void __launch_bounds__(256) k_enc_uniform(const EncUniform B, const l
   for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < B.N; j += gridDim.x * blockDim.x * 2)
     enc_uniform_elem(B, e, i, j, (long long)blockIdx.z * bstride);
 }
-__global__ void __launch_bounds__(256) k_galois_perm(u64 *out, const u64 *in, const u32 *perm, int N, const long long bstride) {
-  out += (long long)blockIdx.z * bstride; in += (long long)blockIdx.z * bstride;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
-    galois_perm_elem(out, in, perm, N, blockIdx.y, j);
-}
 
 // ---------------------------------------------------------------------------
 // CUDA backend
@@ -217,15 +212,15 @@ template <int LOGN> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cud
   if constexpr (LOGN <= 14) return launch_fwd_c<LOGN, 1>(L, jobs, st);
   return fail("unsupported cluster size");
 }
-template <int LOGN, int EPI, int CL> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+template <int LOGN, int PRO, int EPI, int CL> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   static std::atomic<bool> done[64];
-  return launch_ntt(k_ntt_inv<LOGN, PRO_PLAIN, EPI, CL>, L, jobs * CL, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CL, st, done);
+  return launch_ntt(k_ntt_inv<LOGN, PRO, EPI, CL>, L, jobs * CL, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CL, st, done);
 }
 template <int LOGN, int CL> static int launch_inv_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  if (L.pro != PRO_PLAIN) return fail("unsupported inverse NTT prologue");
-  if (L.epi == EPI_STORE) return launch_inv_m<LOGN, EPI_STORE, CL>(L, jobs, st);
-  if (L.epi == EPI_ADDHALF) return launch_inv_m<LOGN, EPI_ADDHALF, CL>(L, jobs, st);
-  return fail("unsupported inverse NTT epilogue");
+  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_inv_m<LOGN, PRO_PLAIN, EPI_STORE, CL>(L, jobs, st);
+  if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return launch_inv_m<LOGN, PRO_PLAIN, EPI_ADDHALF, CL>(L, jobs, st);
+  if (L.pro == PRO_GATHER && L.epi == EPI_STORE) return launch_inv_m<LOGN, PRO_GATHER, EPI_STORE, CL>(L, jobs, st);
+  return fail("unsupported inverse NTT prologue/epilogue combination");
 }
 template <int LOGN> static int launch_inv_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   if constexpr (LOGN >= 12) {
@@ -327,13 +322,6 @@ struct CudaBE {
   int enc_round(const EncBatch &B) {
     count();
     k_enc_round<<<dim3((B.N + 255) / 256, B.count, g_batch.batch), 256, 0, st>>>(B, g_batch.stride);
-    CUDA_OK(cudaGetLastError());
-    return 0;
-  }
-  int perm(u64 *out, const u64 *in, const u32 *p, int N, int rows) {
-    count();
-    dim3 g((unsigned)((N + 255) / 256), rows, g_batch.batch);
-    k_galois_perm<<<g, 256, 0, st>>>(out, in, p, N, g_batch.stride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }

@@ -140,18 +140,18 @@ template <class BE> int rescale_impl(BE &be, const CtxView &c, int ell, u64 *out
   return divround_impl(be, c, a, ell * N, sa, ell, pm, ell - 1, out, (ell - 1) * N, (const u64 *)nullptr, 0, work);
 }
 
-// workspace (in u64): that[ell] + ext[ell+1][ell] + acc[2][ell+1] + tmp[2] + permuted ct [2][ell]
+// workspace (in u64): that[ell] + ext[ell+1][ell] + acc[2][ell+1] + tmp[2]
 inline size_t ks_off_ext(const CtxView &c, int ell) { return (size_t)ell * c.N; }
 inline size_t ks_off_acc(const CtxView &c, int ell) { return ks_off_ext(c, ell) + (size_t)(ell + 1) * ell * c.N; }
 inline size_t ks_off_tmp(const CtxView &c, int ell) { return ks_off_acc(c, ell) + (size_t)2 * (ell + 1) * c.N; }
-inline size_t ks_off_pct(const CtxView &c, int ell) { return ks_off_tmp(c, ell) + (size_t)2 * c.N; }
-inline size_t keyswitch_work_elems(const CtxView &c, int ell) { return ks_off_pct(c, ell) + (size_t)2 * ell * c.N; }
+inline size_t keyswitch_work_elems(const CtxView &c, int ell) { return ks_off_tmp(c, ell) + (size_t)2 * c.N; }
 
 // Evaluator::switch_key_inplace (Appendix A.5): out[c][J] = base[c][J] + ks_c[J];
 // base holds `base_polys` (1 or 2) polynomials.
+// Rotations: t and base are the UNrotated c1 / c0 and `nperm` is the NTT-domain permutation of the
+// automorphism, through which they are read (digit iNTT, inner product, mod-down epilogue).
 // Hoisted form (rotations sharing the inverse NTT of their input, exact): `that_in` = iNTT of the
-// UNrotated digits, `ctab` the coefficient-domain signed gather of the automorphism, `nperm` its
-// NTT-domain permutation; t and base are then the unrotated c1 / c0 and are read through nperm.
+// unrotated digits, read by the mod-up through `ctab`, the coefficient-domain signed gather.
 template <class BE>
 int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, const u64 *key, const u64 *base, int base_polys, u64 *work,
                    const u64 *that_in = nullptr, const u32 *ctab = nullptr, const u32 *nperm = nullptr) {
@@ -166,6 +166,7 @@ int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, co
   if (!that_in) {
     NttLaunch A = base_launch(c);
     A.src = t; A.dst = that; A.inner = ell; A.src_sr = A.dst_sr = N;
+    if (nperm) { A.pro = PRO_GATHER; A.perm = nperm; }   // single rotation: the automorphism is the load pattern
     for (int J = 0; J < ell; J++) A.pmap[J] = (unsigned char)J;
     if (int rc = be.inv(A, ell)) return rc;
   } else if (ell > 15) {
@@ -187,14 +188,14 @@ int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, co
   // 3. inner product with the key rows of the live primes and P
   IpArgs I;
   I.t = t; I.ext = ext; I.key = key; I.acc = acc; I.primes = c.primes; I.ell = ell; I.k = k; I.N = (int)N;
-  I.tperm = that_in ? nperm : nullptr;
+  I.tperm = nperm;
   if (int rc = be.inner(I)) return rc;
   // 4. mod-down by P with rounding, fused with the accumulation into base
   unsigned char pm[32];
   for (int i = 0; i < ell; i++) pm[i] = (unsigned char)i;
   // base holds c0 and c1 (relinearize) or c0 only (rotate: the switched c1 has no base)
   return divround_impl(be, c, acc, (long long)(ell + 1) * N, 2, ell + 1, pm, sp, out, (long long)ell * N, base, (long long)ell * N, tmp,
-                       base_polys, that_in ? nperm : nullptr);
+                       base_polys, nperm);
 }
 
 // Evaluator::relinearize (3 -> 2) -- reference eva/seal/seal_executor.h:200
@@ -206,9 +207,9 @@ template <class BE> int relinearize_impl(BE &be, const CtxView &c, int ell, u64 
 template <class BE>
 int rotate_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, const u32 *perm, const u64 *key, u64 *work) {
   if (ell < 1 || ell > c.k - 1) return be.error("rotate needs 1 <= ell <= k-1");
-  u64 *pct = work + ks_off_pct(c, ell);
-  if (int rc = be.perm(pct, a, perm, (int)c.N, 2 * ell)) return rc;
-  return keyswitch_impl(be, c, ell, out, pct + (size_t)ell * c.N, key, pct, 1, work);
+  // no permuted copy: c1 enters the digit iNTT through the permutation (PRO_GATHER), the inner product
+  // and the mod-down epilogue read c1 / c0 through it as well
+  return keyswitch_impl(be, c, ell, out, a + (size_t)ell * c.N, key, a, 1, work, nullptr, nullptr, perm);
 }
 
 

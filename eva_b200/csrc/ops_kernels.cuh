@@ -138,8 +138,3 @@ EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j) {
   st2(A.acc + ((size_t)1 * (A.ell + 1) + mi) * N + j, r1);
 }
 
-// NTT-domain Galois automorphism: out[res][j] = in[res][perm[j]]
-EVAB_HD void galois_perm_elem(u64 *out, const u64 *in, const u32 *perm, int N, int res, int j) {
-  const size_t off = (size_t)res * N;
-  out[off + j] = EVAB_LDG(in + off + EVAB_LDG(perm + j));
-}

@@ -78,6 +78,7 @@ template <int LOGN, bool INV, int CL> static void run_ntt_c(const NttLaunch &L, 
   } else {
     if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_STORE, CL>(L, jobs);
     if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_ADDHALF, CL>(L, jobs);
+    if (L.pro == PRO_GATHER && L.epi == EPI_STORE) return run_ntt_m<LOGN, true, PRO_GATHER, EPI_STORE, CL>(L, jobs);
   }
   abort();
 }
@@ -159,11 +160,6 @@ struct EmuBE {
   }
   int enc_round(const EncBatch &B) {
     for (u32 e = 0; e < B.count; e++) for (u32 j = 0; j < B.N; j++) ::enc_round(B, e, j);
-    return 0;
-  }
-  int perm(u64 *out, const u64 *in, const u32 *p, int N, int rows) {
-    for (int r = 0; r < rows; r++)
-      for (int j = 0; j < N; j++) galois_perm_elem(out, in, p, N, r, j);
     return 0;
   }
 };
