@@ -20,6 +20,7 @@ _SIGS = {
     "evab_ctx_k": (ci, [vp]),
     "evab_ctx_device": (ci, [vp]),
     "evab_ctx_sm_count": (ci, [vp]),
+    "evab_mem_info": (ci, [vp, C.POINTER(szt), C.POINTER(szt)]),
     "evab_malloc": (ci, [vp, szt, C.POINTER(vp), vp]),
     "evab_free": (ci, [vp, vp, vp]),
     "evab_upload": (ci, [vp, vp, vp, szt, vp]),

@@ -392,6 +392,11 @@ extern "C" uint64_t evab_ctx_N(const evab_ctx *c) { return c->v.N; }
 extern "C" int evab_ctx_k(const evab_ctx *c) { return c->v.k; }
 extern "C" int evab_ctx_device(const evab_ctx *c) { return c->device; }
 extern "C" int evab_ctx_sm_count(const evab_ctx *c) { return c->sms; }
+extern "C" int evab_mem_info(evab_ctx *c, size_t *free_bytes, size_t *total_bytes) {
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaMemGetInfo(free_bytes, total_bytes));
+  return 0;
+}
 
 extern "C" int evab_malloc(evab_ctx *c, size_t bytes, void **p, void *stream) {
   CUDA_OK(cudaSetDevice(c->device));

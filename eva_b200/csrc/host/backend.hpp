@@ -172,12 +172,30 @@ public:
     auto now = [] { return std::chrono::steady_clock::now(); };
     double tPlan = 0, tStage = 0, tRun = 0, tDown = 0;
     auto t00 = now();
+    // replicas are bounded by device memory (an arena each): with R replicas chunk g runs on replica g % R
+    // after that replica's previous chunk has completed (its outputs are already on their way to the host)
+    int R = (B + F - 1) / F;
+    {
+      Executor &first = executorFor(program, std::min(F, B), 0);
+      std::size_t freeB = 0, totalB = 0;
+      check(evab_mem_info(s_->dev->ctx(), &freeB, &totalB));
+      const std::size_t per = std::max<std::size_t>(first.arenaBytes(), 1);
+      std::size_t have = 1;   // replica 0 exists; count the ones already built for this program
+      while ((int)have < R && program.attachment(planKey(std::min(F, B), (int)have))) have++;
+      const std::size_t extra = (std::size_t)(0.8 * (double)freeB) / per;
+      R = (int)std::max<std::size_t>(1, std::min<std::size_t>((std::size_t)R, have + extra));
+      if (const char *cap = std::getenv("EVAB_MAX_REPLICAS")) R = std::max(1, std::min(R, std::atoi(cap)));   // tests / tuning
+    }
+    std::vector<char> busy(R, 0);
     for (int b0 = 0, g = 0; b0 < B; b0 += F, g++) {
       const int nb = std::min(F, B - b0);
+      const int r = g % R;
       auto t0 = now();
-      Executor &ex = executorFor(program, nb, g);
+      Executor &ex = executorFor(program, nb, r);
       void *st = ex.mainStream();
-      streams.push_back(st);
+      if (busy[r]) s_->dev->sync(st);   // the replica's arena is reused: wait for its previous chunk
+      busy[r] = 1;
+      if (std::find(streams.begin(), streams.end(), st) == streams.end()) streams.push_back(st);
       auto t1 = now();
       for (int b = 0; b < nb; b++) stageInputs(ex, program, *inputs[b0 + b], st, b);
       auto t2 = now();

@@ -91,6 +91,7 @@ public:
   std::size_t cipherOpCount() const { return cipherOps_; }
   // private stream used by B200Public::execute for H2D -> run -> D2H of this plan,
   // so that execute() calls on different programs overlap on the GPU
+  std::size_t arenaBytes() const { return (stride_ * (std::size_t)opt_.batch + 8 + rawStride_ * (std::size_t)opt_.batch + 8) * 8; }
   void *mainStream() {
     if (!mainStream_) { check(evab_stream_create(dev_->ctx(), &mainStream_)); streams_.push_back(mainStream_); }
     return mainStream_;

@@ -44,6 +44,8 @@ int evab_ctx_k(const evab_ctx *ctx);
 int evab_ctx_device(const evab_ctx *ctx);
 /* number of SMs of the context's device (grid sizing for callers/benchmarks) */
 int evab_ctx_sm_count(const evab_ctx *ctx);
+/* free / total device memory in bytes (the host layer bounds the number of concurrent plan replicas with it) */
+int evab_mem_info(evab_ctx *ctx, size_t *free_bytes, size_t *total_bytes);
 
 /* ---- device memory (stream-ordered pool) and transfers ---- */
 int evab_malloc(evab_ctx *ctx, size_t bytes, void **d_ptr, void *stream);

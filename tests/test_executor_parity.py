@@ -185,3 +185,32 @@ def test_batched_execute_matches_single():
             for b in range(3):
                 for oname in d["outputs"]:
                     assert np.array_equal(outs3[b].get(oname)[1], outs[b].get(oname)[1])
+
+
+def test_replicas_bounded_by_memory(monkeypatch):
+    """execute_batch with fewer plan replicas than chunks (what happens when the arenas do not all fit in
+    device memory): replicas are reused round-robin after their previous chunk completed; same results"""
+    from eva_b200 import b200
+    d = gl.load_json("polynomial")
+    prog, params, sig, terms = gl.build_program(d)
+    N = d["poly_modulus_degree"]
+    orc = o.Oracle(N, d["prime_bits"]).keygen(3)
+    op = OracleProgram(d, orc)
+    op.prepare_keys()
+    pub = b200.context_from_raw_keys(N, orc.primes, op.rk, {int(e): k for e, k in op.gks.items()})
+    rng = np.random.default_rng(9)
+    vals, want = [], []
+    for b in range(7):
+        val, io_ = b200.B200Valuation(), {}
+        for name_, info in d["signature"].items():
+            x = rng.uniform(-1, 1, d["vec_size"])
+            ct = orc.encrypt(orc.encode(x, 2.0 ** info["scale"], orc.k - 1 - info["level"]), seed=200 + b)
+            val.set_cipher(name_, ct, 2.0 ** info["scale"]); io_[name_] = ("cipher", ct, 2.0 ** info["scale"])
+        vals.append(val); want.append(op.run(io_))
+    for cap, fuse in (("2", 1), ("3", 2), ("1", 1)):
+        monkeypatch.setenv("EVAB_MAX_REPLICAS", cap)
+        pub.set_options(fuse=fuse)
+        outs = pub.execute_batch(prog, vals)
+        for b in range(7):
+            for oname, oid in d["outputs"].items():
+                assert np.array_equal(outs[b].get(oname)[1], want[b][oid][1]), (cap, fuse, b)
