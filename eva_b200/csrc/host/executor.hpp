@@ -63,6 +63,7 @@ struct ExecOptions {
   bool cacheConstants = true;  // encode plan-time-constant plaintexts once per plan instead of on every run
   int batch = 1;               // independent program instances executed by every (fat) kernel launch
   int fuse = 1;                // executeBatch: instances per plan replica (replicas run concurrently)
+  std::map<std::string, int> inputSizes;   // ciphertext inputs that are not size 2 (partial sums of a sharded DAG)
   bool uniformEncode = true;   // replicated scalars are encoded by the one-pass encoder (evab_encode_uniform)
   bool hoistRotations = true;  // rotations of one ciphertext share the inverse NTT of its c1 (exact)
   bool fuseSums = true;        // trees of Add over multiply_plain results / ciphertexts run as one kernel
@@ -143,6 +144,10 @@ private:
           if (!t->encodeAtScale || !t->encodeAtLevel) throw std::runtime_error("input term lacks scale/level (program not compiled?)");
           v.kind = ty == Type::Cipher ? Kind::Cipher : Kind::Plain;
           v.size = 2; v.ell = levelToEll(*t->encodeAtLevel); v.scale = std::ldexp(1.0, (int)*t->encodeAtScale);
+          if (v.kind == Kind::Cipher && !opt_.inputSizes.empty())
+            for (auto &in : prog_.getInputs())
+              if (in.second.get() == t) { auto f = opt_.inputSizes.find(in.first); if (f != opt_.inputSizes.end()) v.size = f->second; }
+          if (v.size < 2 || v.size > 3) throw std::runtime_error("input ciphertext size must be 2 or 3");
           place(v);
         } break;
         case Op::Constant:
