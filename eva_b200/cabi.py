@@ -41,6 +41,7 @@ _SIGS = {
     "evab_ntt_inv": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
     "evab_set_ntt_cluster": (ci, [ci]),
     "evab_sum_terms": (ci, [vp, ci, vp, ci, C.POINTER(vp), C.POINTER(ci), C.POINTER(vp), vp]),
+    "evab_sum_products": (ci, [vp, ci, vp, ci, C.POINTER(vp), C.POINTER(ci), C.POINTER(vp), C.POINTER(ci), vp]),
     "evab_host_alloc": (ci, [szt, C.POINTER(vp)]),
     "evab_host_free": (ci, [vp]),
     "evab_encode_work_bytes": (szt, [vp, ci]),

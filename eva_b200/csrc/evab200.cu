@@ -535,6 +535,10 @@ extern "C" int evab_mul_plain(evab_ctx *c, int ell, uint64_t *o, const uint64_t 
 extern "C" int evab_sum_terms(evab_ctx *c, int ell, uint64_t *o, int n, const uint64_t *const *cts, const int *sizes, const uint64_t *const *pts, void *stream) {
   BE_BEGIN return sum_terms_impl(be, c->v, ell, o, n, cts, sizes, pts);
 }
+extern "C" int evab_sum_products(evab_ctx *c, int ell, uint64_t *o, int n, const uint64_t *const *cts, const int *sizes, const uint64_t *const *seconds, const int *kinds,
+                                 void *stream) {
+  BE_BEGIN return sum_terms_impl(be, c->v, ell, o, n, cts, sizes, seconds, kinds);
+}
 extern "C" int evab_mul(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *b, void *stream) {
   BE_BEGIN return mulct_impl(be, c->v, false, ell, o, a, b);
 }

@@ -46,6 +46,7 @@ struct Step {
   std::size_t work = 0;    // scratch word offset in the stream's workspace (0 = none)
   // fused sum (root Add of a tree of cipher+cipher Adds): out = sum of ct (* pt when pt != null)
   std::vector<std::pair<const Term *, const Term *>> sum;
+  std::vector<int> sumKind;    // per leaf: 0 ciphertext, 1 ciphertext * plaintext, 2 ciphertext (x) ciphertext
   int hoist = -1;              // rotation group sharing one inverse NTT (op == Undef: the step computing it)
   std::uint64_t producer = 0;  // term index, or termCount + group for a hoist step
 };
@@ -260,6 +261,7 @@ private:
     // one kernel; leaves that are single-use multiply_plain results are multiplied on the fly
     // (Sobel / Harris filter taps: sum_i rot_i(x) * w_i).  Same canonical result, see evab_sum_terms.
     std::unordered_map<std::uint64_t, std::vector<std::pair<const Term *, const Term *>>> sumOf;
+    std::unordered_map<std::uint64_t, std::vector<int>> sumKindOf;
     if (opt_.fuseSums) {
       std::vector<int> uses(prog_.termCount(), 0);
       for (auto &t : order_) for (auto &o : t->getOperands()) uses[o->index]++;
@@ -273,10 +275,17 @@ private:
         if (vals_[b->index].kind == Kind::Cipher && vals_[a->index].kind == Kind::Plain) { ct = b; pt = a; return true; }
         return false;
       };
+      // Evaluator::multiply / square of two size-2 ciphertexts (2x2 -> 3)
+      auto cipherMul = [&](const Term *t, const Term *&a, const Term *&b) {
+        if (t->op != Op::Mul) return false;
+        a = t->operandAt(0).get(); b = t->operandAt(1).get();
+        return vals_[a->index].kind == Kind::Cipher && vals_[b->index].kind == Kind::Cipher && vals_[a->index].size == 2 && vals_[b->index].size == 2;
+      };
       for (auto it = order_.rbegin(); it != order_.rend(); ++it) {
         Term *root = *it;
         if (!isCipherAdd(root) || vals_[root->index].fused) continue;
         std::vector<std::pair<const Term *, const Term *>> leaves;
+        std::vector<int> kinds;
         std::vector<const Term *> absorbed;
         std::function<void(const Term *)> expand = [&](const Term *t) {
           const Term *ct = nullptr, *pt = nullptr;
@@ -287,15 +296,19 @@ private:
             expand(t->operandAt(1).get());
           } else if (inner && uses[t->index] == 1 && plainMul(t, ct, pt)) {
             absorbed.push_back(t);
-            leaves.emplace_back(ct, pt);
+            leaves.emplace_back(ct, pt); kinds.push_back(1);
+          } else if (inner && uses[t->index] == 1 && cipherMul(t, ct, pt)) {
+            absorbed.push_back(t);
+            leaves.emplace_back(ct, pt); kinds.push_back(2);
           } else {
-            leaves.emplace_back(t, nullptr);
+            leaves.emplace_back(t, nullptr); kinds.push_back(0);
           }
         };
         expand(root);
         if (absorbed.empty() || leaves.size() > 32) continue;   // a plain two-operand add
         for (const Term *t : absorbed) vals_[t->index].fused = true;
         sumOf[root->index] = std::move(leaves);
+        sumKindOf[root->index] = std::move(kinds);
       }
     }
     // operands a step really reads (fused sums read their leaves)
@@ -367,7 +380,7 @@ private:
       }
       Step st;
       st.term = t; st.op = t->op; st.producer = t->index;
-      { auto f = sumOf.find(t->index); if (f != sumOf.end()) st.sum = f->second; }
+      { auto f = sumOf.find(t->index); if (f != sumOf.end()) { st.sum = f->second; st.sumKind = sumKindOf.at(t->index); } }
       std::vector<std::uint64_t> operands;
       for (const Term *o : stepOperands(t)) operands.push_back(o->index);
       int forced = -1;
@@ -528,7 +541,7 @@ private:
         sizes.push_back(vals_[l.first->index].size);
         pts.push_back(l.second ? arena_.get() + vals_[l.second->index].off : nullptr);
       }
-      check(evab_sum_terms(c, o.ell, out, (int)cts.size(), cts.data(), sizes.data(), pts.data(), stream));
+      check(evab_sum_products(c, o.ell, out, (int)cts.size(), cts.data(), sizes.data(), pts.data(), st.sumKind.data(), stream));
       return;
     }
     auto V = [&](int i) -> const ValueInfo & { return vals_[t.operandAt(i)->index]; };

@@ -74,11 +74,13 @@ template <class BE> int copy_impl(BE &be, const CtxView &c, int ell_in, int ell_
   return be.dyadic(DY_COPY, A);
 }
 
-// out = sum_t (pts[t] ? cts[t] * pts[t] : cts[t]); out size = max ciphertext size.  out may alias
-// none of the inputs (every input is read after other outputs coefficients are written only at
-// the same index, so aliasing a ct of full size is in fact safe, but callers do not rely on it).
+// out = sum of terms; kinds[t] (null = derive from pts: 1 when pts[t], else 0): 0 cts[t], 1 cts[t] * pts[t]
+// (plaintext), 2 cts[t] (x) pts[t] (both size-2 ciphertexts, value of size 3).  sizes[t] = polynomials of
+// cts[t].  Up to 64 products of < 2^120 fit the 128-bit accumulators (32 terms, two products for the
+// middle component of a tensor product).
 template <class BE>
-int sum_terms_impl(BE &be, const CtxView &c, int ell, u64 *out, int nterms, const u64 *const *cts, const int *sizes, const u64 *const *pts) {
+int sum_terms_impl(BE &be, const CtxView &c, int ell, u64 *out, int nterms, const u64 *const *cts, const int *sizes, const u64 *const *pts,
+                   const int *kinds = nullptr) {
   if (ell < 1 || ell > c.k) return be.error("ell out of range");
   if (nterms < 1 || nterms > SUM_MAX_TERMS) return be.error("evab_sum_terms: 1..32 terms");
   SumArgs A;
@@ -86,8 +88,12 @@ int sum_terms_impl(BE &be, const CtxView &c, int ell, u64 *out, int nterms, cons
   A.out = out; A.primes = c.primes; A.n = nterms; A.ell = ell; A.N = (int)c.N; A.sout = 0;
   for (int t = 0; t < nterms; t++) {
     if (sizes[t] < 1 || sizes[t] > 3) return be.error("ciphertext size must be 1..3");
-    A.ct[t] = cts[t]; A.pt[t] = pts ? pts[t] : nullptr; A.size[t] = (unsigned char)sizes[t];
-    if (sizes[t] > A.sout) A.sout = sizes[t];
+    const int kind = kinds ? kinds[t] : ((pts && pts[t]) ? 1 : 0);
+    if (kind < 0 || kind > 2 || (kind && !(pts && pts[t]))) return be.error("evab_sum_terms: bad term kind");
+    if (kind == 2 && sizes[t] != 2) return be.error("evab_sum_terms: ciphertext products need size-2 operands");
+    A.ct[t] = cts[t]; A.pt[t] = pts ? pts[t] : nullptr; A.kind[t] = (unsigned char)kind;
+    A.size[t] = (unsigned char)(kind == 2 ? 3 : sizes[t]);
+    if ((int)A.size[t] > A.sout) A.sout = A.size[t];
   }
   return be.sum(A);
 }

@@ -40,16 +40,19 @@ template <int OP> EVAB_HD void dyadic_elem(const DyArgs &A, int res, int j) {
   st2(A.out + off + j, r);
 }
 
-// fused sum of terms, term t = ct[t] * pt[t] (multiply_plain) or ct[t] (pt[t] == null):
-// a chain of Evaluator::multiply_plain / Evaluator::add calls (reference seal_executor.h:124,168)
+// fused sum of terms; term t is  ct[t]                      (kind 0: Evaluator::add operand),
+//                               ct[t] * pt[t]              (kind 1: Evaluator::multiply_plain result), or
+//                               ct[t] (x) ct2[t], 2x2 -> 3 (kind 2: Evaluator::multiply / square result)
+// i.e. a chain of multiply_plain / multiply / add calls (reference seal_executor.h:124,162-168)
 // evaluated in one pass.  Products are accumulated in 128 bits and reduced once; the canonical
-// result equals the sequence of canonical mul_plain / add results (exact modular arithmetic).
+// result equals the sequence of canonical products and sums (exact modular arithmetic).
 #define SUM_MAX_TERMS 32
 struct SumArgs {
   u64 *out;
   const u64 *ct[SUM_MAX_TERMS];
-  const u64 *pt[SUM_MAX_TERMS];
-  unsigned char size[SUM_MAX_TERMS];   // polynomials of ct[t]
+  const u64 *pt[SUM_MAX_TERMS];          // kind 1: plaintext [ell][N]; kind 2: second ciphertext [2][ell][N]
+  unsigned char size[SUM_MAX_TERMS];    // polynomials of the term's value (kind 2: 3)
+  unsigned char kind[SUM_MAX_TERMS];
   const PrimeDev *primes;
   int n, ell, N, sout;
 };
@@ -57,23 +60,36 @@ struct SumArgs {
 EVAB_HD void sum_terms_elem(const SumArgs &A, int res, int j, long long off) {
   const int s = res / A.ell, i = res % A.ell;
   const PrimeDev P = A.primes[i];
-  const size_t coff = (size_t)res * A.N + j, poff = (size_t)i * A.N + j;
+  const size_t poly = (size_t)A.ell * A.N;
+  const size_t roff = (size_t)i * A.N + j;          // residue i of polynomial 0
   u64 lx = 0, hx = 0, ly = 0, hy = 0;
   for (int t = 0; t < A.n; t++) {
     if (s >= (int)A.size[t]) continue;
-    const u64x2 v = ld2(A.ct[t] + off + coff);
-    if (A.pt[t]) {
-      const u64x2 w = ld2(A.pt[t] + off + poff);
-      mac128(lx, hx, v.x, w.x); mac128(ly, hy, v.y, w.y);
+    const u64 *a = A.ct[t] + off + roff;
+    if (A.kind[t] == 2) {
+      const u64 *b = A.pt[t] + off + roff;
+      // tensor product component s: (a0 b0, a0 b1 + a1 b0, a1 b1)
+      const u64x2 a_lo = ld2(a + (s == 2 ? poly : 0)), b_hi = ld2(b + (s == 0 ? 0 : poly));
+      mac128(lx, hx, a_lo.x, b_hi.x); mac128(ly, hy, a_lo.y, b_hi.y);
+      if (s == 1) {
+        const u64x2 a1 = ld2(a + poly), b0 = ld2(b);
+        mac128(lx, hx, a1.x, b0.x); mac128(ly, hy, a1.y, b0.y);
+      }
     } else {
-      lx += v.x; hx += (lx < v.x);
-      ly += v.y; hy += (ly < v.y);
+      const u64x2 v = ld2(a + (size_t)s * poly);
+      if (A.kind[t] == 1) {
+        const u64x2 w = ld2(A.pt[t] + off + roff);
+        mac128(lx, hx, v.x, w.x); mac128(ly, hy, v.y, w.y);
+      } else {
+        lx += v.x; hx += (lx < v.x);
+        ly += v.y; hy += (ly < v.y);
+      }
     }
   }
   u64x2 r;
   r.x = barrett128_wide(lx, hx, P.p, P.ratio_lo, P.ratio_hi);
   r.y = barrett128_wide(ly, hy, P.p, P.ratio_lo, P.ratio_hi);
-  st2(A.out + off + coff, r);
+  st2(A.out + off + (size_t)res * A.N + j, r);
 }
 
 struct MulArgs { u64 *out; const u64 *a; const u64 *b; const PrimeDev *primes; int ell, N; };

@@ -211,8 +211,14 @@ def execute_sharded(pub, prog, inputs, rank=0, world=1, plan=None, device=None):
     plan = plan or split_program(prog, world)
     if world == 1 or plan is None:
         return pub.execute(prog, inputs) if rank == 0 else None
+    import os
+    import time
+    t0 = time.perf_counter()
     partial, scale = run_part(pub, plan, rank, inputs)
+    t1 = time.perf_counter()
     gathered = multi.gather_outputs(partial, rank, world, device=device)
-    if rank != 0:
-        return None
-    return run_tail(pub, plan, gathered, scale, inputs)
+    t2 = time.perf_counter()
+    out = run_tail(pub, plan, gathered, scale, inputs) if rank == 0 else None
+    if os.environ.get("EVAB_TRACE"):
+        print("[evab] sharded rank %d: part %.3f ms, gather %.3f ms, tail %.3f ms" % (rank, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3), flush=True)
+    return out

@@ -136,6 +136,12 @@ int evab_mul_plain(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a,
  * performing the calls one by one.  h_* are host arrays of device pointers read during the call. */
 int evab_sum_terms(evab_ctx *ctx, int ell, uint64_t *d_out, int nterms, const uint64_t *const *h_d_cts, const int *h_sizes,
                    const uint64_t *const *h_d_pts, void *stream);
+/* The same with ciphertext products among the terms: h_kinds[t] = 0 (cts[t]), 1 (cts[t] * plaintext
+ * h_d_seconds[t], multiply_plain :168) or 2 (cts[t] (x) ciphertext h_d_seconds[t], both of size 2: the
+ * size-3 result of Evaluator::multiply :164 / square :162).  A sum of products -- e.g. the reduction of
+ * the wide test DAGs -- never materialises the individual products. */
+int evab_sum_products(evab_ctx *ctx, int ell, uint64_t *d_out, int nterms, const uint64_t *const *h_d_cts, const int *h_sizes,
+                      const uint64_t *const *h_d_seconds, const int *h_kinds, void *stream);
 /* Evaluator::multiply :164 (2x2 -> 3) and square :162 */
 int evab_mul(evab_ctx *ctx, int ell, uint64_t *d_out3, const uint64_t *d_a2, const uint64_t *d_b2, void *stream);
 int evab_square(evab_ctx *ctx, int ell, uint64_t *d_out3, const uint64_t *d_a2, void *stream);

@@ -97,6 +97,19 @@ class EmuBackend:
         self._chk(self.lib.emu_sum_terms(self.h, ell, _p(out), n, cp, sz, pp))
         return out
 
+    def sum_products(self, cts, seconds, kinds):
+        """terms of kind 0 (ct), 1 (ct * plaintext) or 2 (ct (x) ct)"""
+        n = len(cts)
+        ell = cts[0].shape[1]
+        sout = max(3 if k == 2 else c.shape[0] for c, k in zip(cts, kinds))
+        out = np.empty((sout, ell, self.N), dtype=np.uint64)
+        cp = (C.c_void_p * n)(*[c.ctypes.data for c in cts])
+        pp = (C.c_void_p * n)(*[(p.ctypes.data if p is not None else None) for p in seconds])
+        sz = (C.c_int * n)(*[c.shape[0] for c in cts])
+        kd = (C.c_int * n)(*kinds)
+        self._chk(self.lib.emu_sum_products(self.h, ell, _p(out), n, cp, sz, pp, kd))
+        return out
+
     def negate(self, a):
         out = np.empty_like(a)
         self._chk(self.lib.emu_negate(self.h, a.shape[1], _p(out), _p(a), a.shape[0]))
@@ -260,6 +273,23 @@ class GpuBackend:
         pp = (C.c_void_p * n)(*[(d.value if d is not None else None) for d in dp])
         sz = (C.c_int * n)(*[c.shape[0] for c in cts])
         self._chk(self.lib.evab_sum_terms(self.h, ell, do, n, cp, sz, pp, None))
+        out = self._down(do, shape)
+        self._free(do, *dc, *[d for d in dp if d is not None])
+        return out
+
+    def sum_products(self, cts, seconds, kinds):
+        n = len(cts)
+        ell = cts[0].shape[1]
+        sout = max(3 if k == 2 else c.shape[0] for c, k in zip(cts, kinds))
+        shape = (sout, ell, self.N)
+        dc = [self._up(c) for c in cts]
+        dp = [self._up(p) if p is not None else None for p in seconds]
+        do = self._alloc(int(np.prod(shape)) * 8)
+        cp = (C.c_void_p * n)(*[d.value for d in dc])
+        pp = (C.c_void_p * n)(*[(d.value if d is not None else None) for d in dp])
+        sz = (C.c_int * n)(*[c.shape[0] for c in cts])
+        kd = (C.c_int * n)(*kinds)
+        self._chk(self.lib.evab_sum_products(self.h, ell, do, n, cp, sz, pp, kd, None))
         out = self._down(do, shape)
         self._free(do, *dc, *[d for d in dp if d is not None])
         return out

@@ -199,6 +199,10 @@ int emu_sum_terms(EmuCtx *c, int ell, uint64_t *o, int n, const uint64_t *const 
   EmuBE be{c};
   return sum_terms_impl(be, c->v, ell, o, n, cts, sizes, pts);
 }
+int emu_sum_products(EmuCtx *c, int ell, uint64_t *o, int n, const uint64_t *const *cts, const int *sizes, const uint64_t *const *seconds, const int *kinds) {
+  EmuBE be{c};
+  return sum_terms_impl(be, c->v, ell, o, n, cts, sizes, seconds, kinds);
+}
 int emu_encode_uniform(EmuCtx *c, int count, const double *values, const double *scales, int ell, uint64_t *out) {
   EmuBE be{c};
   return encode_uniform_impl(be, c->v, count, values, scales, ell, out);

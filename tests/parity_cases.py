@@ -106,6 +106,33 @@ def case_encode_uniform(be, orc):
                 eq(got[e], orc.encode(np.full(8, v), 2.0 ** scale_bits, ell))
 
 
+def case_sum_products(be, orc, ell, nterms=(2, 7, 32)):
+    """sums with ciphertext products (multiply / square) among the terms == the oracle calls one by one"""
+    for n in nterms:
+        cts, seconds, kinds, want = [], [], [], None
+        for t in range(n):
+            kind = (2, 2, 1, 0, 2)[t % 5]
+            a = rand_ct(orc, 3 if kind == 0 and t % 2 else 2, ell, 500 + t)
+            if kind == 2:
+                b = a if t % 7 == 3 else rand_ct(orc, 2, ell, 600 + t)       # a (x) a: square
+                term = orc.square(a) if b is a else orc.mul(a, b)
+            elif kind == 1:
+                b = rand_ct(orc, 1, ell, 700 + t)[0]
+                term = orc.mul_plain(a, b)
+            else:
+                b, term = None, a
+            cts.append(a); seconds.append(b); kinds.append(kind)
+            want = term if want is None else orc.add(want, term)
+        eq(be.sum_products(cts, seconds, kinds), want)
+    # worst case for the 128-bit accumulators: 32 products of residues p-1 (two per middle coefficient)
+    c = np.stack([np.stack([np.full(orc.N, orc.primes[i] - 1, dtype=np.uint64) for i in range(ell)])] * 2)
+    want = None
+    for t in range(32):
+        term = orc.square(c)
+        want = term if want is None else orc.add(want, term)
+    eq(be.sum_products([c] * 32, [c] * 32, [2] * 32), want)
+
+
 def case_rescale(be, orc, ell):
     for size in (2, 3):
         a = rand_ct(orc, size, ell, 10 + size)

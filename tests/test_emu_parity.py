@@ -23,6 +23,7 @@ def test_emu_ops_small(N, bits):
     for ell in (1, 2, 3):
         pc.case_dyadic(be, orc, ell)
         pc.case_sum_terms(be, orc, ell)
+        pc.case_sum_products(be, orc, ell)
         pc.case_keyswitch(be, orc, ell)
         if ell >= 2:
             pc.case_rescale(be, orc, ell)

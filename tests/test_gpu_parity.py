@@ -30,6 +30,7 @@ def test_gpu_ops_small(N, bits):
     for ell in range(1, orc.k):
         pc.case_dyadic(be, orc, ell)
         pc.case_sum_terms(be, orc, ell)
+        pc.case_sum_products(be, orc, ell)
         pc.case_keyswitch(be, orc, ell)
         if ell >= 2:
             pc.case_rescale(be, orc, ell)
