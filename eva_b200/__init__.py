@@ -9,99 +9,109 @@ hand-written CUDA kernels reached through the C-ABI of include/evab200.h.  There
 is no CPU fallback: without the CUDA library or without a GPU the backend raises.
 """
 import numbers
+import threading
 
 from ._eva_b200 import (Op, Program, Term, Type, evaluate, set_num_threads)  # noqa: F401
 
 __version__ = "0.1.0"
 
-_current_program = None
+# the program whose ``with`` block is open (the DSL's free functions Input / Output and the
+# constant conversions build into it); one per thread
+_scope = threading.local()
 
 
-def _curr():
-    if _current_program is None:
+def _open_program():
+    prog = getattr(_scope, "program", None)
+    if prog is None:
         raise RuntimeError("No Program in context")
-    return _current_program
+    return prog
 
 
-def _py_to_term(x, program):
-    if isinstance(x, Expr):
-        return x.term
-    if isinstance(x, list):
-        return program._make_dense_constant(x)
-    if isinstance(x, numbers.Number):
-        return program._make_uniform_constant(x)
-    if isinstance(x, Term):
-        return x
-    raise TypeError("No conversion to Term available for " + str(x))
+def _as_term(value, program):
+    """Term for a DSL operand: an Expr / Term as is, a number or a list as a new Constant of `program`"""
+    if isinstance(value, Expr):
+        return value.term
+    if isinstance(value, Term):
+        return value
+    if isinstance(value, numbers.Number):
+        return program._make_uniform_constant(value)
+    if isinstance(value, list):
+        return program._make_dense_constant(value)
+    raise TypeError("No conversion to Term available for " + str(value))
 
 
 def py_to_eva(x, program=None):
-    """Maps Expr instances, Terms, lists and numbers to Expr (constants are created in `program`)."""
+    """Expr for x: Expr instances pass through; Terms, lists and numbers are wrapped (constants are
+    created in `program`, default: the program in context)."""
     if isinstance(x, Expr):
         return x
-    if program is None:
-        program = _curr()
-    return Expr(_py_to_term(x, program), program)
+    program = program if program is not None else _open_program()
+    return Expr(_as_term(x, program), program)
 
 
 class Expr:
-    """Operator-overloading wrapper around a native Term of an EvaProgram."""
+    """A Term of an EvaProgram with Python operators: + - * (with Exprs, numbers or lists on either side),
+    ** (positive integer powers), << >> (slot rotations) and unary minus."""
 
     def __init__(self, term, program):
-        self.term = term
-        self.program = program
+        self.term, self.program = term, program
 
-    def _bin(self, op, lhs, rhs):
-        return Expr(self.program._make_term(op, [lhs, rhs]), self.program)
+    def _emit(self, op, *operands):
+        return Expr(self.program._make_term(op, [_as_term(o, self.program) for o in operands]), self.program)
 
-    def __add__(self, other): return self._bin(Op.Add, self.term, _py_to_term(other, self.program))
-    def __radd__(self, other): return self._bin(Op.Add, _py_to_term(other, self.program), self.term)
-    def __sub__(self, other): return self._bin(Op.Sub, self.term, _py_to_term(other, self.program))
-    def __rsub__(self, other): return self._bin(Op.Sub, _py_to_term(other, self.program), self.term)
-    def __mul__(self, other): return self._bin(Op.Mul, self.term, _py_to_term(other, self.program))
-    def __rmul__(self, other): return self._bin(Op.Mul, _py_to_term(other, self.program), self.term)
+    def __neg__(self):
+        return self._emit(Op.Negate, self)
 
     def __pow__(self, exponent):
         if exponent < 1:
             raise ValueError("exponent must be greater than zero, got " + str(exponent))
-        result = self.term
-        for _ in range(exponent - 1):
-            result = self.program._make_term(Op.Mul, [result, self.term])
-        return Expr(result, self.program)
+        acc = self
+        for _ in range(1, exponent):     # x * x * ... (a chain: the compiler balances / relinearizes it)
+            acc = acc._emit(Op.Mul, acc, self)
+        return acc
 
-    def __lshift__(self, rotation): return Expr(self.program._make_left_rotation(self.term, rotation), self.program)
-    def __rshift__(self, rotation): return Expr(self.program._make_right_rotation(self.term, rotation), self.program)
-    def __neg__(self): return Expr(self.program._make_term(Op.Negate, [self.term]), self.program)
+    def __lshift__(self, rotation):
+        return Expr(self.program._make_left_rotation(self.term, rotation), self.program)
+
+    def __rshift__(self, rotation):
+        return Expr(self.program._make_right_rotation(self.term, rotation), self.program)
+
+
+def _binary(op, reflected):
+    def method(self, other):
+        return self._emit(op, other, self) if reflected else self._emit(op, self, other)
+    return method
+
+
+for _name, _op in (("add", Op.Add), ("sub", Op.Sub), ("mul", Op.Mul)):
+    setattr(Expr, "__%s__" % _name, _binary(_op, False))
+    setattr(Expr, "__r%s__" % _name, _binary(_op, True))
 
 
 class EvaProgram(Program):
-    """A Program that is also a context manager for the Input/Output free functions."""
-
-    def __init__(self, name, vec_size):
-        super().__init__(name, vec_size)
+    """A Program usable as a ``with`` block: inside it Input(...) / Output(...) add terms to it."""
 
     def __enter__(self):
-        global _current_program
-        if _current_program is not None:
+        if getattr(_scope, "program", None) is not None:
             raise RuntimeError("There is already an EVA Program in context")
-        _current_program = self
+        _scope.program = self
 
     def __exit__(self, exc_type, exc_value, exc_traceback):
-        global _current_program
-        if _current_program is not self:
+        if getattr(_scope, "program", None) is not self:
             raise RuntimeError("This program is not currently in context")
-        _current_program = None
+        _scope.program = None
 
 
 def Input(name, is_encrypted=True):
-    program = _curr()
-    return Expr(program._make_input(name, Type.Cipher if is_encrypted else Type.Raw), program)
+    """a named program input: a ciphertext, or (is_encrypted=False) a raw vector"""
+    prog = _open_program()
+    return Expr(prog._make_input(name, Type.Cipher if is_encrypted else Type.Raw), prog)
 
 
 def Output(name, expr):
-    program = _curr()
-    program._make_output(name, _py_to_term(expr, program))
-
+    """name `expr` as a program output"""
+    prog = _open_program()
+    prog._make_output(name, _as_term(expr, prog))
 
 
 def save(obj, path):

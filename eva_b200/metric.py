@@ -1,13 +1,17 @@
-"""Accuracy metric used by the reference's tests and examples (python/eva/metric.py:6-19)."""
+"""Accuracy metric of the reference's tests and examples (the `eva.metric` module)."""
+import numpy as np
 
 
 def valuation_mse(a, b):
-    """Mean squared error between two valuations (dicts name -> list of numbers)."""
-    if set(a.keys()) != set(b.keys()):
+    """mean over the named vectors of their mean squared difference; both valuations (name -> sequence of
+    numbers) must name the same vectors with the same lengths"""
+    names = sorted(a)
+    if names != sorted(b):
         raise ValueError("Valuations must have the same keys")
-    total = 0.0
-    for k in a.keys():
-        if len(a[k]) != len(b[k]):
+    per_vector = []
+    for name in names:
+        u, v = np.asarray(a[name], dtype=np.float64), np.asarray(b[name], dtype=np.float64)
+        if u.shape != v.shape:
             raise ValueError("Values must have the same length")
-        total += sum((x - y) ** 2 for x, y in zip(a[k], b[k])) / len(a[k])
-    return total / len(a)
+        per_vector.append(float(np.mean((u - v) ** 2)))
+    return float(np.mean(per_vector))

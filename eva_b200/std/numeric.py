@@ -1,12 +1,12 @@
-"""Library helpers (reference python/eva/std/numeric.py:5-21)."""
+"""Library helpers on top of the DSL (the reference ships eva.std.numeric.horizontal_sum)."""
 from .. import py_to_eva
 
 
 def horizontal_sum(x):
-    """Sum of all vector elements, replicated into every slot (log2(n) rotations)."""
-    x = py_to_eva(x)
-    i = 1
-    while i < x.program.vec_size:
-        x = x + (x << i)
-        i <<= 1
-    return x
+    """Every slot of the result holds the sum of all slots of x: rotate-and-add doubling, log2(vec_size) steps."""
+    acc = py_to_eva(x)
+    shift, width = 1, acc.program.vec_size
+    while shift < width:
+        acc = acc + (acc << shift)
+        shift *= 2
+    return acc

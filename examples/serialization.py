@@ -1,6 +1,8 @@
-"""The client / server flow of the reference's examples/serialization.py with every object going
-through files (save / load), executed by the B200 backend.  Run on a GPU box:
-    python examples/serialization.py [workdir]
+"""Three parties, files in between: a developer compiles a program, a key owner (client) generates keys,
+encrypts and later decrypts, an untrusted server with a B200 evaluates.  Every object that changes hands goes
+through save() / load() (the reference's protobuf file format, eva_b200/serialization.py).
+
+    python examples/serialization.py [workdir]      # needs a GPU
 """
 import os
 import sys
@@ -8,46 +10,70 @@ import tempfile
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from eva import EvaProgram, Input, Output, evaluate, save, load  # noqa: E402
+from eva import EvaProgram, Input, Output, evaluate, load, save  # noqa: E402
 from eva.ckks import CKKSCompiler  # noqa: E402
-from eva.seal import generate_keys  # noqa: E402
 from eva.metric import valuation_mse  # noqa: E402
+from eva.seal import generate_keys  # noqa: E402
+
+VEC = 8
+
+
+class Exchange:
+    """the shared directory the parties drop files into"""
+
+    def __init__(self, root):
+        self.root = root
+
+    def put(self, name, obj):
+        save(obj, os.path.join(self.root, name))
+
+    def get(self, name):
+        return load(os.path.join(self.root, name))
+
+
+def developer(box):
+    """writes program.eva, program.evaparams, program.evasignature"""
+    quadratic = EvaProgram('Quadratic', vec_size=VEC)
+    with quadratic:
+        t = Input('t')
+        Output('height', -4.9 * t ** 2 + 12 * t + 1.5)
+    quadratic.set_input_scales(20)
+    quadratic.set_output_ranges(20)
+    compiled, params, signature = CKKSCompiler().compile(quadratic)
+    for name, obj in (('program.eva', compiled), ('program.evaparams', params), ('program.evasignature', signature)):
+        box.put(name, obj)
+
+
+def client_setup(box, samples):
+    """keys from the published parameters; the encrypted samples and the PUBLIC context go to the server"""
+    public_ctx, secret_ctx = generate_keys(box.get('program.evaparams'))
+    box.put('client.sealsecret', secret_ctx)          # stays with the client
+    box.put('server.sealpublic', public_ctx)
+    signature = box.get('program.evasignature')
+    box.put('request.sealvals', load(os.path.join(box.root, 'server.sealpublic')).encrypt(samples, signature))
+
+
+def server(box):
+    """sees only ciphertexts, evaluation keys and the program"""
+    ctx = box.get('server.sealpublic')
+    box.put('response.sealvals', ctx.execute(box.get('program.eva'), box.get('request.sealvals')))
+
+
+def client_finish(box):
+    return box.get('client.sealsecret').decrypt(box.get('response.sealvals'), box.get('program.evasignature'))
 
 
 def main(workdir):
-    path = lambda n: os.path.join(workdir, n)
-    # ---- compile time
-    poly = EvaProgram('Polynomial', vec_size=8)
-    with poly:
-        x = Input('x')
-        Output('y', 3 * x ** 2 + 5 * x - 2)
-    poly.set_output_ranges(20)
-    poly.set_input_scales(20)
-    poly, params, signature = CKKSCompiler().compile(poly)
-    save(poly, path('poly.eva'))
-    save(params, path('poly.evaparams'))
-    save(signature, path('poly.evasignature'))
-    # ---- key generation time
-    public_ctx, secret_ctx = generate_keys(load(path('poly.evaparams')))
-    save(public_ctx, path('poly.sealpublic'))
-    save(secret_ctx, path('poly.sealsecret'))
-    # ---- runtime on the client
-    signature = load(path('poly.evasignature'))
-    public_ctx = load(path('poly.sealpublic'))
-    inputs = {'x': [i for i in range(signature.vec_size)]}
-    save(public_ctx.encrypt(inputs, signature), path('poly_inputs.sealvals'))
-    # ---- runtime on the server
-    poly = load(path('poly.eva'))
-    public_ctx = load(path('poly.sealpublic'))
-    enc_outputs = public_ctx.execute(poly, load(path('poly_inputs.sealvals')))
-    save(enc_outputs, path('poly_outputs.sealvals'))
-    # ---- back on the client
-    secret_ctx = load(path('poly.sealsecret'))
-    outputs = secret_ctx.decrypt(load(path('poly_outputs.sealvals')), signature)
-    reference = evaluate(poly, inputs)
-    mse = valuation_mse(outputs, reference)
-    print('Expected', reference)
-    print('Got', outputs)
+    box = Exchange(workdir)
+    samples = {'t': [0.25 * i for i in range(VEC)]}
+    developer(box)
+    client_setup(box, samples)
+    server(box)
+    heights = client_finish(box)
+    expected = evaluate(box.get('program.eva'), samples)
+    mse = valuation_mse(heights, expected)
+    print('expected ', [round(v, 3) for v in expected['height']])
+    print('decrypted', [round(v, 3) for v in heights['height']])
     print('MSE', mse)
     assert mse < 0.01
     return mse
@@ -57,5 +83,5 @@ if __name__ == '__main__':
     if len(sys.argv) > 1:
         main(sys.argv[1])
     else:
-        with tempfile.TemporaryDirectory() as d:
-            main(d)
+        with tempfile.TemporaryDirectory() as scratch:
+            main(scratch)

@@ -124,6 +124,6 @@ def test_client_server_flow_through_files(tmp_path):
     assert example.main(str(tmp_path)) < 0.01
     # a public-context file holds no secret key material
     from eva_b200 import load
-    blob = open(tmp_path / "poly.sealpublic", "rb").read()
-    sk = load(str(tmp_path / "poly.sealsecret"))._export()["secret_key"]
+    blob = open(tmp_path / "server.sealpublic", "rb").read()
+    sk = load(str(tmp_path / "client.sealsecret"))._export()["secret_key"]
     assert sk.tobytes()[:4096] not in blob
