@@ -177,13 +177,15 @@ public:
     int R = (B + F - 1) / F;
     {
       Executor &first = executorFor(program, std::min(F, B), 0);
-      std::size_t freeB = 0, totalB = 0;
-      check(evab_mem_info(s_->dev->ctx(), &freeB, &totalB));
-      const std::size_t per = std::max<std::size_t>(first.arenaBytes(), 1);
       std::size_t have = 1;   // replica 0 exists; count the ones already built for this program
       while ((int)have < R && program.attachment(planKey(std::min(F, B), (int)have))) have++;
-      const std::size_t extra = (std::size_t)(0.8 * (double)freeB) / per;
-      R = (int)std::max<std::size_t>(1, std::min<std::size_t>((std::size_t)R, have + extra));
+      if ((int)have < R) {    // new arenas are needed: how many fit?  (cudaMemGetInfo is slow: never on the steady path)
+        std::size_t freeB = 0, totalB = 0;
+        check(evab_mem_info(s_->dev->ctx(), &freeB, &totalB));
+        const std::size_t per = std::max<std::size_t>(first.arenaBytes(), 1);
+        const std::size_t extra = (std::size_t)(0.8 * (double)freeB) / per;
+        R = (int)std::max<std::size_t>(1, std::min<std::size_t>((std::size_t)R, have + extra));
+      }
       if (const char *cap = std::getenv("EVAB_MAX_REPLICAS")) R = std::max(1, std::min(R, std::atoi(cap)));   // tests / tuning
     }
     std::vector<char> busy(R, 0);
