@@ -130,10 +130,10 @@ __global__ void __launch_bounds__(256) k_sum_terms(const SumArgs A, const long l
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
     sum_terms_elem(A, blockIdx.y, j, off);
 }
-__global__ void __launch_bounds__(256) k_ks_inner(IpArgs A, const long long bstride) {
-  { const long long off = (long long)blockIdx.z * bstride; A.t += off; A.ext += off; A.acc += off; }
+__global__ void __launch_bounds__(256) k_ks_inner(const IpArgs A, const long long bstride) {
+  const long long off = (long long)blockIdx.z * bstride;   // parameters stay in constant memory: no local copy
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
-    ks_inner_elem(A, blockIdx.y, j);
+    ks_inner_elem(A, blockIdx.y, j, off);
 }
 __global__ void __launch_bounds__(256) k_enc_scatter(const EncBatch B, const long long bstride, const long long vstride) {
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B.N / 2; i += gridDim.x * blockDim.x)

@@ -127,7 +127,8 @@ struct IpArgs {
   const u32 *tperm;   // optional: t is read through this NTT-domain permutation (rotation without a permuted copy)
   int ell, k, N;
 };
-EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j) {
+// off: batch instance offset (words) of t / ext / acc (the key is shared by all instances)
+EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j, long long off = 0) {
   const int row = (mi == A.ell) ? A.k - 1 : mi;
   const PrimeDev P = A.primes[row];
   const size_t N = A.N;
@@ -135,11 +136,11 @@ EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j) {
   for (int J = 0; J < A.ell; J++) {
     u64x2 v;
     if (row == J) {
-      const u64 *tp = A.t + (size_t)J * N;
+      const u64 *tp = A.t + off + (size_t)J * N;
       if (A.tperm) { v.x = EVAB_LDG(tp + EVAB_LDG(A.tperm + j)); v.y = EVAB_LDG(tp + EVAB_LDG(A.tperm + j + 1)); }
       else v = ld2(tp + j);
     } else {
-      v = ld2(A.ext + ((size_t)mi * A.ell + J) * N + j);
+      v = ld2(A.ext + off + ((size_t)mi * A.ell + J) * N + j);
     }
     const u64x2 k0 = ld2(A.key + (((size_t)J * 2 + 0) * A.k + row) * N + j);
     const u64x2 k1 = ld2(A.key + (((size_t)J * 2 + 1) * A.k + row) * N + j);
@@ -150,7 +151,7 @@ EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j) {
   // ext operands may be lazily reduced (< 16p, see EPI_STORE_LAZY): wide reduction
   r0.x = barrett128_wide(l0x, h0x, P.p, P.ratio_lo, P.ratio_hi); r0.y = barrett128_wide(l0y, h0y, P.p, P.ratio_lo, P.ratio_hi);
   r1.x = barrett128_wide(l1x, h1x, P.p, P.ratio_lo, P.ratio_hi); r1.y = barrett128_wide(l1y, h1y, P.p, P.ratio_lo, P.ratio_hi);
-  st2(A.acc + ((size_t)0 * (A.ell + 1) + mi) * N + j, r0);
-  st2(A.acc + ((size_t)1 * (A.ell + 1) + mi) * N + j, r1);
+  st2(A.acc + off + ((size_t)0 * (A.ell + 1) + mi) * N + j, r0);
+  st2(A.acc + off + ((size_t)1 * (A.ell + 1) + mi) * N + j, r1);
 }
 
