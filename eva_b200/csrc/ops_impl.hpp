@@ -239,7 +239,8 @@ inline u64 *encode_flags(const CtxView &c, int count, cplx *work) { return reint
 
 // Rotations of one ciphertext share the inverse NTT of its c1 (the automorphism commutes with the
 // transform): rotate_prepare_impl computes it once, rotate_prepared_impl is rotate_impl without the
-// permuted copy and without the per-rotation inverse NTTs.  Results are identical to rotate_impl.
+// per-rotation inverse NTTs (the mod-up reads the shared coefficients through the signed
+// coefficient-domain gather).  Results are identical to rotate_impl.
 template <class BE> int rotate_prepare_impl(BE &be, const CtxView &c, int ell, u64 *hoist, const u64 *a) {
   if (ell < 1 || ell > c.k - 1) return be.error("rotate needs 1 <= ell <= k-1");
   NttLaunch A = base_launch(c);

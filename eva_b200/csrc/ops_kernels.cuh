@@ -1,5 +1,5 @@
-// ops_kernels.cuh -- element-wise (dyadic) ciphertext kernels, the key-switch
-// inner product and the Galois permutation, as __host__ __device__ bodies
+// ops_kernels.cuh -- element-wise (dyadic) ciphertext kernels, fused sums of
+// products and the key-switch inner product, as __host__ __device__ bodies
 // (two coefficients per call, 128-bit accesses) shared by the CUDA kernels and
 // the CPU emulator.  Semantics: SURVEY.md Appendix A.4 / A.5 / A.8.
 #pragma once

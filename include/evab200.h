@@ -160,14 +160,14 @@ size_t evab_keyswitch_work_bytes(const evab_ctx *ctx, int ell);
 int evab_relinearize(evab_ctx *ctx, int ell, uint64_t *d_out2, const uint64_t *d_a3, const uint64_t *d_key, void *d_work, void *stream);
 /* Galois element of rotate_vector(steps) (steps>0 left; SEAL GaloisTool::get_elt_from_step) */
 uint64_t evab_galois_elt_from_step(uint64_t N, int steps);
-/* builds and caches the NTT-domain permutation table of galois_elt on the
- * device (blocking); must be called once before evab_rotate uses that element */
+/* builds and caches the permutation tables of galois_elt on the device (NTT domain and signed
+ * coefficient domain; blocking); must be called once before evab_rotate* uses that element */
 int evab_galois_prepare(evab_ctx *ctx, uint64_t galois_elt);
 int evab_rotate(evab_ctx *ctx, int ell, uint64_t *d_out2, const uint64_t *d_a2, uint64_t galois_elt, const uint64_t *d_key, void *d_work, void *stream);
 /* Rotations of the SAME ciphertext share the inverse NTT of its c1 (the automorphism commutes with
  * the transform; SEAL recomputes it inside every rotate_vector :181,:188).  evab_rotate_prepare
  * writes it to d_hoist [ell][N]; evab_rotate_prepared(…, d_hoist, …) then equals evab_rotate bit
- * for bit with fewer transforms and no permuted copy.  Same workspace as evab_rotate; ell <= 15. */
+ * for bit with ell fewer transforms.  Same workspace as evab_rotate; ell <= 15. */
 int evab_rotate_prepare(evab_ctx *ctx, int ell, uint64_t *d_hoist, const uint64_t *d_a, void *stream);
 int evab_rotate_prepared(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, const uint64_t *d_hoist, uint64_t galois_elt,
                          const uint64_t *d_key, void *d_work, void *stream);
