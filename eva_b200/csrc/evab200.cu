@@ -115,15 +115,15 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::
   NttState S;
   PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, smem_view<CL>(sm), DevSync<CL>(), DevHooks<CL>());
 }
-template <int OP> __global__ void __launch_bounds__(256) k_dyadic(DyArgs A, const long long bstride) {
-  { const long long off = (long long)blockIdx.z * bstride; A.out += off; if (A.a) A.a += off; if (A.b) A.b += off; }
+template <int OP> __global__ void __launch_bounds__(256) k_dyadic(const DyArgs A, const long long bstride) {
+  const long long off = (long long)blockIdx.z * bstride;
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
-    dyadic_elem<OP>(A, blockIdx.y, j);
+    dyadic_elem<OP>(A, blockIdx.y, j, off);
 }
-template <bool SQ> __global__ void __launch_bounds__(256) k_mul_ct(MulArgs A, const long long bstride) {
-  { const long long off = (long long)blockIdx.z * bstride; A.out += off; A.a += off; if (A.b) A.b += off; }
+template <bool SQ> __global__ void __launch_bounds__(256) k_mul_ct(const MulArgs A, const long long bstride) {
+  const long long off = (long long)blockIdx.z * bstride;
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
-    mulct_elem<SQ>(A, blockIdx.y, j);
+    mulct_elem<SQ>(A, blockIdx.y, j, off);
 }
 __global__ void __launch_bounds__(256) k_sum_terms(const SumArgs A, const long long bstride) {
   const long long off = (long long)blockIdx.z * bstride;

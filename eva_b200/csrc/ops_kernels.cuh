@@ -20,7 +20,8 @@ EVAB_HD u64x2 ld2(const u64 *p) { return *reinterpret_cast<const u64x2 *>(p); }
 EVAB_HD void st2(u64 *p, u64x2 v) { *reinterpret_cast<u64x2 *>(p) = v; }
 
 // coefficients j, j+1 of output residue `res` (= s*ell + i)
-template <int OP> EVAB_HD void dyadic_elem(const DyArgs &A, int res, int j) {
+// boff: batch instance offset (words) applied to every ciphertext / plaintext pointer
+template <int OP> EVAB_HD void dyadic_elem(const DyArgs &A, int res, int j, long long boff = 0) {
   const int s = res / A.ell, i = res % A.ell;
   const PrimeDev P = A.primes[i];
   const u64 p = P.p;
@@ -28,16 +29,16 @@ template <int OP> EVAB_HD void dyadic_elem(const DyArgs &A, int res, int j) {
   const size_t aoff = ((size_t)s * A.a_ell + i) * A.N;
   const bool has_a = s < A.sa;
   const bool has_b = A.b_is_plain ? (OP == DY_MULPT || s == 0) : (s < A.sb);
-  const size_t boff = A.b_is_plain ? (size_t)i * A.N : off;
+  const size_t poff = A.b_is_plain ? (size_t)i * A.N : off;
   u64x2 va = u64x2{0, 0}, vb = u64x2{0, 0}, r;
-  if (has_a) va = ld2(A.a + aoff + j);
-  if (OP != DY_NEG && OP != DY_COPY && has_b) vb = ld2(A.b + boff + j);
+  if (has_a) va = ld2(A.a + boff + aoff + j);
+  if (OP != DY_NEG && OP != DY_COPY && has_b) vb = ld2(A.b + boff + poff + j);
   if (OP == DY_ADD) { r.x = addmod(va.x, vb.x, p); r.y = addmod(va.y, vb.y, p); }
   else if (OP == DY_SUB) { r.x = submod(va.x, vb.x, p); r.y = submod(va.y, vb.y, p); }
   else if (OP == DY_NEG) { r.x = negmod(va.x, p); r.y = negmod(va.y, p); }
   else if (OP == DY_COPY) { r = va; }
   else { r.x = mulmod(va.x, vb.x, p, P.ratio_lo, P.ratio_hi); r.y = mulmod(va.y, vb.y, p, P.ratio_lo, P.ratio_hi); }
-  st2(A.out + off + j, r);
+  st2(A.out + boff + off + j, r);
 }
 
 // fused sum of terms; term t is  ct[t]                      (kind 0: Evaluator::add operand),
@@ -95,11 +96,13 @@ EVAB_HD void sum_terms_elem(const SumArgs &A, int res, int j, long long off) {
 struct MulArgs { u64 *out; const u64 *a; const u64 *b; const PrimeDev *primes; int ell, N; };
 
 // 2x2 -> 3 tensor product (Evaluator::multiply) or square, residue i, coeffs j,j+1
-template <bool SQUARE> EVAB_HD void mulct_elem(const MulArgs &A, int i, int j) {
+template <bool SQUARE> EVAB_HD void mulct_elem(const MulArgs &A, int i, int j, long long boff = 0) {
   const PrimeDev P = A.primes[i];
   const u64 p = P.p, rl = P.ratio_lo, rh = P.ratio_hi;
   const size_t poly = (size_t)A.ell * A.N, off = (size_t)i * A.N + j;
-  const u64x2 a0 = ld2(A.a + off), a1 = ld2(A.a + poly + off);
+  const u64 *pa = A.a + boff, *pb = SQUARE ? nullptr : A.b + boff;
+  u64 *po = A.out + boff;
+  const u64x2 a0 = ld2(pa + off), a1 = ld2(pa + poly + off);
   u64x2 d0, d1, d2;
   if (SQUARE) {
     d0.x = mulmod(a0.x, a0.x, p, rl, rh); d0.y = mulmod(a0.y, a0.y, p, rl, rh);
@@ -107,7 +110,7 @@ template <bool SQUARE> EVAB_HD void mulct_elem(const MulArgs &A, int i, int j) {
     d1.x = addmod(x0, x0, p); d1.y = addmod(x1, x1, p);
     d2.x = mulmod(a1.x, a1.x, p, rl, rh); d2.y = mulmod(a1.y, a1.y, p, rl, rh);
   } else {
-    const u64x2 b0 = ld2(A.b + off), b1 = ld2(A.b + poly + off);
+    const u64x2 b0 = ld2(pb + off), b1 = ld2(pb + poly + off);
     d0.x = mulmod(a0.x, b0.x, p, rl, rh); d0.y = mulmod(a0.y, b0.y, p, rl, rh);
     // a0*b1 + a1*b0 accumulated in 128 bits, then one reduction: same canonical value
     u64 lo = 0, hi = 0;
@@ -116,7 +119,7 @@ template <bool SQUARE> EVAB_HD void mulct_elem(const MulArgs &A, int i, int j) {
     mac128(lo, hi, a0.y, b1.y); mac128(lo, hi, a1.y, b0.y); d1.y = barrett128(lo, hi, p, rl, rh);
     d2.x = mulmod(a1.x, b1.x, p, rl, rh); d2.y = mulmod(a1.y, b1.y, p, rl, rh);
   }
-  st2(A.out + off, d0); st2(A.out + poly + off, d1); st2(A.out + 2 * poly + off, d2);
+  st2(po + off, d0); st2(po + poly + off, d1); st2(po + 2 * poly + off, d2);
 }
 
 // key-switch inner product over digits (Appendix A.5 step 2):
