@@ -122,3 +122,41 @@ def test_sharded_execution_bit_exact(name, parts):
         assert np.array_equal(got.get(oname)[1], want.get(oname)[1]) and got.get(oname)[2] == want.get(oname)[2]
     # world = 1 degenerates to execute()
     assert np.array_equal(shard.execute_sharded(pub, prog, val).get(list(d["outputs"])[0])[1], want.get(list(d["outputs"])[0])[1])
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_split_random_programs(seed):
+    """random DSL programs (sums of products of rotated / scaled inputs with shared sub-expressions): cutting at
+    the widest sum and summing the parts in the tail reproduces the plaintext semantics, for 2..5 parts"""
+    from eva_b200 import EvaProgram, Input, Output
+    rng = np.random.default_rng(1000 + seed)
+    vec = 16
+    prog = EvaProgram("rand%d" % seed, vec_size=vec)
+    with prog:
+        ins = [Input("x"), Input("y")]
+        pool = list(ins)
+        for _ in range(int(rng.integers(3, 9))):       # shared sub-expressions
+            a, b = pool[int(rng.integers(len(pool)))], pool[int(rng.integers(len(pool)))]
+            kind = int(rng.integers(5))
+            pool.append(a << int(rng.integers(1, vec)) if kind == 0 else a * float(rng.uniform(-2, 2)) if kind == 1 else
+                        a * b if kind == 2 else a - b if kind == 3 else -a)
+        leaves = []
+        for _ in range(int(rng.integers(4, 14))):
+            a = pool[int(rng.integers(len(pool)))]
+            leaves.append(a * pool[int(rng.integers(len(pool)))] if rng.random() < 0.5 else a << int(rng.integers(vec)))
+        total = leaves[0]
+        for leaf in leaves[1:]:
+            total = total + leaf
+        Output("out", total * 0.5 + ins[0])
+        if rng.random() < 0.5:
+            Output("aux", pool[-1])
+    x = {"x": list(rng.uniform(-1, 1, vec)), "y": list(rng.uniform(-1, 1, vec))}
+    want = evaluate(prog, x)
+    for parts in (2, 3, 5):
+        plan = shard.split_program(prog, parts)
+        if plan is None:
+            continue
+        got = _plain_sharded(prog, plan, x)
+        assert set(got) == set(want)
+        for k in want:
+            assert np.allclose(got[k], want[k], rtol=1e-9, atol=1e-9), (seed, parts, k)
