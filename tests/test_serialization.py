@@ -127,3 +127,31 @@ def test_client_server_flow_through_files(tmp_path):
     blob = open(tmp_path / "server.sealpublic", "rb").read()
     sk = load(str(tmp_path / "client.sealsecret"))._export()["secret_key"]
     assert sk.tobytes()[:4096] not in blob
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_compiled_random_programs_roundtrip(seed):
+    """DSL -> CKKSCompiler -> save/load: the compiled program (Encode / Rescale / Relinearize / ModSwitch terms with
+    their attributes), the parameters and the signature survive the file format"""
+    from eva_b200 import EvaProgram, Input, Output
+    from eva_b200.ckks import CKKSCompiler
+    rng = np.random.default_rng(500 + seed)
+    vec = 64
+    prog = EvaProgram("ser%d" % seed, vec_size=vec)
+    with prog:
+        x, y = Input("x"), Input("y", is_encrypted=bool(seed % 3))
+        acc = x * float(rng.uniform(0.5, 1.5)) + y
+        for _ in range(int(rng.integers(1, 4))):
+            k = int(rng.integers(4))
+            acc = acc * x if k == 0 else (acc << int(rng.integers(1, vec))) + acc if k == 1 else acc * [float(v) for v in rng.uniform(-1, 1, vec)] if k == 2 else acc - x
+        Output("z", acc)
+    prog.set_input_scales(30)
+    prog.set_output_ranges(20)
+    compiled, params, sig = CKKSCompiler(config={"warn_vec_size": "false"}).compile(prog)
+    c2, p2, s2 = ser.loads(ser.dumps(compiled)), ser.loads(ser.dumps(params)), ser.loads(ser.dumps(sig))
+    assert ser.program_to_msg(c2).SerializeToString(deterministic=True) == ser.program_to_msg(compiled).SerializeToString(deterministic=True)
+    assert (list(p2.prime_bits), set(p2.rotations), p2.poly_modulus_degree) == (list(params.prime_bits), set(params.rotations), params.poly_modulus_degree)
+    assert {k: (int(v.input_type), v.scale, v.level) for k, v in s2.inputs.items()} == {k: (int(v.input_type), v.scale, v.level) for k, v in sig.inputs.items()}
+    vals = {"x": list(rng.uniform(-1, 1, vec)), "y": list(rng.uniform(-1, 1, vec))}
+    a, b = evaluate(compiled, vals), evaluate(c2, vals)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
