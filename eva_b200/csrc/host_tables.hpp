@@ -76,6 +76,7 @@ inline const char *build_tables(u64 N, int logN, const u64 *primes, int k, const
     P.ratio_lo = (u64)ratio; P.ratio_hi = (u64)(ratio >> 64);
     P.ratio64 = (u64)(((u128)1 << 64) / p);
     P.ninv = powmod(N % p, p - 2, p); P.ninv_s = shoup(P.ninv, p);
+    P.itw1n = mulmod(b[1].x, P.ninv, p); P.itw1n_s = shoup(P.itw1n, p);
     P.tw = tw_base + ((size_t)i * 2 + 0) * N;
     P.itw = tw_base + ((size_t)i * 2 + 1) * N;
   }

@@ -35,6 +35,7 @@ struct PrimeDev {
   u64 ratio_lo, ratio_hi;  // floor(2^128 / p)   (Barrett, 128-bit inputs)
   u64 ratio64;             // floor(2^64 / p)    (Barrett, 64-bit inputs)
   u64 ninv, ninv_s;        // N^-1 mod p and its Shoup companion
+  u64 itw1n, itw1n_s;      // itw[1] * N^-1 mod p (+Shoup): twiddle of the last inverse stage with the scaling folded in
   const u64x2 *tw;         // forward twiddles  {psi^bitrev(i), shoup}   [N]
   const u64x2 *itw;        // inverse twiddles  {psi^-bitrev(i), shoup}  [N]
 };

@@ -268,11 +268,11 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct
       if constexpr (CL > 1) xchg_write_cl<LOGN, CL>(S.x, sm, tid); else xchg_write_c<LOGN>(S.x, sm, tid);
     } else if constexpr (PH == NPH - 1) {
       if constexpr (CL > 1) xchg_read_dist_inv<LOGN, CL>(S.x, sm, ltid); else xchg_read_s<LOGN, 0, 1>(S.x, sm, tid);
-      inv_pass_s<LOGN, 0>(S.x, P.itw, root, P.p, tid, S.b);
+      inv_pass0_scaled<LOGN>(S.x, P.itw, P.p, tid, S.b, P.ninv, P.ninv_s, P.itw1n, P.itw1n_s);   // * N^-1 folded in, canonical
       const u64 half = P.p >> 1;
 #pragma unroll
       for (int k = 0; k < NTT_E; k++) {
-        u64 v = csub(shoup_lazy(S.x[k], P.ninv, P.ninv_s, P.p), P.p);   // * N^-1, canonical
+        u64 v = S.x[k];
         if (EPI == EPI_ADDHALF) v = addmod(v, half, P.p);
         J.dst[idx_s<LOGN, 0>(tid, k)] = v;
       }
