@@ -40,6 +40,9 @@ _SIGS = {
     "evab_ntt_fwd": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
     "evab_ntt_inv": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
     "evab_set_ntt_cluster": (ci, [ci]),
+    "evab_ctx_set_ntt_cluster": (ci, [vp, ci]),
+    "evab_ctx_set_ntt_arith": (ci, [vp, ci]),
+    "evab_ctx_foldmask": (C.c_uint, [vp]),
     "evab_sum_terms": (ci, [vp, ci, vp, ci, C.POINTER(vp), C.POINTER(ci), C.POINTER(vp), vp]),
     "evab_sum_products": (ci, [vp, ci, vp, ci, C.POINTER(vp), C.POINTER(ci), C.POINTER(vp), C.POINTER(ci), vp]),
     "evab_host_alloc": (ci, [szt, C.POINTER(vp)]),

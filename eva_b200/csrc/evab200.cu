@@ -27,10 +27,13 @@ extern "C" int evab_version(void) { return 1; }
 struct evab_ctx {
   CtxView v;
   int device, sms;
+  int ntt_cluster = 0;         // CTAs per residue (0 = automatic), evab_ctx_set_ntt_cluster
   std::vector<u64> primes;
+  std::vector<FoldPrime> fold_host;
   PrimeDev *d_primes = nullptr;
   u64x2 *d_tw = nullptr;
   u64x2 *d_qinv = nullptr;
+  u64x2 *d_qinv_f = nullptr;
   u64 *d_halfmod = nullptr;
   u64 *d_zeros = nullptr;
   cplx *d_roots = nullptr;
@@ -92,11 +95,11 @@ template <int CL> __device__ __forceinline__ SmemView<CL> smem_view(u64 *sm) {
 }
 // CL = 1: one CTA = one residue, T = N/16 threads, 64 registers.
 // CL = 2, 4: one residue over a cluster of CL CTAs of T/CL threads (ntt_core.cuh), CL CTAs per SM more.
-template <int LOGN, int PRO, int EPI, int CL>
+template <int LOGN, int PRO, int EPI, int CL, int AR>
 __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::T / CL)) k_ntt_fwd(const NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
-  typedef FwdBody<LOGN, PRO, EPI, CL> B;
-  const NttJob J = ntt_job(L, blockIdx.x, CL, (long long)blockIdx.y * bstride);
+  typedef FwdBody<LOGN, PRO, EPI, CL, AR> B;
+  const NttJob J = ntt_job_qr(L, blockIdx.y, blockIdx.x / CL, blockIdx.x % CL, (long long)blockIdx.z * bstride);
   if (J.skip) return;
   NttState S;
   const u32 tid = threadIdx.x;
@@ -106,11 +109,11 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::
   PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, smem_view<CL>(sm), DevSync<CL>(), hk);
   B::phE(S, L, J, tid);
 }
-template <int LOGN, int PRO, int EPI, int CL>
+template <int LOGN, int PRO, int EPI, int CL, int AR>
 __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::T / CL)) k_ntt_inv(const NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
-  typedef InvBody<LOGN, PRO, EPI, CL> B;
-  const NttJob J = ntt_job(L, blockIdx.x, CL, (long long)blockIdx.y * bstride);
+  typedef InvBody<LOGN, PRO, EPI, CL, AR> B;
+  const NttJob J = ntt_job_qr(L, blockIdx.y, blockIdx.x / CL, blockIdx.x % CL, (long long)blockIdx.z * bstride);
   if (J.skip) return;
   NttState S;
   PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, smem_view<CL>(sm), DevSync<CL>(), DevHooks<CL>());
@@ -159,80 +162,100 @@ __global__ void __launch_bounds__(256) k_enc_uniform(const EncUniform B, const l
 // CTAs per residue (evab_set_ntt_cluster); 0 = automatic: 128-thread CTAs, i.e. N/2048 CTAs per residue
 // (N=16384: 8, 8192: 4, 4096: 2).  Sobel ops/s and single-instance latency at N=16384:
 // 1: 414k 1.11 ms, 2: 444k 0.76, 4: 477k 0.57, 8: 494k 0.49; N=8192 is fastest at 4 (64-thread CTAs lose).
-static int g_ntt_cluster = 0;
-template <int LOGN> static int ntt_cluster_for() {
+static std::atomic<int> g_ntt_cluster{0};   // default for contexts created afterwards (evab_set_ntt_cluster)
+template <int LOGN> static int ntt_cluster_for(int requested) {
   int most = NttGeom<LOGN>::T / 128 < 1 ? 1 : NttGeom<LOGN>::T / 128;   // keep CTAs at >= 128 threads
   if (most > 8) most = 8;                                                 // portable cluster size
-  int cl = g_ntt_cluster ? g_ntt_cluster : most;
+  int cl = requested ? requested : most;
   if (cl > most) cl = most;
   if (LOGN == 15 && cl < 2) cl = 2;                                       // 2048 threads never fit one CTA
   return cl;
 }
 
-template <class K> static int launch_ntt(K kernel, const NttLaunch &L, size_t ctas, int threads, size_t smem, int cluster, cudaStream_t st, std::atomic<bool> *done) {
+// grid = (inner * cluster, q, batch instance); more than 65535 q's are issued in slices
+template <class K> static int launch_ntt(K kernel, const NttLaunch &L0, size_t jobs, int threads, size_t smem, int cluster, cudaStream_t st, std::atomic<bool> *done) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!done[dev & 63].load()) {
     CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done[dev & 63].store(true);
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)ctas, (unsigned)g_batch.batch);
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, L, g_batch.stride));
+  const size_t inner = (size_t)L0.inner, nq = (jobs + inner - 1) / inner;
+  if (nq * inner != jobs) return fail("NTT launch: job count must be a multiple of the inner dimension");
+  if (nq > 65535 && L0.prime_on_q) return fail("NTT launch: too many polynomials for a prime-per-polynomial launch");
+  for (size_t q0 = 0; q0 < nq; q0 += 65535) {
+    NttLaunch L = L0;
+    const long long o = (long long)q0;
+    L.src += o * L.src_sq; L.dst += o * L.dst_sq;
+    if (L.aux0) L.aux0 += o * L.aux0_sq;
+    if (L.aux1) L.aux1 += o * L.aux1_sq;
+    if (L.cflags) L.cflags += o;
+    L.aux1_polys = L0.aux1_polys - (int)(o > (1 << 30) ? (1 << 30) : o);
+    const size_t n = nq - q0 < 65535 ? nq - q0 : 65535;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(inner * cluster), (unsigned)n, (unsigned)g_batch.batch);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, L, g_batch.stride));
+  }
   return 0;
 }
-template <int LOGN, int PRO, int EPI, int CL> static int launch_fwd_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+template <int LOGN, int PRO, int EPI, int CL, int AR> static int launch_fwd_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   static std::atomic<bool> done[64];
-  return launch_ntt(k_ntt_fwd<LOGN, PRO, EPI, CL>, L, jobs * CL, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CL, st, done);
+  return launch_ntt(k_ntt_fwd<LOGN, PRO, EPI, CL, AR>, L, jobs, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CL, st, done);
 }
-template <int LOGN, int CL> static int launch_fwd_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_fwd_m<LOGN, PRO_PLAIN, EPI_STORE, CL>(L, jobs, st);
-  if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return launch_fwd_m<LOGN, PRO_MODRED, EPI_STORE, CL>(L, jobs, st);
-  if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, PRO_MODRED, EPI_STORE_LAZY, CL>(L, jobs, st);
-  if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return launch_fwd_m<LOGN, PRO_MODRED, EPI_DIVROUND, CL>(L, jobs, st);
-  if (L.pro == PRO_MODRED_SG && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, PRO_MODRED_SG, EPI_STORE_LAZY, CL>(L, jobs, st);
+template <int LOGN, int CL, int AR> static int launch_fwd_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_fwd_m<LOGN, PRO_PLAIN, EPI_STORE, CL, AR>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return launch_fwd_m<LOGN, PRO_MODRED, EPI_STORE, CL, AR>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, PRO_MODRED, EPI_STORE_LAZY, CL, AR>(L, jobs, st);
+  if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return launch_fwd_m<LOGN, PRO_MODRED, EPI_DIVROUND, CL, AR>(L, jobs, st);
+  if (L.pro == PRO_MODRED_SG && L.epi == EPI_STORE_LAZY) return launch_fwd_m<LOGN, PRO_MODRED_SG, EPI_STORE_LAZY, CL, AR>(L, jobs, st);
   return fail("unsupported forward NTT prologue/epilogue combination");
 }
-template <int LOGN> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+template <int LOGN, int AR> static int launch_fwd_a(const NttLaunch &L, size_t jobs, cudaStream_t st, int cluster) {
   if constexpr (LOGN >= 12) {
-    const int cl = ntt_cluster_for<LOGN>();
+    const int cl = ntt_cluster_for<LOGN>(cluster);
     if constexpr (LOGN >= 13) {
-      if (cl == 4) return launch_fwd_c<LOGN, 4>(L, jobs, st);
-      if (cl == 8) return launch_fwd_c<LOGN, 8>(L, jobs, st);
+      if (cl == 4) return launch_fwd_c<LOGN, 4, AR>(L, jobs, st);
+      if (cl == 8) return launch_fwd_c<LOGN, 8, AR>(L, jobs, st);
     }
-    if (cl == 2 || LOGN == 15) return launch_fwd_c<LOGN, 2>(L, jobs, st);
+    if (cl == 2 || LOGN == 15) return launch_fwd_c<LOGN, 2, AR>(L, jobs, st);
   }
-  if constexpr (LOGN <= 14) return launch_fwd_c<LOGN, 1>(L, jobs, st);
+  if constexpr (LOGN <= 14) return launch_fwd_c<LOGN, 1, AR>(L, jobs, st);
   return fail("unsupported cluster size");
 }
-template <int LOGN, int PRO, int EPI, int CL> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  static std::atomic<bool> done[64];
-  return launch_ntt(k_ntt_inv<LOGN, PRO, EPI, CL>, L, jobs * CL, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CL, st, done);
+template <int LOGN> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cudaStream_t st, bool fold, int cluster) {
+  return fold ? launch_fwd_a<LOGN, 1>(L, jobs, st, cluster) : launch_fwd_a<LOGN, 0>(L, jobs, st, cluster);
 }
-template <int LOGN, int CL> static int launch_inv_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
-  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_inv_m<LOGN, PRO_PLAIN, EPI_STORE, CL>(L, jobs, st);
-  if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return launch_inv_m<LOGN, PRO_PLAIN, EPI_ADDHALF, CL>(L, jobs, st);
-  if (L.pro == PRO_GATHER && L.epi == EPI_STORE) return launch_inv_m<LOGN, PRO_GATHER, EPI_STORE, CL>(L, jobs, st);
+template <int LOGN, int PRO, int EPI, int CL, int AR> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  static std::atomic<bool> done[64];
+  return launch_ntt(k_ntt_inv<LOGN, PRO, EPI, CL, AR>, L, jobs, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CL, st, done);
+}
+template <int LOGN, int CL, int AR> static int launch_inv_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_inv_m<LOGN, PRO_PLAIN, EPI_STORE, CL, AR>(L, jobs, st);
+  if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return launch_inv_m<LOGN, PRO_PLAIN, EPI_ADDHALF, CL, AR>(L, jobs, st);
+  if (L.pro == PRO_GATHER && L.epi == EPI_STORE) return launch_inv_m<LOGN, PRO_GATHER, EPI_STORE, CL, AR>(L, jobs, st);
   return fail("unsupported inverse NTT prologue/epilogue combination");
 }
-template <int LOGN> static int launch_inv_t(const NttLaunch &L, size_t jobs, cudaStream_t st) {
+template <int LOGN, int AR> static int launch_inv_a(const NttLaunch &L, size_t jobs, cudaStream_t st, int cluster) {
   if constexpr (LOGN >= 12) {
-    const int cl = ntt_cluster_for<LOGN>();
+    const int cl = ntt_cluster_for<LOGN>(cluster);
     if constexpr (LOGN >= 13) {
-      if (cl == 4) return launch_inv_c<LOGN, 4>(L, jobs, st);
-      if (cl == 8) return launch_inv_c<LOGN, 8>(L, jobs, st);
+      if (cl == 4) return launch_inv_c<LOGN, 4, AR>(L, jobs, st);
+      if (cl == 8) return launch_inv_c<LOGN, 8, AR>(L, jobs, st);
     }
-    if (cl == 2 || LOGN == 15) return launch_inv_c<LOGN, 2>(L, jobs, st);
+    if (cl == 2 || LOGN == 15) return launch_inv_c<LOGN, 2, AR>(L, jobs, st);
   }
-  if constexpr (LOGN <= 14) return launch_inv_c<LOGN, 1>(L, jobs, st);
+  if constexpr (LOGN <= 14) return launch_inv_c<LOGN, 1, AR>(L, jobs, st);
   return fail("unsupported cluster size");
+}
+template <int LOGN> static int launch_inv_t(const NttLaunch &L, size_t jobs, cudaStream_t st, bool fold, int cluster) {
+  return fold ? launch_inv_a<LOGN, 1>(L, jobs, st, cluster) : launch_inv_a<LOGN, 0>(L, jobs, st, cluster);
 }
 
 struct CudaBE {
@@ -247,25 +270,27 @@ struct CudaBE {
   }
   int fwd(const NttLaunch &L, size_t jobs) {
     count();
+    const bool fold = c->v.arith == 0 && ntt_launch_folds(L, jobs, c->v.foldmask);
     switch (c->v.logN) {
-      case 10: return launch_fwd_t<10>(L, jobs, st);
-      case 11: return launch_fwd_t<11>(L, jobs, st);
-      case 12: return launch_fwd_t<12>(L, jobs, st);
-      case 13: return launch_fwd_t<13>(L, jobs, st);
-      case 14: return launch_fwd_t<14>(L, jobs, st);
-      case 15: return launch_fwd_t<15>(L, jobs, st);
+      case 10: return launch_fwd_t<10>(L, jobs, st, fold, c->ntt_cluster);
+      case 11: return launch_fwd_t<11>(L, jobs, st, fold, c->ntt_cluster);
+      case 12: return launch_fwd_t<12>(L, jobs, st, fold, c->ntt_cluster);
+      case 13: return launch_fwd_t<13>(L, jobs, st, fold, c->ntt_cluster);
+      case 14: return launch_fwd_t<14>(L, jobs, st, fold, c->ntt_cluster);
+      case 15: return launch_fwd_t<15>(L, jobs, st, fold, c->ntt_cluster);
     }
     return fail("unsupported N");
   }
   int inv(const NttLaunch &L, size_t jobs) {
     count();
+    const bool fold = c->v.arith == 0 && ntt_launch_folds(L, jobs, c->v.foldmask);
     switch (c->v.logN) {
-      case 10: return launch_inv_t<10>(L, jobs, st);
-      case 11: return launch_inv_t<11>(L, jobs, st);
-      case 12: return launch_inv_t<12>(L, jobs, st);
-      case 13: return launch_inv_t<13>(L, jobs, st);
-      case 14: return launch_inv_t<14>(L, jobs, st);
-      case 15: return launch_inv_t<15>(L, jobs, st);
+      case 10: return launch_inv_t<10>(L, jobs, st, fold, c->ntt_cluster);
+      case 11: return launch_inv_t<11>(L, jobs, st, fold, c->ntt_cluster);
+      case 12: return launch_inv_t<12>(L, jobs, st, fold, c->ntt_cluster);
+      case 13: return launch_inv_t<13>(L, jobs, st, fold, c->ntt_cluster);
+      case 14: return launch_inv_t<14>(L, jobs, st, fold, c->ntt_cluster);
+      case 15: return launch_inv_t<15>(L, jobs, st, fold, c->ntt_cluster);
     }
     return fail("unsupported N");
   }
@@ -330,6 +355,43 @@ struct CudaBE {
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+static void ctx_free(evab_ctx *c) {
+  for (auto &kv : c->perms) cudaFree(kv.second);
+  for (auto &kv : c->cperms) cudaFree(kv.second);
+  cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_qinv); cudaFree(c->d_qinv_f); cudaFree(c->d_halfmod); cudaFree(c->d_zeros);
+  cudaFree(c->d_roots); cudaFree(c->d_slot); cudaFree(c->d_pow2);
+  delete c;
+}
+// device copy of a host table; on failure the caller frees the whole context (no leak on any error path)
+template <class T> static int to_device(T **dst, const T *src, size_t n) {
+  CUDA_OK(cudaMalloc(dst, n * sizeof(T)));
+  CUDA_OK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+static int ctx_build(evab_ctx *c, uint64_t N, int logN, const uint64_t *primes, int k) {
+  const size_t tw_elems = (size_t)k * 4 * N;   // Shoup rows + fold rows (host_tables.hpp)
+  CUDA_OK(cudaMalloc(&c->d_tw, tw_elems * sizeof(u64x2)));
+  evab_host::Tables T;
+  const char *err = evab_host::build_tables(N, logN, primes, k, c->d_tw, T);
+  if (err[0]) return fail(std::string("evab_ctx_create: ") + err);
+  CUDA_OK(cudaMemcpy(c->d_tw, T.tw.data(), tw_elems * sizeof(u64x2), cudaMemcpyHostToDevice));
+  if (to_device(&c->d_primes, T.pd.data(), (size_t)k)) return 1;
+  if (to_device(&c->d_qinv, T.qinv.data(), T.qinv.size())) return 1;
+  if (to_device(&c->d_qinv_f, T.qinv_f.data(), T.qinv_f.size())) return 1;
+  if (to_device(&c->d_halfmod, T.halfmod.data(), T.halfmod.size())) return 1;
+  CUDA_OK(cudaMalloc(&c->d_zeros, 32 * sizeof(u64)));
+  CUDA_OK(cudaMemset(c->d_zeros, 0, 32 * sizeof(u64)));
+  if (to_device(&c->d_roots, reinterpret_cast<const cplx *>(T.roots.data()), (size_t)N)) return 1;
+  if (to_device(&c->d_slot, T.slot_index.data(), (size_t)N)) return 1;
+  if (to_device(&c->d_pow2, T.pow2.data(), T.pow2.size())) return 1;
+  c->v.roots = c->d_roots; c->v.slot_index = c->d_slot; c->v.pow2 = c->d_pow2;
+  c->v.N = N; c->v.logN = logN; c->v.k = k;
+  c->v.primes = c->d_primes; c->v.qinv = c->d_qinv; c->v.qinv_f = c->d_qinv_f; c->v.halfmod = c->d_halfmod; c->v.zeros = c->d_zeros;
+  c->v.foldmask = T.foldmask;
+  c->fold_host = T.fp; c->v.fold_host = c->fold_host.data();
+  c->v.arith = getenv("EVAB_NTT_SHOUP") ? 1 : 0;
+  return 0;
+}
 extern "C" int evab_ctx_create(uint64_t N, const uint64_t *primes, int k, int device, evab_ctx **out) {
   if (!out) return fail("evab_ctx_create: null out");
   *out = nullptr;
@@ -351,30 +413,9 @@ extern "C" int evab_ctx_create(uint64_t N, const uint64_t *primes, int k, int de
 
   evab_ctx *c = new evab_ctx();
   c->device = device; c->sms = prop.multiProcessorCount;
+  c->ntt_cluster = g_ntt_cluster.load();
   c->primes.assign(primes, primes + k);
-  const size_t tw_elems = (size_t)k * 2 * N;
-  if (cudaMalloc(&c->d_tw, tw_elems * sizeof(u64x2)) != cudaSuccess) { delete c; return fail("cudaMalloc failed"); }
-  evab_host::Tables T;
-  const char *err = evab_host::build_tables(N, logN, primes, k, c->d_tw, T);
-  if (err[0]) { cudaFree(c->d_tw); delete c; return fail(std::string("evab_ctx_create: ") + err); }
-  CUDA_OK(cudaMemcpy(c->d_tw, T.tw.data(), tw_elems * sizeof(u64x2), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMalloc(&c->d_primes, k * sizeof(PrimeDev)));
-  CUDA_OK(cudaMemcpy(c->d_primes, T.pd.data(), k * sizeof(PrimeDev), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMalloc(&c->d_qinv, T.qinv.size() * sizeof(u64x2)));
-  CUDA_OK(cudaMemcpy(c->d_qinv, T.qinv.data(), T.qinv.size() * sizeof(u64x2), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMalloc(&c->d_halfmod, T.halfmod.size() * sizeof(u64)));
-  CUDA_OK(cudaMemcpy(c->d_halfmod, T.halfmod.data(), T.halfmod.size() * sizeof(u64), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMalloc(&c->d_zeros, 32 * sizeof(u64)));
-  CUDA_OK(cudaMemset(c->d_zeros, 0, 32 * sizeof(u64)));
-  CUDA_OK(cudaMalloc(&c->d_roots, N * sizeof(cplx)));
-  CUDA_OK(cudaMemcpy(c->d_roots, T.roots.data(), N * sizeof(cplx), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMalloc(&c->d_slot, N * sizeof(u32)));
-  CUDA_OK(cudaMemcpy(c->d_slot, T.slot_index.data(), N * sizeof(u32), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMalloc(&c->d_pow2, T.pow2.size() * sizeof(u64)));
-  CUDA_OK(cudaMemcpy(c->d_pow2, T.pow2.data(), T.pow2.size() * sizeof(u64), cudaMemcpyHostToDevice));
-  c->v.roots = c->d_roots; c->v.slot_index = c->d_slot; c->v.pow2 = c->d_pow2;
-  c->v.N = N; c->v.logN = logN; c->v.k = k;
-  c->v.primes = c->d_primes; c->v.qinv = c->d_qinv; c->v.halfmod = c->d_halfmod; c->v.zeros = c->d_zeros;
+  if (ctx_build(c, N, logN, primes, k)) { ctx_free(c); return 1; }   // g_err is set; every partial allocation is released
   *out = c;
   return 0;
 }
@@ -382,12 +423,20 @@ extern "C" void evab_ctx_destroy(evab_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (auto &kv : c->perms) cudaFree(kv.second);
-  for (auto &kv : c->cperms) cudaFree(kv.second);
-  cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_qinv); cudaFree(c->d_halfmod); cudaFree(c->d_zeros);
-  cudaFree(c->d_roots); cudaFree(c->d_slot); cudaFree(c->d_pow2);
-  delete c;
+  ctx_free(c);
 }
+// per-context tuning knobs (no process-global state): CTAs per residue, NTT arithmetic
+extern "C" int evab_ctx_set_ntt_cluster(evab_ctx *c, int cl) {
+  if (cl != 0 && cl != 1 && cl != 2 && cl != 4 && cl != 8) return fail("evab_ctx_set_ntt_cluster: 0 (automatic), 1, 2, 4 or 8 CTAs per residue");
+  c->ntt_cluster = cl;
+  return 0;
+}
+extern "C" int evab_ctx_set_ntt_arith(evab_ctx *c, int mode) {
+  if (mode != 0 && mode != 1) return fail("evab_ctx_set_ntt_arith: 0 (two-row fold where the primes allow it) or 1 (lazy Shoup everywhere)");
+  c->v.arith = mode;
+  return 0;
+}
+extern "C" unsigned evab_ctx_foldmask(const evab_ctx *c) { return c->v.foldmask; }
 extern "C" uint64_t evab_ctx_N(const evab_ctx *c) { return c->v.N; }
 extern "C" int evab_ctx_k(const evab_ctx *c) { return c->v.k; }
 extern "C" int evab_ctx_device(const evab_ctx *c) { return c->device; }
@@ -503,7 +552,7 @@ extern "C" int evab_ntt_inv(evab_ctx *c, uint64_t *d, size_t count, const int *p
 }
 extern "C" int evab_set_ntt_cluster(int cl) {
   if (cl != 0 && cl != 1 && cl != 2 && cl != 4 && cl != 8) return fail("evab_set_ntt_cluster: 0 (automatic), 1, 2, 4 or 8 CTAs per residue");
-  g_ntt_cluster = cl;
+  g_ntt_cluster.store(cl);   // default of contexts created from now on; existing contexts keep theirs
   return 0;
 }
 extern "C" int evab_encode_uniform(evab_ctx *c, int count, const double *values, const double *scales, int ell, uint64_t *out, void *stream) {

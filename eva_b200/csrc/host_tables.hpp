@@ -16,6 +16,7 @@ inline u64 powmod(u64 a, u64 e, u64 p) {
   return r;
 }
 inline u64 shoup(u64 w, u64 p) { return (u64)(((u128)w << 64) / p); }
+inline u64 row32(u64 w, u64 p) { return (u64)(((u128)w << 32) % p); }   // companion row of the two-row fold product
 inline u32 bitrev(u32 x, int bits) { u32 r = 0; for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r; }
 // numerically smallest primitive 2N-th root of unity mod p (0 if none)
 inline u64 min_root(u64 N, u64 p) {
@@ -47,16 +48,22 @@ struct Tables {
   std::vector<cplxh> roots;        // [N] zeta^bitrev(i), zeta = e^(2 pi i / 2N)   (CKKS encoder)
   std::vector<u32> slot_index;     // [N] matrix_reps_index_map
   std::vector<u64> pow2;           // [k][128] 2^i mod p
-  std::vector<u64x2> tw;       // [k][2][N]  forward / inverse {w, shoup(w)} in bit-reversed power order
+  std::vector<u64x2> tw;       // [k][2][N]  forward / inverse {w, shoup(w)} in bit-reversed power order,
+                               // followed by [k][2][N] {w, w * 2^32 mod p} (fold rows; zero for primes that are not fold-friendly)
   std::vector<PrimeDev> pd;    // tw / itw pointers are filled relative to `tw_base`
   std::vector<u64x2> qinv;     // [last][i]  {q_last^-1 mod q_i, shoup}
+  std::vector<u64x2> qinv_f;   // [last][i]  {q_last^-1 mod q_i, * 2^32 mod q_i}   (fold row)
+  unsigned foldmask = 0;       // bit i: primes[i] is fold-friendly
+  std::vector<FoldPrime> fp;   // [k] fold constants (kernel-parameter copy)
   std::vector<u64> halfmod;    // [last][i]  floor(q_last/2) mod q_i
 };
 
 // returns empty string on success
 inline const char *build_tables(u64 N, int logN, const u64 *primes, int k, const u64x2 *tw_base, Tables &T) {
-  T.tw.assign((size_t)k * 2 * N, u64x2{0, 0});
+  T.tw.assign((size_t)k * 4 * N, u64x2{0, 0});
+  T.foldmask = 0;
   T.pd.resize(k);
+  T.fp.assign(k, FoldPrime{});
   for (int i = 0; i < k; i++) {
     u64 p = primes[i];
     if (p < 3 || (p >> 60)) return "primes must be odd and < 2^60";
@@ -64,10 +71,14 @@ inline const char *build_tables(u64 N, int logN, const u64 *primes, int k, const
     if (!psi) return "prime is not congruent to 1 mod 2N";
     u64 ipsi = powmod(psi, p - 2, p), pw = 1, ipw = 1;
     u64x2 *f = &T.tw[((size_t)i * 2 + 0) * N], *b = &T.tw[((size_t)i * 2 + 1) * N];
+    u64x2 *ff = &T.tw[((size_t)(k + i) * 2 + 0) * N], *fb = &T.tw[((size_t)(k + i) * 2 + 1) * N];
+    const bool fold = prime_foldable(p);
+    if (fold) T.foldmask |= 1u << i;
     for (u64 j = 0; j < N; j++) {
       u32 r = bitrev((u32)j, logN);
       f[r].x = pw; f[r].y = shoup(pw, p);
       b[r].x = ipw; b[r].y = shoup(ipw, p);
+      if (fold) { ff[r].x = pw; ff[r].y = row32(pw, p); fb[r].x = ipw; fb[r].y = row32(ipw, p); }
       pw = mulmod(pw, psi, p); ipw = mulmod(ipw, ipsi, p);
     }
     PrimeDev &P = T.pd[i];
@@ -79,6 +90,13 @@ inline const char *build_tables(u64 N, int logN, const u64 *primes, int k, const
     P.itw1n = mulmod(b[1].x, P.ninv, p); P.itw1n_s = shoup(P.itw1n, p);
     P.tw = tw_base + ((size_t)i * 2 + 0) * N;
     P.itw = tw_base + ((size_t)i * 2 + 1) * N;
+    P.ftw = tw_base + ((size_t)(k + i) * 2 + 0) * N;
+    P.fitw = tw_base + ((size_t)(k + i) * 2 + 1) * N;
+    P.ninv_v = row32(P.ninv, p); P.itw1n_v = row32(P.itw1n, p);
+    P.foldable = fold ? 1u : 0u; P.eps = fold ? fold_eps(p) : 0u;
+    FoldPrime &F = T.fp[i];
+    F.p = p; F.p3 = 3 * p; F.p8 = 8 * p; F.eps = P.eps; F.foldable = P.foldable;
+    F.ftw = P.ftw; F.fitw = P.fitw; F.ninv = P.ninv; F.ninv_v = P.ninv_v; F.itw1n = P.itw1n; F.itw1n_v = P.itw1n_v;
   }
   T.roots.resize(N); T.slot_index.resize(N);
   for (u64 i = 0; i < N; i++) unit_root(bitrev((u32)i, logN), 2 * N, T.roots[i].re, T.roots[i].im);
@@ -91,6 +109,7 @@ inline const char *build_tables(u64 N, int logN, const u64 *primes, int k, const
   T.pow2.assign((size_t)k * 128, 0);
   for (int i = 0; i < k; i++) { u64 v = 1 % primes[i]; for (int e = 0; e < 128; e++) { T.pow2[(size_t)i * 128 + e] = v; v = mulmod(v, 2, primes[i]); } }
   T.qinv.assign((size_t)k * k, u64x2{0, 0});
+  T.qinv_f.assign((size_t)k * k, u64x2{0, 0});
   T.halfmod.assign((size_t)k * k, 0);
   for (int last = 0; last < k; last++)
     for (int i = 0; i < k; i++) {
@@ -98,6 +117,7 @@ inline const char *build_tables(u64 N, int logN, const u64 *primes, int k, const
       u64 p = primes[i], ql = primes[last];
       u64 inv = powmod(ql % p, p - 2, p);
       T.qinv[(size_t)last * k + i] = u64x2{inv, shoup(inv, p)};
+      T.qinv_f[(size_t)last * k + i] = u64x2{inv, row32(inv, p)};
       T.halfmod[(size_t)last * k + i] = (ql >> 1) % p;
     }
   return "";

@@ -38,7 +38,21 @@ struct PrimeDev {
   u64 itw1n, itw1n_s;      // itw[1] * N^-1 mod p (+Shoup): twiddle of the last inverse stage with the scaling folded in
   const u64x2 *tw;         // forward twiddles  {psi^bitrev(i), shoup}   [N]
   const u64x2 *itw;        // inverse twiddles  {psi^-bitrev(i), shoup}  [N]
+  // fold-friendly primes (prime_foldable): the same tables with the companion row {w, w * 2^32 mod p}
+  const u64x2 *ftw, *fitw;
+  u64 ninv_v, itw1n_v;     // companion rows of ninv / itw1n
+  u32 eps;                 // 2^61 mod p
+  u32 foldable;
 };
+
+// per-prime constants of the fold arithmetic, carried in the kernel parameters (constant bank -> uniform registers)
+struct FoldPrime {
+  u64 p, p3, p8;             // p, 3p, 8p
+  u32 eps, foldable;         // 2^61 mod p
+  const u64x2 *ftw, *fitw;   // {w, w * 2^32 mod p} forward / inverse, bit-reversed power order
+  u64 ninv, ninv_v, itw1n, itw1n_v;
+};
+constexpr int NTT_MAX_PRIMES = 24;
 
 // x >= c ? x - c : x
 EVAB_HD u64 csub(u64 x, u64 c) { return x >= c ? x - c : x; }
@@ -86,6 +100,58 @@ EVAB_HD u64 shoup_mad4(u64 y, u64 w, u64 ws, u64 np, u64 c) {
 #else
   const u64 q = (u64)s1 * y1 + (((u64)s1 * y0) >> 32) + (((u64)s0 * y1) >> 32);
   return c + w * y + q * np;
+#endif
+}
+
+// ---- "two-row fold" multiplication for SEAL's 60-bit NTT primes -------------------------------
+// CoeffModulus::Create scans downwards from 2^60 in steps of 2N, so every 60-bit prime of an EVA
+// program has the form p = 2^60 - delta with delta < 2^25 ("fold-friendly": prime_foldable()).  For
+// those, 2^61 = 2p + eps with eps = 2*delta < 2^26, and a product by a known constant w needs no
+// quotient at all: with the companion row v = w * 2^32 mod p stored beside w,
+//     S = y0*w + y1*v          (y = y1*2^32 + y0, ANY u64;  S == y*w mod p,  S < 2^33 p < 2^93)
+//     r = (S mod 2^61) + (S >> 61) * eps                      (r == y*w mod p,  r < 2^61 + 2^58 < 2.2501 p)
+// which is 4 + 1 IMAD.WIDE.U32 and no 32-bit low multiplies -- against 6 wide + 4 low for the lazy
+// Shoup product (the fma pipe bounds the transforms: profiles/r02_pipe_model.md).  The inputs of a
+// product are unconstrained, so butterflies only ever have to keep their *sums* below 2^64.
+// Bounds are tracked at compile time in units of p/16 (B16: value < B16 * p / 16; 16p < 2^64).
+constexpr int FB_CANON = 16;    // [0, p)
+constexpr int FB_MUL = 37;      // fold_mul result   (< 2.2501 p)
+constexpr int FB_FOLD = 33;     // fold61 result     (< 2^61 + 7 * 2^26 < 2.0001 p)
+constexpr int FB_MAX = 256;     // 16 p < 2^64
+EVAB_HD bool prime_foldable(u64 p) { return p < (1ull << 60) && p > (1ull << 60) - (1ull << 25); }
+EVAB_HD u32 fold_eps(u64 p) { return (u32)(((1ull << 60) - p) << 1); }   // 2^61 mod p
+
+EVAB_HD u64 madw32(u32 a, u32 b, u64 c) {
+#if defined(__CUDA_ARCH__)
+  u64 d; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c)); return d;
+#else
+  return (u64)a * b + c;
+#endif
+}
+// any u64 -> congruent value < 2^61 + 7*eps
+EVAB_HD u64 fold61(u64 x, u32 eps) { return madw32((u32)(x >> 61), eps, x & ((1ull << 61) - 1)); }
+// x < 16p -> canonical [0,p): x = h*2^60 + l == l + h*delta, which is < p + 2^29; one conditional subtraction
+EVAB_HD u64 fold_canon(u64 x, u32 eps, u64 p) {
+  const u64 r = madw32((u32)(x >> 60), eps >> 1, x & ((1ull << 60) - 1));
+  return r >= p ? r - p : r;
+}
+EVAB_HD u64 fold_mul(u64 y, u64 w, u64 v, u32 eps) {
+  const u32 y0 = (u32)y, y1 = (u32)(y >> 32);
+#if defined(__CUDA_ARCH__)
+  const u64 B = madw32(y1, (u32)(v >> 32), madw32(y0, (u32)(w >> 32), 0));
+  const u64 A = madw32(y0, (u32)w, 0), A2 = madw32(y1, (u32)v, 0);
+  u32 s0, s1, s2, H;
+  asm("{\n\t.reg .u32 t;\n\t"
+      "add.cc.u32 %0, %3, %5;\n\taddc.cc.u32 t, %4, %6;\n\taddc.u32 %2, %8, 0;\n\t"
+      "add.cc.u32 %1, t, %7;\n\taddc.u32 %2, %2, 0;\n\t}"
+      : "=r"(s0), "=r"(s1), "=r"(s2)
+      : "r"((u32)A), "r"((u32)(A >> 32)), "r"((u32)A2), "r"((u32)(A2 >> 32)), "r"((u32)B), "r"((u32)(B >> 32)));
+  asm("shf.l.wrap.b32 %0, %1, %2, 3;" : "=r"(H) : "r"(s1), "r"(s2));
+  u64 L; asm("mov.b64 %0, {%1, %2};" : "=l"(L) : "r"(s0), "r"(s1 & 0x1fffffffu));
+  return madw32(H, eps, 0) + L;
+#else
+  const unsigned __int128 S = (unsigned __int128)y0 * w + (unsigned __int128)y1 * v;
+  return (u64)(S & ((1ull << 61) - 1)) + (u64)(S >> 61) * eps;
 #endif
 }
 

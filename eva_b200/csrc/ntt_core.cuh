@@ -338,3 +338,134 @@ EVAB_HD void scale_canon(u64 (&x)[NTT_E], u64 c, u64 cs, u64 p) {
 #pragma unroll
   for (int k = 0; k < NTT_E; k++) x[k] = csub(shoup_lazy(x[k], c, cs, p), p);
 }
+
+// ---------------------------------------------------------------------------
+// The same passes in "two-row fold" arithmetic (modarith.cuh: fold_mul) for fold-friendly primes
+// p = 2^60 - delta: 5 wide multiplies per butterfly instead of 6 wide + 4 low.  The multiplicand of a
+// product may be ANY u64, so only sums need room; every register carries its own compile-time bound
+// bb[k] in units of p/16 (the loops are fully unrolled, the bounds fold to constants) and a value is
+// folded (3 instructions) only when the next sum could reach 16p.
+// ---------------------------------------------------------------------------
+struct FoldP { u64 p, p3, p8; u32 eps; };
+#if defined(EVAB_BOUND_CHECK) && !defined(__CUDA_ARCH__)
+#include <cstdio>
+#include <cstdlib>
+// test builds of the CPU emulator: every tracked bound is verified against the value it describes
+#define EVAB_CHECK_BOUND(x, b, F) do { if ((unsigned __int128)(x) * 16 >= (unsigned __int128)(b) * (F).p || (b) > FB_MAX) { \
+  fprintf(stderr, "bound violated at %s:%d: %llu !< %d/16 p\n", __FILE__, __LINE__, (unsigned long long)(x), (int)(b)); abort(); } } while (0)
+#else
+#define EVAB_CHECK_BOUND(x, b, F) do {} while (0)
+#endif
+template <class FPr> EVAB_HD FoldP fold_params(const FPr &P) { FoldP F; F.p = P.p; F.p3 = P.p3; F.p8 = P.p8; F.eps = P.eps; return F; }
+
+template <int D> EVAB_HD void ffwd_stage(u64 (&x)[NTT_E], int (&bb)[NTT_E], const u64x2 *tw, u32 tw0, const FoldP &F) {
+#pragma unroll
+  for (int g = 0; g < NTT_E / 2 / D; g++) {
+    const u64x2 w = ldg_tw(tw + tw0 + g);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+      const int k = g * 2 * D + j;
+      u64 X = x[k];
+      int bx = bb[k];
+      if (bx + 48 > FB_MAX) { X = fold61(X, F.eps); bx = FB_FOLD; }
+      const u64 t = fold_mul(x[k + D], w.x, w.y, F.eps);   // < 2.2501 p
+      x[k] = X + t;
+      x[k + D] = X + F.p3 - t;
+      bb[k] = bx + FB_MUL;
+      bb[k + D] = bx + 48;
+      EVAB_CHECK_BOUND(t, FB_MUL, F); EVAB_CHECK_BOUND(x[k], bb[k], F); EVAB_CHECK_BOUND(x[k + D], bb[k + D], F);
+    }
+  }
+}
+// the exchange between two passes hands register k of one thread to some other register of another thread:
+// past a pass, every register takes the largest bound
+EVAB_HD void bounds_merge(int (&bb)[NTT_E]) {
+  int m = 0;
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) m = bb[k] > m ? bb[k] : m;
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) bb[k] = m;
+}
+template <int LOGN, int J> EVAB_HD void ffwd_pass_s(u64 (&x)[NTT_E], int (&bb)[NTT_E], const u64x2 *tw, const FoldP &F, u32 tid) {
+  const u32 H = tid >> NttGeom<LOGN>::lowbits(J);
+  constexpr int s0 = NTT_EL * J;
+  ffwd_stage<8>(x, bb, tw, (1u << (s0 + 0)) + (H << 0), F);
+  ffwd_stage<4>(x, bb, tw, (1u << (s0 + 1)) + (H << 1), F);
+  ffwd_stage<2>(x, bb, tw, (1u << (s0 + 2)) + (H << 2), F);
+  ffwd_stage<1>(x, bb, tw, (1u << (s0 + 3)) + (H << 3), F);
+  bounds_merge(bb);
+}
+template <int LOGN> EVAB_HD void ffwd_pass_c(u64 (&x)[NTT_E], int (&bb)[NTT_E], const u64x2 *tw, const FoldP &F, u32 tid) {
+  constexpr int R = NttGeom<LOGN>::R;
+  if (R >= 4) ffwd_stage<8>(x, bb, tw, (1u << (LOGN - 4)) + (tid << 0), F);
+  if (R >= 3) ffwd_stage<4>(x, bb, tw, (1u << (LOGN - 3)) + (tid << 1), F);
+  if (R >= 2) ffwd_stage<2>(x, bb, tw, (1u << (LOGN - 2)) + (tid << 2), F);
+  if (R >= 1) ffwd_stage<1>(x, bb, tw, (1u << (LOGN - 1)) + (tid << 3), F);
+}
+// every register (< 16p) to canonical [0,p)
+EVAB_HD void fcanon(u64 (&x)[NTT_E], const FoldP &F) {
+#pragma unroll
+  for (int k = 0; k < NTT_E; k++) x[k] = fold_canon(x[k], F.eps, F.p);
+}
+
+// Gentleman-Sande butterfly: X' = X + Y, Y' = (X - Y + C p) w with C p >= Y.  Folds X / Y first when a sum would leave the u64.
+EVAB_HD void finv_bfly(u64 &xa, u64 &xb, int &ba, int &bby, const u64x2 &w, const FoldP &F) {
+  u64 X = xa, Y = xb;
+  int bx = ba, by = bby;
+  if (by > 128) { Y = fold61(Y, F.eps); by = FB_FOLD; }
+  const bool big = by > 48;                       // bias 8p instead of 3p
+  if (bx + (big ? 128 : 48) > FB_MAX || bx + by > FB_MAX) { X = fold61(X, F.eps); bx = FB_FOLD; }
+  xa = X + Y;
+  xb = fold_mul(X - Y + (big ? F.p8 : F.p3), w.x, w.y, F.eps);
+  ba = bx + by;
+  bby = FB_MUL;
+  EVAB_CHECK_BOUND(X, bx, F); EVAB_CHECK_BOUND(Y, by, F); EVAB_CHECK_BOUND(xa, ba, F); EVAB_CHECK_BOUND(xb, bby, F);
+}
+template <int D> EVAB_HD void finv_stage(u64 (&x)[NTT_E], int (&bb)[NTT_E], const u64x2 *tw, u32 tw0, const FoldP &F) {
+#pragma unroll
+  for (int g = 0; g < NTT_E / 2 / D; g++) {
+    const u64x2 w = ldg_tw(tw + tw0 + g);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+      const int k = g * 2 * D + j;
+      finv_bfly(x[k], x[k + D], bb[k], bb[k + D], w, F);
+    }
+  }
+}
+template <int LOGN> EVAB_HD void finv_pass_c(u64 (&x)[NTT_E], int (&bb)[NTT_E], const u64x2 *tw, const FoldP &F, u32 tid) {
+  constexpr int R = NttGeom<LOGN>::R;
+  if (R >= 1) finv_stage<1>(x, bb, tw, (1u << (LOGN - 1)) + (tid << 3), F);
+  if (R >= 2) finv_stage<2>(x, bb, tw, (1u << (LOGN - 2)) + (tid << 2), F);
+  if (R >= 3) finv_stage<4>(x, bb, tw, (1u << (LOGN - 3)) + (tid << 1), F);
+  if (R >= 4) finv_stage<8>(x, bb, tw, (1u << (LOGN - 4)) + (tid << 0), F);
+  bounds_merge(bb);
+}
+template <int LOGN, int J> EVAB_HD void finv_pass_s(u64 (&x)[NTT_E], int (&bb)[NTT_E], const u64x2 *tw, const FoldP &F, u32 tid) {
+  const u32 H = tid >> NttGeom<LOGN>::lowbits(J);
+  constexpr int s0 = NTT_EL * J;
+  finv_stage<1>(x, bb, tw, (1u << (s0 + 3)) + (H << 3), F);
+  finv_stage<2>(x, bb, tw, (1u << (s0 + 2)) + (H << 2), F);
+  finv_stage<4>(x, bb, tw, (1u << (s0 + 1)) + (H << 1), F);
+  finv_stage<8>(x, bb, tw, (1u << (s0 + 0)) + (H << 0), F);
+  bounds_merge(bb);
+}
+// strided pass 0 of the inverse, N^-1 folded into its last stage (see inv_pass0_scaled); `half` != 0
+// adds floor(p/2) before the canonicalisation (EPI_ADDHALF).  Output canonical.
+template <int LOGN, class FPr> EVAB_HD void finv_pass0_scaled(u64 (&x)[NTT_E], int (&bb)[NTT_E], const u64x2 *tw, const FoldP &F, u32 tid, const FPr &P, u64 half) {
+  const u32 H = tid >> NttGeom<LOGN>::lowbits(0);
+  finv_stage<1>(x, bb, tw, (1u << 3) + (H << 3), F);
+  finv_stage<2>(x, bb, tw, (1u << 2) + (H << 2), F);
+  finv_stage<4>(x, bb, tw, (1u << 1) + (H << 1), F);
+#pragma unroll
+  for (int k = 0; k < NTT_E / 2; k++) {
+    u64 X = x[k], Y = x[k + NTT_E / 2];
+    int bx = bb[k], by = bb[k + NTT_E / 2];
+    if (by > 128) { Y = fold61(Y, F.eps); by = FB_FOLD; }
+    const bool big = by > 48;
+    if (bx + (big ? 128 : 48) > FB_MAX || bx + by > FB_MAX) { X = fold61(X, F.eps); bx = FB_FOLD; }
+    // products < 2.2501 p, + half < 2.7501 p: fold_canon takes anything below 16p
+    x[k] = fold_canon(fold_mul(X + Y, P.ninv, P.ninv_v, F.eps) + half, F.eps, F.p);
+    x[k + NTT_E / 2] = fold_canon(fold_mul(X - Y + (big ? F.p8 : F.p3), P.itw1n, P.itw1n_v, F.eps) + half, F.eps, F.p);
+    bb[k] = bb[k + NTT_E / 2] = FB_CANON;
+  }
+}

@@ -32,6 +32,7 @@ struct NttLaunch {
                                // transform is that value everywhere, written without running the NTT
   const PrimeDev *primes;
   const u64x2 *consts;         // EPI_DIVROUND: {c, shoup(c)} per prime index; PRO_MODRED: .x of subtab
+  const u64x2 *consts_f;       // EPI_DIVROUND, fold arithmetic: {c, c * 2^32 mod p}
   const u64 *subtab;           // PRO_MODRED: value to subtract per prime index (canonical mod that prime)
   long long src_sq, src_sr, dst_sq, dst_sr, aux0_sq, aux0_sr, aux1_sq, aux1_sr;
   int inner;                   // jobs per q
@@ -41,9 +42,19 @@ struct NttLaunch {
   int aux1_polys;              // aux1 applies to q < aux1_polys only (rotate: c0 has a base, c1 none)
   unsigned char pmap[32];
   unsigned char pmap2[32];
+  FoldPrime fp[NTT_MAX_PRIMES];   // indexed by prime index (filled by base_launch from CtxView::fold_host)
 };
 
-struct NttState { u64 x[NTT_E]; int b; };
+// fold arithmetic applies when every prime the launch computes in is fold-friendly (bit i of foldmask: prime i)
+inline bool ntt_launch_folds(const NttLaunch &L, size_t jobs, unsigned foldmask) {
+  const size_t np = L.prime_on_q ? (jobs + (size_t)L.inner - 1) / (size_t)L.inner : (size_t)L.inner;
+  if (np > 32) return false;
+  for (size_t i = 0; i < np; i++)
+    if (!((foldmask >> L.pmap[i]) & 1u)) return false;
+  return true;
+}
+
+struct NttState { u64 x[NTT_E]; int b; int bb[NTT_E]; };   // b: Shoup path bound (units of p); bb: fold path, per register, units of p/16
 
 struct NttJob {
   const u64 *src; u64 *dst; const u64 *aux0; const u64 *aux1;
@@ -53,11 +64,11 @@ struct NttJob {
 };
 
 // boff: element offset of this batch instance (evab_set_batch), applied to every data pointer
-EVAB_HD NttJob ntt_job(const NttLaunch &L, u32 cta, int ctas_per_job, long long boff = 0) {
+// job (q, r), CTA h of its cluster.  The CUDA grid is (inner * CL, q, batch), so that the prime index is a plain
+// table lookup on block indices (warp-uniform: the per-prime constants land in uniform registers)
+EVAB_HD NttJob ntt_job_qr(const NttLaunch &L, u32 q, u32 r, u32 h, long long boff = 0) {
   NttJob J;
-  u32 job = cta / ctas_per_job;
-  J.h = cta % ctas_per_job;
-  u32 q = job / L.inner, r = job % L.inner;
+  J.h = h;
   J.pi = L.prime_on_q ? L.pmap[q] : L.pmap[r];
   J.skip = L.skip_diag && (L.pmap[q] == L.pmap2[r]);
   J.spi = L.pmap2[r];
@@ -67,6 +78,10 @@ EVAB_HD NttJob ntt_job(const NttLaunch &L, u32 cta, int ctas_per_job, long long 
   J.aux0 = L.aux0 ? L.aux0 + q * L.aux0_sq + r * L.aux0_sr + boff : nullptr;
   J.aux1 = (L.aux1 && (int)q < L.aux1_polys) ? L.aux1 + q * L.aux1_sq + r * L.aux1_sr + boff : nullptr;
   return J;
+}
+EVAB_HD NttJob ntt_job(const NttLaunch &L, u32 cta, int ctas_per_job, long long boff = 0) {
+  const u32 job = cta / ctas_per_job;
+  return ntt_job_qr(L, job / L.inner, job % L.inner, cta % ctas_per_job, boff);
 }
 
 // PRO_MODRED: the source holds canonical residues of prime `srcp`; when srcp <= 2p one
@@ -142,7 +157,8 @@ template <int LOGN> EVAB_HD void fwd_const_poly(const NttJob &J, u32 tid) {
 //   2j-1, 2j   : exchange read + pass j   |   exchange write        (1 <= j <= P-2)
 //   2(P-1)-1   : exchange read + last (contiguous) pass
 //   phE        : fused epilogue + store
-template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct FwdBody {
+// AR = 0: lazy Shoup butterflies (any prime < 2^60); AR = 1: two-row fold arithmetic (every prime of the launch fold-friendly)
+template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1, int AR = 0> struct FwdBody {
   typedef NttGeom<LOGN> G;
   typedef ClGeom<LOGN, CL> C;
   static constexpr int NPH = G::NPH;
@@ -157,6 +173,28 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct
     for (int k = 0; k < NTT_E; k++) S.x[k] = pro_load<PRO, CHEAP>(L, J, P, idx_s<LOGN, 0>(tid, k), sub);
     S.b = 1;
   }
+  // fold arithmetic: the multiplicand of a product may be any u64, so the reduction of the source residues to
+  // this prime disappears: x = v + (p - sub) < 2^60 + p
+  static EVAB_HD void load0_fold(NttState &S, const NttLaunch &L, const NttJob &J, const PrimeDev &P, u32 tid, u64 sub) {
+    constexpr bool MR = (PRO == PRO_MODRED || PRO == PRO_MODRED_SG);
+    const u64 add = L.fp[J.pi].p - sub;
+#pragma unroll
+    for (int k = 0; k < NTT_E; k++) {
+      const u32 idx = idx_s<LOGN, 0>(tid, k);
+      u64 v;
+      if (PRO == PRO_MODRED_SG) {
+        const u32 e = EVAB_LDG(L.perm + idx);
+        v = EVAB_LDG(J.src + (e >> 1));
+        if ((e & 1u) && v) v = L.fp[J.spi].p - v;   // canonical negation mod the source prime
+      } else if (PRO == PRO_GATHER) {
+        v = EVAB_LDG(J.src + EVAB_LDG(L.perm + idx));
+      } else {
+        v = EVAB_LDG(J.src + idx);
+      }
+      S.x[k] = MR ? v + add : v;
+      S.bb[k] = MR ? 2 * FB_CANON + 1 : FB_CANON;
+    }
+  }
   // ltid: thread index inside the CTA; the passes run on the virtual thread id
   template <int PH, class Hooks> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid, const SmemView<CL> &smv, Hooks hk) {
     const PrimeDev P = L.primes[J.pi];
@@ -167,17 +205,24 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct
       constexpr bool MR = (PRO == PRO_MODRED || PRO == PRO_MODRED_SG);
       const u64 sub = MR ? EVAB_LDG(L.subtab + J.pi) : 0;
       const bool cheap = MR && (L.primes[J.spi].p <= 2 * P.p);   // CTA-uniform
-      if (cheap) load0<true>(S, L, J, P, tid, sub); else load0<false>(S, L, J, P, tid, sub);
-      fwd_pass_s<LOGN, 0>(S.x, P.tw, root, P.p, tid, S.b);
+      if constexpr (AR == 1) {
+        load0_fold(S, L, J, P, tid, sub);
+        ffwd_pass_s<LOGN, 0>(S.x, S.bb, L.fp[J.pi].ftw, fold_params(L.fp[J.pi]), tid);
+      } else {
+        if (cheap) load0<true>(S, L, J, P, tid, sub); else load0<false>(S, L, J, P, tid, sub);
+        fwd_pass_s<LOGN, 0>(S.x, P.tw, root, P.p, tid, S.b);
+      }
       if constexpr (CL > 1) { hk.wait(); xchg_write_dist_fwd<LOGN, CL>(S.x, smv, tid); }   // peers are resident (arrive at kernel start)
       else xchg_write_s<LOGN, 0, 1>(S.x, sm, tid);
     } else if constexpr (PH == NPH - 1) {
       if constexpr (CL > 1) xchg_read_cl<LOGN, CL>(S.x, sm, tid); else xchg_read_c<LOGN>(S.x, sm, tid);
-      fwd_pass_c<LOGN>(S.x, P.tw, root, P.p, tid, S.b);
+      if constexpr (AR == 1) ffwd_pass_c<LOGN>(S.x, S.bb, L.fp[J.pi].ftw, fold_params(L.fp[J.pi]), tid);
+      else fwd_pass_c<LOGN>(S.x, P.tw, root, P.p, tid, S.b);
     } else if constexpr (PH % 2 == 1) {
       constexpr int j = (PH + 1) / 2;
       if constexpr (CL > 1) xchg_read_sl<LOGN, j, j, CL>(S.x, sm, tid); else xchg_read_s<LOGN, j, j>(S.x, sm, tid);
-      fwd_pass_s<LOGN, j>(S.x, P.tw, root, P.p, tid, S.b);
+      if constexpr (AR == 1) ffwd_pass_s<LOGN, j>(S.x, S.bb, L.fp[J.pi].ftw, fold_params(L.fp[J.pi]), tid);
+      else fwd_pass_s<LOGN, j>(S.x, P.tw, root, P.p, tid, S.b);
     } else {
       constexpr int j = PH / 2;
       if constexpr (CL > 1) {
@@ -194,6 +239,7 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct
     const PrimeDev P = L.primes[J.pi];
     const u32 tid = vtid(J, ltid);
     const size_t base = (size_t)tid << NTT_EL;
+    if constexpr (AR == 1) { phE_fold(S, L, J, P, base); return; }
     if (EPI == EPI_DIVROUND) {
       // (aux0 - x) * c [+ aux1] without canonicalising x first: x < b*p, so
       // aux0 + b*p - x is positive and < 16p; the Shoup product lands in [0,2p).
@@ -233,13 +279,50 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct
     if (EPI != EPI_STORE_LAZY) canon(S.x, P.p, S.b);
     store16(J.dst + base, S.x);
   }
+  // the same epilogues in fold arithmetic
+  static EVAB_HD void phE_fold(NttState &S, const NttLaunch &L, const NttJob &J, const PrimeDev &P, size_t base) {
+    const FoldP F = fold_params(L.fp[J.pi]);
+    if (EPI == EPI_DIVROUND) {
+      // (aux0 - x) * c [+ aux1]: aux0 + C p - x with C p >= x is a valid multiplicand as it stands
+      const u64x2 c = ldg_tw(L.consts_f + J.pi);
+#pragma unroll
+      for (int q = 0; q < NTT_E / 4; q++) {
+        u64 a[4];
+        load4(a, J.aux0 + base + 4 * q);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          u64 x = S.x[4 * q + k];
+          int bx = S.bb[4 * q + k];
+          if (bx > 128) { x = fold61(x, F.eps); bx = FB_FOLD; }
+          a[k] = fold_mul(a[k] + (bx > 48 ? F.p8 : F.p3) - x, c.x, c.y, F.eps);   // < 2.2501 p
+        }
+        if (J.aux1) {
+          u64 d[4];
+          if (L.aux1_perm) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) d[k] = EVAB_LDG(J.aux1 + EVAB_LDG(L.aux1_perm + base + 4 * q + k));
+          } else {
+            load4(d, J.aux1 + base + 4 * q);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) a[k] += d[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) a[k] = fold_canon(a[k], F.eps, F.p);
+        store4(J.dst + base + 4 * q, a);
+      }
+      return;
+    }
+    if (EPI != EPI_STORE_LAZY) fcanon(S.x, F);
+    store16(J.dst + base, S.x);
+  }
 };
 
 // ------------------------------ inverse ------------------------------------
 // Phases: 0: contiguous load + last-pass stages + exchange write;
 //         then for j = P-2 .. 1: exchange read + pass j | exchange write;
 //         last: exchange read + pass 0 + scale by N^-1 + epilogue store (strided, coalesced).
-template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct InvBody {
+template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1, int AR = 0> struct InvBody {
   typedef NttGeom<LOGN> G;
   typedef ClGeom<LOGN, CL> C;
   static constexpr int NPH = G::NPH;
@@ -264,17 +347,29 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct
         load16(S.x, J.src + base);
       }
       S.b = 1;
-      inv_pass_c<LOGN>(S.x, P.itw, root, P.p, tid, S.b);
+      if constexpr (AR == 1) {
+#pragma unroll
+        for (int k = 0; k < NTT_E; k++) S.bb[k] = FB_CANON;
+        finv_pass_c<LOGN>(S.x, S.bb, L.fp[J.pi].fitw, fold_params(L.fp[J.pi]), tid);
+      } else {
+        inv_pass_c<LOGN>(S.x, P.itw, root, P.p, tid, S.b);
+      }
       if constexpr (CL > 1) xchg_write_cl<LOGN, CL>(S.x, sm, tid); else xchg_write_c<LOGN>(S.x, sm, tid);
     } else if constexpr (PH == NPH - 1) {
       if constexpr (CL > 1) xchg_read_dist_inv<LOGN, CL>(S.x, sm, ltid); else xchg_read_s<LOGN, 0, 1>(S.x, sm, tid);
-      inv_pass0_scaled<LOGN>(S.x, P.itw, P.p, tid, S.b, P.ninv, P.ninv_s, P.itw1n, P.itw1n_s);   // * N^-1 folded in, canonical
-      const u64 half = P.p >> 1;
+      const u64 half = (AR == 1 ? L.fp[J.pi].p : P.p) >> 1;
+      if constexpr (AR == 1) {
+        finv_pass0_scaled<LOGN>(S.x, S.bb, L.fp[J.pi].fitw, fold_params(L.fp[J.pi]), tid, L.fp[J.pi], EPI == EPI_ADDHALF ? half : 0);   // canonical, half added
 #pragma unroll
-      for (int k = 0; k < NTT_E; k++) {
-        u64 v = S.x[k];
-        if (EPI == EPI_ADDHALF) v = addmod(v, half, P.p);
-        J.dst[idx_s<LOGN, 0>(tid, k)] = v;
+        for (int k = 0; k < NTT_E; k++) J.dst[idx_s<LOGN, 0>(tid, k)] = S.x[k];
+      } else {
+        inv_pass0_scaled<LOGN>(S.x, P.itw, P.p, tid, S.b, P.ninv, P.ninv_s, P.itw1n, P.itw1n_s);   // * N^-1 folded in, canonical
+#pragma unroll
+        for (int k = 0; k < NTT_E; k++) {
+          u64 v = S.x[k];
+          if (EPI == EPI_ADDHALF) v = addmod(v, half, P.p);
+          J.dst[idx_s<LOGN, 0>(tid, k)] = v;
+        }
       }
     } else if constexpr (PH % 2 == 1) {
       constexpr int j = G::P - 2 - (PH - 1) / 2;
@@ -286,7 +381,8 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1> struct
         if constexpr (j == G::P - 2) xchg_read_sc<LOGN, j>(S.x, sm, tid);
         else xchg_read_s<LOGN, j, j + 1>(S.x, sm, tid);
       }
-      inv_pass_s<LOGN, j>(S.x, P.itw, root, P.p, tid, S.b);
+      if constexpr (AR == 1) finv_pass_s<LOGN, j>(S.x, S.bb, L.fp[J.pi].fitw, fold_params(L.fp[J.pi]), tid);
+      else inv_pass_s<LOGN, j>(S.x, P.itw, root, P.p, tid, S.b);
     } else {
       constexpr int j = G::P - 2 - (PH - 2) / 2;   // pass that just ran
       if constexpr (CL > 1) {

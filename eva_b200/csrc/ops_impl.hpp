@@ -17,6 +17,10 @@ struct CtxView {
   const cplx *roots;        // [N]   CKKS encoder tables
   const u32 *slot_index;    // [N]
   const u64 *pow2;          // [k][128]
+  const u64x2 *qinv_f;      // [k][k]   fold rows of qinv
+  unsigned foldmask;        // bit i: prime i is fold-friendly (modarith.cuh prime_foldable)
+  const FoldPrime *fold_host;   // [k] HOST array: per-prime fold constants, copied into every NttLaunch
+  int arith;                // 0: fold arithmetic where every prime of a launch allows it; 1: lazy Shoup everywhere
 };
 
 // Backend concept:
@@ -31,6 +35,7 @@ inline NttLaunch base_launch(const CtxView &c) {
   NttLaunch L;
   memset(&L, 0, sizeof(L));
   L.primes = c.primes;
+  for (int i = 0; i < c.k && i < NTT_MAX_PRIMES; i++) L.fp[i] = c.fold_host[i];
   L.inner = 1;
   L.aux1_polys = 1 << 30;
   return L;
@@ -131,6 +136,7 @@ int divround_impl(BE &be, const CtxView &c, const u64 *in, long long in_poly_str
   B.pro = PRO_MODRED; B.epi = EPI_DIVROUND;
   B.subtab = c.halfmod + (size_t)last * c.k;
   B.consts = c.qinv + (size_t)last * c.k;
+  B.consts_f = c.qinv_f + (size_t)last * c.k;
   return be.fwd(B, (size_t)npoly * (nres - 1));
 }
 

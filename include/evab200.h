@@ -97,7 +97,14 @@ int evab_ntt_inv(evab_ctx *ctx, uint64_t *d_data, size_t count, const int *prime
 /* Tuning knob (process-wide): spread every residue transform of 4096 <= N <= 16384 over a thread-block
  * cluster of 1, 2, 4 or 8 CTAs (distributed shared memory exchange), capped so that a CTA keeps at least
  * 128 threads; 0 (default) = that cap.  Results are identical. */
-int evab_set_ntt_cluster(int ctas_per_residue);
+int evab_set_ntt_cluster(int ctas_per_residue);   /* default for contexts created afterwards */
+/* The same knob per context (no process-global state on the op path), and the NTT arithmetic:
+ * 0 (default) = "two-row fold" butterflies (5 wide multiplies) in every launch whose primes are all
+ * SEAL-style 60-bit primes p = 2^60 - delta, delta < 2^25 (evab_ctx_foldmask: bit i = prime i qualifies),
+ * lazy Shoup butterflies otherwise; 1 = lazy Shoup everywhere.  Results are identical bit for bit. */
+int evab_ctx_set_ntt_cluster(evab_ctx *ctx, int ctas_per_residue);
+int evab_ctx_set_ntt_arith(evab_ctx *ctx, int mode);
+unsigned evab_ctx_foldmask(const evab_ctx *ctx);
 
 /* ---- CKKS encoder on the device: seal::CKKSEncoder::encode at seal_executor.h:242
  * (and seal.cpp:68,80).  Encodes `count` vectors in one batch: vector e has

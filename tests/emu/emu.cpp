@@ -34,7 +34,7 @@ template <class B, int CL, int NPH> struct EmuPhases<B, CL, NPH, NPH> {
 
 // one residue over a cluster of CL CTAs (CL = 1: a single CTA); distributed shared memory = the
 // SmemView's peer pointers
-template <int LOGN, bool INV, int PRO, int EPI, int CL> static void run_ntt_m(const NttLaunch &L, size_t jobs) {
+template <int LOGN, bool INV, int PRO, int EPI, int CL, int AR> static void run_ntt_m(const NttLaunch &L, size_t jobs) {
   typedef NttGeom<LOGN> G;
   constexpr int Tc = G::T / CL;                // threads per CTA
   constexpr size_t SMC = (size_t)G::N / CL;    // shared-memory words per CTA
@@ -55,12 +55,12 @@ template <int LOGN, bool INV, int PRO, int EPI, int CL> static void run_ntt_m(co
       continue;
     }
     if (!INV) {
-      typedef FwdBody<LOGN, PRO, EPI, CL> B;
+      typedef FwdBody<LOGN, PRO, EPI, CL, AR> B;
       EmuPhases<B, CL, 0, B::NPH>::run(stc.data(), Tc, CL, L, J, sm);
       for (int h = 0; h < CL; h++)
         for (u32 t = 0; t < (u32)Tc; t++) B::phE(stc[(size_t)h * Tc + t], L, J[h], t);
     } else {
-      typedef InvBody<LOGN, PRO, EPI, CL> B;
+      typedef InvBody<LOGN, PRO, EPI, CL, AR> B;
       EmuPhases<B, CL, 0, B::NPH>::run(stc.data(), Tc, CL, L, J, sm);
     }
   }
@@ -68,52 +68,58 @@ template <int LOGN, bool INV, int PRO, int EPI, int CL> static void run_ntt_m(co
 
 static int g_cl = 1;   // emu_set_cluster: CTAs per residue for N >= 4096 (1, 2, 4)
 
-template <int LOGN, bool INV, int CL> static void run_ntt_c(const NttLaunch &L, size_t jobs) {
+template <int LOGN, bool INV, int CL, int AR> static void run_ntt_c(const NttLaunch &L, size_t jobs) {
   if (!INV) {
-    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, false, PRO_PLAIN, EPI_STORE, CL>(L, jobs);
-    if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return run_ntt_m<LOGN, false, PRO_MODRED, EPI_STORE, CL>(L, jobs);
-    if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, false, PRO_MODRED, EPI_STORE_LAZY, CL>(L, jobs);
-    if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return run_ntt_m<LOGN, false, PRO_MODRED, EPI_DIVROUND, CL>(L, jobs);
-    if (L.pro == PRO_MODRED_SG && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, false, PRO_MODRED_SG, EPI_STORE_LAZY, CL>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, false, PRO_PLAIN, EPI_STORE, CL, AR>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_STORE) return run_ntt_m<LOGN, false, PRO_MODRED, EPI_STORE, CL, AR>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, false, PRO_MODRED, EPI_STORE_LAZY, CL, AR>(L, jobs);
+    if (L.pro == PRO_MODRED && L.epi == EPI_DIVROUND) return run_ntt_m<LOGN, false, PRO_MODRED, EPI_DIVROUND, CL, AR>(L, jobs);
+    if (L.pro == PRO_MODRED_SG && L.epi == EPI_STORE_LAZY) return run_ntt_m<LOGN, false, PRO_MODRED_SG, EPI_STORE_LAZY, CL, AR>(L, jobs);
   } else {
-    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_STORE, CL>(L, jobs);
-    if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_ADDHALF, CL>(L, jobs);
-    if (L.pro == PRO_GATHER && L.epi == EPI_STORE) return run_ntt_m<LOGN, true, PRO_GATHER, EPI_STORE, CL>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_STORE, CL, AR>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_ADDHALF, CL, AR>(L, jobs);
+    if (L.pro == PRO_GATHER && L.epi == EPI_STORE) return run_ntt_m<LOGN, true, PRO_GATHER, EPI_STORE, CL, AR>(L, jobs);
   }
   abort();
 }
-template <int LOGN, bool INV> static void run_ntt(const NttLaunch &L, size_t jobs) {
+template <int LOGN, bool INV, int AR> static void run_ntt_a(const NttLaunch &L, size_t jobs) {
   if constexpr (LOGN >= 12) {
-    if (g_cl == 4) return run_ntt_c<LOGN, INV, 4>(L, jobs);
-    if (g_cl == 8) return run_ntt_c<LOGN, INV, 8>(L, jobs);
-    if (g_cl == 2 || LOGN == 15) return run_ntt_c<LOGN, INV, 2>(L, jobs);   // 2^15: at least 2 CTAs
+    if (g_cl == 4) return run_ntt_c<LOGN, INV, 4, AR>(L, jobs);
+    if (g_cl == 8) return run_ntt_c<LOGN, INV, 8, AR>(L, jobs);
+    if (g_cl == 2 || LOGN == 15) return run_ntt_c<LOGN, INV, 2, AR>(L, jobs);   // 2^15: at least 2 CTAs
   }
-  if constexpr (LOGN <= 14) return run_ntt_c<LOGN, INV, 1>(L, jobs);
+  if constexpr (LOGN <= 14) return run_ntt_c<LOGN, INV, 1, AR>(L, jobs);
+}
+static int g_folded = 0;   // launches that took the fold path (emu_fold_launches)
+template <int LOGN, bool INV> static void run_ntt(const NttLaunch &L, size_t jobs, bool fold) {
+  if (fold) { g_folded++; run_ntt_a<LOGN, INV, 1>(L, jobs); } else run_ntt_a<LOGN, INV, 0>(L, jobs);
 }
 
 struct EmuBE {
   const EmuCtx *c;
   int error(const char *m) { g_err = m; return 1; }
   int fwd(const NttLaunch &L, size_t jobs) {
+    const bool fold = c->v.arith == 0 && ntt_launch_folds(L, jobs, c->v.foldmask);
     switch (c->v.logN) {
-      case 10: run_ntt<10, false>(L, jobs); break;
-      case 11: run_ntt<11, false>(L, jobs); break;
-      case 12: run_ntt<12, false>(L, jobs); break;
-      case 13: run_ntt<13, false>(L, jobs); break;
-      case 14: run_ntt<14, false>(L, jobs); break;
-      case 15: run_ntt<15, false>(L, jobs); break;
+      case 10: run_ntt<10, false>(L, jobs, fold); break;
+      case 11: run_ntt<11, false>(L, jobs, fold); break;
+      case 12: run_ntt<12, false>(L, jobs, fold); break;
+      case 13: run_ntt<13, false>(L, jobs, fold); break;
+      case 14: run_ntt<14, false>(L, jobs, fold); break;
+      case 15: run_ntt<15, false>(L, jobs, fold); break;
       default: return error("unsupported N");
     }
     return 0;
   }
   int inv(const NttLaunch &L, size_t jobs) {
+    const bool fold = c->v.arith == 0 && ntt_launch_folds(L, jobs, c->v.foldmask);
     switch (c->v.logN) {
-      case 10: run_ntt<10, true>(L, jobs); break;
-      case 11: run_ntt<11, true>(L, jobs); break;
-      case 12: run_ntt<12, true>(L, jobs); break;
-      case 13: run_ntt<13, true>(L, jobs); break;
-      case 14: run_ntt<14, true>(L, jobs); break;
-      case 15: run_ntt<15, true>(L, jobs); break;
+      case 10: run_ntt<10, true>(L, jobs, fold); break;
+      case 11: run_ntt<11, true>(L, jobs, fold); break;
+      case 12: run_ntt<12, true>(L, jobs, fold); break;
+      case 13: run_ntt<13, true>(L, jobs, fold); break;
+      case 14: run_ntt<14, true>(L, jobs, fold); break;
+      case 15: run_ntt<15, true>(L, jobs, fold); break;
       default: return error("unsupported N");
     }
     return 0;
@@ -170,20 +176,27 @@ EmuCtx *emu_ctx_create(uint64_t N, const uint64_t *primes, int k) {
   int logN = 0;
   while ((1ull << logN) < N) logN++;
   EmuCtx *c = new EmuCtx();
-  c->T.tw.resize((size_t)k * 2 * N);
   const char *err = evab_host::build_tables(N, logN, primes, k, nullptr, c->T);
   if (err[0]) { g_err = err; delete c; return nullptr; }
   for (int i = 0; i < k; i++) {  // re-point the tables at the final host storage
     c->T.pd[i].tw = c->T.tw.data() + ((size_t)i * 2 + 0) * N;
     c->T.pd[i].itw = c->T.tw.data() + ((size_t)i * 2 + 1) * N;
+    c->T.pd[i].ftw = c->T.tw.data() + ((size_t)(k + i) * 2 + 0) * N;
+    c->T.pd[i].fitw = c->T.tw.data() + ((size_t)(k + i) * 2 + 1) * N;
   }
   c->zeros.assign(32, 0);
   c->v.N = N; c->v.logN = logN; c->v.k = k;
   c->v.primes = c->T.pd.data(); c->v.qinv = c->T.qinv.data(); c->v.halfmod = c->T.halfmod.data(); c->v.zeros = c->zeros.data();
+  c->v.qinv_f = c->T.qinv_f.data(); c->v.foldmask = c->T.foldmask; c->v.arith = 0;
+  for (int i = 0; i < k; i++) { c->T.fp[i].ftw = c->T.pd[i].ftw; c->T.fp[i].fitw = c->T.pd[i].fitw; }
+  c->v.fold_host = c->T.fp.data();
   c->v.roots = reinterpret_cast<const cplx *>(c->T.roots.data()); c->v.slot_index = c->T.slot_index.data(); c->v.pow2 = c->T.pow2.data();
   return c;
 }
 void emu_ctx_destroy(EmuCtx *c) { delete c; }
+int emu_ctx_set_ntt_arith(EmuCtx *c, int mode) { c->v.arith = mode; return 0; }
+unsigned emu_ctx_foldmask(EmuCtx *c) { return c->v.foldmask; }
+int emu_fold_launches() { return g_folded; }
 int emu_ntt_fwd(EmuCtx *c, uint64_t *d, size_t count, const int *pidx, int np) { EmuBE be{c}; return ntt_batch_impl(be, c->v, false, d, count, pidx, np); }
 int emu_ntt_inv(EmuCtx *c, uint64_t *d, size_t count, const int *pidx, int np) { EmuBE be{c}; return ntt_batch_impl(be, c->v, true, d, count, pidx, np); }
 int emu_add(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *b, int sb) { EmuBE be{c}; return dyadic_impl<DY_ADD>(be, c->v, ell, o, a, sa, b, sb, 0); }
