@@ -138,8 +138,15 @@ EVAB_HD u64 fold_canon(u64 x, u32 eps, u64 p) {
 EVAB_HD u64 fold_mul(u64 y, u64 w, u64 v, u32 eps) {
   const u32 y0 = (u32)y, y1 = (u32)(y >> 32);
 #if defined(__CUDA_ARCH__)
-  const u64 B = madw32(y1, (u32)(v >> 32), madw32(y0, (u32)(w >> 32), 0));
-  const u64 A = madw32(y0, (u32)w, 0), A2 = madw32(y1, (u32)v, 0);
+  // One asm statement per multiply: ptxas then keeps the accumulating forms (IMAD.WIDE with a 64-bit addend,
+  // IMAD.WIDE with carry-out) instead of splitting them into multiply + add pairs.  15 instructions per
+  // butterfly (5 wide multiplies) against 18 when the products are written as C expressions; seven
+  // formulations were compared by SASS count and on the device (profiles/r02_ntt_fold.md).
+  u64 B, A;
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(B) : "r"(y0), "r"((u32)(w >> 32)));
+  asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(B) : "r"(y1), "r"((u32)(v >> 32)));
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(A) : "r"(y0), "r"((u32)w));
+  const u64 A2 = madw32(y1, (u32)v, 0);
   u32 s0, s1, s2, H;
   asm("{\n\t.reg .u32 t;\n\t"
       "add.cc.u32 %0, %3, %5;\n\taddc.cc.u32 t, %4, %6;\n\taddc.u32 %2, %8, 0;\n\t"

@@ -98,39 +98,60 @@ template <int LOGN> EVAB_HD u32 swz_c(u32 idx) {
   return (row << NTT_EL) | ((((e >> 1) ^ swz_rowf<LOGN>(row)) << 1) | (e & 1u));
 }
 
-template <int LOGN, int J, int JR> EVAB_HD void xchg_write_s(const u64 (&x)[NTT_E], u64 *sm, u32 tid) {
+// Every exchange layout above is GF(2)-linear in the bits of (thread, k) -- shifts, masks and XORs of
+// disjoint fields -- so addr(v, k) = addr(v, 0) ^ addr(0, k): one thread-dependent base and a compile-time
+// constant per register, i.e. ONE logic instruction per access (none when the two parts share no bit and
+// the constant becomes the immediate offset of the access) instead of re-deriving the swizzle per element.
+// A::at(v, k) = element index inside the CTA's slice; A::disjoint = the k part never overlaps the thread part.
+EVAB_HD u64 *xelem(u64 *sm, u32 byte_off) { return reinterpret_cast<u64 *>(reinterpret_cast<char *>(sm) + byte_off); }
+EVAB_HD const u64 *xelem(const u64 *sm, u32 byte_off) { return reinterpret_cast<const u64 *>(reinterpret_cast<const char *>(sm) + byte_off); }
+template <class A> EVAB_HD void lin_write(const u64 (&x)[NTT_E], u64 *sm, u32 v) {
+  const u32 b0 = A::at(v, 0) << 3;
 #pragma unroll
-  for (int k = 0; k < NTT_E; k++) sm[swz_s<LOGN, JR>(idx_s<LOGN, J>(tid, k))] = x[k];
+  for (int k = 0; k < NTT_E; k++) {
+    const u32 ck = A::at(0, (u32)k) << 3;
+    *xelem(sm, A::disjoint ? b0 + ck : b0 ^ ck) = x[k];
+  }
 }
-template <int LOGN, int J, int JR> EVAB_HD void xchg_read_s(u64 (&x)[NTT_E], const u64 *sm, u32 tid) {
+template <class A> EVAB_HD void lin_read(u64 (&x)[NTT_E], const u64 *sm, u32 v) {
+  const u32 b0 = A::at(v, 0) << 3;
 #pragma unroll
-  for (int k = 0; k < NTT_E; k++) x[k] = sm[swz_s<LOGN, JR>(idx_s<LOGN, J>(tid, k))];
+  for (int k = 0; k < NTT_E; k++) {
+    const u32 ck = A::at(0, (u32)k) << 3;
+    x[k] = *xelem(sm, A::disjoint ? b0 + ck : b0 ^ ck);
+  }
 }
+// strided pass J <-> layout of strided pass JR; MASK = slice mask of a cluster-distributed residue (or ~0)
+template <int LOGN, int J, int JR, u32 MASK> struct AddrS {
+  static constexpr bool disjoint = NttGeom<LOGN>::lowbits(JR) >= 4;   // no swizzle: the k field stays where it is
+  static EVAB_HD u32 at(u32 v, u32 k) { return swz_s<LOGN, JR>(idx_s<LOGN, J>(v, k)) & MASK; }
+};
+// strided pass J <-> rows of the contiguous last pass
+template <int LOGN, int J, u32 MASK> struct AddrSC {
+  static constexpr bool disjoint = false;
+  static EVAB_HD u32 at(u32 v, u32 k) { return swz_c<LOGN>(idx_s<LOGN, J>(v, k)) & MASK; }
+};
+template <int LOGN, int J, int JR> EVAB_HD void xchg_write_s(const u64 (&x)[NTT_E], u64 *sm, u32 tid) { lin_write<AddrS<LOGN, J, JR, ~0u>>(x, sm, tid); }
+template <int LOGN, int J, int JR> EVAB_HD void xchg_read_s(u64 (&x)[NTT_E], const u64 *sm, u32 tid) { lin_read<AddrS<LOGN, J, JR, ~0u>>(x, sm, tid); }
 // strided pass J = P-2 side of the contiguous exchange
-template <int LOGN, int J> EVAB_HD void xchg_write_sc(const u64 (&x)[NTT_E], u64 *sm, u32 tid) {
-#pragma unroll
-  for (int k = 0; k < NTT_E; k++) sm[swz_c<LOGN>(idx_s<LOGN, J>(tid, k))] = x[k];
-}
-template <int LOGN, int J> EVAB_HD void xchg_read_sc(u64 (&x)[NTT_E], const u64 *sm, u32 tid) {
-#pragma unroll
-  for (int k = 0; k < NTT_E; k++) x[k] = sm[swz_c<LOGN>(idx_s<LOGN, J>(tid, k))];
-}
+template <int LOGN, int J> EVAB_HD void xchg_write_sc(const u64 (&x)[NTT_E], u64 *sm, u32 tid) { lin_write<AddrSC<LOGN, J, ~0u>>(x, sm, tid); }
+template <int LOGN, int J> EVAB_HD void xchg_read_sc(u64 (&x)[NTT_E], const u64 *sm, u32 tid) { lin_read<AddrSC<LOGN, J, ~0u>>(x, sm, tid); }
+// contiguous side: the 16-byte chunk c of row `row` sits at chunk c ^ f(row): base ^ (c << 4) in bytes
+template <u32 MASK> EVAB_HD u32 row_base_bytes(u32 v, u32 f) { return ((((v << NTT_EL) & MASK) | (f << 1)) << 3); }
 template <int LOGN> EVAB_HD void xchg_read_c(u64 (&x)[NTT_E], const u64 *sm, u32 tid) {
-  const u64x2 *row = reinterpret_cast<const u64x2 *>(sm + ((size_t)tid << NTT_EL));
-  const u32 f = swz_rowf<LOGN>(tid);
+  const u32 b0 = row_base_bytes<~0u>(tid, swz_rowf<LOGN>(tid));
 #pragma unroll
   for (int c = 0; c < NTT_E / 2; c++) {
-    u64x2 v = row[c ^ f];
+    const u64x2 v = *reinterpret_cast<const u64x2 *>(xelem(sm, b0 ^ ((u32)c << 4)));
     x[2 * c] = v.x; x[2 * c + 1] = v.y;
   }
 }
 template <int LOGN> EVAB_HD void xchg_write_c(const u64 (&x)[NTT_E], u64 *sm, u32 tid) {
-  u64x2 *row = reinterpret_cast<u64x2 *>(sm + ((size_t)tid << NTT_EL));
-  const u32 f = swz_rowf<LOGN>(tid);
+  const u32 b0 = row_base_bytes<~0u>(tid, swz_rowf<LOGN>(tid));
 #pragma unroll
   for (int c = 0; c < NTT_E / 2; c++) {
     u64x2 v; v.x = x[2 * c]; v.y = x[2 * c + 1];
-    row[c ^ f] = v;
+    *reinterpret_cast<u64x2 *>(xelem(sm, b0 ^ ((u32)c << 4))) = v;
   }
 }
 
@@ -158,38 +179,24 @@ template <int LOGN, int CL> struct ClGeom {
   static constexpr u32 mask = NC - 1u;
 };
 // local (masked) variants of the exchanges above; v = virtual thread id
-template <int LOGN, int J, int JR, int CL> EVAB_HD void xchg_write_sl(const u64 (&x)[NTT_E], u64 *sm, u32 v) {
-#pragma unroll
-  for (int k = 0; k < NTT_E; k++) sm[swz_s<LOGN, JR>(idx_s<LOGN, J>(v, k)) & ClGeom<LOGN, CL>::mask] = x[k];
-}
-template <int LOGN, int J, int JR, int CL> EVAB_HD void xchg_read_sl(u64 (&x)[NTT_E], const u64 *sm, u32 v) {
-#pragma unroll
-  for (int k = 0; k < NTT_E; k++) x[k] = sm[swz_s<LOGN, JR>(idx_s<LOGN, J>(v, k)) & ClGeom<LOGN, CL>::mask];
-}
-template <int LOGN, int J, int CL> EVAB_HD void xchg_write_scl(const u64 (&x)[NTT_E], u64 *sm, u32 v) {
-#pragma unroll
-  for (int k = 0; k < NTT_E; k++) sm[swz_c<LOGN>(idx_s<LOGN, J>(v, k)) & ClGeom<LOGN, CL>::mask] = x[k];
-}
-template <int LOGN, int J, int CL> EVAB_HD void xchg_read_scl(u64 (&x)[NTT_E], const u64 *sm, u32 v) {
-#pragma unroll
-  for (int k = 0; k < NTT_E; k++) x[k] = sm[swz_c<LOGN>(idx_s<LOGN, J>(v, k)) & ClGeom<LOGN, CL>::mask];
-}
+template <int LOGN, int J, int JR, int CL> EVAB_HD void xchg_write_sl(const u64 (&x)[NTT_E], u64 *sm, u32 v) { lin_write<AddrS<LOGN, J, JR, ClGeom<LOGN, CL>::mask>>(x, sm, v); }
+template <int LOGN, int J, int JR, int CL> EVAB_HD void xchg_read_sl(u64 (&x)[NTT_E], const u64 *sm, u32 v) { lin_read<AddrS<LOGN, J, JR, ClGeom<LOGN, CL>::mask>>(x, sm, v); }
+template <int LOGN, int J, int CL> EVAB_HD void xchg_write_scl(const u64 (&x)[NTT_E], u64 *sm, u32 v) { lin_write<AddrSC<LOGN, J, ClGeom<LOGN, CL>::mask>>(x, sm, v); }
+template <int LOGN, int J, int CL> EVAB_HD void xchg_read_scl(u64 (&x)[NTT_E], const u64 *sm, u32 v) { lin_read<AddrSC<LOGN, J, ClGeom<LOGN, CL>::mask>>(x, sm, v); }
 template <int LOGN, int CL> EVAB_HD void xchg_read_cl(u64 (&x)[NTT_E], const u64 *sm, u32 v) {
-  const u64x2 *row = reinterpret_cast<const u64x2 *>(sm + (((size_t)v << NTT_EL) & ClGeom<LOGN, CL>::mask));
-  const u32 f = swz_rowf<LOGN>(v);
+  const u32 b0 = row_base_bytes<ClGeom<LOGN, CL>::mask>(v, swz_rowf<LOGN>(v));
 #pragma unroll
   for (int c = 0; c < NTT_E / 2; c++) {
-    u64x2 t = row[c ^ f];
+    const u64x2 t = *reinterpret_cast<const u64x2 *>(xelem(sm, b0 ^ ((u32)c << 4)));
     x[2 * c] = t.x; x[2 * c + 1] = t.y;
   }
 }
 template <int LOGN, int CL> EVAB_HD void xchg_write_cl(const u64 (&x)[NTT_E], u64 *sm, u32 v) {
-  u64x2 *row = reinterpret_cast<u64x2 *>(sm + (((size_t)v << NTT_EL) & ClGeom<LOGN, CL>::mask));
-  const u32 f = swz_rowf<LOGN>(v);
+  const u32 b0 = row_base_bytes<ClGeom<LOGN, CL>::mask>(v, swz_rowf<LOGN>(v));
 #pragma unroll
   for (int c = 0; c < NTT_E / 2; c++) {
     u64x2 t; t.x = x[2 * c]; t.y = x[2 * c + 1];
-    row[c ^ f] = t;
+    *reinterpret_cast<u64x2 *>(xelem(sm, b0 ^ ((u32)c << 4))) = t;
   }
 }
 // forward, pass 0 -> pass 1: element k of virtual thread v has natural index (k << (n-4)) | v; its
