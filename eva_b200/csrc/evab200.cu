@@ -60,41 +60,95 @@ extern "C" int evab_set_batch(int batch, size_t stride_words, size_t value_strid
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-// barrier after a phase: 0 = block, 1 = cluster (release / acquire: the exchange just written lives
-// partly in the peers' shared memory), 2 = none
-template <int CL> struct DevSync {
-  __device__ __forceinline__ void operator()(int kind) const {
-    if (CL > 1 && kind == 1) {
-      asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-      asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-    } else if (kind != 2) {
-      __syncthreads();
-    }
+// ---- cluster protocol of the one exchange that crosses CTAs (CL > 1) ---------------------------------------
+// Round 1 used barrier.cluster.arrive.release / wait.acquire around the distributed-shared-memory stores; ptxas
+// turns those into MEMBAR.ALL.GPU + ERRBAR on the arrive and CCTL.IVALL (L1 invalidate) on the wait -- 7 % of
+// all stall samples on the fences and 8 % on the barrier itself (profiles/r02_ntt_fold.md).  Now every CTA owns
+// two mbarriers behind its exchange slice:
+//   full : completes when the N/CL * 8 bytes of the distributed exchange have landed in this CTA's slice.  The
+//          writers use st.async (asynchronous DSMEM store that reports its bytes to the receiver's mbarrier), the
+//          receiver's threads spin on try_wait: no fence, no block barrier, no L1 invalidate.
+//   free : (inverse only) counts one arrival per warp of the whole cluster once that warp has read its slice for
+//          the last time; a CTA waits on its own copy before it stores into its peers.
+// One relaxed cluster barrier at kernel start makes the initialised mbarriers visible (as in CUTLASS prologues).
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+template <int LOGN, int CL> struct DevCluster {
+  static constexpr u32 SLICE_BYTES = (u32)(NttGeom<LOGN>::N / CL) * 8u;
+  static constexpr u32 WARPS = (u32)(NttGeom<LOGN>::T / CL) / 32u;
+  u32 full, free_;   // shared::cta addresses of this CTA's barriers
+};
+template <int LOGN, int CL> struct DevSmemView {
+  u64 *local;
+  u32 peer32[CL];    // shared::cluster address of every rank's slice; its `full` barrier sits SLICE_BYTES behind
+  __device__ __forceinline__ void put(int r, u32 idx, u64 v) const {
+    const u32 a = peer32[r] + (idx << 3), mb = peer32[r] + DevCluster<LOGN, CL>::SLICE_BYTES;
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(a), "l"(v), "r"(mb) : "memory");
   }
 };
-// split cluster barrier ordering the distributed-shared-memory stores after the peers' last reads
-template <int CL> struct DevHooks {
-  __device__ __forceinline__ void arrive() const { if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
-  __device__ __forceinline__ void wait() const { if (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+template <int LOGN, int CL> __device__ __forceinline__ DevSmemView<LOGN, CL> dev_smem_view(u64 *sm) {
+  DevSmemView<LOGN, CL> v;
+  v.local = sm;
+  const u32 base = smem_u32(sm);
+#pragma unroll
+  for (int r = 0; r < CL; r++) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(v.peer32[r]) : "r"(base), "r"(r));
+  return v;
+}
+template <int LOGN, int CL> struct DevHooks {
+  DevCluster<LOGN, CL> c;
+  __device__ __forceinline__ explicit DevHooks(u64 *sm) {
+    c.full = smem_u32(sm) + DevCluster<LOGN, CL>::SLICE_BYTES;
+    c.free_ = c.full + 8;
+  }
+  __device__ __forceinline__ void start() const {
+    if (CL == 1) return;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(c.full) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c.free_), "r"((u32)CL * DevCluster<LOGN, CL>::WARPS) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      // the one arrival of `full`, announcing the bytes the peers (and this CTA) will deliver
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(c.full), "r"(DevCluster<LOGN, CL>::SLICE_BYTES) : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  }
+  __device__ __forceinline__ void ready() const {
+    if (CL > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+  }
+  __device__ __forceinline__ void released() const {
+    if (CL == 1) return;
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0) {
+      const u32 mine = c.free_;
+#pragma unroll
+      for (int r = 0; r < CL; r++) {
+        u32 remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(mine), "r"(r));
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+      }
+    }
+  }
+  static __device__ __forceinline__ void spin(u32 bar) {
+    asm volatile("{\n\t.reg .pred p;\n\tEVAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@!p bra EVAB_WAIT;\n\t}" ::"r"(bar) : "memory");
+  }
+  __device__ __forceinline__ void acquire_free() const { if (CL > 1) spin(c.free_); }
+  __device__ __forceinline__ void landed() const { if (CL > 1) spin(c.full); }
 };
-template <int CL> __device__ __forceinline__ SmemView<CL> smem_view(u64 *sm) {
+// barrier after a phase: 0 = block, 1 = the distributed exchange has landed in this CTA's slice, 2 = none
+template <int LOGN, int CL> struct DevSync {
+  DevHooks<LOGN, CL> hk;
+  __device__ __forceinline__ void operator()(int kind) const {
+    if (CL > 1 && kind == 1) hk.landed();
+    else if (kind != 2) __syncthreads();
+  }
+};
+template <int CL> __device__ __forceinline__ SmemView<CL> smem_view(u64 *sm) {   // CL = 1: plain view
   SmemView<CL> v;
   v.local = sm;
 #pragma unroll
-  for (int r = 0; r < CL; r++) {
-    if (CL > 1) {
-      // generic address of the same shared-memory offset in CTA r of this cluster
-      u64 *p;
-      asm volatile("mapa.u64 %0, %1, %2;\n" : "=l"(p) : "l"(sm), "r"(r));
-      v.peer[r] = p;
-    } else {
-      v.peer[r] = sm;
-    }
-  }
+  for (int r = 0; r < CL; r++) v.peer[r] = sm;
   return v;
 }
 // CL = 1: one CTA = one residue, T = N/16 threads, 64 registers.
-// CL = 2, 4: one residue over a cluster of CL CTAs of T/CL threads (ntt_core.cuh), CL CTAs per SM more.
+// CL = 2, 4, 8: one residue over a cluster of CL CTAs of T/CL threads (ntt_core.cuh), CL CTAs per SM more.
 template <int LOGN, int PRO, int EPI, int CL, int AR>
 __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::T / CL)) k_ntt_fwd(const NttLaunch L, const long long bstride) {
   extern __shared__ __align__(16) u64 sm[];
@@ -104,9 +158,11 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::
   NttState S;
   const u32 tid = threadIdx.x;
   if (PRO == PRO_PLAIN && EPI == EPI_STORE && J.bcast) { fwd_const_poly<LOGN>(J, B::vtid(J, tid)); return; }
-  const DevHooks<CL> hk;
-  hk.arrive();   // this CTA is resident: peers may store into its shared memory (waited on in phase 0)
-  PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, smem_view<CL>(sm), DevSync<CL>(), hk);
+  const DevHooks<LOGN, CL> hk(sm);
+  hk.start();
+  hk.ready();   // kernel start: nothing cached yet, the acquire (L1 invalidate) costs nothing
+  if constexpr (CL > 1) PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, dev_smem_view<LOGN, CL>(sm), DevSync<LOGN, CL>{hk}, hk);
+  else PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, smem_view<1>(sm), DevSync<LOGN, CL>{hk}, hk);
   B::phE(S, L, J, tid);
 }
 template <int LOGN, int PRO, int EPI, int CL, int AR>
@@ -116,7 +172,11 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::
   const NttJob J = ntt_job_qr(L, blockIdx.y, blockIdx.x / CL, blockIdx.x % CL, (long long)blockIdx.z * bstride);
   if (J.skip) return;
   NttState S;
-  PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, smem_view<CL>(sm), DevSync<CL>(), DevHooks<CL>());
+  const DevHooks<LOGN, CL> hk(sm);
+  hk.start();
+  hk.ready();   // kernel start: nothing cached yet, the acquire costs nothing
+  if constexpr (CL > 1) PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, dev_smem_view<LOGN, CL>(sm), DevSync<LOGN, CL>{hk}, hk);
+  else PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, smem_view<1>(sm), DevSync<LOGN, CL>{hk}, hk);
 }
 template <int OP> __global__ void __launch_bounds__(256) k_dyadic(const DyArgs A, const long long bstride) {
   const long long off = (long long)blockIdx.z * bstride;
@@ -207,7 +267,7 @@ template <class K> static int launch_ntt(K kernel, const NttLaunch &L0, size_t j
 }
 template <int LOGN, int PRO, int EPI, int CL, int AR> static int launch_fwd_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   static std::atomic<bool> done[64];
-  return launch_ntt(k_ntt_fwd<LOGN, PRO, EPI, CL, AR>, L, jobs, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CL, st, done);
+  return launch_ntt(k_ntt_fwd<LOGN, PRO, EPI, CL, AR>, L, jobs, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64) + (CL > 1 ? 16 : 0), CL, st, done);
 }
 template <int LOGN, int CL, int AR> static int launch_fwd_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_fwd_m<LOGN, PRO_PLAIN, EPI_STORE, CL, AR>(L, jobs, st);
@@ -234,7 +294,7 @@ template <int LOGN> static int launch_fwd_t(const NttLaunch &L, size_t jobs, cud
 }
 template <int LOGN, int PRO, int EPI, int CL, int AR> static int launch_inv_m(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   static std::atomic<bool> done[64];
-  return launch_ntt(k_ntt_inv<LOGN, PRO, EPI, CL, AR>, L, jobs, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64), CL, st, done);
+  return launch_ntt(k_ntt_inv<LOGN, PRO, EPI, CL, AR>, L, jobs, NttGeom<LOGN>::T / CL, (size_t)NttGeom<LOGN>::N / CL * sizeof(u64) + (CL > 1 ? 16 : 0), CL, st, done);
 }
 template <int LOGN, int CL, int AR> static int launch_inv_c(const NttLaunch &L, size_t jobs, cudaStream_t st) {
   if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_inv_m<LOGN, PRO_PLAIN, EPI_STORE, CL, AR>(L, jobs, st);

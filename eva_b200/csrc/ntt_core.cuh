@@ -168,6 +168,9 @@ template <int LOGN> EVAB_HD void xchg_write_c(const u64 (&x)[NTT_E], u64 *sm, u3
 template <int CL> struct SmemView {
   u64 *local;        // this CTA's slice
   u64 *peer[CL];     // generic pointers to every rank's slice (peer[rank] == local)
+  // store into rank r's slice (host replay: a plain store; the device view in evab200.cu issues an asynchronous
+  // distributed-shared-memory store that signals the receiver's mbarrier)
+  EVAB_HD void put(int r, u32 idx, u64 v) const { peer[r][idx] = v; }
 };
 template <int LOGN, int CL> struct ClGeom {
   static_assert(CL == 1 || CL == 2 || CL == 4 || CL == 8, "cluster size 1, 2, 4 or 8");
@@ -201,22 +204,22 @@ template <int LOGN, int CL> EVAB_HD void xchg_write_cl(const u64 (&x)[NTT_E], u6
 }
 // forward, pass 0 -> pass 1: element k of virtual thread v has natural index (k << (n-4)) | v; its
 // reader is a pass-1 thread of rank k >> (4 - LGC) (compile-time per k)
-template <int LOGN, int CL> EVAB_HD void xchg_write_dist_fwd(const u64 (&x)[NTT_E], const SmemView<CL> &sm, u32 v) {
+template <int LOGN, int CL, class SMV> EVAB_HD void xchg_write_dist_fwd(const u64 (&x)[NTT_E], const SMV &sm, u32 v) {
   typedef ClGeom<LOGN, CL> C;
 #pragma unroll
-  for (int k = 0; k < NTT_E; k++) sm.peer[k >> (NTT_EL - C::LGC)][idx_s<LOGN, 0>(v, (u32)k) & C::mask] = x[k];
+  for (int k = 0; k < NTT_E; k++) sm.put(k >> (NTT_EL - C::LGC), idx_s<LOGN, 0>(v, (u32)k) & C::mask, x[k]);
 }
 // inverse, pass 1 -> pass 0: the reader of natural index i is the pass-0 virtual thread
 // v0 = i mod T, element k0 = i / T; it is stored in v0's CTA at (k0 << log2 Tc) | (v0 mod Tc).
 // For a pass-1 writer (v, k1): k0 = v >> (n-8), v0 = (k1 << (n-8)) | (v mod 2^(n-8)), rank = k1 >> (4-LGC).
-template <int LOGN, int CL> EVAB_HD void xchg_write_dist_inv(const u64 (&x)[NTT_E], const SmemView<CL> &sm, u32 v) {
+template <int LOGN, int CL, class SMV> EVAB_HD void xchg_write_dist_inv(const u64 (&x)[NTT_E], const SMV &sm, u32 v) {
   typedef ClGeom<LOGN, CL> C;
   constexpr int lb = NttGeom<LOGN>::lowbits(1);
   const u32 k0 = v >> lb, L = v & ((1u << lb) - 1u);
 #pragma unroll
   for (int k = 0; k < NTT_E; k++) {
     const u32 v0 = ((u32)k << lb) | L;
-    sm.peer[k >> (NTT_EL - C::LGC)][(k0 << C::LGT) | (v0 & (u32)(C::Tc - 1))] = x[k];
+    sm.put(k >> (NTT_EL - C::LGC), (k0 << C::LGT) | (v0 & (u32)(C::Tc - 1)), x[k]);
   }
 }
 template <int LOGN, int CL> EVAB_HD void xchg_read_dist_inv(u64 (&x)[NTT_E], const u64 *sm, u32 tid) {

@@ -196,7 +196,7 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1, int AR
     }
   }
   // ltid: thread index inside the CTA; the passes run on the virtual thread id
-  template <int PH, class Hooks> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid, const SmemView<CL> &smv, Hooks hk) {
+  template <int PH, class SMV, class Hooks> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid, const SMV &smv, Hooks hk) {
     const PrimeDev P = L.primes[J.pi];
     const u32 root = 1;   // twiddle root prefix of a full transform
     const u32 tid = vtid(J, ltid);
@@ -212,7 +212,7 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1, int AR
         if (cheap) load0<true>(S, L, J, P, tid, sub); else load0<false>(S, L, J, P, tid, sub);
         fwd_pass_s<LOGN, 0>(S.x, P.tw, root, P.p, tid, S.b);
       }
-      if constexpr (CL > 1) { hk.wait(); xchg_write_dist_fwd<LOGN, CL>(S.x, smv, tid); }   // peers are resident (arrive at kernel start)
+      if constexpr (CL > 1) xchg_write_dist_fwd<LOGN, CL>(S.x, smv, tid);   // peers are resident, their barriers initialised (hk.start / hk.ready at kernel start)
       else xchg_write_s<LOGN, 0, 1>(S.x, sm, tid);
     } else if constexpr (PH == NPH - 1) {
       if constexpr (CL > 1) xchg_read_cl<LOGN, CL>(S.x, sm, tid); else xchg_read_c<LOGN>(S.x, sm, tid);
@@ -333,7 +333,7 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1, int AR
   static EVAB_HD constexpr int sync_kind(int ph) { return CL == 1 ? 0 : (ph == NPH - 2 ? 1 : (ph == NPH - 3 ? 2 : 0)); }
   static EVAB_HD u32 vtid(const NttJob &J, u32 tid) { return CL > 1 ? J.h * (u32)C::Tc + tid : tid; }
 
-  template <int PH, class Hooks> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid, const SmemView<CL> &smv, Hooks hk) {
+  template <int PH, class SMV, class Hooks> static EVAB_HD void phase(NttState &S, const NttLaunch &L, const NttJob &J, u32 ltid, const SMV &smv, Hooks hk) {
     const PrimeDev P = L.primes[J.pi];
     const u32 root = 1;   // twiddle root prefix of a full transform
     const u32 tid = vtid(J, ltid);
@@ -376,17 +376,18 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1, int AR
       if constexpr (CL > 1) {
         if constexpr (j == G::P - 2) xchg_read_scl<LOGN, j, CL>(S.x, sm, tid);
         else xchg_read_sl<LOGN, j, j + 1, CL>(S.x, sm, tid);
-        if constexpr (j == 1) hk.arrive();
       } else {
         if constexpr (j == G::P - 2) xchg_read_sc<LOGN, j>(S.x, sm, tid);
         else xchg_read_s<LOGN, j, j + 1>(S.x, sm, tid);
       }
       if constexpr (AR == 1) finv_pass_s<LOGN, j>(S.x, S.bb, L.fp[J.pi].fitw, fold_params(L.fp[J.pi]), tid);
       else inv_pass_s<LOGN, j>(S.x, P.itw, root, P.p, tid, S.b);
+      // the butterflies above consumed every value read from this CTA's slice: from here on the peers may overwrite it
+      if constexpr (CL > 1 && j == 1) hk.released();
     } else {
       constexpr int j = G::P - 2 - (PH - 2) / 2;   // pass that just ran
       if constexpr (CL > 1) {
-        if constexpr (j == 1) { hk.wait(); xchg_write_dist_inv<LOGN, CL>(S.x, smv, tid); }
+        if constexpr (j == 1) { hk.acquire_free(); xchg_write_dist_inv<LOGN, CL>(S.x, smv, tid); }
         else xchg_write_sl<LOGN, j, j, CL>(S.x, sm, tid);
       } else {
         xchg_write_s<LOGN, j, j>(S.x, sm, tid);
@@ -395,9 +396,13 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1, int AR
   }
 };
 
-// sync(kind): barrier after a phase (B::sync_kind); hk: split cluster barrier (arrive / wait) used to
-// order the stores into a peer's shared memory after that peer's last reads of it
-struct NoHooks { EVAB_HD void arrive() const {} EVAB_HD void wait() const {} };
+// sync(kind): barrier after a phase (B::sync_kind: 0 block, 1 "the distributed exchange has landed", 2 none).
+// hk: cluster protocol around the one exchange that crosses CTAs --
+//   start()         kernel start: barriers initialised, CTA announced to its cluster
+//   ready()         every peer is resident and initialised (before the first store into a peer)
+//   released()      (inverse) this thread has read its slice for the last time before the peers overwrite it
+//   acquire_free()  (inverse) every CTA of the cluster has released its slice
+struct NoHooks { EVAB_HD void start() const {} EVAB_HD void ready() const {} EVAB_HD void released() const {} EVAB_HD void acquire_free() const {} };
 template <class B, int PH, int NPH> struct PhaseLoop {
   template <class SM, class Sync, class Hooks> static EVAB_HD void run(NttState &S, const NttLaunch &L, const NttJob &J, u32 tid, const SM &sm, Sync sync, Hooks hk) {
     B::template phase<PH>(S, L, J, tid, sm, hk);
