@@ -69,6 +69,9 @@ struct ExecOptions {
   bool hoistRotations = true;  // rotations of one ciphertext share the inverse NTT of its c1 (exact)
   bool fuseSums = true;        // trees of Add over multiply_plain results / ciphertexts run as one kernel
   bool dedupConstants = true;  // Encode terms of identical constants at the same (level, scale) share one plaintext
+  bool dedupTerms = true;      // identical ciphertext terms (same op, same attributes, same operands) are evaluated once and
+                               // aliased: the compiled wide DAG of tests/large_programs.py style repeats each of its 127
+                               // distinct rotations 64 times.  Same bits; still counted as executed IR terms.
 };
 
 // scoped evab_set_batch: ops issued by this thread act on `batch` instances
@@ -135,9 +138,27 @@ private:
     rawsB_.assign(opt_.batch, std::vector<std::vector<double>>(prog_.termCount()));
     std::size_t arenaWords = 0;
     auto place = [&](ValueInfo &v) { v.off = arenaWords; arenaWords += (std::size_t)(v.kind == Kind::Cipher ? v.size : 1) * v.ell * N_; };
+    byIndex_.assign(prog_.termCount(), nullptr);
+    canon_.resize(prog_.termCount());
+    for (std::size_t i = 0; i < canon_.size(); i++) canon_[i] = i;
+    std::map<std::tuple<int, long long, std::uint64_t, std::uint64_t>, std::uint64_t> seenTerm;
     for (auto &t : order_) {
       ValueInfo &v = vals_[t->index];
+      byIndex_[t->index] = t;
       auto a = [&](int i) -> const ValueInfo & { return vals_[t->operandAt(i)->index]; };
+      if (opt_.dedupTerms && t->numOperands() >= 1 && vals_[t->operandAt(0)->index].kind != Kind::Raw &&
+          (t->op == Op::Add || t->op == Op::Sub || t->op == Op::Mul || t->op == Op::Negate || t->op == Op::RotateLeftConst ||
+           t->op == Op::RotateRightConst || t->op == Op::Relinearize || t->op == Op::ModSwitch || t->op == Op::Rescale)) {
+        const long long attr = t->rotation ? (long long)*t->rotation : (t->rescaleDivisor ? (long long)*t->rescaleDivisor : 0);
+        const std::uint64_t o0 = canon_[t->operandAt(0)->index], o1 = t->numOperands() > 1 ? canon_[t->operandAt(1)->index] : ~0ull;
+        auto ins = seenTerm.emplace(std::make_tuple((int)t->op, attr, o0, o1), t->index);
+        if (!ins.second && vals_[ins.first->second].kind == Kind::Cipher) {
+          canon_[t->index] = ins.first->second;
+          v = vals_[ins.first->second]; v.alias = true;     // same value: shares the first occurrence's storage
+          cipherOps_++;                                      // still an executed IR term of the program
+          continue;
+        }
+      }
       switch (t->op) {
         case Op::Input: {
           const Type ty = t->type.value_or(Type::Cipher);
@@ -264,13 +285,13 @@ private:
     std::unordered_map<std::uint64_t, std::vector<int>> sumKindOf;
     if (opt_.fuseSums) {
       std::vector<int> uses(prog_.termCount(), 0);
-      for (auto &t : order_) for (auto &o : t->getOperands()) uses[o->index]++;
+      for (auto &t : order_) if (canon_[t->index] == t->index) for (auto &o : t->getOperands()) uses[canon_[o->index]]++;
       auto isCipherAdd = [&](const Term *t) {
         return t->op == Op::Add && vals_[t->operandAt(0)->index].kind == Kind::Cipher && vals_[t->operandAt(1)->index].kind == Kind::Cipher;
       };
       auto plainMul = [&](const Term *t, const Term *&ct, const Term *&pt) {
         if (t->op != Op::Mul) return false;
-        const Term *a = t->operandAt(0).get(), *b = t->operandAt(1).get();
+        const Term *a = C(t->operandAt(0).get()), *b = C(t->operandAt(1).get());
         if (vals_[a->index].kind == Kind::Cipher && vals_[b->index].kind == Kind::Plain) { ct = a; pt = b; return true; }
         if (vals_[b->index].kind == Kind::Cipher && vals_[a->index].kind == Kind::Plain) { ct = b; pt = a; return true; }
         return false;
@@ -278,12 +299,12 @@ private:
       // Evaluator::multiply / square of two size-2 ciphertexts (2x2 -> 3)
       auto cipherMul = [&](const Term *t, const Term *&a, const Term *&b) {
         if (t->op != Op::Mul) return false;
-        a = t->operandAt(0).get(); b = t->operandAt(1).get();
+        a = C(t->operandAt(0).get()); b = C(t->operandAt(1).get());
         return vals_[a->index].kind == Kind::Cipher && vals_[b->index].kind == Kind::Cipher && vals_[a->index].size == 2 && vals_[b->index].size == 2;
       };
       for (auto it = order_.rbegin(); it != order_.rend(); ++it) {
         Term *root = *it;
-        if (!isCipherAdd(root) || vals_[root->index].fused) continue;
+        if (!isCipherAdd(root) || vals_[root->index].fused || vals_[root->index].alias) continue;
         std::vector<std::pair<const Term *, const Term *>> leaves;
         std::vector<int> kinds;
         std::vector<const Term *> absorbed;
@@ -292,8 +313,8 @@ private:
           const bool inner = t != root;
           if ((!inner || uses[t->index] == 1) && isCipherAdd(t) && leaves.size() + 2 <= 30) {
             if (inner) absorbed.push_back(t);
-            expand(t->operandAt(0).get());
-            expand(t->operandAt(1).get());
+            expand(C(t->operandAt(0).get()));
+            expand(C(t->operandAt(1).get()));
           } else if (inner && uses[t->index] == 1 && plainMul(t, ct, pt)) {
             absorbed.push_back(t);
             leaves.emplace_back(ct, pt); kinds.push_back(1);
@@ -315,7 +336,7 @@ private:
     auto stepOperands = [&](const Term *t) {
       std::vector<const Term *> ops;
       auto f = sumOf.find(t->index);
-      if (f == sumOf.end()) { for (auto &o : t->getOperands()) ops.push_back(o.get()); return ops; }
+      if (f == sumOf.end()) { for (auto &o : t->getOperands()) ops.push_back(C(o.get())); return ops; }
       for (auto &l : f->second) { ops.push_back(l.first); if (l.second) ops.push_back(l.second); }
       return ops;
     };
@@ -328,12 +349,12 @@ private:
       std::map<std::uint64_t, std::vector<const Term *>> bySrc;
       for (auto &t : order_)
         if ((t->op == Op::RotateLeftConst || t->op == Op::RotateRightConst) && *t->rotation != 0 && vals_[t->index].kind == Kind::Cipher &&
-            vals_[t->index].ell <= 15)
-          bySrc[t->operandAt(0)->index].push_back(t);
+            vals_[t->index].ell <= 15 && !vals_[t->index].alias)
+          bySrc[canon_[t->operandAt(0)->index]].push_back(t);
       for (auto &kv : bySrc) {
         if (kv.second.size() < 2) continue;
         const int gid = (int)hoistSrc.size();
-        hoistSrc.push_back(kv.second.front()->operandAt(0).get());
+        hoistSrc.push_back(C(kv.second.front()->operandAt(0).get()));
         hoistOff_.push_back(arenaWords);
         arenaWords += (std::size_t)vals_[kv.first].ell * N_;
         for (const Term *r : kv.second) hoistOf[r->index] = gid;
@@ -375,7 +396,7 @@ private:
       const ValueInfo &v = vals_[t->index];
       const bool device = (v.kind == Kind::Cipher || v.kind == Kind::Plain) && t->op != Op::Input && !v.alias && !v.fused;
       if (!device) {
-        if (v.alias) streamOf[t->index] = streamOf[t->operandAt(0)->index];
+        if (v.alias) streamOf[t->index] = streamOf[aliasSource(t)];
         continue;
       }
       Step st;
@@ -411,7 +432,7 @@ private:
     // resolve alias chains (Output of X shares X's storage; Output(Output) never occurs)
     for (auto &t : order_) {
       ValueInfo &v = vals_[t->index];
-      if (v.alias) { const ValueInfo &src = vals_[t->operandAt(0)->index]; v.off = src.off; }
+      if (v.alias) { const ValueInfo &src = vals_[aliasSource(t)]; v.off = src.off; }
     }
     for (auto &st : steps_) {
       auto it = recordAfter_.find(st.producer);
@@ -440,6 +461,9 @@ private:
         check(evab_galois_prepare(dev_->ctx(), elt));
       }
   }
+  // canonical (first) occurrence of a term that repeats an earlier one (dedupTerms)
+  const Term *C(const Term *t) const { return byIndex_[canon_[t->index]]; }
+  std::uint64_t aliasSource(const Term *t) const { return canon_[t->index] != t->index ? canon_[t->index] : t->operandAt(0)->index; }
   int levelToEll(std::uint32_t level) const {
     const int ell = k_ - 1 - (int)level;
     if (ell < 1) throw std::runtime_error("level exceeds the modulus chain");
@@ -616,6 +640,8 @@ private:
   u64 N_;
   int k_;
   std::vector<Term *> order_;
+  std::vector<Term *> byIndex_;          // term index -> term
+  std::vector<std::uint64_t> canon_;     // term index -> index of the first identical term (itself when unique)
   std::vector<ValueInfo> vals_;
   std::vector<std::vector<std::vector<double>>> rawsB_;   // [instance][term]
   std::size_t stride_ = 0, rawStride_ = 0;

@@ -138,12 +138,13 @@ PYBIND11_MODULE(_eva_b200, m) {
       .def("execute_batch", [](B200Public &p, Program &prog, const std::vector<const B200Valuation *> &in) { return p.executeMany(prog, in); },
            py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>(),
            "Execute one compiled program on a list of valuations with batched kernels; returns a list of valuations")
-      .def("set_options", [](B200Public &p, int streams, bool graph, bool cache, bool dedup, int fuse, bool fuseSums, bool hoist, bool uniformEncode) {
+      .def("set_options", [](B200Public &p, int streams, bool graph, bool cache, bool dedup, int fuse, bool fuseSums, bool hoist, bool uniformEncode, bool dedupTerms) {
              p.options.numStreams = streams; p.options.useGraph = graph; p.options.cacheConstants = cache; p.options.dedupConstants = dedup;
              p.options.fuse = fuse; p.options.fuseSums = fuseSums; p.options.hoistRotations = hoist; p.options.uniformEncode = uniformEncode;
+             p.options.dedupTerms = dedupTerms;
            },
            py::arg("num_streams") = 8, py::arg("use_graph") = true, py::arg("cache_constants") = true, py::arg("dedup_constants") = true,
-           py::arg("fuse") = 1, py::arg("fuse_sums") = true, py::arg("hoist_rotations") = true, py::arg("uniform_encode") = true)
+           py::arg("fuse") = 1, py::arg("fuse_sums") = true, py::arg("hoist_rotations") = true, py::arg("uniform_encode") = true, py::arg("dedup_terms") = true)
       .def("set_input_sizes", [](B200Public &p, const std::map<std::string, int> &sizes) { p.options.inputSizes = sizes; },
            "ciphertext inputs that are not size 2 (name -> polynomials); applies to plans built afterwards")
       .def("drop_plan", &B200Public::dropExecutor, py::arg("program"), py::arg("batch") = 1, py::arg("replica") = 0)
@@ -178,6 +179,49 @@ PYBIND11_MODULE(_eva_b200, m) {
       .def("run_resident", [](B200Public &p, Program &prog, std::uintptr_t stream, int batch, int replica) { p.executorFor(prog, batch, replica).run((void *)stream); },
            py::arg("program"), py::arg("stream"), py::arg("batch") = 1, py::arg("replica") = 0, py::call_guard<py::gil_scoped_release>())
       .def("sync", [](B200Public &p, std::uintptr_t stream) { p.shared()->dev->sync((void *)stream); }, py::call_guard<py::gil_scoped_release>())
+      // ---- device-resident plumbing of the DAG-sharded mode (eva_b200/shard.py): where a plan keeps its named
+      // inputs and outputs in device memory, so that NCCL can gather partial ciphertexts straight from one
+      // rank's arena into another's (no host staging), and a download of the outputs of a resident run
+      .def("io_pointers", [](B200Public &p, Program &prog, int batch, int replica) {
+        Executor &ex = p.executorFor(prog, batch, replica);
+        const std::size_t N = p.shared()->dev->N();
+        auto describe = [&](const Term::Ptr &t) -> py::object {
+          const ValueInfo &vi = ex.info(t);
+          if (vi.kind != Kind::Cipher && vi.kind != Kind::Plain) return py::none();
+          const std::size_t polys = vi.kind == Kind::Cipher ? (std::size_t)vi.size : 1;
+          py::dict d;
+          d["ptr"] = (std::uintptr_t)ex.valuePtr(t, 0); d["bytes"] = polys * (std::size_t)vi.ell * N * 8;
+          d["size"] = (int)polys; d["ell"] = vi.ell; d["scale"] = vi.scale; d["cipher"] = vi.kind == Kind::Cipher;
+          return d;
+        };
+        py::dict ins, outs;
+        for (auto &in : prog.getInputs()) ins[py::str(in.first)] = describe(in.second);
+        for (auto &o : prog.getOutputs()) outs[py::str(o.first)] = describe(o.second);
+        py::dict r; r["inputs"] = ins; r["outputs"] = outs;
+        return r;
+      }, py::arg("program"), py::arg("batch") = 1, py::arg("replica") = 0)
+      .def("download_outputs", [](B200Public &p, Program &prog, std::uintptr_t stream, int replica) {
+        Executor &ex = p.executorFor(prog, 1, replica);
+        auto dev = p.shared()->dev;
+        const std::size_t N = dev->N();
+        B200Valuation out;
+        for (auto &o : prog.getOutputs()) {
+          const ValueInfo &vi = ex.info(o.second);
+          if (vi.kind == Kind::Cipher) {
+            HostCipher h; h.size = vi.size; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.size * vi.ell * N);
+            dev->download(h.data.data(), ex.valuePtr(o.second, 0), h.data.size() * 8, (void *)stream);
+            out[o.first] = std::move(h);
+          } else if (vi.kind == Kind::Plain) {
+            HostPlain h; h.ell = vi.ell; h.scale = vi.scale; h.data.resize((std::size_t)vi.ell * N);
+            dev->download(h.data.data(), ex.valuePtr(o.second, 0), h.data.size() * 8, (void *)stream);
+            out[o.first] = std::move(h);
+          } else {
+            out[o.first] = std::make_shared<ConstantValue>(prog.getVecSize(), ex.rawValue(o.second->index, 0));
+          }
+        }
+        dev->sync((void *)stream);
+        return out;
+      }, py::arg("program"), py::arg("stream"), py::arg("replica") = 0, py::call_guard<py::gil_scoped_release>())
       // ---- test hooks
       .def("debug_value", [](B200Public &p, Program &prog, std::uint64_t index, int batch, int b) -> py::object {
         Executor &ex = p.executorFor(prog, batch);

@@ -1,0 +1,573 @@
+"""DAG-sharded execution of ONE compiled program over the GPUs of a box (BASELINE configs
+"Harris corner detector 1 -> 8 GPUs DAG-sharded" and "synthetic wide DAG (>= 4096 parallel ciphertext
+multiplications) across 8 x B200").
+
+The reference runs independent terms of one program on different CPU threads with shared operands
+(/root/reference/eva/common/multicore_program_traversal.h:55-79).  On GPUs operands are not shared, so the
+DAG is cut where an exchange is cheapest and exact: at sums.  A tree of cipher Add terms can be summed in any
+grouping with bit-identical results (modular addition is exact, commutative and associative), therefore
+
+    stage s, rank r : the cones of the leaves assigned to r, ending in ONE partial sum per cut root;
+    exchange        : the partial sums of every rank, gathered (NCCL) straight from one arena into the other
+                      -- all-gather for an inner cut (every rank goes on), gather on rank 0 for the last one;
+    next stage      : adds the gathered partials (that IS the cut value) and continues.
+
+Several cuts at the same depth share one stage (Harris: the two 3x3 gradient sums, then the three 3x3
+pooling sums).  A cut is taken only when a cost model says it pays: leaves are assigned so that expensive
+shared sub-terms (rotations, relinearizations, ciphertext products) are SPLIT between the ranks rather than
+recomputed -- leaves with the same expensive ancestors go to the same rank, and a full a x b grid of
+two-ancestor leaves (the wide DAG: rot(x, i) * rot(y, j)) is blocked in two dimensions -- and the estimated
+time saved must exceed the price of the exchange.  Everything here is host-side graph surgery through the
+same Program / Term API the DSL uses; the stage programs run on the ordinary executor of every rank, their
+partial ciphertexts never leave device memory.
+"""
+import os
+import time
+
+from . import Op, Program, Type
+from .shard import infer, _add_trees, _ATTR_COPY
+
+# rough single-instance costs in microseconds on a B200 (tools/op_throughput.py, profiles/): only the ratios matter
+_COST = {Op.RotateLeftConst: 12.0, Op.RotateRightConst: 12.0, Op.Relinearize: 12.0, Op.Rescale: 5.0, Op.ModSwitch: 1.5,
+         Op.Mul: 3.0, Op.Add: 1.5, Op.Sub: 1.5, Op.Negate: 1.5, Op.Encode: 0.5}
+_EXPENSIVE = (Op.RotateLeftConst, Op.RotateRightConst, Op.Relinearize)
+EXCHANGE_US = 45.0     # one NCCL (all-)gather of a ciphertext per rank on NVSwitch + the stage boundary
+
+
+def _cost(t, info):
+    if info[t.index].type != Type.Cipher:
+        return 0.0
+    if t.op == Op.Mul and sum(1 for o in t.operands if info[o.index].type == Type.Cipher) == 2:
+        return 4.0
+    return _COST.get(t.op, 0.0)
+
+
+def canonical(prog):
+    """term index -> first identical term (same op, same attributes, same canonical operands).  The reference
+    compiler does not share repeated sub-expressions -- its wide DAG holds 8192 rotation terms, 127 of them
+    distinct -- and a duplicate is the same value, so plans, cost estimates and stage programs work on the
+    representatives (the executor aliases duplicates as well: ExecOptions::dedupTerms)."""
+    rep, seen = {}, {}
+    for t in prog.terms():
+        a = t.attributes
+        if t.op in (Op.Input, Op.Output):
+            rep[t.index] = t
+            continue
+        key = (int(t.op), a.get("RotationAttribute"), a.get("RescaleDivisorAttribute"), a.get("EncodeAtScaleAttribute"), a.get("EncodeAtLevelAttribute"),
+               tuple(a["ConstantValueAttribute"]) if "ConstantValueAttribute" in a else None, tuple(rep[o.index].index for o in t.operands))
+        rep[t.index] = seen.setdefault(key, t)
+    return rep
+
+
+_REP = {}     # program identity -> canonical map of the program being planned (set by plan_stages)
+
+
+def _ops(t):
+    rep = _REP.get("rep")
+    return [rep[o.index] for o in t.operands] if rep else list(t.operands)
+
+
+def _cone(t, stop):
+    """indices of t and of everything it depends on, not descending below `stop` terms (iterative)"""
+    seen, stack = set(), [t]
+    while stack:
+        u = stack.pop()
+        if u.index in seen or u.index in stop:
+            continue
+        seen.add(u.index)
+        stack.extend(_ops(u))
+    return seen
+
+
+def _clone(dst, memo, root, in_names):
+    """copy `root` and its operands into dst (iterative: DAGs deeper than the recursion limit are fine);
+    memo maps source term index -> Term of dst and is where cut values / inputs are substituted"""
+    stack = [root]
+    while stack:
+        t = stack[-1]
+        if t.index in memo:
+            stack.pop()
+            continue
+        pending = [o for o in _ops(t) if o.index not in memo]
+        if pending:
+            stack.extend(pending)
+            continue
+        stack.pop()
+        args = [memo[o.index] for o in _ops(t)]
+        a = t.attributes
+        if t.op == Op.Input:
+            n = dst._make_input(in_names[t.index], Type(a.get("TypeAttribute", Type.Cipher)))
+        elif t.op == Op.Constant:
+            v = list(a["ConstantValueAttribute"])
+            n = dst._make_uniform_constant(v[0]) if len(v) == 1 else dst._make_dense_constant(v)
+        elif t.op == Op.RotateLeftConst:
+            n = dst._make_left_rotation(args[0], a["RotationAttribute"])
+        elif t.op == Op.RotateRightConst:
+            n = dst._make_right_rotation(args[0], a["RotationAttribute"])
+        else:
+            n = dst._make_term(t.op, args)
+        keep = {k: (Type(a[k]) if k == "TypeAttribute" else a[k]) for k in _ATTR_COPY if k in a and not (t.op == Op.Input and k == "TypeAttribute")}
+        if keep:
+            n._set_attributes(keep)
+        memo[t.index] = n
+    return memo[root.index]
+
+
+def _sum(dst, xs):
+    while len(xs) > 1:
+        xs = [dst._make_term(Op.Add, [xs[i], xs[i + 1]]) if i + 1 < len(xs) else xs[i] for i in range(0, len(xs), 2)]
+    return xs[0]
+
+
+def _assign(leaf_sigs, nranks):
+    """leaf -> rank.  leaf_sigs[i] = tuple of the expensive private ancestors of leaf i (sorted term indices).
+    Leaves with equal signatures stay together; a full a x b grid of two-ancestor signatures is blocked in two
+    dimensions (a/pa + b/pb distinct ancestors per rank instead of a + b/P); otherwise groups go, largest first,
+    to the rank that needs the fewest new ancestors (ties: the least loaded)."""
+    n = len(leaf_sigs)
+    pairs = [s for s in leaf_sigs if len(s) == 2]
+    if len(pairs) == n and n >= nranks:
+        # two families (e.g. the rotations of x and those of y): 2-colour the ancestors along the pairs
+        colour, adj = {}, {}
+        for a, b in pairs:
+            adj.setdefault(a, set()).add(b); adj.setdefault(b, set()).add(a)
+        ok = True
+        for start in adj:
+            if start in colour:
+                continue
+            colour[start] = 0
+            todo = [start]
+            while todo and ok:
+                u = todo.pop()
+                for w in adj[u]:
+                    if w not in colour:
+                        colour[w] = 1 - colour[u]; todo.append(w)
+                    elif colour[w] == colour[u]:
+                        ok = False
+        if ok:
+            oriented = [(a, b) if colour[a] == 0 else (b, a) for a, b in pairs]
+            A = sorted({p[0] for p in oriented}); B = sorted({p[1] for p in oriented})
+            if len(A) * len(B) == n and len(set(oriented)) == n:
+                best = None
+                for pa in range(1, nranks + 1):
+                    if nranks % pa == 0 and pa <= len(A) and nranks // pa <= len(B):
+                        pb = nranks // pa
+                        c = -(-len(A) // pa) + -(-len(B) // pb)
+                        if best is None or c < best[0]:
+                            best = (c, pa, pb)
+                if best:
+                    _, pa, pb = best
+                    ia = {a: i * pa // len(A) for i, a in enumerate(A)}
+                    ib = {b: j * pb // len(B) for j, b in enumerate(B)}
+                    return [ia[p[0]] * pb + ib[p[1]] for p in oriented]
+    groups = {}
+    for i, s in enumerate(leaf_sigs):
+        groups.setdefault(s, []).append(i)
+    have = [set() for _ in range(nranks)]
+    load = [0] * nranks
+    out = [0] * n
+    # empty signatures (cheap leaves) last: they only balance the load
+    for s, members in sorted(groups.items(), key=lambda kv: (-len(kv[0]) * len(kv[1]), kv[1][0])):
+        if s:
+            r = min(range(nranks), key=lambda q: (len(set(s) - have[q]) * 1000 + load[q], q))
+            have[r].update(s)
+            for i in members:
+                out[i] = r
+            load[r] += len(members) + 10 * len(s)
+        else:
+            for i in members:
+                r = min(range(nranks), key=lambda q: (load[q], q))
+                out[i] = r
+                load[r] += 1
+    return out
+
+
+class Stage:
+    """roots: cut terms of the source program (indices); progs[r]: the program of rank r, with one output
+    "partial_<root>" per root; nranks: ranks that contribute (the others idle through this stage);
+    leaves[r]: number of leaves rank r sums; est_*: cost-model estimates in microseconds"""
+
+    def __init__(self):
+        self.roots, self.progs, self.nranks, self.leaves = [], [], 0, []
+        self.est_single = self.est_sharded = 0.0
+
+
+class StagePlan:
+    def __init__(self, prog, nparts):
+        self.source, self.nparts, self.stages, self.tail = prog, nparts, [], None
+        self.partial_names = {}    # program name -> {input name: (root, rank)}
+        self.input_sizes = {}      # partial input name -> polynomials
+
+    def describe(self):
+        return [{"roots": len(s.roots), "ranks": s.nranks, "leaves_per_rank": s.leaves, "est_single_us": round(s.est_single, 1),
+                 "est_sharded_us": round(s.est_sharded, 1)} for s in self.stages]
+
+
+def plan_stages(prog, nparts, exchange_us=EXCHANGE_US, force=False):
+    """cut `prog` (compiled) into stages for `nparts` ranks; None when no cut pays (or nparts < 2).
+    force=True keeps every candidate cut regardless of the cost model (tests)."""
+    if nparts < 2:
+        return None
+    info = infer(prog)
+    terms = prog.terms()
+    byidx = {t.index: t for t in terms}
+    rep = canonical(prog)
+    _REP["rep"] = rep
+    try:
+        return _plan_stages(prog, nparts, exchange_us, force, info, terms, byidx, rep)
+    finally:
+        _REP.pop("rep", None)
+
+
+def _plan_stages(prog, nparts, exchange_us, force, info, terms, byidx, rep):
+    trees = {r: (root, [rep[l.index] for l in leaves]) for r, (root, leaves) in _add_trees(prog, info).items() if rep[r].index == r}
+    in_names = {t.index: n for n, t in prog.inputs.items()}
+    out_names = {t.index: n for n, t in prog.outputs.items()}
+    order = {t.index: i for i, t in enumerate(terms)}
+    # candidate cuts in topological order, with their depth in cuts
+    cands = sorted((r for r, (_, lv) in trees.items() if len(lv) >= 2), key=lambda r: order[r])
+    accepted, depth = [], {}
+    plan = StagePlan(prog, nparts)
+    stop_inputs = {t.index for t in terms if t.op == Op.Input}
+    # group candidates by cut depth (number of accepted cuts below them), stage by stage
+    remaining = list(cands)
+    stage_no = 0
+    while remaining:
+        avail = set(stop_inputs) | set(accepted)
+        # candidates whose cone contains no other remaining candidate
+        ready = []
+        for r in remaining:
+            cone = _cone(byidx[r], avail)
+            if not any(o != r and o in cone for o in remaining):
+                ready.append(r)
+        if not ready:
+            break
+        st = _build_stage(prog, info, byidx, trees, ready, avail, nparts, in_names, stage_no, plan, exchange_us, force)
+        remaining = [r for r in remaining if r not in ready]
+        if st is not None:
+            plan.stages.append(st)
+            accepted.extend(st.roots)
+            stage_no += 1
+    if not plan.stages:
+        return None
+    # tail (rank 0): everything after the last cuts
+    tail = Program(prog.name + ".tail", prog.vec_size)
+    memo = _cut_inputs(tail, plan, prog, info, accepted, byidx, set(stop_inputs) | set(accepted), [t for t in terms if t.op == Op.Output])
+    for t in terms:
+        if t.op == Op.Output:
+            src = _clone(tail, memo, rep[t.operands[0].index], in_names)
+            o = tail._make_output(out_names[t.index], src)
+            if "RangeAttribute" in t.attributes:
+                o._set_attributes({"RangeAttribute": t.attributes["RangeAttribute"]})
+    plan.tail = tail
+    return plan
+
+
+def _cut_inputs(dst, plan, prog, info, cuts, byidx, avail, sinks):
+    """memo for cloning into dst: every cut value that the cones of `sinks` reach becomes the sum of its gathered
+    partials, which enter dst as inputs cut<root>_p<rank>"""
+    need = set()
+    for s in sinks:
+        stack, seen = [s], set()
+        while stack:
+            u = stack.pop()
+            if u.index in seen:
+                continue
+            seen.add(u.index)
+            if u.index in cuts:
+                need.add(u.index)
+                continue
+            stack.extend(_ops(u))
+    memo = {}
+    names = plan.partial_names.setdefault(dst.name, {})
+    for c in sorted(need):
+        st = next(s for s in plan.stages if c in s.roots)
+        ri = info[c]
+        parts = []
+        for r in range(st.nranks):
+            nm = "cut%d_p%d" % (c, r)
+            x = dst._make_input(nm, Type.Cipher)
+            x._set_attributes({"EncodeAtScaleAttribute": ri.scale, "EncodeAtLevelAttribute": ri.level})
+            names[nm] = (c, r)
+            parts.append(x)
+        memo[c] = _sum(dst, parts)
+    return memo
+
+
+def _build_stage(prog, info, byidx, trees, roots, avail, nparts, in_names, stage_no, plan, exchange_us, force):
+    # leaves of all roots of this stage, their private cones and expensive-ancestor signatures
+    leaves = []   # (root, leaf term)
+    for r in roots:
+        for lf in trees[r][1]:
+            leaves.append((r, lf))
+    cones = [_cone(lf, avail) for _, lf in leaves]
+    shared_all = set.intersection(*cones) if cones else set()
+    # signature of a leaf: its expensive ancestors that other leaves need as well (what an assignment can share or split)
+    count = {}
+    for cn in cones:
+        for i in cn:
+            count[i] = count.get(i, 0) + 1
+    sigs = []
+    for cn in cones:
+        sigs.append(tuple(sorted(i for i in cn - shared_all if count[i] > 1 and (byidx[i].op in _EXPENSIVE or _cost(byidx[i], info) >= 4.0))))
+    nranks = min(nparts, min(len(trees[r][1]) for r in roots))
+    if nranks < 2:
+        return None
+    assign = _assign(sigs, nranks)
+    # every rank must hold at least one leaf of every root (its partial sum must exist): repair greedily
+    for r in roots:
+        idx = [i for i, (rr, _) in enumerate(leaves) if rr == r]
+        for q in range(nranks):
+            if not any(assign[i] == q for i in idx):
+                donor = max(range(nranks), key=lambda d: sum(1 for i in idx if assign[i] == d))
+                mv = next(i for i in idx if assign[i] == donor)
+                assign[mv] = q
+    cost = lambda ids: sum(_cost(byidx[i], info) for i in ids)
+    union_all = set().union(*cones)
+    per_rank = [set().union(*[cones[i] for i in range(len(leaves)) if assign[i] == q]) for q in range(nranks)]
+    est_single = cost(union_all)
+    est_sharded = max(cost(s) for s in per_rank) + exchange_us
+    if not force and est_single - est_sharded <= 0:
+        return None
+    st = Stage()
+    st.roots, st.nranks, st.est_single, st.est_sharded = list(roots), nranks, est_single, est_sharded
+    st.leaves = [sum(1 for a in assign if a == q) for q in range(nranks)]
+    cuts = [c for s in plan.stages for c in s.roots]
+    for q in range(nranks):
+        p = Program("%s.s%d.r%d" % (prog.name, stage_no, q), prog.vec_size)
+        mine = [lf for i, (_, lf) in enumerate(leaves) if assign[i] == q]
+        memo = _cut_inputs(p, plan, prog, info, cuts, byidx, avail, mine)
+        for r in roots:
+            mine_r = [_clone(p, memo, lf, in_names) for i, (rr, lf) in enumerate(leaves) if rr == r and assign[i] == q]
+            p._make_output("partial_%d" % r, _sum(p, mine_r))
+        st.progs.append(p)
+    return st
+
+
+def finalize_sizes(plan):
+    """polynomial count of every partial (a rank that sums only relinearized leaves sends 2 polynomials, one that
+    holds a raw product sends 3): consumers declare their inputs with the producer's size"""
+    sizes = {}
+    for st in plan.stages:
+        for q, p in enumerate(st.progs):
+            _declare(plan, p)
+            pi = infer_with_sizes(p, plan.input_sizes)
+            for r in st.roots:
+                sizes[(r, q)] = pi[p.outputs["partial_%d" % r].index].size
+        for pname, names in plan.partial_names.items():
+            for nm, (c, r) in names.items():
+                if (c, r) in sizes:
+                    plan.input_sizes[nm] = sizes[(c, r)]
+    return sizes
+
+
+def infer_with_sizes(p, input_sizes):
+    info = infer(p)
+    # infer() assumes size-2 inputs; partial inputs may carry 3 polynomials: propagate through Adds
+    names = {t.index: n for n, t in p.inputs.items()}
+    for t in p.terms():
+        if t.op == Op.Input and names.get(t.index) in input_sizes:
+            info[t.index].size = input_sizes[names[t.index]]
+        elif info[t.index].type == Type.Cipher and t.op in (Op.Add, Op.Sub, Op.Negate, Op.ModSwitch, Op.Rescale, Op.Output):
+            ciph = [info[o.index] for o in t.operands if info[o.index].type == Type.Cipher]
+            if ciph:
+                info[t.index].size = max(i.size for i in ciph)
+    return info
+
+
+def _declare(plan, p):
+    pass
+
+
+# ------------------------------------------------------------------------------------------------- execution
+def run_plain(plan, x):
+    """plaintext semantics of the staged plan (tests, CPU): every rank's stage programs through `evaluate`,
+    partial sums handed on exactly as the device path does"""
+    from . import evaluate
+    have = {}
+    for st in plan.stages:
+        for q, p in enumerate(st.progs):
+            ins = {}
+            for nm in p.inputs:
+                ins[nm] = have[plan.partial_names[p.name][nm]] if nm in plan.partial_names.get(p.name, {}) else x[nm]
+            out = evaluate(p, ins)
+            for r in st.roots:
+                have[(r, q)] = out["partial_%d" % r]
+    ins = {}
+    for nm in plan.tail.inputs:
+        ins[nm] = have[plan.partial_names[plan.tail.name][nm]] if nm in plan.partial_names.get(plan.tail.name, {}) else x[nm]
+    return evaluate(plan.tail, ins)
+
+
+class _DevMem:
+    """zero-copy view of device memory for torch.as_tensor (CUDA array interface)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+def _tensor(ptr, nbytes):
+    import torch
+    return torch.as_tensor(_DevMem(ptr, nbytes), device="cuda")
+
+
+class ShardedRunner:
+    """One rank's side of the staged execution.  Built once per (context, plan): stage plans (arena + captured
+    CUDA graph) of this rank, tensors aliasing the partial-sum slots, gather buffers.  run(inputs) then is:
+    H2D of the inputs this rank needs, and per stage one graph launch + one NCCL collective per cut root."""
+
+    def __init__(self, pub, plan, rank, world):
+        import torch
+        self.pub, self.plan, self.rank, self.world = pub, plan, rank, world
+        finalize_sizes(plan)
+        pub.set_input_sizes(dict(plan.input_sizes))
+        try:
+            self.my = []            # per stage: (program or None, io)
+            self.consumers = {}     # root -> list of (program, io) on this rank that read its partials
+            progs = []
+            for st in plan.stages:
+                p = st.progs[rank] if rank < st.nranks else None
+                progs.append(p)
+            if rank == 0:
+                progs.append(plan.tail)
+            self.io = {}
+            for p in progs:
+                if p is not None:
+                    self.io[p.name] = pub.io_pointers(p)
+            for p in progs:
+                if p is None:
+                    continue
+                for nm, (c, r) in plan.partial_names.get(p.name, {}).items():
+                    self.consumers.setdefault(c, [])
+                    if p not in [q for q, _ in self.consumers[c]]:
+                        self.consumers[c].append((p, self.io[p.name]))
+            self.progs = progs
+        finally:
+            pub.set_input_sizes({})
+        self.bufs = {}
+        self.torch = torch
+
+    def _slots(self, p, io, root, nranks):
+        names = {v: k for k, v in self.plan.partial_names[p.name].items()}
+        return [io["inputs"][names[(root, r)]] for r in range(nranks)]
+
+    def run(self, inputs, stream=None):
+        torch = self.torch
+        import torch.distributed as dist
+        plan, pub, rank, world = self.plan, self.pub, self.rank, self.world
+        st_ptr = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        # inputs of the source program go to every stage program of this rank that reads them
+        for p in self.progs:
+            if p is None:
+                continue
+            sub = _subset(inputs, set(p.inputs) - set(plan.partial_names.get(p.name, {})))
+            pub.stage_inputs(p, [sub], st_ptr)
+        for si, st in enumerate(plan.stages):
+            p = self.progs[si]
+            last = si == len(plan.stages) - 1
+            if p is not None:
+                pub.run_resident(p, st_ptr)
+            for root in st.roots:
+                key = "partial_%d" % root
+                sizes = [plan.input_sizes["cut%d_p%d" % (root, r)] for r in range(st.nranks)]
+                ell_bytes = None
+                if p is not None:
+                    o = self.io[p.name]["outputs"][key]
+                    ell_bytes = o["bytes"] // o["size"]
+                cons = self.consumers.get(root, [])
+                if ell_bytes is None:
+                    s0 = self._slots(*cons[0], root, st.nranks)[0] if cons else None
+                    ell_bytes = s0["bytes"] // s0["size"] if s0 else 0
+                nbytes = max(sizes) * ell_bytes
+                if p is not None and o["bytes"] == nbytes:
+                    send = _tensor(o["ptr"], nbytes)
+                else:   # idle rank, or a partial with fewer polynomials than the widest: staged through a buffer
+                    send = self._buf(("send", root), nbytes)
+                    if p is not None:
+                        send[: o["bytes"] // 8].copy_(_tensor(o["ptr"], o["bytes"]))
+                # destination: the slots of the first consumer when they are laid out back to back, else a buffer
+                dst = None
+                direct = False
+                if cons and all(s == max(sizes) for s in sizes) and st.nranks == world:
+                    slots = self._slots(*cons[0], root, st.nranks)
+                    if all(slots[r + 1]["ptr"] - slots[r]["ptr"] == nbytes for r in range(st.nranks - 1)):
+                        dst = _tensor(slots[0]["ptr"], nbytes * world)
+                        direct = True
+                if dst is None:
+                    dst = self._buf(("recv", root), nbytes * world)
+                if last and world > 1:
+                    # the final gather: only rank 0 (the tail) needs the partials
+                    if rank == 0:
+                        dist.gather(send, [dst[r * (nbytes // 8):(r + 1) * (nbytes // 8)] for r in range(world)], dst=0)
+                    else:
+                        dist.gather(send, None, dst=0)
+                elif world > 1:
+                    dist.all_gather_into_tensor(dst, send)
+                else:
+                    dst[: nbytes // 8].copy_(send)
+                for ci, (cp, cio) in enumerate(cons):
+                    if direct and ci == 0:
+                        continue
+                    slots = self._slots(cp, cio, root, st.nranks)
+                    for r in range(st.nranks):
+                        _tensor(slots[r]["ptr"], slots[r]["bytes"]).copy_(dst[r * (nbytes // 8): r * (nbytes // 8) + slots[r]["bytes"] // 8])
+        if rank != 0:
+            return None
+        pub.run_resident(plan.tail, st_ptr)
+        return pub.download_outputs(plan.tail, st_ptr)
+
+    def _buf(self, key, nbytes):
+        b = self.bufs.get(key)
+        if b is None or b.numel() * 8 < nbytes:
+            b = self.torch.empty(nbytes // 8, dtype=self.torch.int64, device="cuda")
+            self.bufs[key] = b
+        return b[: nbytes // 8]
+
+
+def _subset(inputs, names):
+    from . import b200
+    out = b200.B200Valuation()
+    for name in inputs.names():
+        if name in names:
+            kind, arr, scale = inputs.get(name)
+            if kind == "cipher":
+                out.set_cipher(name, arr, scale)
+            elif kind == "plain":
+                out.set_plain(name, arr, scale)
+            else:
+                out.set_raw(name, list(arr))
+    return out
+
+
+def execute_local(pub, plan, inputs):
+    """every rank's share of the staged plan run one after the other on THIS GPU, partial sums copied between
+    the arenas on the device -- the single-process check that a plan reproduces execute(prog) bit for bit
+    (tests; the multi-GPU path is ShardedRunner under torchrun)"""
+    import torch
+    finalize_sizes(plan)
+    pub.set_input_sizes(dict(plan.input_sizes))
+    try:
+        st = torch.cuda.current_stream().cuda_stream
+        partial = {}
+
+        def feed(p):
+            sub = _subset(inputs, set(p.inputs) - set(plan.partial_names.get(p.name, {})))
+            pub.stage_inputs(p, [sub], st)
+            pio = pub.io_pointers(p)
+            for nm, (c, r) in plan.partial_names.get(p.name, {}).items():
+                s = pio["inputs"][nm]
+                _tensor(s["ptr"], s["bytes"]).copy_(partial[(c, r)][: s["bytes"] // 8])
+            return pio
+        for stg in plan.stages:
+            for q, p in enumerate(stg.progs):
+                pio = feed(p)
+                pub.run_resident(p, st)
+                for root in stg.roots:
+                    o = pio["outputs"]["partial_%d" % root]
+                    assert o["size"] == plan.input_sizes["cut%d_p%d" % (root, q)]
+                    partial[(root, q)] = _tensor(o["ptr"], o["bytes"]).clone()
+        feed(plan.tail)
+        pub.run_resident(plan.tail, st)
+        return pub.download_outputs(plan.tail, st)
+    finally:
+        pub.set_input_sizes({})

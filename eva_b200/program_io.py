@@ -13,7 +13,15 @@ _ATTR = {"rotation": "RotationAttribute", "divisor": "RescaleDivisorAttribute", 
 
 
 def load_json(name):
-    with open(os.path.join(HERE, "golden", "programs", name + ".json")) as f:
+    """a reference-compiled program by name, or any path to a .json / .json.gz dump"""
+    path = name if os.path.sep in name or name.endswith((".json", ".gz")) else os.path.join(HERE, "golden", "programs", name + ".json")
+    if not os.path.exists(path) and os.path.exists(path + ".gz"):
+        path += ".gz"
+    if path.endswith(".gz"):
+        import gzip
+        with gzip.open(path, "rt") as f:
+            return json.load(f)
+    with open(path) as f:
         return json.load(f)
 
 

@@ -103,14 +103,30 @@ class OracleProgram:
         if op == "Rescale": return ("cipher", orc.rescale(x[1]), x[2] / 2.0 ** t["divisor"])   # seal_executor.h:214
         raise RuntimeError("Unhandled op " + op)
 
-    def run(self, inputs, threads=1):
-        """inputs: name -> value tuple.  returns id -> value for every term."""
+    def run(self, inputs, threads=1, keep=None):
+        """inputs: name -> value tuple.  returns id -> value for every term; with keep=<ids> a value is dropped
+        after its last use unless listed (the 16k-term wide DAG would otherwise hold ~10 GB of intermediates)."""
         V = {}
         for tid, name in self.in_names.items():
             V[tid] = inputs[name]
+        left = None
+        if keep is not None:
+            keep = set(keep)
+            left = {}
+            for tid in self.order:
+                for a in self.terms[tid]["args"]:
+                    left[a] = left.get(a, 0) + 1
+
+        def release(tid):
+            for a in self.terms[tid]["args"]:
+                left[a] -= 1
+                if left[a] == 0 and a not in keep:
+                    V.pop(a, None)
         if threads <= 1:
             for tid in self.order:
                 V[tid] = self.exec_term(self.terms[tid], V)
+                if left is not None:
+                    release(tid)
             return V
         uses = {tid: [] for tid in self.order}
         pending = {}
@@ -135,6 +151,8 @@ class OracleProgram:
                 return
             ready = []
             with lock:
+                if left is not None:
+                    release(tid)
                 for u in uses[tid]:
                     pending[u] -= 1
                     if pending[u] == 0:
