@@ -412,114 +412,149 @@ def _tensor(ptr, nbytes):
 
 
 class ShardedRunner:
-    """One rank's side of the staged execution.  Built once per (context, plan): stage plans (arena + captured
-    CUDA graph) of this rank, tensors aliasing the partial-sum slots, gather buffers.  run(inputs) then is:
-    H2D of the inputs this rank needs, and per stage one graph launch + one NCCL collective per cut root."""
+    """One rank's side of the staged execution.  Built once per (context, plan): the stage plans of this rank
+    (arena + captured CUDA graph each), tensors aliasing the partial-sum slots of those arenas, and the
+    schedule of collectives.  run(inputs) is then: H2D of the inputs this rank reads, and per stage one graph
+    launch + one NCCL (all-)gather per cut root, issued on the current CUDA stream; nothing is staged through
+    the host and nothing is allocated."""
 
     def __init__(self, pub, plan, rank, world):
         import torch
-        self.pub, self.plan, self.rank, self.world = pub, plan, rank, world
+        self.torch, self.pub, self.plan, self.rank, self.world = torch, pub, plan, rank, world
         finalize_sizes(plan)
         pub.set_input_sizes(dict(plan.input_sizes))
         try:
-            self.my = []            # per stage: (program or None, io)
-            self.consumers = {}     # root -> list of (program, io) on this rank that read its partials
-            progs = []
-            for st in plan.stages:
-                p = st.progs[rank] if rank < st.nranks else None
-                progs.append(p)
-            if rank == 0:
-                progs.append(plan.tail)
-            self.io = {}
-            for p in progs:
-                if p is not None:
-                    self.io[p.name] = pub.io_pointers(p)
-            for p in progs:
-                if p is None:
-                    continue
-                for nm, (c, r) in plan.partial_names.get(p.name, {}).items():
-                    self.consumers.setdefault(c, [])
-                    if p not in [q for q, _ in self.consumers[c]]:
-                        self.consumers[c].append((p, self.io[p.name]))
-            self.progs = progs
+            self.progs = [(st.progs[rank] if rank < st.nranks else None) for st in plan.stages] + ([plan.tail] if rank == 0 else [])
+            self.io = {p.name: pub.io_pointers(p) for p in self.progs if p is not None}
         finally:
             pub.set_input_sizes({})
         self.bufs = {}
-        self.torch = torch
-
-    def _slots(self, p, io, root, nranks):
-        names = {v: k for k, v in self.plan.partial_names[p.name].items()}
-        return [io["inputs"][names[(root, r)]] for r in range(nranks)]
-
-    def run(self, inputs, stream=None):
-        torch = self.torch
-        import torch.distributed as dist
-        plan, pub, rank, world = self.plan, self.pub, self.rank, self.world
-        st_ptr = torch.cuda.current_stream().cuda_stream if stream is None else stream
-        # inputs of the source program go to every stage program of this rank that reads them
+        self.subsets = {}
+        consumers = {}     # root -> [program] of this rank reading its partials
         for p in self.progs:
-            if p is None:
-                continue
-            sub = _subset(inputs, set(p.inputs) - set(plan.partial_names.get(p.name, {})))
-            pub.stage_inputs(p, [sub], st_ptr)
+            if p is not None:
+                for nm, (c, r) in plan.partial_names.get(p.name, {}).items():
+                    if p not in consumers.setdefault(c, []):
+                        consumers[c].append(p)
+        # static schedule: per stage, per root: (send tensor, optional pre-copy, recv tensor, gather?, post-copies)
+        self.schedule = []
         for si, st in enumerate(plan.stages):
             p = self.progs[si]
             last = si == len(plan.stages) - 1
-            if p is not None:
-                pub.run_resident(p, st_ptr)
+            ops = []
             for root in st.roots:
-                key = "partial_%d" % root
                 sizes = [plan.input_sizes["cut%d_p%d" % (root, r)] for r in range(st.nranks)]
-                ell_bytes = None
-                if p is not None:
-                    o = self.io[p.name]["outputs"][key]
-                    ell_bytes = o["bytes"] // o["size"]
-                cons = self.consumers.get(root, [])
-                if ell_bytes is None:
-                    s0 = self._slots(*cons[0], root, st.nranks)[0] if cons else None
-                    ell_bytes = s0["bytes"] // s0["size"] if s0 else 0
-                nbytes = max(sizes) * ell_bytes
-                if p is not None and o["bytes"] == nbytes:
-                    send = _tensor(o["ptr"], nbytes)
-                else:   # idle rank, or a partial with fewer polynomials than the widest: staged through a buffer
-                    send = self._buf(("send", root), nbytes)
-                    if p is not None:
-                        send[: o["bytes"] // 8].copy_(_tensor(o["ptr"], o["bytes"]))
-                # destination: the slots of the first consumer when they are laid out back to back, else a buffer
-                dst = None
-                direct = False
-                if cons and all(s == max(sizes) for s in sizes) and st.nranks == world:
-                    slots = self._slots(*cons[0], root, st.nranks)
-                    if all(slots[r + 1]["ptr"] - slots[r]["ptr"] == nbytes for r in range(st.nranks - 1)):
-                        dst = _tensor(slots[0]["ptr"], nbytes * world)
-                        direct = True
-                if dst is None:
-                    dst = self._buf(("recv", root), nbytes * world)
-                if last and world > 1:
-                    # the final gather: only rank 0 (the tail) needs the partials
-                    if rank == 0:
-                        dist.gather(send, [dst[r * (nbytes // 8):(r + 1) * (nbytes // 8)] for r in range(world)], dst=0)
-                    else:
-                        dist.gather(send, None, dst=0)
-                elif world > 1:
-                    dist.all_gather_into_tensor(dst, send)
+                cons = consumers.get(root, [])
+                o = self.io[p.name]["outputs"]["partial_%d" % root] if p is not None else None
+                if o is not None:
+                    poly_bytes = o["bytes"] // o["size"]
+                elif cons:
+                    s0 = self._slots(cons[0], root, st.nranks)[0]
+                    poly_bytes = s0["bytes"] // s0["size"]
                 else:
-                    dst[: nbytes // 8].copy_(send)
-                for ci, (cp, cio) in enumerate(cons):
+                    poly_bytes = self._poly_bytes(root)
+                nbytes, words = max(sizes) * poly_bytes, max(sizes) * poly_bytes // 8
+                pre = None
+                if o is not None and o["bytes"] == nbytes:
+                    send = _tensor(o["ptr"], nbytes)
+                else:     # idle rank, or fewer polynomials than the widest partial: through a zero-padded buffer
+                    send = self._buf(("send", root), nbytes)
+                    send.zero_()
+                    if o is not None:
+                        pre = (send[: o["bytes"] // 8], _tensor(o["ptr"], o["bytes"]))
+                recv, direct = None, False
+                need_recv = cons and (not last or rank == 0)
+                if need_recv and all(sz == max(sizes) for sz in sizes) and st.nranks == world:
+                    slots = self._slots(cons[0], root, st.nranks)
+                    if all(slots[r + 1]["ptr"] - slots[r]["ptr"] == nbytes for r in range(st.nranks - 1)):
+                        recv, direct = _tensor(slots[0]["ptr"], nbytes * world), True    # NCCL writes into the consumer's arena
+                if recv is None and (not last or rank == 0 or len(st.roots) > 1):
+                    recv = self._buf(("recv", root), nbytes * world)
+                post = []
+                for ci, cp in enumerate(cons):
                     if direct and ci == 0:
                         continue
-                    slots = self._slots(cp, cio, root, st.nranks)
-                    for r in range(st.nranks):
-                        _tensor(slots[r]["ptr"], slots[r]["bytes"]).copy_(dst[r * (nbytes // 8): r * (nbytes // 8) + slots[r]["bytes"] // 8])
-        if rank != 0:
-            return None
-        pub.run_resident(plan.tail, st_ptr)
-        return pub.download_outputs(plan.tail, st_ptr)
+                    for r, sl in enumerate(self._slots(cp, root, st.nranks)):
+                        post.append((_tensor(sl["ptr"], sl["bytes"]), recv[r * words: r * words + sl["bytes"] // 8]))
+                ops.append({"send": send, "pre": pre, "recv": recv, "words": words, "post": post, "direct": direct})
+            self.schedule.append((p, last, ops))
+
+    def _poly_bytes(self, root):
+        """bytes of one polynomial of cut `root` for a rank that neither produces nor reads it (it still takes
+        part in the collective with a zero buffer): ell residues of N coefficients at the cut's level"""
+        ell = len(self.pub.primes()) - 1 - infer(self.plan.source)[root].level
+        for io in self.io.values():
+            for e in list(io["inputs"].values()) + list(io["outputs"].values()):
+                if e is not None:
+                    return e["bytes"] // e["size"] // e["ell"] * ell
+        raise RuntimeError("rank %d holds no plan of the sharded program" % self.rank)
+
+    def _slots(self, p, root, nranks):
+        names = {v: k for k, v in self.plan.partial_names[p.name].items()}
+        io = self.io[p.name]
+        return [io["inputs"][names[(root, r)]] for r in range(nranks)]
+
+    def _inputs_for(self, inputs):
+        key = id(inputs)
+        if key not in self.subsets:
+            self.subsets.clear()
+            self.subsets[key] = [(p, _subset(inputs, set(p.inputs) - set(self.plan.partial_names.get(p.name, {})))) for p in self.progs if p is not None]
+        return self.subsets[key]
+
+    def run(self, inputs, stream=None):
+        torch, pub, rank, world = self.torch, self.pub, self.rank, self.world
+        import torch.distributed as dist
+        st_ptr = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        trace = os.environ.get("EVAB_TRACE")
+        marks = [("start", time.perf_counter())]
+
+        def mark(name):
+            if trace:
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+        for p, sub in self._inputs_for(inputs):     # H2D of the source inputs into every stage arena that reads them
+            if sub.names():
+                pub.stage_inputs(p, [sub], st_ptr)
+        mark("h2d")
+        for si, (p, last, ops) in enumerate(self.schedule):
+            if p is not None:
+                pub.run_resident(p, st_ptr)
+            mark("stage%d" % si)
+            for op in ops:
+                if op["pre"] is not None:
+                    op["pre"][0].copy_(op["pre"][1])
+            if world > 1:
+                if last and len(ops) == 1:        # the final gather: only rank 0 (the tail) needs the partials
+                    op = ops[0]
+                    w = op["words"]
+                    dist.gather(op["send"], [op["recv"][r * w:(r + 1) * w] for r in range(world)] if rank == 0 else None, dst=0)
+                elif len(ops) == 1:
+                    dist.all_gather_into_tensor(ops[0]["recv"], ops[0]["send"])
+                else:           # several cut roots in one stage: ONE grouped NCCL launch for all of them
+                    with dist._coalescing_manager(device=torch.device("cuda", torch.cuda.current_device())):
+                        for op in ops:
+                            dist.all_gather_into_tensor(op["recv"], op["send"])
+            else:
+                for op in ops:
+                    op["recv"][: op["words"]].copy_(op["send"])
+            for op in ops:
+                for dst, src in op["post"]:
+                    dst.copy_(src)
+            mark("exchange%d" % si)
+        out = None
+        if rank == 0:
+            pub.run_resident(self.plan.tail, st_ptr)
+            mark("tail")
+            out = pub.download_outputs(self.plan.tail, st_ptr)
+            mark("d2h")
+        if trace:
+            print("[evab] sharded rank %d: " % rank + ", ".join("%s %.3f ms" % (n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])), flush=True)
+        return out
 
     def _buf(self, key, nbytes):
         b = self.bufs.get(key)
         if b is None or b.numel() * 8 < nbytes:
-            b = self.torch.empty(nbytes // 8, dtype=self.torch.int64, device="cuda")
+            b = self.torch.zeros(nbytes // 8, dtype=self.torch.int64, device="cuda")
             self.bufs[key] = b
         return b[: nbytes // 8]
 

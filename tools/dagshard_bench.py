@@ -53,13 +53,13 @@ def measure(workload, rank, world, local, steps, warmup):
     res = {"workload": "%s compiled by the reference compiler: N=%d prime_bits=%s, %d ciphertext ops" % (workload, d["poly_modulus_degree"], d["prime_bits"], nops),
            "cipher_ops": nops, "n_gpus": world}
 
-    def timed(fn):
+    def timed(fn, collective=False):
         for _ in range(warmup):
             out = fn()
         torch.cuda.synchronize()
         ts = []
         for _ in range(steps):
-            if world > 1:
+            if collective:       # every rank is here (the single-GPU runs above are rank 0's alone: no barrier there)
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -86,7 +86,8 @@ def measure(workload, rank, world, local, steps, warmup):
                 print(json.dumps(res))
             return res
         runner = dagshard.ShardedRunner(pub, plan, rank, world)
-        out, t_shard = timed(lambda: runner.run(val))
+        dist.barrier()
+        out, t_shard = timed(lambda: runner.run(val), collective=True)
         (t_shard,) = multi.max_over_ranks([t_shard], world, device="cuda")
         if rank == 0:
             same = all(np.array_equal(out.get(o)[1], single.get(o)[1]) for o in d["outputs"])
