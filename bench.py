@@ -24,8 +24,25 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-WORKLOAD = "sobel"          # tests/golden/programs/sobel.json
+WORKLOAD = "sobel"          # workloads/sobel.json: the reference compiler's output for examples/image_processing.py
 METRIC = "ciphertext-ops/sec"
+
+
+def load_workload(name):
+    """a reference-compiled program dump by name (workloads/, then the test fixtures) or by path -- plain json/gzip,
+    so that the CPU reference arm never imports the product package"""
+    import gzip
+    cands = [name] if (os.path.sep in name or name.endswith((".json", ".gz"))) else \
+        [os.path.join(ROOT, dd, name + ext) for dd in ("workloads", os.path.join("tests", "golden", "programs")) for ext in (".json", ".json.gz")]
+    path = next((c for c in cands if os.path.exists(c)), cands[0])
+    with (gzip.open(path, "rt") if path.endswith(".gz") else open(path)) as f:
+        return json.load(f)
+
+
+def bench_config(name, d, nops, B):
+    """identical in both arms (the driver compares them)"""
+    return {"workload": workload_desc(name, d, nops) + "; one step = batch of %d independent program instances (images) per GPU" % B,
+            "instances_per_step": B, "l2": "GPU arm: flushed between timed steps (256 MiB memset, untimed)"}
 
 
 def load_peaks():
@@ -109,18 +126,12 @@ def multi_seed(rank, index):
     return multi.instance_seed(rank, index)
 
 
-def run_ours(args):
-    if args.ntt_cluster is not None:
-        from eva_b200 import cabi
-        assert cabi.load().evab_set_ntt_cluster(args.ntt_cluster) == 0
+def measure_workload(args, name, steps, rank, world, local):
+    """device-resident value, e2e through execute_batch and single-instance latency of one workload"""
     import torch
     import torch.distributed as dist
     from eva_b200 import b200, program_io
-    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    d = program_io.load_json(args.workload)
+    d = load_workload(name)
     B = args.instances
     N = d["poly_modulus_degree"]
     primes = b200.create_coeff_modulus(N, d["prime_bits"])
@@ -189,14 +200,15 @@ def run_ours(args):
     sampler.start()
     # ---- device-resident value: K steps, each bracketed by events, L2 flushed between steps (untimed)
     barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for i in range(args.steps):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
         flush.zero_()
         ev[i][0].record(main)
         step_resident()
         ev[i][1].record(main)
     barrier()
-    t_res = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    step_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    t_res = sum(step_ms) * 1e-3
     # ---- single-instance latency (batch-1 plan, one graph launch, nothing else on the GPU)
     prog0 = prog
     pub.stage_inputs(prog0, all_vals[:1], main.cuda_stream)
@@ -214,7 +226,7 @@ def run_ours(args):
     #      G concurrent execute_batch() calls of F valuations each per step
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         outs = pub.execute_batch(prog, all_vals)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
@@ -229,27 +241,64 @@ def run_ours(args):
         gathered = multi.gather_outputs(oarr, rank, world, device="cuda")
         assert rank != 0 or len(gathered) == world
         t_res, t_e2e = multi.max_over_ranks([t_res, t_e2e], world, device="cuda")
-    total_ops = multi.aggregate_ops(nops, B, args.steps, world)
+    total_ops = multi.aggregate_ops(nops, B, steps, world)
     result = {
-        "metric": METRIC, "value": total_ops / t_res, "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": total_ops / t_res, "unit": "ops/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": t_res / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_desc(args.workload, d, nops) + "; one step = batch of %d independent program instances (images) per GPU" % B,
-                   "instances_per_gpu": B,
+        "config": bench_config(name, d, nops, B),
+        "step_ms": {"median": step_ms[len(step_ms) // 2], "p95": step_ms[min(len(step_ms) - 1, int(0.95 * len(step_ms)))], "min": step_ms[0], "max": step_ms[-1],
+                    "note": "per-step CUDA-event durations on this rank (the headline uses their sum, max over ranks)"},
+        "details": {"instances_per_gpu": B,
                    "parallelism": "replicas x%d GPUs (independent program instances, no data-path collective; NCCL gather of outputs)" % world,
                    "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("%d concurrent cuda-graphs" % G if not args.no_graph else "streams") + " x %d instances fused per kernel launch, %d streams inside a plan" % (F, args.streams),
                    "const_encode": "cached per plan" if not args.no_const_cache else ("every Encode term is evaluated on the GPU inside every execute, as in the reference"
                                     + ("; identical constants share one plaintext and replicated scalars use the one-pass encoder (bit-identical to the FP64 FFT + NTT path)" if not args.no_dedup else ""))},
-        "e2e": {"value": total_ops / t_e2e, "unit": "ops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,
+        "e2e": {"value": total_ops / t_e2e, "unit": "ops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / steps * 1e3,
                 "note": "one B200Public.execute_batch(program, %d host-resident valuations) call per step: %d concurrent plan replicas x %d fused instances, page-locked host buffers, H2D + graph + D2H per replica stream (host wall clock)" % (B, G, F)},
         "single_instance": {"latency_ms": lat[len(lat) // 2], "ops_per_s": nops / (lat[len(lat) // 2] * 1e-3)},
-        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches": int(launches_per_step * steps),
         "clocks": clocks,
     }
+    for g in range(G):
+        pub.drop_plan(prog, F, g)       # release the replicas' arenas before the next workload
+    pub.drop_plan(prog, 1)
+    return result, pub, main
+
+
+def run_ours(args):
+    if args.ntt_cluster is not None:
+        from eva_b200 import cabi
+        assert cabi.load().evab_set_ntt_cluster(args.ntt_cluster) == 0
+    import torch
+    import torch.distributed as dist
+    from eva_b200 import b200
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    result, pub, main = measure_workload(args, args.workload, args.steps, rank, world, local)
+    if world == 1 and not args.no_extras:
+        # BASELINE configs 1 and 4 next to the headline (config 3): same measurement, fewer steps
+        extras = {}
+        for name in ("harris", "polynomial"):
+            if name != args.workload:
+                r, _, _ = measure_workload(args, name, max(5, args.steps // 5), rank, world, local)
+                extras[name] = {"workload": r["config"]["workload"], "value": r["value"], "unit": "ops/s", "ms_per_step": r["ms_per_step"],
+                                "e2e_value": r["e2e"]["value"], "single_instance": r["single_instance"]}
+        result["other_workloads"] = extras
+    if world > 1 and not args.no_dag_sharded:
+        # north_star's other multi-GPU mode: ONE compiled program sharded over the GPUs (BASELINE configs 4 and 5)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import dagshard_bench
+        shard_res = []
+        for wl in ("wide4096", "harris"):
+            shard_res.append(dagshard_bench.measure(wl, rank, world, local, steps=20, warmup=3, quiet=True))
+        result["dag_sharded"] = [{k: r.get(k) for k in ("workload", "cipher_ops", "ms_single_gpu", "ms_sharded", "speedup", "bit_identical", "stages", "note") if k in r} for r in shard_res]
     if rank == 0:
         result["roofline"] = ntt_roofline(pub, b200.create_coeff_modulus(16384, [60] * 4), 16384, main.cuda_stream)   # always the BASELINE shape
         if world == 1 and not args.no_cpu:
-            result["cpu_baseline"] = cpu_baseline(d, B, sample_steps=1)
+            result["cpu_baseline"] = cpu_baseline(load_workload(args.workload), args.instances, sample_steps=1, single_thread=True)
         print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
@@ -299,7 +348,7 @@ def ntt_roofline(pub, primes, N, stream):
             "algorithmic_bytes_per_launch": algo, "launch_ms": ms}
 
 
-def cpu_baseline(d, B, sample_steps=1, threads=None):
+def cpu_baseline(d, B, sample_steps=1, threads=None, single_thread=False):
     """the oracle port of the reference's CPU path on the host cores: the same step
     (a batch of B Sobel instances) scheduled on one dependency-counting thread pool"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -324,17 +373,22 @@ def cpu_baseline(d, B, sample_steps=1, threads=None):
     for _ in range(sample_steps):
         run_many(op, batch, threads)
     dt = time.perf_counter() - t0
-    return {"value": nops * B * sample_steps / dt, "unit": "ops/s", "cores": threads, "kind": "port", "ops_per_instance": nops,
-            "sample": "%d step(s) of %d program instances (%d ops each) on the oracle port (not SEAL), one dependency-counting thread pool over %d threads" % (sample_steps, B, nops, threads),
-            "ms_per_step": dt / sample_steps * 1e3}
+    res = {"value": nops * B * sample_steps / dt, "unit": "ops/s", "cores": threads, "kind": "port", "ops_per_instance": nops,
+           "sample": "%d step(s) of %d program instances (%d ops each) on the oracle port (not SEAL), one dependency-counting thread pool over %d threads" % (sample_steps, B, nops, threads),
+           "ms_per_step": dt / sample_steps * 1e3}
+    if single_thread:      # the 1-thread figure next to the all-core one (one program instance, sequential)
+        t0 = time.perf_counter()
+        op.run(batch[0], threads=1, keep=set())
+        dt1 = time.perf_counter() - t0
+        res["single_thread"] = {"value": nops / dt1, "unit": "ops/s", "cores": 1, "sample": "1 program instance (%d ops), sequential" % nops}
+    return res
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
-    from eva_b200 import program_io  # JSON loader only (no GPU work on this arm)
-    d = program_io.load_json(args.workload)
+    d = load_workload(args.workload)     # plain json: this arm never imports the product package or its libraries
     cb = None
     t0 = time.perf_counter()
     # each step is a bounded sample of the workload: as many program instances of the batch as the host
@@ -346,9 +400,9 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     res = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": workload_desc(args.workload, d, nops) + "; one step = batch of %d independent program instances" % args.instances,
-                      "instances_per_gpu": args.instances, "cpu_sample_instances_per_step": Bs,
-                      "note": "reference SEAL+Galois path cannot be built (SEAL absent); CPU oracle port of the same path, all host threads"},
+           "config": bench_config(args.workload, d, nops, args.instances),
+           "details": {"cpu_sample_instances_per_step": Bs,
+                       "note": "reference SEAL+Galois path cannot be built (SEAL absent); CPU oracle port of the same path, all host threads; each step is a bounded sample of the batch"},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": dt}
     print(json.dumps(res))
 
@@ -368,7 +422,9 @@ def main():
     ap.set_defaults(no_const_cache=True)
     ap.add_argument("--no-dedup", action="store_true", help="encode every Encode term separately even when constants repeat")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default=WORKLOAD, help="fixture under tests/golden/programs (default: the BASELINE workload, sobel); e.g. harris")
+    ap.add_argument("--no-extras", action="store_true", help="skip the Harris / polynomial lines (other_workloads)")
+    ap.add_argument("--no-dag-sharded", action="store_true", help="N > 1: skip the DAG-sharded wide4096 / Harris measurement (dag_sharded)")
+    ap.add_argument("--workload", default=WORKLOAD, help="program under workloads/ (default: the BASELINE workload, sobel); e.g. harris")
     ap.add_argument("--ntt-cluster", type=int, default=None, help="CTAs per residue transform (1, 2, 4); default: library default")
     args = ap.parse_args()
     if args.impl == "reference":

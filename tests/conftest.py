@@ -22,6 +22,11 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     if not hasattr(config, "workerinput"):      # xdist workers inherit the controller's build
         _ensure_built()
+    # the test fixtures (programs compiled by the reference compiler) are found by name next to the shipped workloads
+    from eva_b200 import program_io
+    fixtures = os.path.join(ROOT, "tests", "golden", "programs")
+    if fixtures not in program_io.SEARCH:
+        program_io.SEARCH.append(fixtures)
 
 
 def _have_gpu():

@@ -241,13 +241,16 @@ def main():
         jobs.append(("feat_" + p.name, (p, s, r), None))
     for name, (p, s, r), cfg in jobs:
         d = run(p, s, r, cfg)
+        # the BASELINE workloads ship with the product (workloads/), everything else is a test fixture
+        dest = os.path.join(HERE, "..", "..", "workloads") if name in ("sobel", "harris", "polynomial", "wide4096") else out
+        os.makedirs(dest, exist_ok=True)
         if name == "wide4096":
             import gzip
             d.pop("source", None)    # the 16k-line source dump is reproducible from wide(4096)
-            with gzip.open(os.path.join(out, name + ".json.gz"), "wt") as f:
+            with gzip.open(os.path.join(dest, name + ".json.gz"), "wt") as f:
                 json.dump(d, f, separators=(",", ":"))
         else:
-            with open(os.path.join(out, name + ".json"), "w") as f:
+            with open(os.path.join(dest, name + ".json"), "w") as f:
                 json.dump(d, f, separators=(",", ":"))
         print(name, d.get("error") or (d["poly_modulus_degree"], d["prime_bits"], d["rotations"], len(d["terms"])))
 

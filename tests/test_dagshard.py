@@ -12,6 +12,10 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from eva_b200 import Op, dagshard, evaluate, program_io  # noqa: E402
 
+_FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "programs")
+if _FIX not in program_io.SEARCH:      # also in the spawned gloo workers, which never see conftest.py
+    program_io.SEARCH.append(_FIX)
+
 
 def _close(a, b):
     return all(np.allclose(a[k], b[k], rtol=1e-9, atol=1e-9) for k in b) and set(a) == set(b)

@@ -10,6 +10,10 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from eva_b200 import evaluate, program_io, shard  # noqa: E402
 
+_FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "programs")
+if _FIX not in program_io.SEARCH:      # also in the spawned gloo workers, which never see conftest.py
+    program_io.SEARCH.append(_FIX)
+
 
 def _plain_sharded(prog, plan, x):
     partials = {"partial_%d" % r: evaluate(p, {k: x[k] for k in p.inputs})["partial"] for r, p in enumerate(plan.parts)}

@@ -44,7 +44,7 @@ def setup(workload, local):
     return d, prog, pub, val
 
 
-def measure(workload, rank, world, local, steps, warmup):
+def measure(workload, rank, world, local, steps, warmup, quiet=False):
     import torch
     import torch.distributed as dist
     from eva_b200 import dagshard, multi
@@ -83,7 +83,8 @@ def measure(workload, rank, world, local, steps, warmup):
         if plan is None:
             if rank == 0:
                 res["note"] = "the cost model finds no cut that pays"
-                print(json.dumps(res))
+                if not quiet:
+                    print(json.dumps(res))
             return res
         runner = dagshard.ShardedRunner(pub, plan, rank, world)
         dist.barrier()
@@ -93,7 +94,7 @@ def measure(workload, rank, world, local, steps, warmup):
             same = all(np.array_equal(out.get(o)[1], single.get(o)[1]) for o in d["outputs"])
             res.update({"ms_sharded": t_shard * 1e3, "speedup": res["ms_single_gpu"] / (t_shard * 1e3), "bit_identical": bool(same),
                         "stages": plan.describe(), "exchange": "NCCL all_gather_into_tensor between stages, gather on rank 0 for the last cut; device pointers, no host staging"})
-    if rank == 0:
+    if rank == 0 and not quiet:
         print(json.dumps(res), flush=True)
     return res
 
