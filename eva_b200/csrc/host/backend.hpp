@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include "executor.hpp"
 #include <atomic>
+#include <mutex>
 #include <tuple>
 #include <variant>
 
@@ -52,6 +53,7 @@ struct Shared {
   std::shared_ptr<Device> dev;
   std::unique_ptr<CkksClient> client;
   KeySet keys;
+  std::mutex execMutex;   // serialises execute / executeMany callers of one context (see executeMany)
 };
 
 // the cached plan of one (program, context) pair; owned by the Program
@@ -124,25 +126,36 @@ public:
   }
   void dropExecutor(Program &program, int batch = 1, int replica = 0) { program.attach(planKey(batch, replica), nullptr); }
 
-  // upload host inputs into the executor's arena (H2D on `stream`)
+  // upload host inputs into the executor's arena (H2D on `stream`).  Client-supplied valuations are untrusted
+  // (they may come from a file): every buffer is checked against the shape the plan expects before any copy.
   void stageInputs(Executor &ex, Program &program, const B200Valuation &inputs, void *stream, int b = 0) {
     const u64 N = s_->dev->N();
     for (auto &in : inputs) {
       auto term = program.getInput(in.first);
       const ValueInfo &vi = ex.info(term);
       if (auto *c = std::get_if<HostCipher>(&in.second)) {
-        if (vi.kind != Kind::Cipher || c->ell != vi.ell || c->size != vi.size) throw std::runtime_error("input " + in.first + ": ciphertext does not match the program signature");
+        if (vi.kind != Kind::Cipher || c->ell != vi.ell || c->size != vi.size || c->data.size() != (std::size_t)vi.size * vi.ell * N)
+          throw std::runtime_error("input " + in.first + ": ciphertext does not match the program signature");
         s_->dev->upload(ex.valuePtr(term, b), c->data.data(), c->data.size() * 8, stream);
       } else if (auto *p = std::get_if<HostPlain>(&in.second)) {
-        if (vi.kind != Kind::Plain || p->ell != vi.ell) throw std::runtime_error("input " + in.first + ": plaintext does not match the program signature");
+        if (vi.kind != Kind::Plain || p->ell != vi.ell || p->data.size() != (std::size_t)vi.ell * N)
+          throw std::runtime_error("input " + in.first + ": plaintext does not match the program signature");
         s_->dev->upload(ex.valuePtr(term, b), p->data.data(), (std::size_t)p->ell * N * 8, stream);
       } else {
+        if (vi.kind != Kind::Raw) throw std::runtime_error("input " + in.first + ": raw vector does not match the program signature");
         auto &cv = std::get<std::shared_ptr<ConstantValue>>(in.second);
         std::vector<double> x;
         cv->expandTo(x, program.getVecSize());
         ex.setRawInput(in.first, x, b);
       }
     }
+  }
+  // plans and arenas are cached on the Program: a call that omits an input would silently compute on the previous
+  // call's ciphertext.  The reference builds a fresh executor per call and fails on the missing value
+  // (seal_executor.h:264); so does this.
+  static void requireAllInputs(Program &program, const B200Valuation &inputs) {
+    for (auto &in : program.getInputs())
+      if (inputs.values.find(in.first) == inputs.values.end()) throw std::runtime_error("Missing input value: " + in.first);
   }
   // SEALPublic::execute -- reference eva/seal/seal.cpp:104-122.  Host buffers in,
   // host buffers out: H2D of the inputs, the DAG on the GPU, D2H of the outputs.
@@ -164,6 +177,10 @@ public:
   std::vector<B200Valuation> executeMany(Program &program, const std::vector<const B200Valuation *> &inputs) {
     const int B = (int)inputs.size();
     if (B < 1) throw std::invalid_argument("execute needs at least one valuation");
+    for (auto *v : inputs) requireAllInputs(program, *v);
+    // one caller at a time per context: plan replicas own single arenas and raw-input buffers (the reference's
+    // execute is re-entrant because it builds a new executor per call; concurrent callers are serialised here)
+    std::lock_guard<std::mutex> guard(s_->execMutex);
     const int F = std::max(1, std::min(options.fuse, B));
     std::vector<B200Valuation> outs(B);
     std::vector<void *> streams;
@@ -277,7 +294,8 @@ generateKeys(const CKKSParameters &params, int device = 0, std::uint64_t seed = 
   auto primes = hmod::createCoeffModulus(params.polyModulusDegree, bits);
   auto s = std::make_shared<Shared>();
   s->dev = std::make_shared<Device>(params.polyModulusDegree, primes, device);
-  if (!seed) { std::random_device rd; seed = ((std::uint64_t)rd() << 32) ^ rd(); }
+  // seed == 0 (the default): keys and encryption randomness from a CSPRNG keyed with 256 bits of OS entropy;
+  // a non-zero seed is the deterministic test path (host/csprng.hpp)
   s->client = std::make_unique<CkksClient>(s->dev, seed);
   std::vector<int> rots(params.rotations.begin(), params.rotations.end());
   s->client->keygen(s->keys, rots);

@@ -9,6 +9,7 @@
 #include "runtime.hpp"
 #include <cmath>
 #include <random>
+#include "csprng.hpp"
 
 namespace evab {
 
@@ -212,12 +213,14 @@ struct KeySet {
 
 class CkksClient {
 public:
+  // seed == 0: ChaCha20 stream keyed with 256 bits of OS entropy (the secure default); any other value: a deterministic
+  // stream for reproducible tests and fixtures ONLY (csprng.hpp)
   CkksClient(std::shared_ptr<Device> dev, std::uint64_t seed) : dev_(std::move(dev)), enc_(dev_), rng_(seed), N_(dev_->N()), k_(dev_->k()) {}
   CkksEncoder &encoder() { return enc_; }
 
   void keygen(KeySet &K, const std::vector<int> &rotationSteps) {
     std::vector<int> s(N_);
-    for (auto &v : s) v = (int)(rng_() % 3) - 1;  // uniform ternary
+    for (auto &v : s) v = (int)rng_.below(3) - 1;  // uniform ternary
     K.sk = smallToDeviceNtt(s, k_);
     K.pk = DBuf(dev_, (std::size_t)2 * k_ * N_);
     encZeroSym(K, K.pk.get(), K.pk.get() + (std::size_t)k_ * N_);
@@ -241,7 +244,7 @@ public:
     if (ell < 1 || ell > k_ - 1) throw std::invalid_argument("encryption level out of range");
     const int nres = ell + 1;
     std::vector<int> u(N_);
-    for (auto &v : u) v = (int)(rng_() % 3) - 1;
+    for (auto &v : u) v = (int)rng_.below(3) - 1;
     DBuf ud = smallToDeviceNtt(u, nres);
     DBuf big(dev_, (std::size_t)2 * nres * N_);
     for (int c = 0; c < 2; c++) {
@@ -351,7 +354,7 @@ private:
 
   std::shared_ptr<Device> dev_;
   CkksEncoder enc_;
-  std::mt19937_64 rng_;
+  ChaChaRng rng_;
   u64 N_;
   int k_;
 };

@@ -18,6 +18,14 @@ typedef py::array_t<std::uint64_t, py::array::c_style | py::array::forcecast> u6
 static std::vector<u64> toVec(const u64arr &a) { return std::vector<u64>(a.data(), a.data() + a.size()); }
 static HostBuf toHostBuf(const u64arr &a) { HostBuf b(a.size()); std::memcpy(b.data(), a.data(), a.size() * 8); return b; }
 
+// key material loaded from files / callers: shapes are checked against (k, N) before anything reaches the device
+static void requireShape(const u64arr &a, std::initializer_list<std::size_t> shape, const char *what) {
+  bool ok = (std::size_t)a.ndim() == shape.size();
+  std::size_t i = 0;
+  for (std::size_t d : shape) { if (ok && (std::size_t)a.shape(i) != d) ok = false; i++; }
+  if (!ok) throw std::runtime_error(std::string(what) + " does not match the parameters (modulus count / degree)");
+}
+
 PYBIND11_MODULE(_eva_b200, m) {
   m.doc() = "B200-native EVA backend";
 
@@ -111,6 +119,7 @@ PYBIND11_MODULE(_eva_b200, m) {
         v[name] = std::move(h);
       }, "test/benchmark hook: inject a raw ciphertext [size][ell][N]")
       .def("set_plain", [](B200Valuation &v, const std::string &name, const u64arr &data, double scale) {
+        if (data.ndim() != 2) throw std::runtime_error("plaintext array must be [ell][N]");
         HostPlain h; h.data = toHostBuf(data); h.ell = (int)data.shape(0); h.scale = scale; v[name] = std::move(h);
       })
       .def("set_raw", [](B200Valuation &v, const std::string &name, const std::vector<double> &x) { v[name] = std::make_shared<ConstantValue>(x.size(), x); })
@@ -276,7 +285,10 @@ PYBIND11_MODULE(_eva_b200, m) {
   mb.def("context_from_raw_keys", [](std::uint64_t N, const std::vector<u64> &primes, const u64arr &relin, const std::map<u64, u64arr> &galois, int device) {
     auto s = std::make_shared<Shared>();
     s->dev = std::make_shared<Device>(N, primes, device);
-    s->client = std::make_unique<CkksClient>(s->dev, 1);
+    s->client = std::make_unique<CkksClient>(s->dev, 0);   // evaluation context; any encryption through it draws OS entropy
+    const std::size_t kk = primes.size();
+    requireShape(relin, {kk - 1, 2, kk, (std::size_t)N}, "relinearization key");
+    for (auto &g : galois) requireShape(g.second, {kk - 1, 2, kk, (std::size_t)N}, "Galois key");
     s->keys.relin = DBuf(s->dev, relin.size());
     s->dev->upload(s->keys.relin.get(), relin.data(), relin.size() * 8);
     for (auto &g : galois) {
@@ -292,11 +304,12 @@ PYBIND11_MODULE(_eva_b200, m) {
   mb.def("public_from_raw", [](std::uint64_t N, const std::vector<u64> &primes, py::object pk, py::object relin, const std::map<u64, u64arr> &galois, int device) {
     auto s = std::make_shared<Shared>();
     s->dev = std::make_shared<Device>(N, primes, device);
-    std::random_device rd;
-    s->client = std::make_unique<CkksClient>(s->dev, ((std::uint64_t)rd() << 32) ^ rd());
+    s->client = std::make_unique<CkksClient>(s->dev, 0);   // OS entropy (csprng.hpp)
     auto up = [&](DBuf &dst, const u64arr &a) { dst = DBuf(s->dev, a.size()); s->dev->upload(dst.get(), a.data(), a.size() * 8); s->dev->sync(); };
-    if (!pk.is_none()) up(s->keys.pk, py::cast<u64arr>(pk));
-    if (!relin.is_none()) up(s->keys.relin, py::cast<u64arr>(relin));
+    const std::size_t kk = primes.size();
+    if (!pk.is_none()) { requireShape(py::cast<u64arr>(pk), {2, kk, (std::size_t)N}, "public key"); up(s->keys.pk, py::cast<u64arr>(pk)); }
+    if (!relin.is_none()) { requireShape(py::cast<u64arr>(relin), {kk - 1, 2, kk, (std::size_t)N}, "relinearization key"); up(s->keys.relin, py::cast<u64arr>(relin)); }
+    for (auto &g : galois) requireShape(g.second, {kk - 1, 2, kk, (std::size_t)N}, "Galois key");
     for (auto &g : galois) {
       check(evab_galois_prepare(s->dev->ctx(), g.first));
       DBuf d;
@@ -308,7 +321,8 @@ PYBIND11_MODULE(_eva_b200, m) {
   mb.def("secret_from_raw", [](std::uint64_t N, const std::vector<u64> &primes, const u64arr &sk, int device) {
     auto s = std::make_shared<Shared>();
     s->dev = std::make_shared<Device>(N, primes, device);
-    s->client = std::make_unique<CkksClient>(s->dev, 1);
+    s->client = std::make_unique<CkksClient>(s->dev, 0);
+    requireShape(sk, {primes.size(), (std::size_t)N}, "secret key");
     s->keys.sk = DBuf(s->dev, sk.size());
     s->dev->upload(s->keys.sk.get(), sk.data(), sk.size() * 8);
     s->dev->sync();
