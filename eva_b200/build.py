@@ -41,8 +41,8 @@ def build(force=False, verbose=False):
         import pybind11
         import sysconfig
         cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fvisibility=hidden",
-               "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"],
-               os.path.join(HOST, "pymodule.cpp"), "-o", ext, "-L" + LIBDIR, "-levab200", "-Wl,-rpath,$ORIGIN/lib"]
+               "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"], "-I" + os.path.join(os.path.dirname(NVCC), "..", "include"),
+               os.path.join(HOST, "pymodule.cpp"), "-o", ext, "-L" + LIBDIR, "-levab200", "-ldl", "-Wl,-rpath,$ORIGIN/lib"]
         subprocess.check_call(cmd)
     return LIB
 

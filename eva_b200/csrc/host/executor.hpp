@@ -13,6 +13,8 @@
 #pragma once
 #include "ckks_client.hpp"
 #include "ir.hpp"
+#include "logging.hpp"
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -113,7 +115,7 @@ public:
   // (graph launch or multi-stream replay); does not synchronise.
   void run(void *stream) {
     if (rawDirty_) { evalRawAndEncodes(stream); rawDirty_ = false; }
-    if (opt_.useGraph) {
+    if (opt_.useGraph && verbosity() < 2) {   // debug verbosity: step-by-step replay so that every term is reported
       if (!graph_ || !graphValid_) capture();
       check(evab_graph_launch(dev_->ctx(), graph_, stream));
     } else {
@@ -549,8 +551,33 @@ private:
                       arena_.get() + g.workOff, stream));
   }
   // ---------------------------------------------------------------- execution
+  // Tracing (reference eva/seal/seal_executor.h:280-294 prints every term at EVA_VERBOSITY >= debug; SURVEY section 5
+  // asks for NVTX ranges): with EVA_VERBOSITY=debug the plan is replayed step by step (no CUDA graph) and every
+  // step prints the reference's line -- followed by the stream it was issued on -- and is wrapped in an NVTX range
+  // named after its term, so that nsys / ncu timelines read in program terms.  EVAB_NVTX=1 gives the ranges alone.
+  struct TraceScope {
+    bool nvtx;
+    TraceScope(const Step &st, bool print, bool nvtx_) : nvtx(nvtx_) {
+      if (!print && !nvtx) return;
+      char name[96];
+      const Term &t = *st.term;
+      if (st.op == Op::Undef) std::snprintf(name, sizeof(name), "t%lu.hoist", (unsigned long)t.index);
+      else std::snprintf(name, sizeof(name), "t%lu %s%s", (unsigned long)t.index, opName(t.op), st.sum.empty() ? "" : "(fused sum)");
+      if (print) {
+        std::printf("EVA: Execute t%lu = %s(", (unsigned long)t.index, st.op == Op::Undef ? "InverseNTT" : opName(t.op));
+        bool first = true;
+        for (auto &o : t.getOperands()) { std::printf(first ? "t%lu" : ",t%lu", (unsigned long)o->index); first = false; }
+        std::printf(")  [stream %d%s]\n", st.stream, st.sum.empty() ? "" : ", fused sum");
+        std::fflush(stdout);
+      }
+      if (nvtx) nvtxRangePushA(name);
+    }
+    ~TraceScope() { if (nvtx) nvtxRangePop(); }
+  };
+  static bool traceNvtx() { static const bool v = std::getenv("EVAB_NVTX") != nullptr || verbosity() >= 2; return v; }
   void issue(const Step &st, void *stream) {
     const Term &t = *st.term;
+    TraceScope trace(st, verbosity() >= 2, traceNvtx());
     evab_ctx *c = dev_->ctx();
     const ValueInfo &o = vals_[t.index];
     u64 *out = arena_.get() + o.off;

@@ -258,3 +258,34 @@ def test_randomness_default_is_os_entropy_and_seed_is_reproducible():
     # uniform halves of the public key look uniform: mean of the top byte near 127.5 is too weak a test to be worth it;
     # check instead that no residue repeats between the two independently keyed contexts
     assert len(np.intersect1d(pk(a)[1, 0, :256], pk(b)[1, 0, :256])) == 0
+
+
+def test_debug_verbosity_prints_every_executed_term():
+    """EVA_VERBOSITY=debug: the reference prints `EVA: Execute t<i> = <Op>(t<j>,...)` per term
+    (eva/seal/seal_executor.h:280-294); so does the plan replay (with the stream it went to), inside NVTX ranges"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "from eva import EvaProgram, Input, Output\n"
+        "from eva.ckks import CKKSCompiler\n"
+        "from eva.seal import generate_keys\n"
+        "p = EvaProgram('poly', vec_size=64)\n"
+        "with p:\n"
+        "    x = Input('x')\n"
+        "    Output('y', 3 * x ** 2 + 5 * x - 2)\n"
+        "p.set_output_ranges(30); p.set_input_scales(30)\n"
+        "c, params, sig = CKKSCompiler({'warn_vec_size': 'false'}).compile(p)\n"
+        "pub, sec = generate_keys(params)\n"
+        "out = sec.decrypt(pub.execute(c, pub.encrypt({'x': [0.5] * 64}, sig)), sig)\n"
+        "print('RESULT', out['y'][0])\n")
+    env = dict(os.environ, EVA_VERBOSITY="debug", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("EVA: Execute t")]
+    ops = {l.split("= ")[1].split("(")[0] for l in lines}
+    assert {"Mul", "Relinearize", "Rescale", "Add"} <= ops, ops
+    assert all("[stream " in l for l in lines)
+    res = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
+    assert abs(float(res[0].split()[1]) - (3 * 0.25 + 2.5 - 2)) < 1e-3
