@@ -126,12 +126,12 @@ def multi_seed(rank, index):
     return multi.instance_seed(rank, index)
 
 
-def measure_workload(args, name, steps, rank, world, local):
+def measure_workload(args, wl, steps, rank, world, local):
     """device-resident value, e2e through execute_batch and single-instance latency of one workload"""
     import torch
     import torch.distributed as dist
     from eva_b200 import b200, program_io
-    d = load_workload(name)
+    d = load_workload(wl)
     B = args.instances
     N = d["poly_modulus_degree"]
     primes = b200.create_coeff_modulus(N, d["prime_bits"])
@@ -246,7 +246,7 @@ def measure_workload(args, name, steps, rank, world, local):
         "metric": METRIC, "value": total_ops / t_res, "unit": "ops/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
         "ms_per_step": t_res / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": bench_config(name, d, nops, B),
+        "config": bench_config(wl, d, nops, B),
         "step_ms": {"median": step_ms[len(step_ms) // 2], "p95": step_ms[min(len(step_ms) - 1, int(0.95 * len(step_ms)))], "min": step_ms[0], "max": step_ms[-1],
                     "note": "per-step CUDA-event durations on this rank (the headline uses their sum, max over ranks)"},
         "details": {"instances_per_gpu": B,

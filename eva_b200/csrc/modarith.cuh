@@ -212,3 +212,25 @@ EVAB_HD void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
   lo += pl;
   hi += ph + (lo < pl);
 }
+
+// any 128-bit value (hi:lo) -> canonical [0,p) for a fold-friendly prime: 2^64 == 8 eps (mod p), so
+//   y  = lo + hi * 8eps            (94 bits: three wide multiplies' worth of work instead of a 128-bit Barrett
+//   y' = y_lo64 + y_hi30 * 8eps     quotient -- 5 IMAD.WIDE against ~20 multiply instructions)
+//   r  = (y' mod 2^61) + (y' >> 61) * eps,   then fold_canon.
+EVAB_HD u64 fold_reduce128(u64 lo, u64 hi, u32 eps, u64 p) {
+  const u32 e64 = eps << 3;
+  const u64 m0 = madw32((u32)hi, e64, 0), m1 = madw32((u32)(hi >> 32), e64, 0);   // hi * 8eps = m0 + m1 * 2^32
+  const u64 s = lo + m0;
+  const u64 t = s + (m1 << 32);
+  const u64 yh = (m1 >> 32) + (u64)(s < lo) + (u64)(t < s);                       // < 2^30
+  const u64 v = t + madw32((u32)yh, e64, 0);
+  const u32 c2 = (u32)(v < t);
+  const u64 r = madw32((u32)(v >> 61) + 8u * c2, eps, v & ((1ull << 61) - 1));  // < 2^61 + 2^30
+  return fold_canon(r, eps, p);
+}
+// reductions used by the element-wise kernels: fold arithmetic when the prime allows it, Barrett otherwise
+EVAB_HD u64 reduce128(u64 lo, u64 hi, const PrimeDev &P) {
+  return P.foldable ? fold_reduce128(lo, hi, P.eps, P.p) : barrett128_wide(lo, hi, P.p, P.ratio_lo, P.ratio_hi);
+}
+EVAB_HD u64 mulmod_p(u64 a, u64 b, const PrimeDev &P) { return reduce128(a * b, mulhi64(a, b), P); }
+

@@ -37,7 +37,7 @@ template <int OP> EVAB_HD void dyadic_elem(const DyArgs &A, int res, int j, long
   else if (OP == DY_SUB) { r.x = submod(va.x, vb.x, p); r.y = submod(va.y, vb.y, p); }
   else if (OP == DY_NEG) { r.x = negmod(va.x, p); r.y = negmod(va.y, p); }
   else if (OP == DY_COPY) { r = va; }
-  else { r.x = mulmod(va.x, vb.x, p, P.ratio_lo, P.ratio_hi); r.y = mulmod(va.y, vb.y, p, P.ratio_lo, P.ratio_hi); }
+  else { r.x = mulmod_p(va.x, vb.x, P); r.y = mulmod_p(va.y, vb.y, P); }
   st2(A.out + boff + off + j, r);
 }
 
@@ -88,8 +88,8 @@ EVAB_HD void sum_terms_elem(const SumArgs &A, int res, int j, long long off) {
     }
   }
   u64x2 r;
-  r.x = barrett128_wide(lx, hx, P.p, P.ratio_lo, P.ratio_hi);
-  r.y = barrett128_wide(ly, hy, P.p, P.ratio_lo, P.ratio_hi);
+  r.x = reduce128(lx, hx, P);
+  r.y = reduce128(ly, hy, P);
   st2(A.out + off + (size_t)res * A.N + j, r);
 }
 
@@ -98,26 +98,26 @@ struct MulArgs { u64 *out; const u64 *a; const u64 *b; const PrimeDev *primes; i
 // 2x2 -> 3 tensor product (Evaluator::multiply) or square, residue i, coeffs j,j+1
 template <bool SQUARE> EVAB_HD void mulct_elem(const MulArgs &A, int i, int j, long long boff = 0) {
   const PrimeDev P = A.primes[i];
-  const u64 p = P.p, rl = P.ratio_lo, rh = P.ratio_hi;
+  const u64 p = P.p;
   const size_t poly = (size_t)A.ell * A.N, off = (size_t)i * A.N + j;
   const u64 *pa = A.a + boff, *pb = SQUARE ? nullptr : A.b + boff;
   u64 *po = A.out + boff;
   const u64x2 a0 = ld2(pa + off), a1 = ld2(pa + poly + off);
   u64x2 d0, d1, d2;
   if (SQUARE) {
-    d0.x = mulmod(a0.x, a0.x, p, rl, rh); d0.y = mulmod(a0.y, a0.y, p, rl, rh);
-    u64 x0 = mulmod(a0.x, a1.x, p, rl, rh), x1 = mulmod(a0.y, a1.y, p, rl, rh);
+    d0.x = mulmod_p(a0.x, a0.x, P); d0.y = mulmod_p(a0.y, a0.y, P);
+    u64 x0 = mulmod_p(a0.x, a1.x, P), x1 = mulmod_p(a0.y, a1.y, P);
     d1.x = addmod(x0, x0, p); d1.y = addmod(x1, x1, p);
-    d2.x = mulmod(a1.x, a1.x, p, rl, rh); d2.y = mulmod(a1.y, a1.y, p, rl, rh);
+    d2.x = mulmod_p(a1.x, a1.x, P); d2.y = mulmod_p(a1.y, a1.y, P);
   } else {
     const u64x2 b0 = ld2(pb + off), b1 = ld2(pb + poly + off);
-    d0.x = mulmod(a0.x, b0.x, p, rl, rh); d0.y = mulmod(a0.y, b0.y, p, rl, rh);
+    d0.x = mulmod_p(a0.x, b0.x, P); d0.y = mulmod_p(a0.y, b0.y, P);
     // a0*b1 + a1*b0 accumulated in 128 bits, then one reduction: same canonical value
     u64 lo = 0, hi = 0;
-    mac128(lo, hi, a0.x, b1.x); mac128(lo, hi, a1.x, b0.x); d1.x = barrett128(lo, hi, p, rl, rh);
+    mac128(lo, hi, a0.x, b1.x); mac128(lo, hi, a1.x, b0.x); d1.x = reduce128(lo, hi, P);
     lo = hi = 0;
-    mac128(lo, hi, a0.y, b1.y); mac128(lo, hi, a1.y, b0.y); d1.y = barrett128(lo, hi, p, rl, rh);
-    d2.x = mulmod(a1.x, b1.x, p, rl, rh); d2.y = mulmod(a1.y, b1.y, p, rl, rh);
+    mac128(lo, hi, a0.y, b1.y); mac128(lo, hi, a1.y, b0.y); d1.y = reduce128(lo, hi, P);
+    d2.x = mulmod_p(a1.x, b1.x, P); d2.y = mulmod_p(a1.y, b1.y, P);
   }
   st2(po + off, d0); st2(po + poly + off, d1); st2(po + 2 * poly + off, d2);
 }
@@ -152,8 +152,8 @@ EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j, long long off = 0) {
   }
   u64x2 r0, r1;
   // ext operands may be lazily reduced (< 16p, see EPI_STORE_LAZY): wide reduction
-  r0.x = barrett128_wide(l0x, h0x, P.p, P.ratio_lo, P.ratio_hi); r0.y = barrett128_wide(l0y, h0y, P.p, P.ratio_lo, P.ratio_hi);
-  r1.x = barrett128_wide(l1x, h1x, P.p, P.ratio_lo, P.ratio_hi); r1.y = barrett128_wide(l1y, h1y, P.p, P.ratio_lo, P.ratio_hi);
+  r0.x = reduce128(l0x, h0x, P); r0.y = reduce128(l0y, h0y, P);
+  r1.x = reduce128(l1x, h1x, P); r1.y = reduce128(l1y, h1y, P);
   st2(A.acc + off + ((size_t)0 * (A.ell + 1) + mi) * N + j, r0);
   st2(A.acc + off + ((size_t)1 * (A.ell + 1) + mi) * N + j, r1);
 }
