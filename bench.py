@@ -338,7 +338,7 @@ def ntt_roofline(pub, primes, N, stream):
     # DRAM traffic of the same launch from the committed ncu --set full capture (profiles/)
     traffic, traffic_src = None, None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_ntt_fwd_final.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_ntt_fwd.json")))
         if prof.get("residues_per_launch") == cnt:
             traffic, traffic_src = prof["traffic_bytes_per_launch"], prof["source"]
     except Exception:

@@ -180,8 +180,13 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::
 }
 template <int OP> __global__ void __launch_bounds__(256) k_dyadic(const DyArgs A, const long long bstride) {
   const long long off = (long long)blockIdx.z * bstride;
-  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4; j < A.N; j += gridDim.x * blockDim.x * 4)
     dyadic_elem<OP>(A, blockIdx.y, j, off);
+}
+__global__ void __launch_bounds__(256) k_mul_plain(const DyArgs A, const long long bstride) {
+  const long long off = (long long)blockIdx.z * bstride;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4; j < A.N; j += gridDim.x * blockDim.x * 4)
+    mulpt_elem(A, blockIdx.y, j, off);
 }
 template <bool SQ> __global__ void __launch_bounds__(256) k_mul_ct(const MulArgs A, const long long bstride) {
   const long long off = (long long)blockIdx.z * bstride;
@@ -323,8 +328,8 @@ struct CudaBE {
   cudaStream_t st;
   int error(const char *m) { return fail(m); }
   void count(unsigned n = 1) const { c->launches.fetch_add(n, std::memory_order_relaxed); }
-  dim3 grid(int rows) const {
-    int per_row = (int)(c->v.N / 2 / 256);
+  dim3 grid(int rows, int per_thread = 2) const {
+    int per_row = (int)(c->v.N / per_thread / 256);
     if (per_row < 1) per_row = 1;
     return dim3(per_row, rows, g_batch.batch);
   }
@@ -356,13 +361,13 @@ struct CudaBE {
   }
   int dyadic(int op, const DyArgs &A) {
     count();
-    dim3 g = grid(A.sout * A.ell);
+    dim3 g = grid(A.sout * A.ell, 4);
     switch (op) {
       case DY_ADD: k_dyadic<DY_ADD><<<g, 256, 0, st>>>(A, g_batch.stride); break;
       case DY_SUB: k_dyadic<DY_SUB><<<g, 256, 0, st>>>(A, g_batch.stride); break;
       case DY_NEG: k_dyadic<DY_NEG><<<g, 256, 0, st>>>(A, g_batch.stride); break;
       case DY_COPY: k_dyadic<DY_COPY><<<g, 256, 0, st>>>(A, g_batch.stride); break;
-      default: k_dyadic<DY_MULPT><<<g, 256, 0, st>>>(A, g_batch.stride); break;
+      default: k_mul_plain<<<grid(A.ell, 4), 256, 0, st>>>(A, g_batch.stride); break;   // one thread: the same coefficients of every polynomial
     }
     CUDA_OK(cudaGetLastError());
     return 0;

@@ -18,8 +18,24 @@ struct DyArgs {
 
 EVAB_HD u64x2 ld2(const u64 *p) { return *reinterpret_cast<const u64x2 *>(p); }
 EVAB_HD void st2(u64 *p, u64x2 v) { *reinterpret_cast<u64x2 *>(p) = v; }
+// 4 contiguous coefficients = one 256-bit global access
+EVAB_HD void load4g(u64 (&a)[4], const u64 *p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a[0]), "=l"(a[1]), "=l"(a[2]), "=l"(a[3]) : "l"(p));
+#else
+  for (int k = 0; k < 4; k++) a[k] = p[k];
+#endif
+}
+EVAB_HD void store4g(u64 *p, const u64 (&a)[4]) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]) : "memory");
+#else
+  for (int k = 0; k < 4; k++) p[k] = a[k];
+#endif
+}
 
-// coefficients j, j+1 of output residue `res` (= s*ell + i)
+// coefficients j .. j+3 of output residue `res` (= s*ell + i): one 256-bit access per operand (a full 32-byte
+// sector per lane, twice the bytes in flight of the 128-bit version: multiply_plain went from 54 % to HBM-bound)
 // boff: batch instance offset (words) applied to every ciphertext / plaintext pointer
 template <int OP> EVAB_HD void dyadic_elem(const DyArgs &A, int res, int j, long long boff = 0) {
   const int s = res / A.ell, i = res % A.ell;
@@ -30,15 +46,33 @@ template <int OP> EVAB_HD void dyadic_elem(const DyArgs &A, int res, int j, long
   const bool has_a = s < A.sa;
   const bool has_b = A.b_is_plain ? (OP == DY_MULPT || s == 0) : (s < A.sb);
   const size_t poff = A.b_is_plain ? (size_t)i * A.N : off;
-  u64x2 va = u64x2{0, 0}, vb = u64x2{0, 0}, r;
-  if (has_a) va = ld2(A.a + boff + aoff + j);
-  if (OP != DY_NEG && OP != DY_COPY && has_b) vb = ld2(A.b + boff + poff + j);
-  if (OP == DY_ADD) { r.x = addmod(va.x, vb.x, p); r.y = addmod(va.y, vb.y, p); }
-  else if (OP == DY_SUB) { r.x = submod(va.x, vb.x, p); r.y = submod(va.y, vb.y, p); }
-  else if (OP == DY_NEG) { r.x = negmod(va.x, p); r.y = negmod(va.y, p); }
-  else if (OP == DY_COPY) { r = va; }
-  else { r.x = mulmod_p(va.x, vb.x, P); r.y = mulmod_p(va.y, vb.y, P); }
-  st2(A.out + boff + off + j, r);
+  u64 va[4] = {0, 0, 0, 0}, vb[4] = {0, 0, 0, 0}, r[4];
+  if (has_a) load4g(va, A.a + boff + aoff + j);
+  if (OP != DY_NEG && OP != DY_COPY && has_b) load4g(vb, A.b + boff + poff + j);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (OP == DY_ADD) r[e] = addmod(va[e], vb[e], p);
+    else if (OP == DY_SUB) r[e] = submod(va[e], vb[e], p);
+    else if (OP == DY_NEG) r[e] = negmod(va[e], p);
+    else if (OP == DY_COPY) r[e] = va[e];
+    else r[e] = mulmod_p(va[e], vb[e], P);
+  }
+  store4g(A.out + boff + off + j, r);
+}
+
+// Evaluator::multiply_plain: coefficients j .. j+3 of residue i of EVERY polynomial of the ciphertext -- the plaintext
+// is loaded once per thread instead of once per polynomial (algorithmic traffic (2s + 1) ell R)
+EVAB_HD void mulpt_elem(const DyArgs &A, int i, int j, long long boff = 0) {
+  const PrimeDev P = A.primes[i];
+  u64 w[4];
+  load4g(w, A.b + boff + (size_t)i * A.N + j);
+  for (int s = 0; s < A.sa; s++) {
+    u64 v[4];
+    load4g(v, A.a + boff + ((size_t)s * A.a_ell + i) * A.N + j);
+#pragma unroll
+    for (int e = 0; e < 4; e++) v[e] = mulmod_p(v[e], w[e], P);
+    store4g(A.out + boff + ((size_t)s * A.ell + i) * A.N + j, v);
+  }
 }
 
 // fused sum of terms; term t is  ct[t]                      (kind 0: Evaluator::add operand),

@@ -125,8 +125,13 @@ struct EmuBE {
     return 0;
   }
   int dyadic(int op, const DyArgs &A) {
+    if (op == DY_MULPT) {
+      for (int i = 0; i < A.ell; i++)
+        for (int j = 0; j < A.N; j += 4) mulpt_elem(A, i, j);
+      return 0;
+    }
     for (int res = 0; res < A.sout * A.ell; res++)
-      for (int j = 0; j < A.N; j += 2) switch (op) {
+      for (int j = 0; j < A.N; j += 4) switch (op) {
           case DY_ADD: dyadic_elem<DY_ADD>(A, res, j); break;
           case DY_SUB: dyadic_elem<DY_SUB>(A, res, j); break;
           case DY_NEG: dyadic_elem<DY_NEG>(A, res, j); break;

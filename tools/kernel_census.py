@@ -1,0 +1,86 @@
+"""One launch of every kernel of the evaluator at the Sobel shape (N = 16384, level-0 ell = 4, 64 instances per launch),
+inside a cudaProfiler range, for the per-kernel ncu table of profiles/ (run under gpurun):
+
+    ncu --profile-from-start off --metrics <see tools/kernel_census_report.py> --csv --log-file gpurun_out/census.csv python tools/kernel_census.py
+
+Prints one JSON line per op with the algorithmic bytes per launch so that the report can set measured DRAM
+traffic against them."""
+import ctypes as C, json, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+from eva_b200 import cabi
+from tools.microbench import gen_primes
+lib = cabi.load(); torch.cuda.set_device(0)
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+N, k, ell, B = 16384, 5, 4, 64
+R = 8 * N
+pa = np.array(gen_primes(N, [60] * k), dtype=np.uint64)
+h = C.c_void_p(); assert lib.evab_ctx_create(N, pa.ctypes.data_as(cabi.u64p), k, 0, C.byref(h)) == 0
+lib.evab_galois_prepare(h, 3)
+key = torch.randint(0, 1 << 59, (k - 1, 2, k, N), dtype=torch.int64, device="cuda")
+P = lambda t: C.c_void_p(t.data_ptr())
+ws = lib.evab_keyswitch_work_bytes(h, ell) // 8
+stride = (3 * ell * N * 4 + ws + 64 + 63) // 64 * 64          # a3 | a2 | b2 | out | work per instance
+buf = torch.randint(0, 1 << 59, (B, stride), dtype=torch.int64, device="cuda")
+a3, a2 = buf[0, :3 * ell * N], buf[0, 3 * ell * N:5 * ell * N]
+b2, hoist = buf[0, 5 * ell * N:7 * ell * N], buf[0, 7 * ell * N:8 * ell * N]
+out, work = buf[0, 9 * ell * N:12 * ell * N], buf[0, 12 * ell * N:12 * ell * N + ws]
+pt = torch.randint(0, 1 << 59, (ell, N), dtype=torch.int64, device="cuda")   # plaintext shared by the instances (stride 0 would need a second batch stride; per-instance copy below)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+
+def sum_products():
+    n = 9
+    cts = (C.c_void_p * n)(*[a2.data_ptr()] * n)
+    pts = (C.c_void_p * n)(*[b2.data_ptr()] * n)
+    sizes = (C.c_int * n)(*[2] * n)
+    kinds = (C.c_int * n)(*[1] * n)
+    return lib.evab_sum_products(h, ell, P(out), n, cts, sizes, pts, kinds, st)
+
+
+ops = [
+    ("add", lambda: lib.evab_add(h, ell, P(out), P(a2), 2, P(b2), 2, st), 3 * 2 * ell * R),
+    ("negate", lambda: lib.evab_negate(h, ell, P(out), P(a2), 2, st), 2 * 2 * ell * R),
+    ("multiply_plain", lambda: lib.evab_mul_plain(h, ell, P(out), P(a2), 2, P(b2), st), 5 * ell * R),
+    ("multiply", lambda: lib.evab_mul(h, ell, P(out), P(a2), P(b2), st), 7 * ell * R),
+    ("square", lambda: lib.evab_square(h, ell, P(out), P(a2), st), 5 * ell * R),
+    ("sum of 9 multiply_plain (fused)", sum_products, (9 * 3 + 2) * ell * R),
+    ("mod_switch", lambda: lib.evab_mod_switch(h, ell, P(out), P(a2), 2, st), 2 * 2 * (ell - 1) * R),
+    ("rescale (size 3)", lambda: lib.evab_rescale(h, ell, P(out), P(a3), 3, P(work), st), 3 * (2 * ell - 1) * R),
+    ("relinearize", lambda: lib.evab_relinearize(h, ell, P(out), P(a3), P(key), P(work), st), (2 * ell * ell + 7 * ell) * R),
+    ("rotate", lambda: lib.evab_rotate(h, ell, P(out), P(a2), 3, P(key), P(work), st), (2 * ell * ell + 6 * ell) * R),
+    ("rotate_prepare", lambda: lib.evab_rotate_prepare(h, ell, P(hoist), P(a2), st), 2 * ell * R),
+    ("rotate_prepared", lambda: lib.evab_rotate_prepared(h, ell, P(out), P(a2), P(hoist), 3, P(key), P(work), st), (2 * ell * ell + 5 * ell) * R),
+]
+for name, fn, _ in ops:       # warm-up outside the profiled range
+    lib.evab_set_batch(B, stride, 0); assert fn() == 0; lib.evab_set_batch(1, 0, 0)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+for name, fn, algo in ops:
+    flush.zero_()
+    lib.evab_set_batch(B, stride, 0)
+    l0 = lib.evab_launch_count(h)
+    assert fn() == 0
+    n = lib.evab_launch_count(h) - l0
+    lib.evab_set_batch(1, 0, 0)
+    torch.cuda.synchronize()
+    print(json.dumps({"op": name, "launches": int(n), "instances": B, "algorithmic_bytes_per_instance": algo}), flush=True)
+# the encoder (E row): one batch of 23 vectors as in a Sobel execute (dense 4096-slot vectors) + replicated scalars
+cnt = 8
+vals = torch.rand((cnt, N // 2), dtype=torch.float64, device="cuda")
+ptrs = (C.c_void_p * cnt)(*[vals[i].data_ptr() for i in range(cnt)])
+vec = (C.c_uint32 * cnt)(*[N // 2] * cnt)
+sc = (C.c_double * cnt)(*[2.0 ** 30] * cnt)
+wbytes = lib.evab_encode_work_bytes(h, cnt)
+ework = torch.empty(wbytes, dtype=torch.uint8, device="cuda")
+eout = torch.empty((cnt, ell, N), dtype=torch.int64, device="cuda")
+l0 = lib.evab_launch_count(h)
+assert lib.evab_encode(h, cnt, ptrs, vec, sc, ell, P(eout), P(ework), st) == 0
+print(json.dumps({"op": "encode (8 dense vectors)", "launches": int(lib.evab_launch_count(h) - l0), "instances": 1, "algorithmic_bytes_per_instance": cnt * (N // 2 * 8 + ell * R)}), flush=True)
+uv = (C.c_double * cnt)(*[0.5] * cnt)
+l0 = lib.evab_launch_count(h)
+assert lib.evab_encode_uniform(h, cnt, uv, sc, ell, P(eout), st) == 0
+print(json.dumps({"op": "encode_uniform (8 scalars)", "launches": int(lib.evab_launch_count(h) - l0), "instances": 1, "algorithmic_bytes_per_instance": cnt * ell * R}), flush=True)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+lib.evab_ctx_destroy(h)
