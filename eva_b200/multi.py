@@ -20,16 +20,24 @@ def gather_outputs(out_host, rank, world, device=None):
     world arrays on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
-    t = torch.from_numpy(np.ascontiguousarray(out_host).view(np.int64))
-    if device is not None:
-        t = t.to(device)
     if world == 1:
         return [out_host]
+    # ranks may hold a different number of polynomials (a partial sum of relinearized leaves has 2, one with a raw
+    # product 3): agree on the largest leading dimension, pad with zero polynomials, trim after the gather
+    lead = torch.tensor([out_host.shape[0]], dtype=torch.int64, device=device if device is not None else "cpu")
+    leads = [torch.empty_like(lead) for _ in range(world)]
+    dist.all_gather(leads, lead)
+    leads = [int(x.item()) for x in leads]
+    padded = np.zeros((max(leads),) + tuple(out_host.shape[1:]), dtype=np.uint64)
+    padded[: out_host.shape[0]] = out_host
+    t = torch.from_numpy(padded.view(np.int64))
+    if device is not None:
+        t = t.to(device)
     gathered = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
     dist.gather(t, gathered, dst=0)
     if rank != 0:
         return None
-    return [g.cpu().numpy().view(np.uint64) for g in gathered]
+    return [np.ascontiguousarray(g.cpu().numpy().view(np.uint64)[: leads[r]]) for r, g in enumerate(gathered)]
 
 
 def max_over_ranks(times, world, device=None):

@@ -1,4 +1,5 @@
-"""Sharding ONE compiled program across GPUs (BASELINE configs "Harris 1->8 GPUs
+"""(Round-1 single-cut sharding, kept for its tests and helpers; the staged, device-resident successor is
+eva_b200/dagshard.py.)  Sharding ONE compiled program across GPUs (BASELINE configs "Harris 1->8 GPUs
 DAG-sharded", "wide DAG across 8 x B200").
 
 Independent ciphertext ops of the DAG run on different GPUs and the only exchange is one final
@@ -77,42 +78,51 @@ def _add_trees(prog, info):
         if not cipher_add(root) or root.index in absorbed:
             continue
         leaves = []
-
-        def expand(t, inner):
+        stack = [(root, False)]          # iterative: an unbalanced chain of Adds may be thousands of terms deep
+        while stack:
+            t, inner = stack.pop()
             if cipher_add(t) and (not inner or uses.get(t.index, 0) == 1):
                 if inner:
                     absorbed.add(t.index)
-                for o in t.operands:
-                    expand(o, True)
+                for o in reversed(list(t.operands)):
+                    stack.append((o, True))
             else:
                 leaves.append(t)
-        expand(root, False)
         trees[root.index] = (root, leaves)
     return trees
 
 
-def _clone(dst, memo, t, in_names):
-    """copy term t (and, recursively, its operands) of the source program into dst"""
-    if t.index in memo:
-        return memo[t.index]
-    args = [_clone(dst, memo, o, in_names) for o in t.operands]
-    a = t.attributes
-    if t.op == Op.Input:
-        n = dst._make_input(in_names[t.index], Type(a.get("TypeAttribute", Type.Cipher)))
-    elif t.op == Op.Constant:
-        v = list(a["ConstantValueAttribute"])
-        n = dst._make_uniform_constant(v[0]) if len(v) == 1 else dst._make_dense_constant(v)
-    elif t.op == Op.RotateLeftConst:
-        n = dst._make_left_rotation(args[0], a["RotationAttribute"])
-    elif t.op == Op.RotateRightConst:
-        n = dst._make_right_rotation(args[0], a["RotationAttribute"])
-    else:
-        n = dst._make_term(t.op, args)
-    keep = {k: (Type(a[k]) if k == "TypeAttribute" else a[k]) for k in _ATTR_COPY if k in a and not (t.op == Op.Input and k == "TypeAttribute")}
-    if keep:
-        n._set_attributes(keep)
-    memo[t.index] = n
-    return n
+def _clone(dst, memo, root, in_names):
+    """copy term `root` (and its operands) of the source program into dst -- iterative, any depth"""
+    stack = [root]
+    while stack:
+        t = stack[-1]
+        if t.index in memo:
+            stack.pop()
+            continue
+        pending = [o for o in t.operands if o.index not in memo]
+        if pending:
+            stack.extend(pending)
+            continue
+        stack.pop()
+        args = [memo[o.index] for o in t.operands]
+        a = t.attributes
+        if t.op == Op.Input:
+            n = dst._make_input(in_names[t.index], Type(a.get("TypeAttribute", Type.Cipher)))
+        elif t.op == Op.Constant:
+            v = list(a["ConstantValueAttribute"])
+            n = dst._make_uniform_constant(v[0]) if len(v) == 1 else dst._make_dense_constant(v)
+        elif t.op == Op.RotateLeftConst:
+            n = dst._make_left_rotation(args[0], a["RotationAttribute"])
+        elif t.op == Op.RotateRightConst:
+            n = dst._make_right_rotation(args[0], a["RotationAttribute"])
+        else:
+            n = dst._make_term(t.op, args)
+        keep = {k: (Type(a[k]) if k == "TypeAttribute" else a[k]) for k in _ATTR_COPY if k in a and not (t.op == Op.Input and k == "TypeAttribute")}
+        if keep:
+            n._set_attributes(keep)
+        memo[t.index] = n
+    return memo[root.index]
 
 
 def _sum(dst, xs):
@@ -126,8 +136,10 @@ class ShardPlan:
     """parts[r]: Program computing output "partial"; tail: Program with inputs partial_<r>; partial_size:
     polynomials of a partial ciphertext; root_index: the term of the original program that was cut"""
 
-    def __init__(self, parts, tail, partial_size, root_index, leaves_per_part):
+    def __init__(self, parts, tail, partial_size, root_index, leaves_per_part, part_sizes=None):
         self.parts, self.tail, self.partial_size, self.root_index, self.leaves_per_part = parts, tail, partial_size, root_index, leaves_per_part
+        # polynomials of each part's partial sum: a part holding only relinearized leaves sends 2, one with a raw product 3
+        self.part_sizes = part_sizes or [partial_size] * len(parts)
 
 
 def split_program(prog, nparts):
@@ -166,7 +178,8 @@ def split_program(prog, nparts):
             a = t.attributes
             if "RangeAttribute" in a:
                 o._set_attributes({"RangeAttribute": a["RangeAttribute"]})
-    return ShardPlan(parts, tail, ri.size, root.index, [bounds[r + 1] - bounds[r] for r in range(nparts)])
+    part_sizes = [infer(p)[p.outputs["partial"].index].size for p in parts]
+    return ShardPlan(parts, tail, ri.size, root.index, [bounds[r + 1] - bounds[r] for r in range(nparts)], part_sizes)
 
 
 def _subset(inputs, names):
@@ -192,7 +205,7 @@ def run_part(pub, plan, rank, inputs):
 
 def run_tail(pub, plan, partials, scale, inputs):
     """rank 0: sum of the gathered partial ciphertexts and everything after the cut"""
-    pub.set_input_sizes({"partial_%d" % r: plan.partial_size for r in range(len(partials))})
+    pub.set_input_sizes({"partial_%d" % r: int(p.shape[0]) for r, p in enumerate(partials)})   # each part's own size (2 or 3)
     tail_inputs = _subset(inputs, set(plan.tail.inputs))
     for r, p in enumerate(partials):
         tail_inputs.set_cipher("partial_%d" % r, p, scale)
