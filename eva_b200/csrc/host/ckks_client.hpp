@@ -241,14 +241,21 @@ public:
   }
   // Encryptor::encrypt with the public key; d_pt[ell][N]; returns ct [2][ell][N]
   DBuf encrypt(const KeySet &K, const u64 *d_pt, int ell) {
-    if (ell < 1 || ell > k_ - 1) throw std::invalid_argument("encryption level out of range");
-    const int nres = ell + 1;
     std::vector<int> u(N_);
     for (auto &v : u) v = (int)rng_.below(3) - 1;
+    const std::vector<int> e0 = sampleCbd(), e1 = sampleCbd();
+    return encryptWith(K, d_pt, ell, u, e0, e1);
+  }
+  // the deterministic core (also a test hook: the same (u, e0, e1) through the oracle gives the same bits):
+  // (pk0 u + e0, pk1 u + e1) one level up, divided by the extra prime with rounding, + the plaintext
+  DBuf encryptWith(const KeySet &K, const u64 *d_pt, int ell, const std::vector<int> &u, const std::vector<int> &e0, const std::vector<int> &e1) {
+    if (ell < 1 || ell > k_ - 1) throw std::invalid_argument("encryption level out of range");
+    if (u.size() != N_ || e0.size() != N_ || e1.size() != N_) throw std::invalid_argument("randomness must have N entries");
+    const int nres = ell + 1;
     DBuf ud = smallToDeviceNtt(u, nres);
     DBuf big(dev_, (std::size_t)2 * nres * N_);
     for (int c = 0; c < 2; c++) {
-      DBuf e = smallToDeviceNtt(sampleCbd(), nres);
+      DBuf e = smallToDeviceNtt(c ? e1 : e0, nres);
       u64 *dst = big.get() + (std::size_t)c * nres * N_;
       check(evab_mul_plain(dev_->ctx(), nres, dst, K.pk.get() + (std::size_t)c * k_ * N_, 1, ud.get(), nullptr));
       check(evab_add_plain(dev_->ctx(), nres, dst, dst, 1, e.get(), nullptr));

@@ -258,6 +258,20 @@ PYBIND11_MODULE(_eva_b200, m) {
         dev->sync();
         return a;
       }, py::arg("values"), py::arg("scale"), py::arg("ell"), py::arg("host") = false)
+      // test hook: Encryptor::encrypt of a plaintext polynomial [ell][N] with EXPLICIT randomness -> ciphertext [2][ell][N]
+      .def("encrypt_poly", [](B200Public &p, const u64arr &pt, const std::vector<int> &u, const std::vector<int> &e0, const std::vector<int> &e1) {
+        auto s = p.shared();
+        if (!s->keys.pk) throw std::runtime_error("this context has no public key");
+        if (pt.ndim() != 2 || (std::size_t)pt.shape(1) != s->dev->N()) throw std::runtime_error("plaintext array must be [ell][N]");
+        const int ell = (int)pt.shape(0);
+        DBuf d(s->dev, pt.size());
+        s->dev->upload(d.get(), pt.data(), pt.size() * 8);
+        DBuf ct = s->client->encryptWith(s->keys, d.get(), ell, u, e0, e1);
+        u64arr a({(std::size_t)2, (std::size_t)ell, (std::size_t)s->dev->N()});
+        s->dev->download(a.mutable_data(), ct.get(), a.size() * 8);
+        s->dev->sync();
+        return a;
+      }, py::arg("plaintext"), py::arg("u"), py::arg("e0"), py::arg("e1"))
       .def("decode", [](B200Public &p, const u64arr &pt, double scale) {
         auto dev = p.shared()->dev;
         DBuf d(dev, pt.size());
@@ -266,6 +280,24 @@ PYBIND11_MODULE(_eva_b200, m) {
       });
   py::class_<B200Secret>(mb, "B200Secret", "The secret part of the context: decryption")
       .def("decrypt", &B200Secret::decrypt, py::arg("enc_outputs"), py::arg("signature"))
+      // test hook: Decryptor::decrypt of a raw ciphertext [size][ell][N] -> plaintext polynomial [ell][N] (before decoding)
+      .def("decrypt_poly", [](B200Secret &x, const u64arr &ct) {
+        auto s = x.shared();
+        if (ct.ndim() != 3 || (std::size_t)ct.shape(2) != s->dev->N()) throw std::runtime_error("ciphertext array must be [size][ell][N]");
+        DBuf d(s->dev, ct.size());
+        s->dev->upload(d.get(), ct.data(), ct.size() * 8);
+        DBuf pt = s->client->decrypt(s->keys, d.get(), (int)ct.shape(0), (int)ct.shape(1));
+        u64arr a({(std::size_t)ct.shape(1), (std::size_t)s->dev->N()});
+        s->dev->download(a.mutable_data(), pt.get(), a.size() * 8);
+        s->dev->sync();
+        return a;
+      }, py::arg("ciphertext"))
+      .def("decode", [](B200Secret &x, const u64arr &pt, double scale) {
+        auto s = x.shared();
+        DBuf d(s->dev, pt.size());
+        s->dev->upload(d.get(), pt.data(), pt.size() * 8);
+        return s->client->encoder().decode(d.get(), (int)pt.shape(0), scale);
+      }, py::arg("plaintext"), py::arg("scale"))
       // serialization (eva_b200/serialization.py): secret key image [k][N] + the modulus chain
       .def("_export", [](B200Secret &x) {
         auto s = x.shared();

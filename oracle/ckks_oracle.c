@@ -817,22 +817,20 @@ const u64 *ora_keys_galois(ora_keys *K, u64 elt) {
 
 /* Encryptor::encrypt (public key) -- encrypt zero one level up, divide and
  * round by that level's last prime, add the plaintext to c0. */
-int ora_encrypt(const ora_keys *K, int ell, const u64 *pt, u64 seed, u64 *ct) {
+/* Encryptor::encrypt with the public key and EXPLICIT randomness (u ternary, e0 / e1 small): the deterministic core
+ * of ora_encrypt, so that the product's encryptor can be compared bit for bit on the same (u, e0, e1). */
+int ora_encrypt_with(const ora_keys *K, int ell, const u64 *pt, const int *u, const int *e0, const int *e1, u64 *ct) {
     const ora_ctx *c = K->c; const u64 N = c->N; const int k = c->k;
     if (ell < 1 || ell > k - 1) return -1;
     const int nres = ell + 1;
-    ora_rng rng; rng.s = seed ^ 0xC0FFEE1234ull;
-    int *u = (int *)malloc(N * sizeof(int)), *e = (int *)malloc(N * sizeof(int));
     u64 *ur = (u64 *)malloc((size_t)nres * N * sizeof(u64));
     u64 *buf = (u64 *)malloc(((size_t)nres + 1) * N * sizeof(u64));
-    sample_ternary(&rng, N, u);
     small_to_rns(c, u, nres, ur);
     for (int i = 0; i < nres; i++) ora_ntt_fwd(c, i, ur + (size_t)i * N);
     int idx[ORA_MAXK];
     for (int i = 0; i < nres; i++) idx[i] = i;
     for (int cc = 0; cc < 2; cc++) {
-        sample_cbd(&rng, N, e);
-        small_to_rns(c, e, nres, buf);
+        small_to_rns(c, cc ? e1 : e0, nres, buf);
         for (int i = 0; i < nres; i++) {
             const ora_prime *m = &c->pr[i];
             u64 *x = buf + (size_t)i * N;
@@ -847,8 +845,19 @@ int ora_encrypt(const ora_keys *K, int ell, const u64 *pt, u64 seed, u64 *ct) {
         const u64 p = c->pr[i].p;
         for (u64 j = 0; j < N; j++) ct[(size_t)i * N + j] = addm(ct[(size_t)i * N + j], pt[(size_t)i * N + j], p);
     }
-    free(u); free(e); free(ur); free(buf);
+    free(ur); free(buf);
     return 0;
+}
+int ora_encrypt(const ora_keys *K, int ell, const u64 *pt, u64 seed, u64 *ct) {
+    const ora_ctx *c = K->c; const u64 N = c->N;
+    ora_rng rng; rng.s = seed ^ 0xC0FFEE1234ull;
+    int *u = (int *)malloc(N * sizeof(int)), *e0 = (int *)malloc(N * sizeof(int)), *e1 = (int *)malloc(N * sizeof(int));
+    sample_ternary(&rng, N, u);
+    sample_cbd(&rng, N, e0);
+    sample_cbd(&rng, N, e1);
+    const int rc = ora_encrypt_with(K, ell, pt, u, e0, e1, ct);
+    free(u); free(e0); free(e1);
+    return rc;
 }
 
 /* Decryptor::decrypt (CKKS): pt = c0 + c1*s + c2*s^2 (NTT domain) */

@@ -109,6 +109,7 @@ const u64 *ora_keys_galois(ora_keys *k, u64 elt);
  * or lower; lower levels are produced by encrypting at that level directly
  * (SEAL Encryptor::encrypt at plain.parms_id()).  out ct[2][ell][N]. */
 int ora_encrypt(const ora_keys *k, int ell, const u64 *pt, u64 seed, u64 *ct);
+int ora_encrypt_with(const ora_keys *k, int ell, const u64 *pt, const int *u, const int *e0, const int *e1, u64 *ct);
 /* pt[ell][N] = sum_i ct[i] * s^i */
 int ora_decrypt(const ora_keys *k, int ell, const u64 *ct, int size, u64 *pt);
 

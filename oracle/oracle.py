@@ -252,6 +252,18 @@ class Oracle:
         assert lib.ora_encrypt(C.c_void_p(self.keys), ell, _p(pt), C.c_uint64(seed), _p(ct)) == 0
         return ct
 
+    def encrypt_with(self, pt, u, e0, e1):
+        """encrypt with explicit randomness (ternary u, small e0 / e1: int32 arrays of N)"""
+        ell = pt.shape[0]
+        ct = np.empty((2, ell, self.N), dtype=np.uint64)
+        ip = C.POINTER(C.c_int)
+        arrs = [np.ascontiguousarray(x, dtype=np.int32) for x in (u, e0, e1)]
+        assert lib.ora_encrypt_with(C.c_void_p(self.keys), ell, _p(pt), *[a.ctypes.data_as(ip) for a in arrs], _p(ct)) == 0
+        return ct
+
+    def public_key(self):
+        return self._view(lib.ora_keys_public(self.keys), (2, self.k, self.N))
+
     def decrypt(self, ct):
         pt = np.empty((ct.shape[1], self.N), dtype=np.uint64)
         assert lib.ora_decrypt(C.c_void_p(self.keys), ct.shape[1], _p(ct), ct.shape[0], _p(pt)) == 0

@@ -127,3 +127,31 @@ def test_gpu_cluster_distributed_ntt(N, bits, cl):
     finally:
         assert lib.evab_set_ntt_cluster(0) == 0   # library default (automatic)
     assert lib.evab_set_ntt_cluster(3) != 0
+
+
+@pytest.mark.parametrize("N,bits", [(4096, [60, 20, 60, 60]), (16384, [60] * 5)])
+def test_encrypt_decrypt_decode_bit_exact_vs_oracle(N, bits):
+    """SURVEY 8f-1: the client side on the device.  Encryptor::encrypt with the oracle's public key and the SAME
+    randomness (u, e0, e1) gives the oracle's ciphertext bit for bit at every level; Decryptor::decrypt with the
+    oracle's secret key gives the oracle's plaintext polynomial (sizes 2 and 3); decoding it gives the oracle's doubles."""
+    from eva_b200 import b200
+    orc = pc.get_oracle(N, bits).keygen(5)
+    pub = b200.public_from_raw(N, orc.primes, orc.public_key(), None, {})
+    sec = b200.secret_from_raw(N, orc.primes, orc.secret_key())
+    rng = np.random.default_rng(N)
+    for ell in range(1, orc.k):
+        vals = rng.uniform(-1, 1, N // 2)
+        pt = orc.encode(vals, 2.0 ** 30, ell)
+        u = rng.integers(-1, 2, N).astype(np.int32)
+        e0, e1 = rng.integers(-20, 21, N).astype(np.int32), rng.integers(-20, 21, N).astype(np.int32)
+        want = orc.encrypt_with(pt, u, e0, e1)
+        got = pub.encrypt_poly(pt, [int(x) for x in u], [int(x) for x in e0], [int(x) for x in e1])
+        assert np.array_equal(got, want), "encrypt differs at ell=%d" % ell
+        dp = sec.decrypt_poly(want)
+        assert np.array_equal(dp, orc.decrypt(want)), "decrypt differs at ell=%d" % ell
+        ct3 = orc.mul(want, want)        # a size-3 ciphertext: c0 + c1 s + c2 s^2
+        assert np.array_equal(sec.decrypt_poly(ct3), orc.decrypt(ct3))
+        dec = np.asarray(sec.decode(dp, 2.0 ** 30))
+        ref = orc.decode(orc.decrypt(want), 2.0 ** 30)
+        assert np.array_equal(dec[: N // 2], ref), "decode differs at ell=%d" % ell
+        assert np.max(np.abs(dec[: N // 2] - vals)) < 1e-4
