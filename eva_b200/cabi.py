@@ -39,6 +39,13 @@ _SIGS = {
     "evab_launch_count": (u64, [vp]),
     "evab_ntt_fwd": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
     "evab_ntt_inv": (ci, [vp, vp, szt, C.POINTER(ci), ci, vp]),
+    "evab_rotate_modup_ext_bytes": (szt, [vp, ci]),
+    "evab_rotate_modup_work_bytes": (szt, [vp, ci]),
+    "evab_hoist_const_bytes": (szt, [vp, ci]),
+    "evab_rotate_modup_prepare": (ci, [vp, ci, vp, vp, vp, vp, vp]),
+    "evab_rotate_hoist_const": (ci, [vp, ci, u64, vp, vp, vp, vp]),
+    "evab_rotate_modup_prepared": (ci, [vp, ci, vp, vp, vp, u64, vp, vp, vp, vp]),
+    "evab_memset_zero": (ci, [vp, vp, szt, vp]),
     "evab_set_ntt_cluster": (ci, [ci]),
     "evab_ctx_set_ntt_cluster": (ci, [vp, ci]),
     "evab_ctx_set_ntt_arith": (ci, [vp, ci]),

@@ -203,6 +203,12 @@ __global__ void __launch_bounds__(256) k_ks_inner(const IpArgs A, const long lon
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
     ks_inner_elem(A, blockIdx.y, j, off);
 }
+__global__ void __launch_bounds__(256) k_hoist_const(const HoistConstArgs A) {
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2) hoist_const_elem(A, blockIdx.y, j);
+}
+__global__ void __launch_bounds__(256) k_hoist_indicator(u64 *out, const u32 *ctab, int N) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) hoist_indicator_elem(out, ctab, N, blockIdx.y, j);
+}
 __global__ void __launch_bounds__(256) k_enc_scatter(const EncBatch B, const long long bstride, const long long vstride) {
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B.N / 2; i += gridDim.x * blockDim.x)
     enc_scatter(B, blockIdx.y, i, (long long)blockIdx.z * bstride, (long long)blockIdx.z * vstride);
@@ -305,6 +311,7 @@ template <int LOGN, int CL, int AR> static int launch_inv_c(const NttLaunch &L, 
   if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return launch_inv_m<LOGN, PRO_PLAIN, EPI_STORE, CL, AR>(L, jobs, st);
   if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return launch_inv_m<LOGN, PRO_PLAIN, EPI_ADDHALF, CL, AR>(L, jobs, st);
   if (L.pro == PRO_GATHER && L.epi == EPI_STORE) return launch_inv_m<LOGN, PRO_GATHER, EPI_STORE, CL, AR>(L, jobs, st);
+  if (L.pro == PRO_PLAIN && L.epi == EPI_STORE_ZFLAG) return launch_inv_m<LOGN, PRO_PLAIN, EPI_STORE_ZFLAG, CL, AR>(L, jobs, st);
   return fail("unsupported inverse NTT prologue/epilogue combination");
 }
 template <int LOGN, int AR> static int launch_inv_a(const NttLaunch &L, size_t jobs, cudaStream_t st, int cluster) {
@@ -388,6 +395,18 @@ struct CudaBE {
   int inner(const IpArgs &A) {
     count();
     k_ks_inner<<<grid(A.ell + 1), 256, 0, st>>>(A, g_batch.stride);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int hoist_indicator(u64 *out, const u32 *ctab, int N, int rows) {
+    count();
+    k_hoist_indicator<<<dim3((N + 255) / 256, rows), 256, 0, st>>>(out, ctab, N);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int hoist_const(const HoistConstArgs &A) {
+    count();
+    k_hoist_const<<<dim3((A.N / 2 + 255) / 256, A.ell + 1), 256, 0, st>>>(A);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -706,6 +725,35 @@ extern "C" int evab_rotate_prepared(evab_ctx *c, int ell, uint64_t *o, const uin
     perm = it->second; ctab = c->cperms.at(elt);
   }
   BE_BEGIN return rotate_prepared_impl(be, c->v, ell, o, a, hoist, perm, ctab, key, (u64 *)work);
+}
+static int galois_tables(evab_ctx *c, uint64_t elt, u32 **perm, u32 **ctab, const char *who) {
+  std::lock_guard<std::mutex> g(c->mu);
+  auto it = c->perms.find(elt);
+  if (it == c->perms.end()) return fail(std::string(who) + ": call evab_galois_prepare(elt) first");
+  *perm = it->second; *ctab = c->cperms.at(elt);
+  return 0;
+}
+extern "C" size_t evab_rotate_modup_work_bytes(const evab_ctx *c, int ell) { return rotate_modup_work_elems(c->v, ell) * sizeof(u64); }
+extern "C" size_t evab_rotate_modup_ext_bytes(const evab_ctx *c, int ell) { return (size_t)(ell + 1) * ell * c->v.N * sizeof(u64); }
+extern "C" size_t evab_hoist_const_bytes(const evab_ctx *c, int ell) { return hoist_const_elems(c->v, ell) * sizeof(u64); }
+extern "C" int evab_rotate_modup_prepare(evab_ctx *c, int ell, uint64_t *that, uint64_t *ext, const uint64_t *a, uint64_t *zflag, void *stream) {
+  BE_BEGIN return rotate_modup_prepare_impl(be, c->v, ell, that, ext, a, zflag);
+}
+extern "C" int evab_rotate_hoist_const(evab_ctx *c, int ell, uint64_t elt, const uint64_t *key, uint64_t *out, uint64_t *tmp, void *stream) {
+  u32 *perm = nullptr, *ctab = nullptr;
+  if (galois_tables(c, elt, &perm, &ctab, "evab_rotate_hoist_const")) return 1;
+  BE_BEGIN return hoist_const_impl(be, c->v, ell, ctab, key, out, tmp);
+}
+extern "C" int evab_rotate_modup_prepared(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *ext, uint64_t elt, const uint64_t *key,
+                                          const uint64_t *cadd, void *work, void *stream) {
+  u32 *perm = nullptr, *ctab = nullptr;
+  if (galois_tables(c, elt, &perm, &ctab, "evab_rotate_modup_prepared")) return 1;
+  BE_BEGIN return rotate_modup_prepared_impl(be, c->v, ell, o, a, ext, perm, key, cadd, (u64 *)work);
+}
+extern "C" int evab_memset_zero(evab_ctx *c, void *d, size_t bytes, void *stream) {
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaMemsetAsync(d, 0, bytes, S(stream)));
+  return 0;
 }
 extern "C" int evab_rotate(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, uint64_t elt, const uint64_t *key, void *work, void *stream) {
   u32 *perm = nullptr;

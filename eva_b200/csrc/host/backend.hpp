@@ -113,12 +113,13 @@ public:
     if (batch < 1 || batch > 65535 || replica < 0 || replica > 65535) throw std::invalid_argument("batch / replica out of range");
     const std::uint64_t key = planKey(batch, replica);
     auto h = std::static_pointer_cast<PlanHolder>(program.attachment(key));
-    if (!h || h->termCount != program.termCount()) {
+    if (!h || h->termCount != program.termCount() || h->opt.hoistModUp != options.hoistModUp) {   // stale plan: rebuilt
       h = std::make_shared<PlanHolder>();
       h->keepAlive = s_;
       ExecOptions o = options;
       o.batch = batch;
       h->exec = std::make_unique<Executor>(s_->dev, s_->client->encoder(), s_->keys, program, o);
+      h->opt = o;
       h->termCount = program.termCount();
       program.attach(key, h);
     }
@@ -175,12 +176,25 @@ public:
   // replica (arena + captured graph) and all replicas are in flight at once: H2D, graph and D2H of
   // different chunks overlap, and 148 SMs are filled by concurrency rather than by launch width.
   std::vector<B200Valuation> executeMany(Program &program, const std::vector<const B200Valuation *> &inputs) {
-    const int B = (int)inputs.size();
-    if (B < 1) throw std::invalid_argument("execute needs at least one valuation");
+    if (inputs.empty()) throw std::invalid_argument("execute needs at least one valuation");
     for (auto *v : inputs) requireAllInputs(program, *v);
     // one caller at a time per context: plan replicas own single arenas and raw-input buffers (the reference's
     // execute is re-entrant because it builds a new executor per call; concurrent callers are serialised here)
     std::lock_guard<std::mutex> guard(s_->execMutex);
+    bool redo = false;
+    std::vector<B200Valuation> outs = executeManyLocked(program, inputs, redo);
+    if (redo) {
+      // a digit of a rotated ciphertext held a zero coefficient: the shared mod-up of that rotation group is not SEAL's value
+      // (ops_impl.hpp hoisted_modup).  Redo the call on plans without it -- exact, and from now on for this context.
+      if (verbosity() >= 1) std::fprintf(stderr, "EVA: zero digit coefficient met; rotation groups of this context no longer share their mod-up\n");
+      options.hoistModUp = false;      // executorFor rebuilds every plan whose option differs
+      outs = executeManyLocked(program, inputs, redo);
+    }
+    return outs;
+  }
+  std::vector<B200Valuation> executeManyLocked(Program &program, const std::vector<const B200Valuation *> &inputs, bool &redo) {
+    const int B = (int)inputs.size();
+    redo = false;
     const int F = std::max(1, std::min(options.fuse, B));
     std::vector<B200Valuation> outs(B);
     std::vector<void *> streams;
@@ -241,6 +255,8 @@ public:
     }
     auto t4 = now();
     for (void *st : streams) s_->dev->sync(st);
+    for (int b0 = 0, g = 0; b0 < B; b0 += F, g++)
+      if (g < R && executorFor(program, std::min(F, B - b0), g % R).flagsRaised()) redo = true;
     if (trace) {
       auto t5 = now();
       std::fprintf(stderr, "[evab] executeMany B=%d F=%d: plan %.3f stage %.3f run %.3f enqueue-total %.3f sync %.3f ms\n", B, F, tPlan * 1e3, tStage * 1e3, tRun * 1e3,

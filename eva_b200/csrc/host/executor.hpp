@@ -69,6 +69,8 @@ struct ExecOptions {
   std::map<std::string, int> inputSizes;   // ciphertext inputs that are not size 2 (partial sums of a sharded DAG)
   bool uniformEncode = true;   // replicated scalars are encoded by the one-pass encoder (evab_encode_uniform)
   bool hoistRotations = true;  // rotations of one ciphertext share the inverse NTT of its c1 (exact)
+  bool hoistModUp = true;      // ... and the mod-up of its digits (exact, ops_impl.hpp hoisted_modup); a zero coefficient in a digit
+                               // raises a flag and the caller redoes the run without this option (B200Public::executeMany)
   bool fuseSums = true;        // trees of Add over multiply_plain results / ciphertexts run as one kernel
   bool dedupConstants = true;  // Encode terms of identical constants at the same (level, scale) share one plaintext
   bool dedupTerms = true;      // identical ciphertext terms (same op, same attributes, same operands) are evaluated once and
@@ -90,6 +92,7 @@ public:
   }
   ~Executor() {
     if (graph_) evab_graph_destroy(dev_->ctx(), graph_);
+    if (hostFlags_) evab_host_free(hostFlags_);
     for (void *e : events_) evab_event_destroy(dev_->ctx(), e);
     for (void *s : streams_) evab_stream_destroy(dev_->ctx(), s);
   }
@@ -121,6 +124,15 @@ public:
     } else {
       replay(stream);
     }
+    for (int b = 0; numFlags_ && b < opt_.batch; b++)   // travels with the outputs; read by flagsRaised() once the stream is synchronised
+      dev_->download(hostFlags_ + (std::size_t)b * 8 * numFlags_, arena_.get() + (std::size_t)b * stride_ + flagsOff_, 8 * numFlags_ * 8, stream);
+  }
+  // after the run's stream has been synchronised: did a digit of a rotation group hold a zero coefficient?  (The shared mod-up is
+  // then not the reference's value; the caller must redo the run with hoistModUp off.  Probability ~ N ell 2^-60 per ciphertext.)
+  bool flagsRaised() const {
+    for (std::size_t i = 0; i < 8 * numFlags_ * (std::size_t)opt_.batch; i++)
+      if (hostFlags_[i]) return true;
+    return false;
   }
   void setRawInput(const std::string &name, const std::vector<double> &v, int b = 0) {
     auto t = prog_.getInput(name);
@@ -359,8 +371,16 @@ private:
         hoistSrc.push_back(C(kv.second.front()->operandAt(0).get()));
         hoistOff_.push_back(arenaWords);
         arenaWords += (std::size_t)vals_[kv.first].ell * N_;
+        if (opt_.hoistModUp) {   // the extended digits [ell+1][ell][N], shared by the rotations of this ciphertext
+          hoistExtOff_.push_back(arenaWords);
+          arenaWords += evab_rotate_modup_ext_bytes(dev_->ctx(), vals_[kv.first].ell) / 8;
+        }
         for (const Term *r : kv.second) hoistOf[r->index] = gid;
       }
+    }
+    if (opt_.hoistModUp && !hoistSrc.empty()) {   // one zero-coefficient flag per group (64 bytes apart: no false sharing of the atomics)
+      flagsOff_ = arenaWords; numFlags_ = hoistSrc.size();
+      arenaWords += 8 * numFlags_;
     }
     // ---- stream assignment + event edges.  Producers are identified by term index, or TC + group
     // for the hoist pseudo steps.
@@ -461,7 +481,19 @@ private:
         const u64 elt = galoisElt(*st.term);
         if (!keys_.galois.count(elt)) throw std::invalid_argument("Galois key not present");
         check(evab_galois_prepare(dev_->ctx(), elt));
+        // shared mod-up: the key-dependent constant of (element, level), computed once per plan
+        if (opt_.hoistModUp && st.hoist >= 0) {
+          const int ell = vals_[st.term->index].ell;
+          auto key = std::make_pair(elt, ell);
+          if (!hoistConst_.count(key)) {
+            DBuf cadd(dev_, evab_hoist_const_bytes(dev_->ctx(), ell) / 8), tmp(dev_, (std::size_t)(ell + 1) * N_);
+            check(evab_rotate_hoist_const(dev_->ctx(), ell, elt, keys_.galois.at(elt).get(), cadd.get(), tmp.get(), nullptr));
+            dev_->sync();
+            hoistConst_.emplace(key, std::move(cadd));
+          }
+        }
       }
+    if (numFlags_) check(evab_host_alloc(8 * numFlags_ * 8 * (std::size_t)opt_.batch, (void **)&hostFlags_));
   }
   // canonical (first) occurrence of a term that repeats an earlier one (dedupTerms)
   const Term *C(const Term *t) const { return byIndex_[canon_[t->index]]; }
@@ -582,7 +614,11 @@ private:
     const ValueInfo &o = vals_[t.index];
     u64 *out = arena_.get() + o.off;
     if (st.op == Op::Undef) {   // shared inverse NTT of a rotation group's input
-      check(evab_rotate_prepare(c, o.ell, arena_.get() + hoistOff_[st.hoist], arena_.get() + o.off, stream));
+      if (opt_.hoistModUp)
+        check(evab_rotate_modup_prepare(c, o.ell, arena_.get() + hoistOff_[st.hoist], arena_.get() + hoistExtOff_[st.hoist], arena_.get() + o.off,
+                                        arena_.get() + flagsOff_ + 8 * (std::size_t)st.hoist, stream));
+      else
+        check(evab_rotate_prepare(c, o.ell, arena_.get() + hoistOff_[st.hoist], arena_.get() + o.off, stream));
       return;
     }
     if (!st.sum.empty()) {   // fused multiply_plain / add tree
@@ -621,7 +657,10 @@ private:
         if (*t.rotation == 0) check(evab_copy(c, o.ell, out, P(0), 2, stream));  // rotate_vector(0): copy
         else {
           const u64 elt = galoisElt(t);
-          if (st.hoist >= 0) check(evab_rotate_prepared(c, o.ell, out, P(0), arena_.get() + hoistOff_[st.hoist], elt, keys_.galois.at(elt).get(), work, stream));
+          if (st.hoist >= 0 && opt_.hoistModUp)
+            check(evab_rotate_modup_prepared(c, o.ell, out, P(0), arena_.get() + hoistExtOff_[st.hoist], elt, keys_.galois.at(elt).get(),
+                                             hoistConst_.at(std::make_pair(elt, o.ell)).get(), work, stream));
+          else if (st.hoist >= 0) check(evab_rotate_prepared(c, o.ell, out, P(0), arena_.get() + hoistOff_[st.hoist], elt, keys_.galois.at(elt).get(), work, stream));
           else check(evab_rotate(c, o.ell, out, P(0), elt, keys_.galois.at(elt).get(), work, stream));
         }
         break;
@@ -636,6 +675,8 @@ private:
     evab_ctx *c = dev_->ctx();
     BatchGuard bg(opt_.batch, stride_, rawStride_);
     void *forkEv = events_[numEvents_ + usedStreams_];
+    for (int b = 0; numFlags_ && b < opt_.batch; b++)   // zero-coefficient flags of the shared mod-ups
+      check(evab_memset_zero(c, arena_.get() + (std::size_t)b * stride_ + flagsOff_, 8 * numFlags_ * 8, stream));
     check(evab_event_record(c, forkEv, stream));
     for (int s = 0; s < usedStreams_; s++) check(evab_stream_wait_event(c, streams_[s], forkEv));
     for (auto &st : steps_) {
@@ -677,6 +718,10 @@ private:
   std::unordered_map<std::uint64_t, int> groupIndex_;
   std::unordered_map<std::uint64_t, std::size_t> rawOff_;
   std::vector<std::size_t> hoistOff_;   // arena word offset of every hoist buffer
+  std::vector<std::size_t> hoistExtOff_;                     // ... and of the group's extended digits (hoistModUp)
+  std::size_t flagsOff_ = 0, numFlags_ = 0;                  // zero-coefficient flags, 8 words apart
+  std::map<std::pair<u64, int>, DBuf> hoistConst_;           // (galois element, ell) -> cadd [2][ell+1][N]
+  u64 *hostFlags_ = nullptr;                                 // page-locked copy of the flags of the last run
   std::unordered_map<std::uint64_t, Term *> encodeAlias_;  // Encode term -> identical earlier Encode term
   std::unordered_set<std::uint64_t> rawUploaded_;
   std::size_t rawWords_ = 0;

@@ -22,12 +22,15 @@ enum : int {
   EPI_ADDHALF = 1,   // dst[idx] = (x + half) mod p        (half = floor(p/2))
   EPI_DIVROUND = 2,  // dst[idx] = (aux0[idx] - x) * c mod p  [+ aux1[idx] mod p]
   EPI_STORE_LAZY = 3,  // dst[idx] = x without canonicalisation (x < 16p; consumer reduces)
+  EPI_STORE_ZFLAG = 4, // inverse: EPI_STORE, and *zflag is set when any stored coefficient is zero (shared mod-up of
+                       // rotation groups: see hoisted_modup in ops_impl.hpp)
 };
 
 struct NttLaunch {
   const u64 *src; u64 *dst; const u64 *aux0; const u64 *aux1;
   const u32 *perm;             // PRO_GATHER / PRO_MODRED_SG
   const u32 *aux1_perm;        // EPI_DIVROUND: aux1 is read through this permutation (NTT-domain automorphism)
+  u64 *zflag;                  // EPI_STORE_ZFLAG: one word (per batch instance), OR-ed with 1 when a zero coefficient is stored
   const u64 *cflags;           // optional [q]: 0 = polynomial q is constant (only coefficient 0 set): its
                                // transform is that value everywhere, written without running the NTT
   const PrimeDev *primes;
@@ -56,8 +59,15 @@ inline bool ntt_launch_folds(const NttLaunch &L, size_t jobs, unsigned foldmask)
 
 struct NttState { u64 x[NTT_E]; int b; int bb[NTT_E]; };   // b: Shoup path bound (units of p); bb: fold path, per register, units of p/16
 
+EVAB_HD void flag_or(u64 *f) {
+#if defined(__CUDA_ARCH__)
+  atomicOr(reinterpret_cast<unsigned long long *>(f), 1ull);
+#else
+  *f |= 1ull;
+#endif
+}
 struct NttJob {
-  const u64 *src; u64 *dst; const u64 *aux0; const u64 *aux1;
+  const u64 *src; u64 *dst; const u64 *aux0; const u64 *aux1; u64 *zflag;
   u32 pi; u32 h; bool skip;
   bool bcast;  // constant polynomial (cflags)
   u32 spi;   // prime index of the values stored in src (PRO_MODRED)
@@ -77,6 +87,7 @@ EVAB_HD NttJob ntt_job_qr(const NttLaunch &L, u32 q, u32 r, u32 h, long long bof
   J.dst = L.dst + q * L.dst_sq + r * L.dst_sr + boff;
   J.aux0 = L.aux0 ? L.aux0 + q * L.aux0_sq + r * L.aux0_sr + boff : nullptr;
   J.aux1 = (L.aux1 && (int)q < L.aux1_polys) ? L.aux1 + q * L.aux1_sq + r * L.aux1_sr + boff : nullptr;
+  J.zflag = L.zflag ? L.zflag + boff : nullptr;
   return J;
 }
 EVAB_HD NttJob ntt_job(const NttLaunch &L, u32 cta, int ctas_per_job, long long boff = 0) {
@@ -360,16 +371,21 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1, int AR
       const u64 half = (AR == 1 ? L.fp[J.pi].p : P.p) >> 1;
       if constexpr (AR == 1) {
         finv_pass0_scaled<LOGN>(S.x, S.bb, L.fp[J.pi].fitw, fold_params(L.fp[J.pi]), tid, L.fp[J.pi], EPI == EPI_ADDHALF ? half : 0);   // canonical, half added
+        bool zero = false;
 #pragma unroll
-        for (int k = 0; k < NTT_E; k++) J.dst[idx_s<LOGN, 0>(tid, k)] = S.x[k];
+        for (int k = 0; k < NTT_E; k++) { J.dst[idx_s<LOGN, 0>(tid, k)] = S.x[k]; zero = zero || S.x[k] == 0; }
+        if (EPI == EPI_STORE_ZFLAG && zero) flag_or(J.zflag);
       } else {
         inv_pass0_scaled<LOGN>(S.x, P.itw, P.p, tid, S.b, P.ninv, P.ninv_s, P.itw1n, P.itw1n_s);   // * N^-1 folded in, canonical
 #pragma unroll
+        bool zero = false;
         for (int k = 0; k < NTT_E; k++) {
           u64 v = S.x[k];
           if (EPI == EPI_ADDHALF) v = addmod(v, half, P.p);
           J.dst[idx_s<LOGN, 0>(tid, k)] = v;
+          zero = zero || v == 0;
         }
+        if (EPI == EPI_STORE_ZFLAG && zero) flag_or(J.zflag);
       }
     } else if constexpr (PH % 2 == 1) {
       constexpr int j = G::P - 2 - (PH - 1) / 2;

@@ -164,11 +164,45 @@ inline size_t keyswitch_work_elems(const CtxView &c, int ell) { return ks_off_tm
 // automorphism, through which they are read (digit iNTT, inner product, mod-down epilogue).
 // Hoisted form (rotations sharing the inverse NTT of their input, exact): `that_in` = iNTT of the
 // unrotated digits, read by the mod-up through `ctab`, the coefficient-domain signed gather.
+// step 2 of A.5: ext[m][J] = NTT_m(that[J] mod m) for every output modulus m != q_J; `ctab` != null reads the digits through
+// the signed coefficient-domain gather of an automorphism
+template <class BE> int ks_modup(BE &be, const CtxView &c, int ell, const u64 *that, u64 *ext, const u32 *ctab) {
+  const long long N = (long long)c.N;
+  const int sp = c.k - 1;
+  NttLaunch B = base_launch(c);
+  B.src = that; B.src_sq = 0; B.src_sr = N;
+  B.dst = ext; B.dst_sq = (long long)ell * N; B.dst_sr = N;
+  B.inner = ell; B.prime_on_q = 1; B.skip_diag = 1; B.pro = ctab ? PRO_MODRED_SG : PRO_MODRED;
+  B.perm = ctab;
+  // the extended digits only feed the 128-bit inner product, which reduces lazily:
+  // skip their canonicalisation while the accumulated sum stays below 2^128
+  B.epi = (ell <= 15) ? EPI_STORE_LAZY : EPI_STORE;
+  B.subtab = c.zeros;
+  for (int mi = 0; mi <= ell; mi++) B.pmap[mi] = (unsigned char)(mi == ell ? sp : mi);
+  for (int J = 0; J < ell; J++) B.pmap2[J] = (unsigned char)J;
+  return be.fwd(B, (size_t)(ell + 1) * ell);
+}
+// steps 3 and 4: inner product with the key rows of the live primes and P, then the mod-down by P with rounding fused with
+// the accumulation into base (c0 and c1 for relinearize, c0 only for a rotation: the switched c1 has no base)
+template <class BE>
+int ks_finish(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, const u64 *ext, const u64 *key, const u64 *base, int base_polys, u64 *acc, u64 *tmp,
+              const u32 *nperm, const u32 *eperm, const u64 *cadd) {
+  const long long N = (long long)c.N;
+  const int k = c.k, sp = k - 1;
+  IpArgs I;
+  I.t = t; I.ext = ext; I.key = key; I.acc = acc; I.primes = c.primes; I.ell = ell; I.k = k; I.N = (int)N;
+  I.tperm = nperm; I.eperm = eperm; I.cadd = cadd;
+  if (int rc = be.inner(I)) return rc;
+  unsigned char pm[32];
+  for (int i = 0; i < ell; i++) pm[i] = (unsigned char)i;
+  return divround_impl(be, c, acc, (long long)(ell + 1) * N, 2, ell + 1, pm, sp, out, (long long)ell * N, base, (long long)ell * N, tmp,
+                       base_polys, nperm);
+}
 template <class BE>
 int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, const u64 *key, const u64 *base, int base_polys, u64 *work,
                    const u64 *that_in = nullptr, const u32 *ctab = nullptr, const u32 *nperm = nullptr) {
   const long long N = (long long)c.N;
-  const int k = c.k, sp = k - 1;
+  const int k = c.k;
   if (ell < 1 || ell > k - 1) return be.error("key switching needs 1 <= ell <= k-1");
   u64 *that = work;
   u64 *ext = work + ks_off_ext(c, ell);
@@ -184,30 +218,8 @@ int keyswitch_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *t, co
   } else if (ell > 15) {
     return be.error("hoisted key switching supports ell <= 15");
   }
-  // 2. ext[m][J] = NTT_m(that[J] mod m) for every output modulus m != q_J
-  NttLaunch B = base_launch(c);
-  B.src = that_in ? that_in : that; B.src_sq = 0; B.src_sr = N;
-  B.dst = ext; B.dst_sq = (long long)ell * N; B.dst_sr = N;
-  B.inner = ell; B.prime_on_q = 1; B.skip_diag = 1; B.pro = that_in ? PRO_MODRED_SG : PRO_MODRED;
-  B.perm = ctab;
-  // the extended digits only feed the 128-bit inner product, which reduces lazily:
-  // skip their canonicalisation while the accumulated sum stays below 2^128
-  B.epi = (ell <= 15) ? EPI_STORE_LAZY : EPI_STORE;
-  B.subtab = c.zeros;
-  for (int mi = 0; mi <= ell; mi++) B.pmap[mi] = (unsigned char)(mi == ell ? sp : mi);
-  for (int J = 0; J < ell; J++) B.pmap2[J] = (unsigned char)J;
-  if (int rc = be.fwd(B, (size_t)(ell + 1) * ell)) return rc;
-  // 3. inner product with the key rows of the live primes and P
-  IpArgs I;
-  I.t = t; I.ext = ext; I.key = key; I.acc = acc; I.primes = c.primes; I.ell = ell; I.k = k; I.N = (int)N;
-  I.tperm = nperm;
-  if (int rc = be.inner(I)) return rc;
-  // 4. mod-down by P with rounding, fused with the accumulation into base
-  unsigned char pm[32];
-  for (int i = 0; i < ell; i++) pm[i] = (unsigned char)i;
-  // base holds c0 and c1 (relinearize) or c0 only (rotate: the switched c1 has no base)
-  return divround_impl(be, c, acc, (long long)(ell + 1) * N, 2, ell + 1, pm, sp, out, (long long)ell * N, base, (long long)ell * N, tmp,
-                       base_polys, nperm);
+  if (int rc = ks_modup(be, c, ell, that_in ? that_in : that, ext, that_in ? ctab : nullptr)) return rc;
+  return ks_finish(be, c, ell, out, t, ext, key, base, base_polys, acc, tmp, nperm, nullptr, nullptr);
 }
 
 // Evaluator::relinearize (3 -> 2) -- reference eva/seal/seal_executor.h:200
@@ -259,6 +271,47 @@ int rotate_prepared_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 
                          u64 *work) {
   if (ell < 1 || ell > c.k - 1) return be.error("rotate needs 1 <= ell <= k-1");
   return keyswitch_impl(be, c, ell, out, a + (size_t)ell * c.N, key, a, 1, work, hoist, ctab, nperm);
+}
+
+// ---- hoisted_modup: rotations of one ciphertext share the inverse NTT AND the mod-up of its c1 -- exactly ---------------
+// SEAL rotates first and decomposes afterwards (A.5 step 1 on sigma_g(c1)): the digit of the rotated ciphertext is the signed
+// coefficient permutation of the unrotated digit, d'[j] = +-that_J[pi(j)] with the canonical negation q_J - v.  Reduced to an
+// output modulus m this is the ring automorphism of w = that_J mod m, EXCEPT that a negated coefficient is (q_J - v) mod m,
+// i.e. sigma_g(w)[j] + (q_J mod m):
+//     NTT_m(d' mod m) = perm_g( NTT_m(that_J mod m) ) + (q_J mod m) * NTT_m(I_g),      I_g = indicator of the negated positions,
+// whenever no negated coefficient of that_J is zero (negate(0) = 0 has no +q_J).  The second term does not depend on the data:
+//     acc_c[m] = sum_J perm_g(ext[m][J]) (.) K_g[J][c][m]  +  cadd_g[c][m],   cadd_g[c][m] = NTT_m(I_g) (.) sum_J (q_J mod m) K_g[J][c][m]
+// so the ell(ell+1) - ell mod-up transforms are done ONCE per ciphertext (rotate_modup_prepare_impl) and a rotation costs an inner
+// product through the permutation + 2 + 2 ell transforms (rotate_modup_prepared_impl): 10 instead of 26 at ell = 4, same bits.
+// A zero coefficient in a digit (probability 2^-60 each) raises `zflag`; the caller must then redo the rotations of that
+// ciphertext on the ordinary path (the executor does, transparently).
+template <class BE> int rotate_modup_prepare_impl(BE &be, const CtxView &c, int ell, u64 *that, u64 *ext, const u64 *a, u64 *zflag) {
+  if (ell < 1 || ell > c.k - 1 || ell > 15) return be.error("hoisted rotation needs 1 <= ell <= min(k-1, 15)");
+  NttLaunch A = base_launch(c);
+  A.src = a + (size_t)ell * c.N; A.dst = that; A.inner = ell; A.src_sr = A.dst_sr = (long long)c.N;
+  A.epi = EPI_STORE_ZFLAG; A.zflag = zflag;
+  for (int J = 0; J < ell; J++) A.pmap[J] = (unsigned char)J;
+  if (int rc = be.inv(A, ell)) return rc;
+  return ks_modup(be, c, ell, that, ext, nullptr);
+}
+inline size_t hoist_const_elems(const CtxView &c, int ell) { return (size_t)2 * (ell + 1) * c.N; }
+// cadd_g for one Galois key at one level; `tmp` holds (ell + 1) * N words
+template <class BE> int hoist_const_impl(BE &be, const CtxView &c, int ell, const u32 *ctab, const u64 *key, u64 *out, u64 *tmp) {
+  if (ell < 1 || ell > c.k - 1) return be.error("hoisted rotation needs 1 <= ell <= k-1");
+  if (int rc = be.hoist_indicator(tmp, ctab, (int)c.N, ell + 1)) return rc;
+  int pidx[32];
+  for (int mi = 0; mi <= ell; mi++) pidx[mi] = mi == ell ? c.k - 1 : mi;
+  if (int rc = ntt_batch_impl(be, c, false, tmp, (size_t)ell + 1, pidx, ell + 1)) return rc;
+  HoistConstArgs H;
+  H.ind = tmp; H.key = key; H.out = out; H.primes = c.primes; H.ell = ell; H.k = c.k; H.N = (int)c.N;
+  return be.hoist_const(H);
+}
+inline size_t rotate_modup_work_elems(const CtxView &c, int ell) { return (size_t)2 * (ell + 1) * c.N + (size_t)2 * c.N; }   // acc + tmp
+template <class BE>
+int rotate_modup_prepared_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, const u64 *ext, const u32 *nperm, const u64 *key, const u64 *cadd, u64 *work) {
+  if (ell < 1 || ell > c.k - 1) return be.error("rotate needs 1 <= ell <= k-1");
+  u64 *acc = work, *tmp = work + (size_t)2 * (ell + 1) * c.N;
+  return ks_finish(be, c, ell, out, a + (size_t)ell * c.N, ext, key, a, 1, acc, tmp, nperm, nperm, cadd);
 }
 
 // seal::CKKSEncoder::encode (vector overload) for a batch of vectors -- reference

@@ -162,6 +162,9 @@ template <bool SQUARE> EVAB_HD void mulct_elem(const MulArgs &A, int i, int j, l
 struct IpArgs {
   const u64 *t, *ext, *key; u64 *acc; const PrimeDev *primes;
   const u32 *tperm;   // optional: t is read through this NTT-domain permutation (rotation without a permuted copy)
+  const u32 *eperm;   // optional: the extended digits are read through the same permutation (they were computed once, unrotated,
+                      // for all rotations of the ciphertext: hoisted_modup), and `cadd` [2][ell+1][N] is added to the result
+  const u64 *cadd;
   int ell, k, N;
 };
 // off: batch instance offset (words) of t / ext / acc (the key is shared by all instances)
@@ -177,7 +180,9 @@ EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j, long long off = 0) {
       if (A.tperm) { v.x = EVAB_LDG(tp + EVAB_LDG(A.tperm + j)); v.y = EVAB_LDG(tp + EVAB_LDG(A.tperm + j + 1)); }
       else v = ld2(tp + j);
     } else {
-      v = ld2(A.ext + off + ((size_t)mi * A.ell + J) * N + j);
+      const u64 *ep = A.ext + off + ((size_t)mi * A.ell + J) * N;
+      if (A.eperm) { v.x = EVAB_LDG(ep + EVAB_LDG(A.eperm + j)); v.y = EVAB_LDG(ep + EVAB_LDG(A.eperm + j + 1)); }
+      else v = ld2(ep + j);
     }
     const u64x2 k0 = ld2(A.key + (((size_t)J * 2 + 0) * A.k + row) * N + j);
     const u64x2 k1 = ld2(A.key + (((size_t)J * 2 + 1) * A.k + row) * N + j);
@@ -188,7 +193,42 @@ EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j, long long off = 0) {
   // ext operands may be lazily reduced (< 16p, see EPI_STORE_LAZY): wide reduction
   r0.x = reduce128(l0x, h0x, P); r0.y = reduce128(l0y, h0y, P);
   r1.x = reduce128(l1x, h1x, P); r1.y = reduce128(l1y, h1y, P);
+  if (A.cadd) {
+    const u64x2 c0 = ld2(A.cadd + ((size_t)0 * (A.ell + 1) + mi) * N + j), c1 = ld2(A.cadd + ((size_t)1 * (A.ell + 1) + mi) * N + j);
+    r0.x = addmod(r0.x, c0.x, P.p); r0.y = addmod(r0.y, c0.y, P.p);
+    r1.x = addmod(r1.x, c1.x, P.p); r1.y = addmod(r1.y, c1.y, P.p);
+  }
   st2(A.acc + off + ((size_t)0 * (A.ell + 1) + mi) * N + j, r0);
   st2(A.acc + off + ((size_t)1 * (A.ell + 1) + mi) * N + j, r1);
 }
 
+// ---- shared mod-up of a rotation group (exact): per Galois key and level, the constant
+//   cadd[c][m] = NTT_m(I_g) (.) sum_{J < ell} (q_J mod m) * key[J][c][row(m)]          (mod m)
+// where I_g is the indicator polynomial of the coefficients the automorphism negates (ops_impl.hpp: hoisted_modup).
+struct HoistConstArgs {
+  const u64 *ind;     // [ell+1][N]  NTT_m(I_g), row order q_0 .. q_{ell-1}, P
+  const u64 *key;     // [k-1][2][k][N]
+  u64 *out;           // [2][ell+1][N]
+  const PrimeDev *primes;
+  int ell, k, N;
+};
+EVAB_HD void hoist_const_elem(const HoistConstArgs &A, int mi, int j) {
+  const int row = (mi == A.ell) ? A.k - 1 : mi;
+  const PrimeDev P = A.primes[row];
+  const size_t N = A.N;
+  const u64x2 ni = ld2(A.ind + (size_t)mi * N + j);
+  for (int c = 0; c < 2; c++) {
+    u64 lx = 0, hx = 0, ly = 0, hy = 0;
+    for (int J = 0; J < A.ell; J++) {
+      const u64 qj = A.primes[J].p % P.p;
+      const u64x2 kv = ld2(A.key + (((size_t)J * 2 + c) * A.k + row) * N + j);
+      mac128(lx, hx, qj, kv.x); mac128(ly, hy, qj, kv.y);
+    }
+    u64x2 r;
+    r.x = mulmod_p(reduce128(lx, hx, P), ni.x, P);
+    r.y = mulmod_p(reduce128(ly, hy, P), ni.y, P);
+    st2(A.out + ((size_t)c * (A.ell + 1) + mi) * N + j, r);
+  }
+}
+// I_g as residues: row mi, coefficient j = sign bit of the coefficient-domain gather table
+EVAB_HD void hoist_indicator_elem(u64 *out, const u32 *ctab, int N, int mi, int j) { out[(size_t)mi * N + j] = EVAB_LDG(ctab + j) & 1u; }

@@ -178,6 +178,25 @@ int evab_rotate(evab_ctx *ctx, int ell, uint64_t *d_out2, const uint64_t *d_a2, 
 int evab_rotate_prepare(evab_ctx *ctx, int ell, uint64_t *d_hoist, const uint64_t *d_a, void *stream);
 int evab_rotate_prepared(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, const uint64_t *d_hoist, uint64_t galois_elt,
                          const uint64_t *d_key, void *d_work, void *stream);
+/* Rotations of the same ciphertext also share the MOD-UP of its c1, exactly (SEAL decomposes sigma_g(c1) inside every
+ * rotate_vector :181,:188; the digit of the rotated ciphertext reduced to an output modulus m equals the NTT-domain permutation
+ * of the unrotated extended digit plus (q_J mod m) * NTT_m(indicator of the negated coefficients), a term that depends on the
+ * Galois key only -- eva_b200/csrc/ops_impl.hpp "hoisted_modup").
+ *   evab_rotate_modup_prepare : d_that [ell][N] = iNTT(c1), d_ext [ell+1][ell][N] = the extended digits, once per ciphertext;
+ *                               *d_zflag |= 1 when a digit holds a zero coefficient: the identity above then does not hold
+ *                               (negate(0) = 0) and the caller must use evab_rotate / evab_rotate_prepared for that ciphertext.
+ *   evab_rotate_hoist_const   : d_cadd [2][ell+1][N] for (galois_elt, key, ell), once per key and level; d_tmp (ell+1)*N words.
+ *   evab_rotate_modup_prepared: == evab_rotate bit for bit, with ell*ell + ell fewer transforms (10 instead of 26 at ell = 4).
+ * ell <= 15. */
+size_t evab_rotate_modup_ext_bytes(const evab_ctx *ctx, int ell);
+size_t evab_rotate_modup_work_bytes(const evab_ctx *ctx, int ell);
+size_t evab_hoist_const_bytes(const evab_ctx *ctx, int ell);
+int evab_rotate_modup_prepare(evab_ctx *ctx, int ell, uint64_t *d_that, uint64_t *d_ext, const uint64_t *d_a, uint64_t *d_zflag, void *stream);
+int evab_rotate_hoist_const(evab_ctx *ctx, int ell, uint64_t galois_elt, const uint64_t *d_key, uint64_t *d_cadd, uint64_t *d_tmp, void *stream);
+int evab_rotate_modup_prepared(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, const uint64_t *d_ext, uint64_t galois_elt,
+                               const uint64_t *d_key, const uint64_t *d_cadd, void *d_work, void *stream);
+/* stream-ordered zero fill (the executor clears its zero-coefficient flags at the start of every run) */
+int evab_memset_zero(evab_ctx *ctx, void *d, size_t bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -181,6 +181,26 @@ class EmuBackend:
             outs.append(out)
         return outs
 
+    def rotate_many_modup(self, a, steps_list, gks):
+        """rotations of one ciphertext sharing inverse NTT AND mod-up (evab_rotate_modup_*): (outputs, zero flag)"""
+        ell = a.shape[1]
+        that = np.empty((ell, self.N), dtype=np.uint64)
+        ext = np.zeros((ell + 1, ell, self.N), dtype=np.uint64)
+        zflag = np.zeros(1, dtype=np.uint64)
+        self._chk(self.lib.emu_rotate_modup_prepare(self.h, ell, _p(that), _p(ext), _p(a), _p(zflag)))
+        self.lib.emu_rotate_modup_work_bytes.restype = C.c_size_t
+        outs = []
+        for s_, gk in zip(steps_list, gks):
+            elt = C.c_uint64(_elt(self.N, s_))
+            cadd = np.empty((2, ell + 1, self.N), dtype=np.uint64)
+            tmp = np.empty((ell + 1, self.N), dtype=np.uint64)
+            self._chk(self.lib.emu_rotate_hoist_const(self.h, ell, elt, _p(gk), _p(cadd), _p(tmp)))
+            out = np.empty((2, ell, self.N), dtype=np.uint64)
+            work = np.zeros(self.lib.emu_rotate_modup_work_bytes(self.h, ell) // 8, dtype=np.uint64)
+            self._chk(self.lib.emu_rotate_modup_prepared(self.h, ell, _p(out), _p(a), _p(ext), elt, _p(gk), _p(cadd), _p(work)))
+            outs.append(out)
+        return outs, int(zflag[0])
+
 
 class GpuBackend:
     """Calls the product C-ABI (include/evab200.h).  Fails loudly if the CUDA
@@ -371,6 +391,35 @@ class GpuBackend:
             self._free(dk, do, dw)
         self._free(da, dh)
         return outs
+
+    def rotate_many_modup(self, a, steps_list, gks):
+        """rotations of one ciphertext sharing inverse NTT AND mod-up (evab_rotate_modup_*): (outputs, zero flag)"""
+        lib = self.lib
+        ell = a.shape[1]
+        da = self._up(a)
+        that = self._alloc(ell * self.N * 8)
+        ext = self._alloc(lib.evab_rotate_modup_ext_bytes(self.h, ell))
+        zf = self._alloc(8)
+        self._chk(lib.evab_memset_zero(self.h, zf, 8, None))
+        self._chk(lib.evab_rotate_modup_prepare(self.h, ell, that, ext, da, zf, None))
+        work = self._alloc(lib.evab_rotate_modup_work_bytes(self.h, ell))
+        outs = []
+        for s_, gk in zip(steps_list, gks):
+            elt = _elt(self.N, s_)
+            if elt not in self._prepared:
+                self._chk(lib.evab_galois_prepare(self.h, C.c_uint64(elt)))
+                self._prepared.add(elt)
+            dk = self._up(gk)
+            cadd = self._alloc(lib.evab_hoist_const_bytes(self.h, ell))
+            tmp = self._alloc((ell + 1) * self.N * 8)
+            self._chk(lib.evab_rotate_hoist_const(self.h, ell, C.c_uint64(elt), dk, cadd, tmp, None))
+            do = self._alloc(2 * ell * self.N * 8)
+            self._chk(lib.evab_rotate_modup_prepared(self.h, ell, do, da, ext, C.c_uint64(elt), dk, cadd, work, None))
+            outs.append(self._down(do, (2, ell, self.N)))
+            self._free(dk, do, cadd, tmp)
+        flag = int(self._down(zf, (1,))[0])
+        self._free(da, that, ext, work, zf)
+        return outs, flag
 
     def rotate(self, a, steps, gk):
         elt = int(self.lib.evab_galois_elt_from_step(C.c_uint64(self.N), steps))

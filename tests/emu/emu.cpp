@@ -79,6 +79,7 @@ template <int LOGN, bool INV, int CL, int AR> static void run_ntt_c(const NttLau
     if (L.pro == PRO_PLAIN && L.epi == EPI_STORE) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_STORE, CL, AR>(L, jobs);
     if (L.pro == PRO_PLAIN && L.epi == EPI_ADDHALF) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_ADDHALF, CL, AR>(L, jobs);
     if (L.pro == PRO_GATHER && L.epi == EPI_STORE) return run_ntt_m<LOGN, true, PRO_GATHER, EPI_STORE, CL, AR>(L, jobs);
+    if (L.pro == PRO_PLAIN && L.epi == EPI_STORE_ZFLAG) return run_ntt_m<LOGN, true, PRO_PLAIN, EPI_STORE_ZFLAG, CL, AR>(L, jobs);
   }
   abort();
 }
@@ -153,6 +154,14 @@ struct EmuBE {
   int inner(const IpArgs &A) {
     for (int mi = 0; mi <= A.ell; mi++)
       for (int j = 0; j < A.N; j += 2) ks_inner_elem(A, mi, j);
+    return 0;
+  }
+  int hoist_indicator(u64 *out, const u32 *ctab, int N, int rows) {
+    for (int mi = 0; mi < rows; mi++) for (int j = 0; j < N; j++) hoist_indicator_elem(out, ctab, N, mi, j);
+    return 0;
+  }
+  int hoist_const(const HoistConstArgs &A) {
+    for (int mi = 0; mi <= A.ell; mi++) for (int j = 0; j < A.N; j += 2) hoist_const_elem(A, mi, j);
     return 0;
   }
   int enc_scatter(const EncBatch &B) {
@@ -238,6 +247,22 @@ int emu_rotate(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, uint64_t elt,
   if (!c->perms.count(elt)) evab_host::galois_table(c->v.N, c->v.logN, elt, c->perms[elt]);
   EmuBE be{c};
   return rotate_impl(be, c->v, ell, o, a, c->perms[elt].data(), key, (u64 *)work);
+}
+// shared mod-up of a rotation group (exact): returns the zero flag through *zflag
+int emu_rotate_modup_prepare(EmuCtx *c, int ell, uint64_t *that, uint64_t *ext, const uint64_t *a, uint64_t *zflag) {
+  EmuBE be{c};
+  return rotate_modup_prepare_impl(be, c->v, ell, that, ext, a, zflag);
+}
+int emu_rotate_hoist_const(EmuCtx *c, int ell, uint64_t elt, const uint64_t *key, uint64_t *out, uint64_t *tmp) {
+  if (!c->cperms.count(elt)) evab_host::galois_coeff_table(c->v.N, elt, c->cperms[elt]);
+  EmuBE be{c};
+  return hoist_const_impl(be, c->v, ell, c->cperms[elt].data(), key, out, tmp);
+}
+size_t emu_rotate_modup_work_bytes(EmuCtx *c, int ell) { return rotate_modup_work_elems(c->v, ell) * 8; }
+int emu_rotate_modup_prepared(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, const uint64_t *ext, uint64_t elt, const uint64_t *key, const uint64_t *cadd, void *work) {
+  if (!c->perms.count(elt)) evab_host::galois_table(c->v.N, c->v.logN, elt, c->perms[elt]);
+  EmuBE be{c};
+  return rotate_modup_prepared_impl(be, c->v, ell, o, a, ext, c->perms[elt].data(), key, cadd, (u64 *)work);
 }
 int emu_rotate_prepare(EmuCtx *c, int ell, uint64_t *hoist, const uint64_t *a) {
   EmuBE be{c};

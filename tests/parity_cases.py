@@ -153,3 +153,17 @@ def case_keyswitch(be, orc, ell, steps=(1, -2)):
     if hasattr(be, "rotate_many"):
         for s, gk, got in zip(steps, gks, be.rotate_many(a2, list(steps), gks)):
             eq(got, orc.rotate(a2, s, gk))
+    # rotations sharing the inverse NTT and the mod-up of the input (exact: ops_impl.hpp hoisted_modup)
+    if hasattr(be, "rotate_many_modup"):
+        outs, flag = be.rotate_many_modup(a2, list(steps), gks)
+        assert flag == 0
+        for s, gk, got in zip(steps, gks, outs):
+            eq(got, orc.rotate(a2, s, gk))
+        # a digit with a zero coefficient: negate(0) = 0 carries no q_J, the shared mod-up must say so (the caller falls back)
+        coeff = orc.ntt_inv(a2[1].copy(), list(range(ell))) if False else None
+        z = a2.copy()
+        c1 = np.stack([orc.ntt_inv(z[1, i], i) for i in range(ell)])
+        c1[0, 5] = 0
+        z[1] = np.stack([orc.ntt_fwd(c1[i], i) for i in range(ell)])
+        _, flag = be.rotate_many_modup(z, list(steps[:1]), gks[:1])
+        assert flag == 1

@@ -214,3 +214,39 @@ def test_replicas_bounded_by_memory(monkeypatch):
         for b in range(7):
             for oname, oid in d["outputs"].items():
                 assert np.array_equal(outs[b].get(oname)[1], want[b][oid][1]), (cap, fuse, b)
+
+
+def test_zero_digit_falls_back_to_the_exact_path():
+    """The shared mod-up of a rotation group assumes no digit coefficient is zero (negate(0) = 0 carries no q_J).  An input
+    whose c1 has a zero coefficient raises the flag; execute() redoes the call on plans without the shared mod-up and still
+    returns the oracle's bits."""
+    from eva_b200 import b200
+    d = gl.load_json("sobel")
+    prog, params, sig, terms = gl.build_program(d)
+    N = d["poly_modulus_degree"]
+    orc = o.Oracle(N, d["prime_bits"]).keygen(1)
+    op = OracleProgram(d, orc)
+    op.prepare_keys()
+    pub = b200.context_from_raw_keys(N, orc.primes, op.rk, {int(e): k for e, k in op.gks.items()})
+    rng = np.random.default_rng(4)
+    (name_, info), = d["signature"].items()
+    ell = orc.k - 1 - info["level"]
+    ct = orc.encrypt(orc.encode(rng.uniform(0, 1, d["vec_size"]), 2.0 ** info["scale"], ell), seed=3)
+    c1 = np.stack([orc.ntt_inv(ct[1, i], i) for i in range(ell)])
+    c1[1, 7] = 0                                     # one zero coefficient in digit 1
+    ct[1] = np.stack([orc.ntt_fwd(c1[i], i) for i in range(ell)])
+    val = b200.B200Valuation()
+    val.set_cipher(name_, ct, 2.0 ** info["scale"])
+    V = op.run({name_: ("cipher", ct, 2.0 ** info["scale"])})
+    for _ in range(2):                               # first call falls back, second runs on the rebuilt plan
+        out = pub.execute(prog, val)
+        for oname, oid in d["outputs"].items():
+            assert np.array_equal(out.get(oname)[1], V[oid][1])
+    # and an ordinary input still matches on the same context
+    ct2 = orc.encrypt(orc.encode(rng.uniform(0, 1, d["vec_size"]), 2.0 ** info["scale"], ell), seed=5)
+    val2 = b200.B200Valuation()
+    val2.set_cipher(name_, ct2, 2.0 ** info["scale"])
+    V2 = op.run({name_: ("cipher", ct2, 2.0 ** info["scale"])})
+    out2 = pub.execute(prog, val2)
+    for oname, oid in d["outputs"].items():
+        assert np.array_equal(out2.get(oname)[1], V2[oid][1])
