@@ -28,7 +28,7 @@ from . import Op, Program, Type
 from .shard import infer, _add_trees, _ATTR_COPY
 
 # rough single-instance costs in microseconds on a B200 (tools/op_throughput.py, profiles/): only the ratios matter
-_COST = {Op.RotateLeftConst: 12.0, Op.RotateRightConst: 12.0, Op.Relinearize: 12.0, Op.Rescale: 5.0, Op.ModSwitch: 1.5,
+_COST = {Op.RotateLeftConst: 7.0, Op.RotateRightConst: 7.0, Op.Relinearize: 9.0, Op.Rescale: 4.0, Op.ModSwitch: 1.5,
          Op.Mul: 3.0, Op.Add: 1.5, Op.Sub: 1.5, Op.Negate: 1.5, Op.Encode: 0.5}
 _EXPENSIVE = (Op.RotateLeftConst, Op.RotateRightConst, Op.Relinearize)
 EXCHANGE_US = 45.0     # one NCCL (all-)gather of a ciphertext per rank on NVSwitch + the stage boundary
