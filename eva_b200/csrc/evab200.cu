@@ -159,8 +159,7 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::
   const u32 tid = threadIdx.x;
   if (PRO == PRO_PLAIN && EPI == EPI_STORE && J.bcast) { fwd_const_poly<LOGN>(J, B::vtid(J, tid)); return; }
   const DevHooks<LOGN, CL> hk(sm);
-  hk.start();
-  hk.ready();   // kernel start: nothing cached yet, the acquire (L1 invalidate) costs nothing
+  hk.start();   // relaxed cluster arrive; the matching wait sits right before the first store into a peer (hk.ready in phase 0)
   if constexpr (CL > 1) PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, dev_smem_view<LOGN, CL>(sm), DevSync<LOGN, CL>{hk}, hk);
   else PhaseLoop<B, 0, B::NPH>::run(S, L, J, tid, smem_view<1>(sm), DevSync<LOGN, CL>{hk}, hk);
   B::phE(S, L, J, tid);
@@ -173,8 +172,7 @@ __global__ void __launch_bounds__(NttGeom<LOGN>::T / CL, 1024 / (NttGeom<LOGN>::
   if (J.skip) return;
   NttState S;
   const DevHooks<LOGN, CL> hk(sm);
-  hk.start();
-  hk.ready();   // kernel start: nothing cached yet, the acquire costs nothing
+  hk.start();   // the matching wait sits right before this CTA first signals its peers (hk.ready in the pass-1 phase)
   if constexpr (CL > 1) PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, dev_smem_view<LOGN, CL>(sm), DevSync<LOGN, CL>{hk}, hk);
   else PhaseLoop<B, 0, B::NPH>::run(S, L, J, threadIdx.x, smem_view<1>(sm), DevSync<LOGN, CL>{hk}, hk);
 }

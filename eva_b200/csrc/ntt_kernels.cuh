@@ -223,7 +223,7 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1, int AR
         if (cheap) load0<true>(S, L, J, P, tid, sub); else load0<false>(S, L, J, P, tid, sub);
         fwd_pass_s<LOGN, 0>(S.x, P.tw, root, P.p, tid, S.b);
       }
-      if constexpr (CL > 1) xchg_write_dist_fwd<LOGN, CL>(S.x, smv, tid);   // peers are resident, their barriers initialised (hk.start / hk.ready at kernel start)
+      if constexpr (CL > 1) { hk.ready(); xchg_write_dist_fwd<LOGN, CL>(S.x, smv, tid); }   // peers resident, barriers initialised: waited for here, behind pass 0
       else xchg_write_s<LOGN, 0, 1>(S.x, sm, tid);
     } else if constexpr (PH == NPH - 1) {
       if constexpr (CL > 1) xchg_read_cl<LOGN, CL>(S.x, sm, tid); else xchg_read_c<LOGN>(S.x, sm, tid);
@@ -399,7 +399,7 @@ template <int LOGN, int PRO = PRO_PLAIN, int EPI = EPI_STORE, int CL = 1, int AR
       if constexpr (AR == 1) finv_pass_s<LOGN, j>(S.x, S.bb, L.fp[J.pi].fitw, fold_params(L.fp[J.pi]), tid);
       else inv_pass_s<LOGN, j>(S.x, P.itw, root, P.p, tid, S.b);
       // the butterflies above consumed every value read from this CTA's slice: from here on the peers may overwrite it
-      if constexpr (CL > 1 && j == 1) hk.released();
+      if constexpr (CL > 1 && j == 1) { hk.ready(); hk.released(); }   // (the start handshake is waited for here, two passes into the kernel)
     } else {
       constexpr int j = G::P - 2 - (PH - 2) / 2;   // pass that just ran
       if constexpr (CL > 1) {

@@ -52,6 +52,21 @@ ops = [
     ("rotate_prepare", lambda: lib.evab_rotate_prepare(h, ell, P(hoist), P(a2), st), 2 * ell * R),
     ("rotate_prepared", lambda: lib.evab_rotate_prepared(h, ell, P(out), P(a2), P(hoist), 3, P(key), P(work), st), (2 * ell * ell + 5 * ell) * R),
 ]
+# rotations sharing inverse NTT and mod-up (evab_rotate_modup_*): the prepare once per ciphertext, then per rotation
+ext = torch.empty((B, lib.evab_rotate_modup_ext_bytes(h, ell) // 8), dtype=torch.int64, device="cuda")
+# the per-instance buffers must follow the batch stride: carve them out of a second strided block
+stride2 = (ell * N + lib.evab_rotate_modup_ext_bytes(h, ell) // 8 + 64 + 63) // 64 * 64
+assert stride2 <= stride, "census layout: the hoist buffers must fit the instance stride"
+that2, ext2, zf2 = buf[0, 7 * ell * N:8 * ell * N], hoist, None
+cadd = torch.empty(lib.evab_hoist_const_bytes(h, ell) // 8, dtype=torch.int64, device="cuda")
+ctmp = torch.empty((ell + 1) * N, dtype=torch.int64, device="cuda")
+assert lib.evab_rotate_hoist_const(h, ell, 3, P(key), P(cadd), P(ctmp), st) == 0
+big = torch.randint(0, 1 << 59, (B, stride), dtype=torch.int64, device="cuda")     # that | ext | flag of every instance, same stride
+bthat, bext, bflag = big[0, :ell * N], big[0, ell * N:ell * N + (ell + 1) * ell * N], big[0, ell * N + (ell + 1) * ell * N:ell * N + (ell + 1) * ell * N + 8]
+ops += [
+    ("rotate_modup_prepare (once per ciphertext)", lambda: lib.evab_rotate_modup_prepare(h, ell, P(bthat), P(bext), P(a2), P(bflag), st), (ell + ell + (ell + 1) * ell) * R),
+    ("rotate_modup_prepared (per rotation)", lambda: lib.evab_rotate_modup_prepared(h, ell, P(out), P(a2), P(bext), 3, P(key), P(cadd), P(work), st), (ell * (ell + 1) + 2 * ell * (ell + 1) + 4 * ell) * R),
+]
 for name, fn, _ in ops:       # warm-up outside the profiled range
     lib.evab_set_batch(B, stride, 0); assert fn() == 0; lib.evab_set_batch(1, 0, 0)
 torch.cuda.synchronize()
