@@ -294,7 +294,7 @@ def run_ours(args):
         shard_res = []
         for wl in ("wide4096", "harris"):
             shard_res.append(dagshard_bench.measure(wl, rank, world, local, steps=20, warmup=3, quiet=True))
-        result["dag_sharded"] = [{k: r.get(k) for k in ("workload", "cipher_ops", "ms_single_gpu", "ms_sharded", "speedup", "bit_identical", "stages", "note") if k in r} for r in shard_res]
+        result["dag_sharded"] = [{k: r.get(k) for k in ("workload", "cipher_ops", "ms_single_gpu", "ms_sharded", "speedup", "bit_identical", "auto_choice", "stages", "note") if k in r} for r in shard_res]
     if rank == 0:
         result["roofline"] = ntt_roofline(pub, b200.create_coeff_modulus(16384, [60] * 4), 16384, main.cuda_stream)   # always the BASELINE shape
         if world == 1 and not args.no_cpu:

@@ -92,7 +92,9 @@ def measure(workload, rank, world, local, steps, warmup, quiet=False):
         (t_shard,) = multi.max_over_ranks([t_shard], world, device="cuda")
         if rank == 0:
             same = all(np.array_equal(out.get(o)[1], single.get(o)[1]) for o in d["outputs"])
-            res.update({"ms_sharded": t_shard * 1e3, "speedup": res["ms_single_gpu"] / (t_shard * 1e3), "bit_identical": bool(same),
+            sp = res["ms_single_gpu"] / (t_shard * 1e3)
+            res.update({"ms_sharded": t_shard * 1e3, "speedup": sp, "bit_identical": bool(same),
+                        "auto_choice": "sharded" if sp > 1.03 else "single GPU (dagshard.AutoShardedRunner measures both and keeps the faster: this plan does not pay at this GPU count)",
                         "stages": plan.describe(), "exchange": "NCCL all_gather_into_tensor between stages, gather on rank 0 for the last cut; device pointers, no host staging"})
     if rank == 0 and not quiet:
         print(json.dumps(res), flush=True)
