@@ -46,6 +46,8 @@ _SIGS = {
     "evab_rotate_hoist_const": (ci, [vp, ci, u64, vp, vp, vp, vp]),
     "evab_rotate_modup_prepared": (ci, [vp, ci, vp, vp, vp, u64, vp, vp, vp, vp]),
     "evab_memset_zero": (ci, [vp, vp, szt, vp]),
+    "evab_decode_work_bytes": (szt, [vp, ci]),
+    "evab_decode": (ci, [vp, ci, vp, C.c_double, vp, vp, vp]),
     "evab_set_ntt_cluster": (ci, [ci]),
     "evab_ctx_set_ntt_cluster": (ci, [vp, ci]),
     "evab_ctx_set_ntt_arith": (ci, [vp, ci]),

@@ -130,3 +130,67 @@ EVAB_HD void enc_uniform_elem(const EncUniform &B, u32 e, u32 i, u32 j, long lon
   u64x2 v; v.x = r; v.y = r;
   *reinterpret_cast<u64x2 *>(B.out + off + ((size_t)e * B.ell + i) * B.N + j) = v;
 }
+
+// ---- decoder on the device: seal::CKKSEncoder::decode as called at reference eva/seal/seal.cpp:132-146.
+// coefficient residues (after the inverse NTT) -> CRT composition to a centred multi-word integer -> double / scale ->
+// forward canonical-embedding FFT (Cooley-Tukey, natural in, bit-reversed out) -> the N/2 slot values.  Same operation
+// order, explicit round-to-nearest, as the host decoder and the oracle (ora_decode): identical doubles.
+#define DEC_MAX_ELL 8
+#define DEC_WORDS (DEC_MAX_ELL + 1)
+struct DecArgs {
+  const u64 *coef;              // [ell][N] coefficient-form residues
+  cplx *work;                   // [N]
+  double *out;                  // [N/2] slot values
+  const cplx *roots;            // [N] zeta^bitrev(i)
+  const u32 *slot_index;        // [N]
+  const PrimeDev *primes;
+  u64 Q[DEC_WORDS], halfQ[DEC_WORDS];        // Q = q_0 ... q_{ell-1}, (Q + 1) / 2
+  u64 punct[DEC_MAX_ELL][DEC_WORDS];         // Q / q_i
+  u64 ipunct[DEC_MAX_ELL];                   // (Q / q_i)^-1 mod q_i
+  double inv_scale;
+  u32 N, ell;
+};
+EVAB_HD int dec_cmp(const u64 *a, const u64 *b, int nw) {
+  for (int i = nw - 1; i >= 0; i--) { if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1; }
+  return 0;
+}
+EVAB_HD void dec_sub(u64 *a, const u64 *b, int nw) {   // a -= b
+  u64 borrow = 0;
+  for (int i = 0; i < nw; i++) { const u64 t = a[i] - b[i], t2 = t - borrow; borrow = (a[i] < b[i]) | (t < borrow); a[i] = t2; }
+}
+// coefficient j -> work[j] = (centred CRT value / scale, 0)
+EVAB_HD void dec_compose(const DecArgs &A, u32 j) {
+  const int nw = (int)A.ell + 1;
+  u64 X[DEC_WORDS];
+  for (int w = 0; w < nw; w++) X[w] = 0;
+  for (u32 i = 0; i < A.ell; i++) {
+    const PrimeDev P = A.primes[i];
+    const u64 v = mulmod(A.coef[(size_t)i * A.N + j], A.ipunct[i], P.p, P.ratio_lo, P.ratio_hi);
+    u64 carry = 0;                                        // X += punct[i] * v
+    for (int w = 0; w < nw; w++) {
+      const u64 lo = A.punct[i][w] * v, hi = mulhi64(A.punct[i][w], v);
+      const u64 s = X[w] + lo, c1 = s < lo;
+      const u64 s2 = s + carry, c2 = s2 < carry;
+      X[w] = s2; carry = hi + c1 + c2;
+    }
+  }
+  while (dec_cmp(X, A.Q, nw) >= 0) dec_sub(X, A.Q, nw);
+  const bool neg = dec_cmp(X, A.halfQ, nw) >= 0;
+  if (neg) { u64 T[DEC_WORDS]; for (int w = 0; w < nw; w++) T[w] = A.Q[w]; dec_sub(T, X, nw); for (int w = 0; w < nw; w++) X[w] = T[w]; }
+  double acc = 0.0, f = A.inv_scale;
+  for (int w = 0; w < nw; w++) { if (X[w]) acc = D_ADD(acc, D_MUL((double)X[w], f)); f = D_MUL(f, 18446744073709551616.0); }
+  cplx c; c.re = neg ? -acc : acc; c.im = 0.0;
+  A.work[j] = c;
+}
+// stage with m groups (m = 1, 2, 4, ...; t = N / (2m)): butterfly b of N/2
+EVAB_HD void dec_fft_bfly(const DecArgs &A, u32 m, u32 b) {
+  const u32 t = A.N / (2 * m), i = b / t, j = 2 * i * t + b % t;
+  const cplx r = A.roots[m + i];
+  cplx *w = A.work;
+  const double vr = D_SUB(D_MUL(w[j + t].re, r.re), D_MUL(w[j + t].im, r.im));
+  const double vi = D_ADD(D_MUL(w[j + t].re, r.im), D_MUL(w[j + t].im, r.re));
+  const double ur = w[j].re, ui = w[j].im;
+  w[j].re = D_ADD(ur, vr); w[j].im = D_ADD(ui, vi);
+  w[j + t].re = D_SUB(ur, vr); w[j + t].im = D_SUB(ui, vi);
+}
+EVAB_HD void dec_gather(const DecArgs &A, u32 i) { A.out[i] = A.work[A.slot_index[i]].re; }

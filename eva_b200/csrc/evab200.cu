@@ -207,6 +207,15 @@ __global__ void __launch_bounds__(256) k_hoist_const(const HoistConstArgs A) {
 __global__ void __launch_bounds__(256) k_hoist_indicator(u64 *out, const u32 *ctab, int N) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) hoist_indicator_elem(out, ctab, N, blockIdx.y, j);
 }
+__global__ void __launch_bounds__(256) k_dec_compose(const DecArgs A) {
+  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < A.N; j += gridDim.x * blockDim.x) dec_compose(A, j);
+}
+__global__ void __launch_bounds__(256) k_dec_fft(const DecArgs A, u32 m) {
+  for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < A.N / 2; b += gridDim.x * blockDim.x) dec_fft_bfly(A, m, b);
+}
+__global__ void __launch_bounds__(256) k_dec_gather(const DecArgs A) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < A.N / 2; i += gridDim.x * blockDim.x) dec_gather(A, i);
+}
 __global__ void __launch_bounds__(256) k_enc_scatter(const EncBatch B, const long long bstride, const long long vstride) {
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < B.N / 2; i += gridDim.x * blockDim.x)
     enc_scatter(B, blockIdx.y, i, (long long)blockIdx.z * bstride, (long long)blockIdx.z * vstride);
@@ -408,6 +417,9 @@ struct CudaBE {
     CUDA_OK(cudaGetLastError());
     return 0;
   }
+  int dec_compose(const DecArgs &A) { count(); k_dec_compose<<<(A.N + 255) / 256, 256, 0, st>>>(A); CUDA_OK(cudaGetLastError()); return 0; }
+  int dec_fft(const DecArgs &A, u32 m) { count(); k_dec_fft<<<(A.N / 2 + 255) / 256, 256, 0, st>>>(A, m); CUDA_OK(cudaGetLastError()); return 0; }
+  int dec_gather(const DecArgs &A) { count(); k_dec_gather<<<(A.N / 2 + 255) / 256, 256, 0, st>>>(A); CUDA_OK(cudaGetLastError()); return 0; }
   int enc_scatter(const EncBatch &B) {
     count();
     k_enc_scatter<<<dim3((B.N / 2 + 255) / 256, B.count, g_batch.batch), 256, 0, st>>>(B, g_batch.stride, g_batch.vstride);
@@ -644,6 +656,12 @@ extern "C" size_t evab_encode_work_bytes(const evab_ctx *c, int count) { return 
 extern "C" int evab_encode(evab_ctx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell,
                            uint64_t *out, void *work, void *stream) {
   BE_BEGIN return encode_impl(be, c->v, count, vals, vec, scales, ell, out, (cplx *)work);
+}
+extern "C" size_t evab_decode_work_bytes(const evab_ctx *c, int ell) { return decode_tmp_elems(c->v, ell) * sizeof(u64) + (size_t)c->v.N * sizeof(cplx); }
+extern "C" int evab_decode(evab_ctx *c, int ell, const uint64_t *pt, double scale, double *d_out, void *work, void *stream) {
+  u64 *tmp = (u64 *)work;
+  cplx *cw = (cplx *)(tmp + decode_tmp_elems(c->v, ell));
+  BE_BEGIN return decode_impl(be, c->v, ell, c->primes.data(), pt, scale, d_out, tmp, cw);
 }
 extern "C" int evab_add(evab_ctx *c, int ell, uint64_t *o, const uint64_t *a, int sa, const uint64_t *b, int sb, void *stream) {
   BE_BEGIN return dyadic_impl<DY_ADD>(be, c->v, ell, o, a, sa, b, sb, 0);

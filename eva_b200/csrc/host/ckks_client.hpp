@@ -4,7 +4,7 @@
 // from seal::CKKSEncoder / KeyGenerator / Encryptor / Decryptor at
 // eva/seal/seal.cpp:24-102,124-146,174-203 and seal_executor.h:217-243
 // (SURVEY.md Appendix A.9-A.11).  All polynomial arithmetic runs on the GPU
-// through the C-ABI; only sampling and the FP64 embedding are host code.
+// through the C-ABI, and so do the encoder's and the decoder's FP64 transforms; only the sampling is host code.
 #pragma once
 #include "runtime.hpp"
 #include <cmath>
@@ -95,8 +95,17 @@ public:
     check(evab_ntt_fwd(dev_->ctx(), d_pt, (std::size_t)ell, idx.data(), ell, stream));
     dev_->sync(stream);
   }
-  // decode device plaintext d_pt[ell][N] (NTT form) -> N/2 real slot values
+  // decode device plaintext d_pt[ell][N] (NTT form) -> N/2 real slot values: inverse NTT, CRT composition and the FP64
+  // forward FFT all run on the device (evab_decode); only the N/2 doubles come back.  (ell > 8: host composition, unembed.)
   std::vector<double> decode(const u64 *d_pt, int ell, double scale) const {
+    if (ell <= 8) {
+      DBuf out(dev_, N_ / 2), work(dev_, evab_decode_work_bytes(dev_->ctx(), ell) / 8 + 1);
+      check(evab_decode(dev_->ctx(), ell, d_pt, scale, reinterpret_cast<double *>(out.get()), work.get(), nullptr));
+      std::vector<double> v(N_ / 2);
+      dev_->download(v.data(), out.get(), v.size() * 8);
+      dev_->sync();
+      return v;
+    }
     DBuf tmp(dev_, (std::size_t)ell * N_);
     check(evab_add_plain(dev_->ctx(), ell, tmp.get(), d_pt, 1, zeroPlain(ell), nullptr));
     std::vector<int> idx(ell);

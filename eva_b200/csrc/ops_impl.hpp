@@ -351,3 +351,42 @@ int encode_impl(BE &be, const CtxView &c, int count, const double *const *d_valu
   L.cflags = encode_flags(c, count, work);
   return be.fwd(L, (size_t)count * ell);
 }
+
+// seal::CKKSEncoder::decode of a plaintext [ell][N] (NTT form) -> N/2 slot values (reference eva/seal/seal.cpp:132-146).
+// d_tmp: ell*N words (the coefficient form), d_work: N complex values, d_out: N/2 doubles.  CRT constants come from the host.
+inline size_t decode_tmp_elems(const CtxView &c, int ell) { return (size_t)ell * c.N; }
+template <class BE>
+int decode_impl(BE &be, const CtxView &c, int ell, const u64 *primes_host, const u64 *pt, double scale, double *out, u64 *tmp, cplx *work) {
+  if (ell < 1 || ell > c.k || ell > DEC_MAX_ELL) return be.error("decode: ell out of range (1..8)");
+  typedef unsigned __int128 u128;
+  const int nw = ell + 1;
+  DecArgs A;
+  memset(&A, 0, sizeof(A));
+  auto big_mul = [&](u64 *x, u64 m) { u64 carry = 0; for (int w = 0; w < nw; w++) { const u128 t = (u128)x[w] * m + carry; x[w] = (u64)t; carry = (u64)(t >> 64); } };
+  auto big_mod = [&](const u64 *x, u64 m) { u128 r = 0; for (int w = nw - 1; w >= 0; w--) r = ((r << 64) | x[w]) % m; return (u64)r; };
+  A.Q[0] = 1;
+  for (int i = 0; i < ell; i++) big_mul(A.Q, primes_host[i]);
+  for (int i = 0; i < ell; i++) {
+    A.punct[i][0] = 1;
+    for (int j = 0; j < ell; j++) if (j != i) big_mul(A.punct[i], primes_host[j]);
+    // inverse by Fermat: q_i prime
+    const u64 p = primes_host[i];
+    u64 base = big_mod(A.punct[i], p), e = p - 2, r = 1;
+    while (e) { if (e & 1) r = (u64)((u128)r * base % p); base = (u64)((u128)base * base % p); e >>= 1; }
+    A.ipunct[i] = r;
+  }
+  for (int w = 0; w < nw; w++) A.halfQ[w] = A.Q[w];
+  { u64 carry = 1; for (int w = 0; w < nw && carry; w++) { A.halfQ[w] += carry; carry = A.halfQ[w] == 0; } }
+  for (int w = 0; w < nw; w++) A.halfQ[w] = (A.halfQ[w] >> 1) | (w + 1 < nw ? A.halfQ[w + 1] << 63 : 0);
+  // coefficient form
+  if (int rc = copy_impl(be, c, ell, ell, tmp, pt, 1)) return rc;
+  int pidx[32];
+  for (int i = 0; i < ell; i++) pidx[i] = i;
+  if (int rc = ntt_batch_impl(be, c, true, tmp, (size_t)ell, pidx, ell)) return rc;
+  A.coef = tmp; A.work = work; A.out = out; A.roots = c.roots; A.slot_index = c.slot_index; A.primes = c.primes;
+  A.inv_scale = 1.0 / scale; A.N = (u32)c.N; A.ell = (u32)ell;
+  if (int rc = be.dec_compose(A)) return rc;
+  for (u32 m = 1; m < A.N; m <<= 1)
+    if (int rc = be.dec_fft(A, m)) return rc;
+  return be.dec_gather(A);
+}

@@ -195,6 +195,11 @@ int evab_rotate_modup_prepare(evab_ctx *ctx, int ell, uint64_t *d_that, uint64_t
 int evab_rotate_hoist_const(evab_ctx *ctx, int ell, uint64_t galois_elt, const uint64_t *d_key, uint64_t *d_cadd, uint64_t *d_tmp, void *stream);
 int evab_rotate_modup_prepared(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, const uint64_t *d_ext, uint64_t galois_elt,
                                const uint64_t *d_key, const uint64_t *d_cadd, void *d_work, void *stream);
+/* seal::CKKSEncoder::decode (seal.cpp:132-146): plaintext d_pt [ell][N] (NTT form) at absolute scale -> N/2 slot values
+ * (doubles, device) -- inverse NTT, CRT composition to a centred multi-word integer, FP64 forward special FFT, all on the
+ * device and bit-identical to the host / oracle decoders.  ell <= 8.  d_work: evab_decode_work_bytes(ctx, ell) bytes. */
+size_t evab_decode_work_bytes(const evab_ctx *ctx, int ell);
+int evab_decode(evab_ctx *ctx, int ell, const uint64_t *d_pt, double scale, double *d_out, void *d_work, void *stream);
 /* stream-ordered zero fill (the executor clears its zero-coefficient flags at the start of every run) */
 int evab_memset_zero(evab_ctx *ctx, void *d, size_t bytes, void *stream);
 

@@ -181,6 +181,12 @@ class EmuBackend:
             outs.append(out)
         return outs
 
+    def decode(self, pt, scale, primes):
+        out = np.empty(self.N // 2, dtype=np.float64)
+        pa = np.array(primes, dtype=np.uint64)
+        self._chk(self.lib.emu_decode(self.h, pt.shape[0], _p(pa), _p(np.ascontiguousarray(pt)), C.c_double(scale), out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def rotate_many_modup(self, a, steps_list, gks):
         """rotations of one ciphertext sharing inverse NTT AND mod-up (evab_rotate_modup_*): (outputs, zero flag)"""
         ell = a.shape[1]
@@ -391,6 +397,17 @@ class GpuBackend:
             self._free(dk, do, dw)
         self._free(da, dh)
         return outs
+
+    def decode(self, pt, scale, primes=None):
+        lib = self.lib
+        ell = pt.shape[0]
+        dp = self._up(pt)
+        do = self._alloc(self.N // 2 * 8)
+        dw = self._alloc(lib.evab_decode_work_bytes(self.h, ell))
+        self._chk(lib.evab_decode(self.h, ell, dp, C.c_double(scale), do, dw, None))
+        out = self._down(do, (self.N // 2,)).view(np.float64)
+        self._free(dp, do, dw)
+        return out
 
     def rotate_many_modup(self, a, steps_list, gks):
         """rotations of one ciphertext sharing inverse NTT AND mod-up (evab_rotate_modup_*): (outputs, zero flag)"""

@@ -164,6 +164,9 @@ struct EmuBE {
     for (int mi = 0; mi <= A.ell; mi++) for (int j = 0; j < A.N; j += 2) hoist_const_elem(A, mi, j);
     return 0;
   }
+  int dec_compose(const DecArgs &A) { for (u32 j = 0; j < A.N; j++) ::dec_compose(A, j); return 0; }
+  int dec_fft(const DecArgs &A, u32 m) { for (u32 b = 0; b < A.N / 2; b++) dec_fft_bfly(A, m, b); return 0; }
+  int dec_gather(const DecArgs &A) { for (u32 i = 0; i < A.N / 2; i++) ::dec_gather(A, i); return 0; }
   int enc_scatter(const EncBatch &B) {
     for (u32 e = 0; e < B.count; e++) for (u32 i = 0; i < B.N / 2; i++) ::enc_scatter(B, e, i);
     return 0;
@@ -238,6 +241,12 @@ size_t emu_encode_work_bytes(EmuCtx *c, int count) { return encode_work_bytes(c-
 int emu_encode(EmuCtx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell, uint64_t *out, void *work) {
   EmuBE be{c};
   return encode_impl(be, c->v, count, vals, vec, scales, ell, out, (cplx *)work);
+}
+int emu_decode(EmuCtx *c, int ell, const uint64_t *primes, const uint64_t *pt, double scale, double *out) {
+  EmuBE be{c};
+  std::vector<u64> tmp(decode_tmp_elems(c->v, ell));
+  std::vector<cplx> work(c->v.N);
+  return decode_impl(be, c->v, ell, primes, pt, scale, out, tmp.data(), work.data());
 }
 size_t emu_rescale_work_bytes(EmuCtx *c, int sa) { return rescale_work_elems(c->v, sa) * 8; }
 int emu_rescale(EmuCtx *c, int ell, uint64_t *o, const uint64_t *a, int sa, void *work) { EmuBE be{c}; return rescale_impl(be, c->v, ell, o, a, sa, (u64 *)work); }

@@ -167,3 +167,18 @@ def case_keyswitch(be, orc, ell, steps=(1, -2)):
         z[1] = np.stack([orc.ntt_fwd(c1[i], i) for i in range(ell)])
         _, flag = be.rotate_many_modup(z, list(steps[:1]), gks[:1])
         assert flag == 1
+
+
+def case_decode(be, orc):
+    """CKKSEncoder::decode on the device: identical doubles to the oracle's decoder at every level, for plaintexts from the
+    encoder and for raw residues (values far beyond the scale: the multi-word path of the CRT composition)"""
+    rng = np.random.default_rng(orc.N + 17)
+    for ell in range(1, min(orc.k, 8) + 1):
+        for scale_bits in (30, 50):
+            pt = orc.encode(rng.uniform(-4, 4, orc.N // 2), 2.0 ** scale_bits, ell)
+            got = be.decode(pt, 2.0 ** scale_bits, orc.primes)
+            want = orc.decode(pt, 2.0 ** scale_bits)
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (ell, scale_bits)
+        raw = np.stack([rng.integers(0, orc.primes[i], orc.N, dtype=np.uint64) for i in range(ell)])
+        got, want = be.decode(raw, 2.0 ** 40, orc.primes), orc.decode(raw, 2.0 ** 40)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), ("raw", ell)

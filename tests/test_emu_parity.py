@@ -76,3 +76,10 @@ def test_emu_cluster_distributed(N, bits, cl):
     pc.case_keyswitch(be, orc, ell, steps=(3,))
     v = np.array([0.5, -1.25, 3.0, 2.0])
     assert np.array_equal(be.encode(v, 2.0 ** 30, ell), orc.encode(v, 2.0 ** 30, ell))
+
+
+@pytest.mark.parametrize("N,bits", [(1024, [40, 50, 60, 60]), (4096, [60, 20, 60, 60])])
+def test_emu_decode(N, bits):
+    """device decoder bodies (CRT composition, FP64 forward FFT) vs the oracle: identical doubles"""
+    orc = pc.get_oracle(N, bits)
+    pc.case_decode(EmuBackend(N, orc.primes), orc)

@@ -155,3 +155,10 @@ def test_encrypt_decrypt_decode_bit_exact_vs_oracle(N, bits):
         ref = orc.decode(orc.decrypt(want), 2.0 ** 30)
         assert np.array_equal(dec[: N // 2], ref), "decode differs at ell=%d" % ell
         assert np.max(np.abs(dec[: N // 2] - vals)) < 1e-4
+
+
+@pytest.mark.parametrize("N,bits", [(4096, [60, 20, 60, 60]), (16384, [60] * 5)])
+def test_gpu_decode_bit_exact(N, bits):
+    """evab_decode: identical doubles to the oracle's decoder"""
+    orc = pc.get_oracle(N, bits)
+    pc.case_decode(_be(N, orc.primes), orc)
