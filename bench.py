@@ -174,7 +174,8 @@ def measure_workload(args, wl, steps, rank, world, local):
             main.wait_event(ev_)
 
     # ---- launches per step: one un-graphed replay of one group's plan, times G
-    opts = dict(num_streams=args.streams, cache_constants=not args.no_const_cache, dedup_constants=not args.no_dedup, fuse=F)
+    opts = dict(num_streams=args.streams, cache_constants=not args.no_const_cache, dedup_constants=not args.no_dedup, fuse=F,
+                approx_hoist=args.approx_hoist)
     pub.set_options(use_graph=False, **opts)
     pub.drop_plan(prog, 1)   # (cipher_op_count above built a batch-1 plan)
     pub.drop_plan(prog, F)
@@ -249,7 +250,7 @@ def measure_workload(args, wl, steps, rank, world, local):
         "config": bench_config(wl, d, nops, B),
         "step_ms": {"median": step_ms[len(step_ms) // 2], "p95": step_ms[min(len(step_ms) - 1, int(0.95 * len(step_ms)))], "min": step_ms[0], "max": step_ms[-1],
                     "note": "per-step CUDA-event durations on this rank (the headline uses their sum, max over ranks)"},
-        "details": {"instances_per_gpu": B,
+        "details": {"instances_per_gpu": B, **({"approx_hoist": "ON: results are NOT bit-identical to the reference (one mod-down per weighted rotation sum)"} if args.approx_hoist else {}),
                    "parallelism": "replicas x%d GPUs (independent program instances, no data-path collective; NCCL gather of outputs)" % world,
                    "l2": "flushed between timed steps (256 MiB memset, untimed)", "scheduler": ("%d concurrent cuda-graphs" % G if not args.no_graph else "streams") + " x %d instances fused per kernel launch, %d streams inside a plan" % (F, args.streams),
                    "const_encode": "cached per plan" if not args.no_const_cache else ("every Encode term is evaluated on the GPU inside every execute, as in the reference"
@@ -421,6 +422,8 @@ def main():
                     help="encode constant plaintexts once per plan instead of inside every execute (default: every execute, like the reference)")
     ap.set_defaults(no_const_cache=True)
     ap.add_argument("--no-dedup", action="store_true", help="encode every Encode term separately even when constants repeat")
+    ap.add_argument("--approx-hoist", action="store_true",
+                    help="NOT bit-exact with the reference: one mod-down per weighted sum of rotations (SURVEY 8f-4); off in every reported line")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the Harris / polynomial lines (other_workloads)")
     ap.add_argument("--no-dag-sharded", action="store_true", help="N > 1: skip the DAG-sharded wide4096 / Harris measurement (dag_sharded)")

@@ -37,7 +37,10 @@ struct EncBatch {
   const PrimeDev *primes;
   const u64 *pow2;                    // [k][128]: 2^i mod p
   u32 N, ell, count;
+  u32 special_row;                    // != 0: the LAST of the ell rows is the residue mod prime `special_row` (the key-switch
+                                      // prime P: plaintexts that multiply un-modded-down key-switch accumulators, lazy_rotsum)
 };
+EVAB_HD u32 enc_prime_of_row(u32 i, u32 ell, u32 special_row) { return (special_row && i + 1 == ell) ? special_row : i; }
 
 // scatter: slot i (and its conjugate slot) <- values[i mod vec]
 // off / voff: per-instance element offsets (u64 words / doubles) of a batched launch
@@ -106,8 +109,10 @@ EVAB_HD void enc_round(const EncBatch &B, u32 e, u32 j, long long off = 0) {
   const double fix = B.scale[e] / (double)B.N;
   const double c = round(D_MUL((B.work + off / 2)[(size_t)e * B.N + j].re, fix));
   if (j > 0 && c != 0.0) (B.flags + off)[e] = 1;
-  for (u32 i = 0; i < B.ell; i++)
-    (B.out + off)[((size_t)e * B.ell + i) * B.N + j] = enc_residue(c, B.primes[i], B.pow2 + (size_t)i * 128);
+  for (u32 i = 0; i < B.ell; i++) {
+    const u32 pi = enc_prime_of_row(i, B.ell, B.special_row);
+    (B.out + off)[((size_t)e * B.ell + i) * B.N + j] = enc_residue(c, B.primes[pi], B.pow2 + (size_t)pi * 128);
+  }
 }
 
 // ---- uniform vectors (every scalar constant of an EVA program, constant_value.h:64-71): all N
@@ -121,12 +126,14 @@ struct EncUniform {
   const PrimeDev *primes;
   const u64 *pow2;
   u32 N, ell, count;
+  u32 special_row;          // see EncBatch
 };
 // coefficients j, j+1 of residue row (e, i)
 EVAB_HD void enc_uniform_elem(const EncUniform &B, u32 e, u32 i, u32 j, long long off = 0) {
   const double re = D_MUL(B.value[e], (double)B.N);            // log2(N) exact doublings of the FFT
   const double c = round(D_MUL(re, B.scale[e] / (double)B.N));
-  const u64 r = enc_residue(c, B.primes[i], B.pow2 + (size_t)i * 128);
+  const u32 pi = enc_prime_of_row(i, B.ell, B.special_row);
+  const u64 r = enc_residue(c, B.primes[pi], B.pow2 + (size_t)pi * 128);
   u64x2 v; v.x = r; v.y = r;
   *reinterpret_cast<u64x2 *>(B.out + off + ((size_t)e * B.ell + i) * B.N + j) = v;
 }

@@ -201,6 +201,28 @@ __global__ void __launch_bounds__(256) k_ks_inner(const IpArgs A, const long lon
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
     ks_inner_elem(A, blockIdx.y, j, off);
 }
+// block = 32 element pairs x n rotations (one warp per rotation); the parts meet in shared memory, one output sum at a time
+__global__ void __launch_bounds__(32 * LRS_MAX) k_lazy_rotsum(const LazyRotSumArgs A, const long long bstride) {
+  __shared__ u64 sh[LRS_MAX][4][32];
+  const long long off = (long long)blockIdx.z * bstride;
+  const int j = (blockIdx.x * 32 + threadIdx.x) * 2, i = threadIdx.y, mi = blockIdx.y;
+  u64 part[LRS_OUT][4];
+  lazy_rotsum_part(A, mi, j, i, off, part);
+#pragma unroll
+  for (int o = 0; o < LRS_OUT; o++) {
+    if (o >= A.nout) break;
+    if (o) __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; c++) sh[i][c][threadIdx.x] = part[o][c];
+    __syncthreads();
+    if (i == o % A.n) {
+      u64 sum[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) { u64 s = 0; for (int r = 0; r < A.n; r++) s += sh[r][c][threadIdx.x]; sum[c] = s; }
+      lazy_rotsum_store(A, mi, j, o, off, sum);
+    }
+  }
+}
 __global__ void __launch_bounds__(256) k_hoist_const(const HoistConstArgs A) {
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2) hoist_const_elem(A, blockIdx.y, j);
 }
@@ -402,6 +424,12 @@ struct CudaBE {
   int inner(const IpArgs &A) {
     count();
     k_ks_inner<<<grid(A.ell + 1), 256, 0, st>>>(A, g_batch.stride);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int lazy_rotsum(const LazyRotSumArgs &A) {
+    count();
+    k_lazy_rotsum<<<dim3(A.N / 64, A.ell + 1, g_batch.batch), dim3(32, A.n), 0, st>>>(A, g_batch.stride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -652,6 +680,13 @@ extern "C" int evab_set_ntt_cluster(int cl) {
 extern "C" int evab_encode_uniform(evab_ctx *c, int count, const double *values, const double *scales, int ell, uint64_t *out, void *stream) {
   BE_BEGIN return encode_uniform_impl(be, c->v, count, values, scales, ell, out);
 }
+extern "C" int evab_encode_uniform_ext(evab_ctx *c, int count, const double *values, const double *scales, int ell, int with_p, uint64_t *out, void *stream) {
+  BE_BEGIN return encode_uniform_impl(be, c->v, count, values, scales, ell, out, with_p);
+}
+extern "C" int evab_encode_ext(evab_ctx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell, int with_p,
+                               uint64_t *out, void *work, void *stream) {
+  BE_BEGIN return encode_impl(be, c->v, count, vals, vec, scales, ell, out, (cplx *)work, with_p);
+}
 extern "C" size_t evab_encode_work_bytes(const evab_ctx *c, int count) { return encode_work_bytes(c->v, count); }
 extern "C" int evab_encode(evab_ctx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell,
                            uint64_t *out, void *work, void *stream) {
@@ -765,6 +800,18 @@ extern "C" int evab_rotate_modup_prepared(evab_ctx *c, int ell, uint64_t *o, con
   u32 *perm = nullptr, *ctab = nullptr;
   if (galois_tables(c, elt, &perm, &ctab, "evab_rotate_modup_prepared")) return 1;
   BE_BEGIN return rotate_modup_prepared_impl(be, c->v, ell, o, a, ext, perm, key, cadd, (u64 *)work);
+}
+extern "C" size_t evab_lazy_rotsum_work_bytes(const evab_ctx *c, int ell, int nout) { return lazy_rotsum_work_elems(c->v, ell, nout) * sizeof(u64); }
+extern "C" int evab_lazy_rotsum(evab_ctx *c, int ell, int nout, uint64_t *o, const uint64_t *a, const uint64_t *ext, int n, const uint64_t *elts,
+                                const uint64_t *const *keys, const uint64_t *const *cadds, const uint64_t *const *wts, void *work, void *stream) {
+  if (n < 1 || n > LRS_MAX) return fail("evab_lazy_rotsum: 1..16 rotations");
+  const u32 *perms[LRS_MAX];
+  for (int i = 0; i < n; i++) {
+    u32 *perm = nullptr, *ctab = nullptr;
+    if (galois_tables(c, elts[i], &perm, &ctab, "evab_lazy_rotsum")) return 1;
+    perms[i] = perm;
+  }
+  BE_BEGIN return lazy_rotsum_impl(be, c->v, ell, nout, o, a, ext, n, perms, keys, cadds, wts, (u64 *)work);
 }
 extern "C" int evab_memset_zero(evab_ctx *c, void *d, size_t bytes, void *stream) {
   CUDA_OK(cudaSetDevice(c->device));

@@ -238,16 +238,21 @@ int rotate_impl(BE &be, const CtxView &c, int ell, u64 *out, const u64 *a, const
 
 
 // seal::CKKSEncoder::encode of vectors whose elements are all equal (scalar constants): see enc_uniform_elem
-template <class BE> int encode_uniform_impl(BE &be, const CtxView &c, int count, const double *values, const double *scales, int ell, u64 *out) {
-  if (ell < 1 || ell > c.k) return be.error("encode: ell out of range");
+// with_p: the plaintexts get ell + 1 rows, the last one being the residue mod the key-switch prime (lazy_rotsum below)
+template <class BE> int encode_uniform_impl(BE &be, const CtxView &c, int count, const double *values, const double *scales, int ell, u64 *out, int with_p = 0) {
+  if (ell < 1 || ell + (with_p ? 1 : 0) > c.k) return be.error("encode: ell out of range");
+  const int ell_in = ell;
+  if (with_p) ell = ell + 1;
   for (int e0 = 0; e0 < count; e0 += ENC_MAX_BATCH) {
     EncUniform B;
     memset(&B, 0, sizeof(B));
     B.count = (u32)((count - e0) < ENC_MAX_BATCH ? (count - e0) : ENC_MAX_BATCH);
     for (u32 e = 0; e < B.count; e++) { B.value[e] = values[e0 + e]; B.scale[e] = scales[e0 + e]; }
     B.out = out + (size_t)e0 * ell * c.N; B.primes = c.primes; B.pow2 = c.pow2; B.N = (u32)c.N; B.ell = (u32)ell;
+    B.special_row = with_p ? (u32)(c.k - 1) : 0u;
     if (int rc = be.enc_uniform(B)) return rc;
   }
+  (void)ell_in;
   return 0;
 }
 
@@ -318,8 +323,9 @@ int rotate_modup_prepared_impl(BE &be, const CtxView &c, int ell, u64 *out, cons
 // eva/seal/seal_executor.h:242.  d_values/vec/scale are host arrays of `count` entries.
 template <class BE>
 int encode_impl(BE &be, const CtxView &c, int count, const double *const *d_values, const u32 *vec, const double *scale, int ell,
-                u64 *out, cplx *work) {
-  if (ell < 1 || ell > c.k) return be.error("encode: ell out of range");
+                u64 *out, cplx *work, int with_p = 0) {
+  if (ell < 1 || ell + (with_p ? 1 : 0) > c.k) return be.error("encode: ell out of range");
+  if (with_p) ell = ell + 1;
   const u32 slots = (u32)(c.N / 2);
   for (int e0 = 0; e0 < count; e0 += ENC_MAX_BATCH) {
     EncBatch B;
@@ -333,6 +339,7 @@ int encode_impl(BE &be, const CtxView &c, int count, const double *const *d_valu
     B.flags = encode_flags(c, count, work) + e0;
     B.roots = c.roots; B.slot_index = c.slot_index; B.primes = c.primes; B.pow2 = c.pow2;
     B.N = (u32)c.N; B.ell = (u32)ell;
+    B.special_row = with_p ? (u32)(c.k - 1) : 0u;
     if (int rc = be.enc_scatter(B)) return rc;
     int done = 0;
     for (u32 g = 1; done < c.logN;) {
@@ -346,10 +353,34 @@ int encode_impl(BE &be, const CtxView &c, int count, const double *const *d_valu
   NttLaunch L = base_launch(c);
   L.src = out; L.dst = out; L.inner = ell;
   L.src_sq = L.dst_sq = (long long)ell * c.N; L.src_sr = L.dst_sr = (long long)c.N;
-  for (int i = 0; i < ell; i++) L.pmap[i] = (unsigned char)i;
+  for (int i = 0; i < ell; i++) L.pmap[i] = (unsigned char)((with_p && i + 1 == ell) ? c.k - 1 : i);
   // scalar constants (the common case in EVA programs) encode to constant polynomials
   L.cflags = encode_flags(c, count, work);
   return be.fwd(L, (size_t)count * ell);
+}
+
+// ---- lazy_rotsum (opt-in, approximate: SURVEY 8f-4): out [2][ell][N] = sum_i w_i (.) rotate(x, g_i) with ONE mod-down for the sum.
+// ext: the shared extended digits of x (rotate_modup_prepare_impl); perms / keys / cadds as for rotate_modup_prepared_impl;
+// out [nout][2][ell][N]; wts[o*n+i]: plaintext [ell+1][N] whose last row is the residue mod P (encode_*_impl with_p), null when rotation i
+// is not part of sum o.  work: lazy_rotsum_work_elems.
+inline size_t lazy_rotsum_work_elems(const CtxView &c, int ell, int nout) { return (size_t)nout * 2 * (ell + 1) * c.N + (size_t)nout * 2 * c.N; }
+template <class BE>
+int lazy_rotsum_impl(BE &be, const CtxView &c, int ell, int nout, u64 *out, const u64 *a, const u64 *ext, int n, const u32 *const *perms,
+                     const u64 *const *keys, const u64 *const *cadds, const u64 *const *wts, u64 *work) {
+  if (ell < 1 || ell > c.k - 1) return be.error("lazy_rotsum needs 1 <= ell <= k-1");
+  if (n < 1 || n > LRS_MAX) return be.error("lazy_rotsum: 1..16 rotations");
+  if (nout < 1 || nout > LRS_OUT) return be.error("lazy_rotsum: 1..4 output sums");
+  const long long N = (long long)c.N;
+  u64 *acc = work, *tmp = work + (size_t)nout * 2 * (ell + 1) * N;
+  LazyRotSumArgs A;
+  memset(&A, 0, sizeof(A));
+  A.t = a + (size_t)ell * N; A.c0 = a; A.ext = ext; A.acc = acc; A.primes = c.primes; A.n = n; A.nout = nout; A.ell = ell; A.k = c.k; A.N = (int)N;
+  for (int i = 0; i < n; i++) { A.perm[i] = perms[i]; A.key[i] = keys[i]; A.cadd[i] = cadds[i]; }
+  for (int o = 0; o < nout; o++) for (int i = 0; i < n; i++) A.wt[o][i] = wts[(size_t)o * n + i];
+  if (int rc = be.lazy_rotsum(A)) return rc;
+  unsigned char pm[32];
+  for (int i = 0; i < ell; i++) pm[i] = (unsigned char)i;
+  return divround_impl(be, c, acc, (long long)(ell + 1) * N, 2 * nout, ell + 1, pm, c.k - 1, out, (long long)ell * N, (const u64 *)nullptr, 0, tmp);
 }
 
 // seal::CKKSEncoder::decode of a plaintext [ell][N] (NTT form) -> N/2 slot values (reference eva/seal/seal.cpp:132-146).

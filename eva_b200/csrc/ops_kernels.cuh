@@ -232,3 +232,67 @@ EVAB_HD void hoist_const_elem(const HoistConstArgs &A, int mi, int j) {
 }
 // I_g as residues: row mi, coefficient j = sign bit of the coefficient-domain gather table
 EVAB_HD void hoist_indicator_elem(u64 *out, const u32 *ctab, int N, int mi, int j) { out[(size_t)mi * N + j] = EVAB_LDG(ctab + j) & 1u; }
+
+// ---- lazy_rotsum (OPT-IN, NOT bit-exact: SURVEY 8f-4) ------------------------------------------------------------------
+// sum_i w_i (.) rotate(x, g_i) for several rotations of ONE ciphertext with plaintext weights, with a single mod-down for the
+// whole sum: T[c][m] = sum_i w_i[m] (.) acc_i[c][m] over the extended basis (q_0 .. q_{ell-1}, P), acc_i the key-switch
+// accumulator of rotation i (shared extended digits through the permutation + cadd, as in ks_inner_elem).  The reference
+// rounds every rotation's accumulator down by P and multiplies afterwards; rounding the weighted sum once differs from that in
+// the last bits (and carries less rounding noise) -- results are graded by the reference's MSE criterion only.
+#define LRS_MAX 16
+#define LRS_OUT 4
+struct LazyRotSumArgs {
+  const u64 *t, *c0, *ext;        // source c1 [ell][N], c0 [ell][N], shared extended digits [ell+1][ell][N]
+  const u32 *perm[LRS_MAX];
+  const u64 *key[LRS_MAX], *cadd[LRS_MAX];
+  const u64 *wt[LRS_OUT][LRS_MAX]; // plaintext weights [ell+1][N], last row mod P (batch instance offset applies); null: rotation not in that sum
+  u64 *acc;                       // [nout][2][ell+1][N]; poly 0 already carries P * sum_i w_i (.) perm_i(c0) (which the division by P gives back)
+  const PrimeDev *primes;
+  int n, nout, ell, k, N;
+};
+// One rotation's share at elements (j, j+1) of row mi, for every output sum it takes part in.  The key-switch inner product of
+// the rotation is computed once and weighted per output; every value is reduced below p, so that up to LRS_MAX of them add up
+// inside 64 bits.  part[o] = { w.(ip0+cadd0) + P.w.perm(c0), w.(ip1+cadd1) } for x and y.
+EVAB_HD void lazy_rotsum_part(const LazyRotSumArgs &A, int mi, int j, int i, long long off, u64 part[LRS_OUT][4]) {
+  const int row = (mi == A.ell) ? A.k - 1 : mi;
+  const PrimeDev P = A.primes[row];
+  const size_t N = A.N;
+  const u32 pj0 = EVAB_LDG(A.perm[i] + j), pj1 = EVAB_LDG(A.perm[i] + j + 1);
+  u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
+#pragma unroll 4
+  for (int J = 0; J < A.ell; J++) {
+    const u64 *src = (row == J) ? A.t + off + (size_t)J * N : A.ext + off + ((size_t)mi * A.ell + J) * N;
+    const u64 vx = EVAB_LDG(src + pj0), vy = EVAB_LDG(src + pj1);
+    const u64x2 k0 = ld2(A.key[i] + (((size_t)J * 2 + 0) * A.k + row) * N + j);
+    const u64x2 k1 = ld2(A.key[i] + (((size_t)J * 2 + 1) * A.k + row) * N + j);
+    mac128(l0x, h0x, vx, k0.x); mac128(l0y, h0y, vy, k0.y);
+    mac128(l1x, h1x, vx, k1.x); mac128(l1y, h1y, vy, k1.y);
+  }
+  const u64x2 c0 = ld2(A.cadd[i] + ((size_t)0 * (A.ell + 1) + mi) * N + j), c1 = ld2(A.cadd[i] + ((size_t)1 * (A.ell + 1) + mi) * N + j);
+  u64 a0x = addmod(reduce128(l0x, h0x, P), c0.x, P.p), a0y = addmod(reduce128(l0y, h0y, P), c0.y, P.p);
+  const u64 a1x = addmod(reduce128(l1x, h1x, P), c1.x, P.p), a1y = addmod(reduce128(l1y, h1y, P), c1.y, P.p);
+  if (mi < A.ell) {   // + P * perm(c0): comes back as perm(c0) from the division by P
+    const u64 *c0p = A.c0 + off + (size_t)mi * N;
+    const u64 pm = A.primes[A.k - 1].p % P.p;
+    a0x = addmod(a0x, mulmod_p(EVAB_LDG(c0p + pj0), pm, P), P.p);
+    a0y = addmod(a0y, mulmod_p(EVAB_LDG(c0p + pj1), pm, P), P.p);
+  }
+#pragma unroll
+  for (int o = 0; o < LRS_OUT; o++) {
+    if (o >= A.nout || !A.wt[o][i]) { part[o][0] = part[o][1] = part[o][2] = part[o][3] = 0; continue; }
+    const u64x2 w = ld2(A.wt[o][i] + off + (size_t)mi * N + j);
+    part[o][0] = mulmod_p(a0x, w.x, P); part[o][1] = mulmod_p(a0y, w.y, P);
+    part[o][2] = mulmod_p(a1x, w.x, P); part[o][3] = mulmod_p(a1y, w.y, P);
+  }
+}
+// sum[4]: the parts of all rotations of output o added up as plain integers (< LRS_MAX * p < 2^64)
+EVAB_HD void lazy_rotsum_store(const LazyRotSumArgs &A, int mi, int j, int o, long long off, const u64 sum[4]) {
+  const int row = (mi == A.ell) ? A.k - 1 : mi;
+  const PrimeDev P = A.primes[row];
+  const size_t N = A.N;
+  u64x2 r0, r1;
+  r0.x = reduce128(sum[0], 0, P); r0.y = reduce128(sum[1], 0, P);
+  r1.x = reduce128(sum[2], 0, P); r1.y = reduce128(sum[3], 0, P);
+  st2(A.acc + off + (((size_t)o * 2 + 0) * (A.ell + 1) + mi) * N + j, r0);
+  st2(A.acc + off + (((size_t)o * 2 + 1) * (A.ell + 1) + mi) * N + j, r1);
+}

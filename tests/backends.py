@@ -208,6 +208,44 @@ class EmuBackend:
         return outs, int(zflag[0])
 
 
+    def lazy_rotsum(self, a, steps_list, gks, weight_sets, scale):
+        """out_o = sum_i encode(weight_sets[o][i]) (.) rotate(a, steps[i]) (None: rotation i not in sum o) with ONE mod-down per
+        sum (evab_lazy_rotsum; approximate by design).  Returns (outs [nout][2][ell][N], plaintexts {(o, i): [ell+1][N]}, zero flag)"""
+        ell = a.shape[1]
+        that = np.empty((ell, self.N), dtype=np.uint64)
+        ext = np.zeros((ell + 1, ell, self.N), dtype=np.uint64)
+        zflag = np.zeros(1, dtype=np.uint64)
+        self._chk(self.lib.emu_rotate_modup_prepare(self.h, ell, _p(that), _p(ext), _p(a), _p(zflag)))
+        n, nout = len(steps_list), len(weight_sets)
+        where = [(o, i) for o in range(nout) for i in range(n) if weight_sets[o][i] is not None]
+        vecs = [np.ascontiguousarray(weight_sets[o][i], dtype=np.float64) for o, i in where]
+        m = len(vecs)
+        ptrs = (C.c_void_p * m)(*[v.ctypes.data for v in vecs])
+        sizes = (C.c_uint32 * m)(*[len(v) for v in vecs])
+        scales = (C.c_double * m)(*([float(scale)] * m))
+        pts = np.empty((m, ell + 1, self.N), dtype=np.uint64)
+        work = np.zeros(self.lib.emu_encode_work_bytes(self.h, m) // 8, dtype=np.uint64)
+        self._chk(self.lib.emu_encode_ext(self.h, m, ptrs, sizes, scales, ell, 1, _p(pts), _p(work)))
+        cadds = []
+        for s_, gk in zip(steps_list, gks):
+            cadd = np.empty((2, ell + 1, self.N), dtype=np.uint64)
+            tmp = np.empty((ell + 1, self.N), dtype=np.uint64)
+            self._chk(self.lib.emu_rotate_hoist_const(self.h, ell, C.c_uint64(_elt(self.N, s_)), _p(gk), _p(cadd), _p(tmp)))
+            cadds.append(cadd)
+        elts = (C.c_uint64 * n)(*[_elt(self.N, s_) for s_ in steps_list])
+        gks = [np.ascontiguousarray(g) for g in gks]
+        keys = (C.c_void_p * n)(*[g.ctypes.data for g in gks])
+        cads = (C.c_void_p * n)(*[c_.ctypes.data for c_ in cadds])
+        wl = [None] * (nout * n)
+        for idx, (o, i) in enumerate(where):
+            wl[o * n + i] = pts[idx].ctypes.data
+        wts = (C.c_void_p * (nout * n))(*wl)
+        self.lib.emu_lazy_rotsum_work_bytes.restype = C.c_size_t
+        lw = np.zeros(self.lib.emu_lazy_rotsum_work_bytes(self.h, ell, nout) // 8, dtype=np.uint64)
+        out = np.empty((nout, 2, ell, self.N), dtype=np.uint64)
+        self._chk(self.lib.emu_lazy_rotsum(self.h, ell, nout, _p(out), _p(a), _p(ext), n, elts, keys, cads, wts, _p(lw)))
+        return out, {oi: pts[idx] for idx, oi in enumerate(where)}, int(zflag[0])
+
 class GpuBackend:
     """Calls the product C-ABI (include/evab200.h).  Fails loudly if the CUDA
     extension is missing -- there is no fallback."""
@@ -451,3 +489,49 @@ class GpuBackend:
         out = self._down(do, shape)
         self._free(da, dk, do, dw)
         return out
+
+    def lazy_rotsum(self, a, steps_list, gks, weight_sets, scale):
+        lib = self.lib
+        ell = a.shape[1]
+        da = self._up(a)
+        that = self._alloc(ell * self.N * 8)
+        ext = self._alloc(lib.evab_rotate_modup_ext_bytes(self.h, ell))
+        zf = self._alloc(8)
+        self._chk(lib.evab_memset_zero(self.h, zf, 8, None))
+        self._chk(lib.evab_rotate_modup_prepare(self.h, ell, that, ext, da, zf, None))
+        n, nout = len(steps_list), len(weight_sets)
+        where = [(o, i) for o in range(nout) for i in range(n) if weight_sets[o][i] is not None]
+        vecs = [np.ascontiguousarray(weight_sets[o][i], dtype=np.float64) for o, i in where]
+        m = len(vecs)
+        dv = [self._up(v.view(np.uint64)) for v in vecs]
+        ptrs = (C.c_void_p * m)(*dv)
+        sizes = (C.c_uint32 * m)(*[len(v) for v in vecs])
+        scales = (C.c_double * m)(*([float(scale)] * m))
+        dpts = self._alloc(m * (ell + 1) * self.N * 8)
+        dw = self._alloc(lib.evab_encode_work_bytes(self.h, m))
+        self._chk(lib.evab_encode_ext(self.h, m, ptrs, sizes, scales, ell, 1, dpts, dw, None))
+        elts, dks, dcs = [], [], []
+        for s_, gk in zip(steps_list, gks):
+            elt = _elt(self.N, s_)
+            if elt not in self._prepared:
+                self._chk(lib.evab_galois_prepare(self.h, C.c_uint64(elt)))
+                self._prepared.add(elt)
+            dk = self._up(gk)
+            cadd = self._alloc(lib.evab_hoist_const_bytes(self.h, ell))
+            tmp = self._alloc((ell + 1) * self.N * 8)
+            self._chk(lib.evab_rotate_hoist_const(self.h, ell, C.c_uint64(elt), dk, cadd, tmp, None))
+            elts.append(elt); dks.append(dk); dcs.append(cadd)
+            self._free(tmp)
+        stride = (ell + 1) * self.N * 8
+        wl = [None] * (nout * n)
+        for idx, (o, i) in enumerate(where):
+            wl[o * n + i] = dpts.value + idx * stride
+        wts = (C.c_void_p * (nout * n))(*wl)
+        work = self._alloc(lib.evab_lazy_rotsum_work_bytes(self.h, ell, nout))
+        do = self._alloc(nout * 2 * ell * self.N * 8)
+        self._chk(lib.evab_lazy_rotsum(self.h, ell, nout, do, da, ext, n, (C.c_uint64 * n)(*elts), (C.c_void_p * n)(*dks), (C.c_void_p * n)(*dcs), wts, work, None))
+        out = self._down(do, (nout, 2, ell, self.N))
+        pts = self._down(dpts, (m, ell + 1, self.N))
+        flag = int(self._down(zf, (1,))[0])
+        self._free(da, that, ext, zf, dpts, dw, work, do, *dv, *dks, *dcs)
+        return out, {oi: pts[idx] for idx, oi in enumerate(where)}, flag

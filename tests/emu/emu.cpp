@@ -156,6 +156,14 @@ struct EmuBE {
       for (int j = 0; j < A.N; j += 2) ks_inner_elem(A, mi, j);
     return 0;
   }
+  int lazy_rotsum(const LazyRotSumArgs &A) {
+    for (int mi = 0; mi <= A.ell; mi++) for (int j = 0; j < A.N; j += 2) {
+      u64 sum[LRS_OUT][4] = {}, part[LRS_OUT][4];
+      for (int i = 0; i < A.n; i++) { lazy_rotsum_part(A, mi, j, i, 0, part); for (int o = 0; o < A.nout; o++) for (int c = 0; c < 4; c++) sum[o][c] += part[o][c]; }
+      for (int o = 0; o < A.nout; o++) lazy_rotsum_store(A, mi, j, o, 0, sum[o]);
+    }
+    return 0;
+  }
   int hoist_indicator(u64 *out, const u32 *ctab, int N, int rows) {
     for (int mi = 0; mi < rows; mi++) for (int j = 0; j < N; j++) hoist_indicator_elem(out, ctab, N, mi, j);
     return 0;
@@ -241,6 +249,25 @@ size_t emu_encode_work_bytes(EmuCtx *c, int count) { return encode_work_bytes(c-
 int emu_encode(EmuCtx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell, uint64_t *out, void *work) {
   EmuBE be{c};
   return encode_impl(be, c->v, count, vals, vec, scales, ell, out, (cplx *)work);
+}
+int emu_encode_ext(EmuCtx *c, int count, const double *const *vals, const uint32_t *vec, const double *scales, int ell, int with_p, uint64_t *out, void *work) {
+  EmuBE be{c};
+  return encode_impl(be, c->v, count, vals, vec, scales, ell, out, (cplx *)work, with_p);
+}
+int emu_encode_uniform_ext(EmuCtx *c, int count, const double *values, const double *scales, int ell, int with_p, uint64_t *out) {
+  EmuBE be{c};
+  return encode_uniform_impl(be, c->v, count, values, scales, ell, out, with_p);
+}
+size_t emu_lazy_rotsum_work_bytes(EmuCtx *c, int ell, int nout) { return lazy_rotsum_work_elems(c->v, ell, nout) * 8; }
+int emu_lazy_rotsum(EmuCtx *c, int ell, int nout, uint64_t *o, const uint64_t *a, const uint64_t *ext, int n, const uint64_t *elts, const uint64_t *const *keys,
+                    const uint64_t *const *cadds, const uint64_t *const *wts, void *work) {
+  const u32 *perms[LRS_MAX];
+  for (int i = 0; i < n && i < LRS_MAX; i++) {
+    if (!c->perms.count(elts[i])) evab_host::galois_table(c->v.N, c->v.logN, elts[i], c->perms[elts[i]]);
+    perms[i] = c->perms[elts[i]].data();
+  }
+  EmuBE be{c};
+  return lazy_rotsum_impl(be, c->v, ell, nout, o, a, ext, n, perms, keys, cadds, wts, (u64 *)work);
 }
 int emu_decode(EmuCtx *c, int ell, const uint64_t *primes, const uint64_t *pt, double scale, double *out) {
   EmuBE be{c};

@@ -182,3 +182,49 @@ def case_decode(be, orc):
         raw = np.stack([rng.integers(0, orc.primes[i], orc.N, dtype=np.uint64) for i in range(ell)])
         got, want = be.decode(raw, 2.0 ** 40, orc.primes), orc.decode(raw, 2.0 ** 40)
         assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), ("raw", ell)
+
+
+def case_lazy_rotsum(be, orc, ell, steps=(1, -1, 7, 64)):
+    """evab_lazy_rotsum (opt-in approx_hoist): out_o = sum_i pt_oi (.) rotate(ct, s_i), one rounding by P per sum, the key-switch
+    inner product of a rotation shared by the sums.  Not the reference's rounding (one per rotation) -- so no bit-exact oracle:
+    the plaintexts it consumes ARE bit-exact (rows mod q equal the oracle encoder's, the extra row is the same integer polynomial
+    mod P), and every sum must decrypt to the same slots as the reference sequence rotate -> multiply_plain -> add within CKKS noise."""
+    N = orc.N
+    xs, wsc = (2.0 ** 40, 2.0 ** 30) if ell >= 2 else (2.0 ** 25, 2.0 ** 20)   # the product has to fit the level's modulus
+    rng = np.random.default_rng(N + ell)
+    x = rng.uniform(-1, 1, N // 2)
+    ct = orc.encrypt(orc.encode(x, xs, ell), seed=11)
+    n = len(steps)
+    sets = [[rng.uniform(-1, 1, N // 2) for _ in steps],                                   # every rotation
+            [rng.uniform(-1, 1, N // 2) if i != 1 else None for i in range(n)],            # one rotation missing
+            [np.full(N // 2, 0.5 - i) if i % 2 == 0 else None for i in range(n)]]          # scalar weights, every other rotation
+    gks = [orc.galois_key(o.galois_elt_from_step(N, s)) for s in steps]
+    outs, pts, flag = be.lazy_rotsum(ct, list(steps), gks, sets, wsc)
+    assert flag == 0
+    rots = [orc.rotate(ct, s, gk) for s, gk in zip(steps, gks)]
+    errs = []
+    for oi, ws in enumerate(sets):
+        want, true_v = None, 0
+        for i, w in enumerate(ws):
+            if w is None:
+                continue
+            eq(pts[(oi, i)][:ell], orc.encode(w, wsc, ell))
+            term = orc.mul_plain(rots[i], pts[(oi, i)][:ell])
+            want = term if want is None else orc.add(want, term)
+            true_v = true_v + w * np.roll(x, -steps[i])
+        got_v, want_v = orc.decode(orc.decrypt(outs[oi]), xs * wsc), orc.decode(orc.decrypt(want), xs * wsc)
+        e_want, e_got = np.abs(want_v - true_v).max(), np.abs(got_v - true_v).max()
+        assert e_want < 64 / wsc + N * 256 / xs and e_got < max(2 * e_want, 1e-7), (oi, e_want, e_got)
+        assert np.abs(got_v - want_v).max() < 2 * (e_want + e_got)
+        errs.append((e_want, e_got))
+    return errs
+
+
+def check_special_row(orc, pt_ext, ell):
+    """rows [0, ell) and the extra row of an encode_ext(with_p=1) plaintext hold the same small integer polynomial"""
+    q0, P = int(orc.primes[0]), int(orc.primes[orc.k - 1])
+    c = orc.ntt_inv(pt_ext[0].copy(), 0).astype(object)
+    c = np.where(c > q0 // 2, c - q0, c)
+    assert max(abs(int(v)) for v in c) < 2 ** 58
+    cp = np.array([int(v) % P for v in c], dtype=np.uint64)
+    eq(pt_ext[ell], orc.ntt_fwd(cp, orc.k - 1))

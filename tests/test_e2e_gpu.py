@@ -289,3 +289,31 @@ def test_debug_verbosity_prints_every_executed_term():
     assert all("[stream " in l for l in lines)
     res = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
     assert abs(float(res[0].split()[1]) - (3 * 0.25 + 2.5 - 2)) < 1e-3
+
+
+def test_approx_hoist_is_opt_in_and_accurate():
+    """set_options(approx_hoist=True): one mod-down per weighted sum of rotations of one ciphertext.
+    Not bit-exact with the reference by construction -- graded like the reference's own tests, by MSE against
+    evaluate() (tests/common.py:30-36), and it has to stay as close to the plaintext result as the exact path."""
+    import math
+    from eva import evaluate
+    from eva.ckks import CKKSCompiler
+    from eva.metric import valuation_mse
+    from eva.seal import generate_keys
+    from tests_programs import harris, sobel
+    for prog, n in ((sobel(), 4096), (harris(), 4096)):
+        img = [0.5 + 0.25 * math.sin(0.1 * (k % 64)) * math.cos(0.07 * (k // 64)) for k in range(n)]
+        compiled, params, signature = CKKSCompiler({'warn_vec_size': 'false'}).compile(prog)
+        reference = evaluate(prog, {'image': img})
+        public_ctx, secret_ctx = generate_keys(params)
+        enc = public_ctx.encrypt({'image': img}, signature)
+        exact = secret_ctx.decrypt(public_ctx.execute(compiled, enc), signature)
+        public_ctx.set_options(approx_hoist=True)
+        approx = secret_ctx.decrypt(public_ctx.execute(compiled, enc), signature)
+        public_ctx.set_options(approx_hoist=False)
+        again = secret_ctx.decrypt(public_ctx.execute(compiled, enc), signature)
+        e_exact, e_approx = valuation_mse(exact, reference), valuation_mse(approx, reference)
+        assert e_exact < 0.01 and e_approx < 0.01
+        assert e_approx < 4 * e_exact + 1e-12, (e_exact, e_approx)
+        assert valuation_mse(approx, exact) < 4 * (e_exact + e_approx) + 1e-12   # two noisy results of the same computation
+        assert valuation_mse(again, exact) == 0.0          # switching the option back rebuilds the exact plan

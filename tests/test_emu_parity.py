@@ -3,6 +3,9 @@ Validates indexing / swizzles / strides / lazy-reduction bounds of the exact
 code the sm_100a kernels execute, for every supported N."""
 import pytest
 
+import numpy as np
+
+from oracle import oracle as o
 import parity_cases as pc
 from backends import EmuBackend
 
@@ -83,3 +86,20 @@ def test_emu_decode(N, bits):
     """device decoder bodies (CRT composition, FP64 forward FFT) vs the oracle: identical doubles"""
     orc = pc.get_oracle(N, bits)
     pc.case_decode(EmuBackend(N, orc.primes), orc)
+
+
+def test_lazy_rotsum_emulated():
+    """opt-in approx_hoist kernels on the CPU emulator: plaintexts with the extra residue row, one mod-down per rotation sum"""
+    N = 1024
+    orc = pc.get_oracle(N, [60, 60, 60, 60])
+    be = EmuBackend(N, orc.primes)
+    for ell in (3, 1):
+        pc.case_lazy_rotsum(be, orc, ell)
+    orc2 = pc.get_oracle(N, [60, 40, 40, 60])
+    be2 = EmuBackend(N, orc2.primes)
+    pc.case_lazy_rotsum(be2, orc2, 2, steps=(2, 5))
+    rng = np.random.default_rng(3)
+    _, pts, _ = be2.lazy_rotsum(orc2.encrypt(orc2.encode(rng.uniform(-1, 1, N // 2), 2.0 ** 40, 2)), [1, 2],
+                                [orc2.galois_key(o.galois_elt_from_step(N, s)) for s in (1, 2)], [[rng.uniform(-8, 8, N // 2), np.full(N // 2, 0.37)]], 2.0 ** 45)
+    for pt in pts.values():
+        pc.check_special_row(orc2, pt, 2)

@@ -162,3 +162,22 @@ def test_gpu_decode_bit_exact(N, bits):
     """evab_decode: identical doubles to the oracle's decoder"""
     orc = pc.get_oracle(N, bits)
     pc.case_decode(_be(N, orc.primes), orc)
+
+
+@pytest.mark.parametrize("N,bits", [(1024, [60, 60, 60, 60]), (16384, [60] * 5), (4096, [60, 40, 40, 60])])
+def test_gpu_lazy_rotsum(N, bits):
+    """opt-in approx_hoist kernels (evab_lazy_rotsum, evab_encode_ext): the plaintexts are bit-exact (rows mod q) and carry
+    the same integers mod P; the sum decrypts to the reference sequence's slots within CKKS noise (it is NOT bit-exact)"""
+    orc = pc.get_oracle(N, bits)
+    be = _be(N, orc.primes)
+    for ell in range(orc.k - 1, 0, -1):
+        pc.case_lazy_rotsum(be, orc, ell)
+    rng = np.random.default_rng(N)
+    ell = orc.k - 1
+    ct = orc.encrypt(orc.encode(rng.uniform(-1, 1, N // 2), 2.0 ** 40, ell))
+    steps = list(range(1, 17))
+    gks = [orc.galois_key(o.galois_elt_from_step(N, s)) for s in steps]
+    _, pts, flag = be.lazy_rotsum(ct, steps, gks, [[rng.uniform(-8, 8, N // 2) for _ in steps]] * 4, 2.0 ** 45)   # 4 sums of 16: the most one call takes
+    assert flag == 0
+    for i in range(3):
+        pc.check_special_row(orc, pts[(0, i)], ell)
