@@ -201,6 +201,15 @@ __global__ void __launch_bounds__(256) k_ks_inner(const IpArgs A, const long lon
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2)
     ks_inner_elem(A, blockIdx.y, j, off);
 }
+__global__ void __launch_bounds__(256) k_scale_c0(const u64 *c0, u64 *ext, const PrimeDev *primes, int ell, int k, int N, const long long bstride) {
+  const long long off = (long long)blockIdx.z * bstride;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) scale_c0_elem(c0, ext, primes, ell, k, N, blockIdx.y, j, off);
+}
+__global__ void __launch_bounds__(256) k_rot_many(const RotManyArgs A, const long long bstride) {
+  const long long off = (long long)blockIdx.z * bstride;
+  const int i = blockIdx.y / (A.ell + 1), mi = blockIdx.y % (A.ell + 1);
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2) rot_many_elem(A, i, mi, j, off);
+}
 // block = 32 element pairs x n rotations (one warp per rotation); the parts meet in shared memory, one output sum at a time
 __global__ void __launch_bounds__(32 * LRS_MAX) k_lazy_rotsum(const LazyRotSumArgs A, const long long bstride) {
   __shared__ u64 sh[LRS_MAX][4][32];
@@ -424,6 +433,18 @@ struct CudaBE {
   int inner(const IpArgs &A) {
     count();
     k_ks_inner<<<grid(A.ell + 1), 256, 0, st>>>(A, g_batch.stride);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int scale_c0(const u64 *c0, u64 *ext, int ell) {
+    count();
+    k_scale_c0<<<grid(ell, 1), 256, 0, st>>>(c0, ext, c->v.primes, ell, c->v.k, (int)c->v.N, g_batch.stride);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int rot_many(const RotManyArgs &A) {
+    count();
+    k_rot_many<<<grid(A.n * (A.ell + 1)), 256, 0, st>>>(A, g_batch.stride);
     CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -800,6 +821,18 @@ extern "C" int evab_rotate_modup_prepared(evab_ctx *c, int ell, uint64_t *o, con
   u32 *perm = nullptr, *ctab = nullptr;
   if (galois_tables(c, elt, &perm, &ctab, "evab_rotate_modup_prepared")) return 1;
   BE_BEGIN return rotate_modup_prepared_impl(be, c->v, ell, o, a, ext, perm, key, cadd, (u64 *)work);
+}
+extern "C" size_t evab_rotate_modup_many_work_bytes(const evab_ctx *c, int ell, int n) { return rotate_modup_many_work_elems(c->v, ell, n) * sizeof(u64); }
+extern "C" int evab_rotate_modup_many(evab_ctx *c, int ell, int n, uint64_t *o, const uint64_t *a, const uint64_t *ext, const uint64_t *elts,
+                                      const uint64_t *const *keys, const uint64_t *const *cadds, void *work, void *stream) {
+  if (n < 1 || n > ROTMANY_MAX) return fail("evab_rotate_modup_many: 1..16 rotations");
+  const u32 *perms[ROTMANY_MAX];
+  for (int i = 0; i < n; i++) {
+    u32 *perm = nullptr, *ctab = nullptr;
+    if (galois_tables(c, elts[i], &perm, &ctab, "evab_rotate_modup_many")) return 1;
+    perms[i] = perm;
+  }
+  BE_BEGIN return rotate_modup_many_impl(be, c->v, ell, n, o, a, ext, perms, keys, cadds, (u64 *)work);
 }
 extern "C" size_t evab_lazy_rotsum_work_bytes(const evab_ctx *c, int ell, int nout) { return lazy_rotsum_work_elems(c->v, ell, nout) * sizeof(u64); }
 extern "C" int evab_lazy_rotsum(evab_ctx *c, int ell, int nout, uint64_t *o, const uint64_t *a, const uint64_t *ext, int n, const uint64_t *elts,

@@ -52,6 +52,7 @@ struct Step {
   int hoist = -1;              // rotation group sharing one inverse NTT (op == Undef: the step computing it)
   std::uint64_t producer = 0;  // term index, or termCount + group for a hoist step
   int lazy = -1;               // approxHoist: index of the lazy rotation sums this pseudo step computes (op == Undef)
+  int chunk = -1;              // rotationChunk: index of the rotation chunk this pseudo step computes (op == Undef)
   std::vector<std::size_t> lazyTemps;  // fused sum: arena offsets of the lazy rotation sums added to the other leaves
 };
 
@@ -63,6 +64,13 @@ struct EncodeGroup {
   bool withP = false;      // plaintexts of this group carry an extra residue row mod the key-switch prime (approxHoist)
 };
 
+// rotationChunk: up to 16 rotations of one hoist group computed by one evab_rotate_modup_many call (3 launches instead of 3 n)
+struct RotChunk {
+  int gid = 0, ell = 0;
+  std::vector<const Term *> rots;
+  std::size_t outOff = 0;                           // their results, contiguous: [n][2][ell][N]
+  bool emitted = false;
+};
 // approxHoist: out_o = sum_i wts[o][i] (.) rots[i] over rotations of one hoist group, each sum rounded down by P once (evab_lazy_rotsum)
 struct LazySum {
   int gid = 0, ell = 0;
@@ -85,6 +93,8 @@ struct ExecOptions {
   bool hoistModUp = true;      // ... and the mod-up of its digits (exact, ops_impl.hpp hoisted_modup); a zero coefficient in a digit
                                // raises a flag and the caller redoes the run without this option (B200Public::executeMany)
   bool fuseSums = true;        // trees of Add over multiply_plain results / ciphertexts run as one kernel
+  int rotationChunk = 0;       // with hoistModUp: rotations of one ciphertext computed per evab_rotate_modup_many call (same bits); 1: one call each;
+                               // 0: chosen per plan (B200Public::executorFor)
   bool approxHoist = false;    // OPT-IN, NOT bit-exact: sums of plaintext-weighted rotations of one ciphertext are rounded down by P
                                // once per sum instead of once per rotation (evab_lazy_rotsum); graded by the MSE criterion only
   bool dedupConstants = true;  // Encode terms of identical constants at the same (level, scale) share one plaintext
@@ -412,6 +422,27 @@ private:
       for (auto &t : order_)
         if (lazyUses[t->index] && lazyUses[t->index] == usesAll[t->index]) vals_[t->index].fused = true;   // the rotation is never materialised
     }
+    // ---- batched rotations: the (materialised) rotations of a hoist group are computed together, 16 per call
+    if (opt_.rotationChunk >= 2 && opt_.hoistModUp) {
+      std::vector<int> open(hoistSrc.size(), -1);
+      for (auto &t : order_) {
+        auto h = hoistOf.find(t->index);
+        if (h == hoistOf.end() || vals_[t->index].fused || canon_[t->index] != t->index) continue;
+        int ci = open[h->second];
+        if (ci < 0 || (int)chunks_[ci].rots.size() >= std::min(16, opt_.rotationChunk)) {
+          ci = open[h->second] = (int)chunks_.size();
+          chunks_.emplace_back();
+          chunks_[ci].gid = h->second; chunks_[ci].ell = vals_[t->index].ell;
+        }
+        chunkOf_[t->index] = ci;
+        chunks_[ci].rots.push_back(t);
+      }
+      for (auto &ch : chunks_) {
+        ch.outOff = arenaWords;
+        for (std::size_t i = 0; i < ch.rots.size(); i++) vals_[ch.rots[i]->index].off = arenaWords + i * 2 * (std::size_t)ch.ell * N_;
+        arenaWords += ch.rots.size() * 2 * (std::size_t)ch.ell * N_;
+      }
+    }
     // ---- Encode groups: one batched device encode per (ell, input-dependent?) group.
     // Static groups (constants only) are encoded once per plan when cacheConstants is
     // set, otherwise every run like the reference (seal_executor.h:303-308).
@@ -471,7 +502,8 @@ private:
     // ---- stream assignment + event edges.  Producers are identified by term index, or TC + group
     // for the hoist pseudo steps.
     const int S = std::max(1, opt_.numStreams);
-    const std::size_t NP = TC + hoistSrc.size() + lazy_.size();
+    const std::size_t NP = TC + hoistSrc.size() + lazy_.size() + chunks_.size();
+    std::unordered_map<std::uint64_t, std::uint64_t> prodOf;   // rotation term -> the chunk step that produces it
     std::vector<int> streamOf(NP, -1), eventOf(NP, -1);
     std::vector<char> chainTaken(NP, 0), hoistDone(hoistSrc.size(), 0);
     std::vector<std::size_t> workWords(S, 0);
@@ -481,7 +513,8 @@ private:
     auto isInput = [&](std::uint64_t id) { return inputTerm[id] != 0; };
     // place one step: continue the chain of a device operand nobody continued yet, else take a new
     // stream round-robin; cross-stream operands become event waits
-    auto emit = [&](Step st, const std::vector<std::uint64_t> &operands, int forced, std::size_t w) {
+    auto emit = [&](Step st, std::vector<std::uint64_t> operands, int forced, std::size_t w) {
+      for (auto &o : operands) if (auto p = prodOf.find(o); p != prodOf.end()) o = p->second;
       int chosen = forced;
       for (std::uint64_t o : operands) {
         const int so = streamOf[o];
@@ -544,6 +577,24 @@ private:
         w = evab_keyswitch_work_bytes(dev_->ctx(), vals_[t->operandAt(0)->index].ell) / 8;
       else if (t->op == Op::Rescale)
         w = evab_rescale_work_bytes(dev_->ctx(), vals_[t->operandAt(0)->index].size) / 8;
+      if (auto co = chunkOf_.find(t->index); co != chunkOf_.end()) {   // computed with the other rotations of its chunk
+        RotChunk &ch = chunks_[co->second];
+        const std::uint64_t cid = TC + hoistSrc.size() + lazy_.size() + (std::size_t)co->second;
+        if (!ch.emitted) {
+          if (!hoistDone[ch.gid]) {
+            Step hs;
+            hs.term = hoistSrc[ch.gid]; hs.op = Op::Undef; hs.hoist = ch.gid; hs.producer = TC + ch.gid;
+            emit(hs, {hoistSrc[ch.gid]->index}, -1, 0);
+            hoistDone[ch.gid] = 1;
+          }
+          Step cs;
+          cs.term = hoistSrc[ch.gid]; cs.op = Op::Undef; cs.chunk = co->second; cs.hoist = ch.gid; cs.producer = cid;
+          emit(cs, {hoistSrc[ch.gid]->index, TC + (std::uint64_t)ch.gid}, -1, evab_rotate_modup_many_work_bytes(dev_->ctx(), ch.ell, (int)ch.rots.size()) / 8);
+          ch.emitted = true;
+          for (const Term *r : ch.rots) { prodOf[r->index] = cid; streamOf[r->index] = streamOf[cid]; }
+        }
+        continue;
+      }
       auto h = hoistOf.find(t->index);
       if (h != hoistOf.end()) {
         const int gid = h->second;
@@ -598,6 +649,19 @@ private:
             dev_->sync();
             hoistConst_.emplace(key, std::move(cadd));
           }
+        }
+      }
+    for (auto &ch : chunks_)
+      for (const Term *r : ch.rots) {
+        const u64 elt = galoisElt(*r);
+        if (!keys_.galois.count(elt)) throw std::invalid_argument("Galois key not present");
+        check(evab_galois_prepare(dev_->ctx(), elt));
+        auto key = std::make_pair(elt, ch.ell);
+        if (!hoistConst_.count(key)) {
+          DBuf cadd(dev_, evab_hoist_const_bytes(dev_->ctx(), ch.ell) / 8), tmp(dev_, (std::size_t)(ch.ell + 1) * N_);
+          check(evab_rotate_hoist_const(dev_->ctx(), ch.ell, elt, keys_.galois.at(elt).get(), cadd.get(), tmp.get(), nullptr));
+          dev_->sync();
+          hoistConst_.emplace(key, std::move(cadd));
         }
       }
     for (auto &Lz : lazy_)
@@ -713,12 +777,14 @@ private:
       if (!print && !nvtx) return;
       char name[96];
       const Term &t = *st.term;
-      if (st.op == Op::Undef) std::snprintf(name, sizeof(name), "t%lu.hoist", (unsigned long)t.index);
+      const char *pseudo = st.chunk >= 0 ? "RotationBatch" : st.lazy >= 0 ? "LazyRotationSums" : "InverseNTT";   // pseudo steps: named after their source term
+      if (st.op == Op::Undef) std::snprintf(name, sizeof(name), "t%lu.%s", (unsigned long)t.index, pseudo);
       else std::snprintf(name, sizeof(name), "t%lu %s%s", (unsigned long)t.index, opName(t.op), st.sum.empty() ? "" : "(fused sum)");
       if (print) {
-        std::printf("EVA: Execute t%lu = %s(", (unsigned long)t.index, st.op == Op::Undef ? "InverseNTT" : opName(t.op));
+        std::printf("EVA: Execute t%lu%s = %s(", (unsigned long)t.index, st.op == Op::Undef ? "'" : "", st.op == Op::Undef ? pseudo : opName(t.op));
         bool first = true;
-        for (auto &o : t.getOperands()) { std::printf(first ? "t%lu" : ",t%lu", (unsigned long)o->index); first = false; }
+        if (st.op == Op::Undef) std::printf("t%lu", (unsigned long)t.index);
+        else for (auto &o : t.getOperands()) { std::printf(first ? "t%lu" : ",t%lu", (unsigned long)o->index); first = false; }
         std::printf(")  [stream %d%s]\n", st.stream, st.sum.empty() ? "" : ", fused sum");
         std::fflush(stdout);
       }
@@ -733,6 +799,21 @@ private:
     evab_ctx *c = dev_->ctx();
     const ValueInfo &o = vals_[t.index];
     u64 *out = arena_.get() + o.off;
+    if (st.chunk >= 0) {   // up to 16 rotations of one ciphertext, three launches
+      const RotChunk &ch = chunks_[st.chunk];
+      if (verbosity() >= 2)
+        for (const Term *r : ch.rots)
+          std::printf("EVA: Execute t%lu = %s(t%lu)  [stream %d, in the batch above]\n", (unsigned long)r->index, opName(r->op), (unsigned long)r->operandAt(0)->index, st.stream);
+      std::vector<u64> elts; std::vector<const u64 *> keys, cadds;
+      for (const Term *r : ch.rots) {
+        const u64 elt = galoisElt(*r);
+        elts.push_back(elt); keys.push_back(keys_.galois.at(elt).get());
+        cadds.push_back(hoistConst_.at(std::make_pair(elt, ch.ell)).get());
+      }
+      check(evab_rotate_modup_many(c, ch.ell, (int)elts.size(), arena_.get() + ch.outOff, arena_.get() + o.off, arena_.get() + hoistExtOff_[ch.gid], elts.data(),
+                                   keys.data(), cadds.data(), arena_.get() + workOff_[st.stream], stream));
+      return;
+    }
     if (st.lazy >= 0) {   // approxHoist: out_o = sum_i w_oi (.) rotate(x, g_i), one mod-down per sum
       const LazySum &Lz = lazy_[st.lazy];
       std::vector<u64> elts; std::vector<const u64 *> keys, cadds, wts;
@@ -853,6 +934,8 @@ private:
   std::unordered_map<std::uint64_t, int> groupIndex_;
   std::unordered_map<std::uint64_t, std::size_t> rawOff_;
   std::vector<std::size_t> hoistOff_;   // arena word offset of every hoist buffer
+  std::vector<RotChunk> chunks_;                             // rotationChunk
+  std::unordered_map<std::uint64_t, int> chunkOf_;
   std::vector<LazySum> lazy_;                                // approxHoist
   std::unordered_map<std::uint64_t, std::vector<std::pair<int, int>>> lazyOfRoot_;   // fused sum -> (lazy sum, output)
   std::set<std::uint64_t> needP_;                            // Encode terms whose plaintext carries the extra row mod P

@@ -297,7 +297,8 @@ template <class BE> int rotate_modup_prepare_impl(BE &be, const CtxView &c, int 
   A.epi = EPI_STORE_ZFLAG; A.zflag = zflag;
   for (int J = 0; J < ell; J++) A.pmap[J] = (unsigned char)J;
   if (int rc = be.inv(A, ell)) return rc;
-  return ks_modup(be, c, ell, that, ext, nullptr);
+  if (int rc = ks_modup(be, c, ell, that, ext, nullptr)) return rc;
+  return be.scale_c0(a, ext, ell);   // P * c0 on the (otherwise unused) diagonal of ext: evab_rotate_modup_many / evab_lazy_rotsum
 }
 inline size_t hoist_const_elems(const CtxView &c, int ell) { return (size_t)2 * (ell + 1) * c.N; }
 // cadd_g for one Galois key at one level; `tmp` holds (ell + 1) * N words
@@ -317,6 +318,26 @@ int rotate_modup_prepared_impl(BE &be, const CtxView &c, int ell, u64 *out, cons
   if (ell < 1 || ell > c.k - 1) return be.error("rotate needs 1 <= ell <= k-1");
   u64 *acc = work, *tmp = work + (size_t)2 * (ell + 1) * c.N;
   return ks_finish(be, c, ell, out, a + (size_t)ell * c.N, ext, key, a, 1, acc, tmp, nperm, nperm, cadd);
+}
+
+// n <= 16 rotations of one ciphertext in three launches (inner products, inverse NTT of the 2n P-rows, forward NTT + division of
+// the 2n ell rows) instead of 3n: out [n][2][ell][N], same bits as n calls of rotate_modup_prepared_impl.
+inline size_t rotate_modup_many_work_elems(const CtxView &c, int ell, int n) { return (size_t)n * 2 * (ell + 1) * c.N + (size_t)n * 2 * c.N; }
+template <class BE>
+int rotate_modup_many_impl(BE &be, const CtxView &c, int ell, int n, u64 *out, const u64 *a, const u64 *ext, const u32 *const *perms,
+                           const u64 *const *keys, const u64 *const *cadds, u64 *work) {
+  if (ell < 1 || ell > c.k - 1) return be.error("rotate needs 1 <= ell <= k-1");
+  if (n < 1 || n > ROTMANY_MAX) return be.error("rotate_modup_many: 1..16 rotations");
+  const long long N = (long long)c.N;
+  u64 *acc = work, *tmp = work + (size_t)n * 2 * (ell + 1) * N;
+  RotManyArgs A;
+  memset(&A, 0, sizeof(A));
+  A.t = a + (size_t)ell * N; A.ext = ext; A.acc = acc; A.primes = c.primes; A.n = n; A.ell = ell; A.k = c.k; A.N = (int)N;
+  for (int i = 0; i < n; i++) { A.perm[i] = perms[i]; A.key[i] = keys[i]; A.cadd[i] = cadds[i]; }
+  if (int rc = be.rot_many(A)) return rc;
+  unsigned char pm[32];
+  for (int i = 0; i < ell; i++) pm[i] = (unsigned char)i;
+  return divround_impl(be, c, acc, (long long)(ell + 1) * N, 2 * n, ell + 1, pm, c.k - 1, out, (long long)ell * N, (const u64 *)nullptr, 0, tmp);
 }
 
 // seal::CKKSEncoder::encode (vector overload) for a batch of vectors -- reference
@@ -374,7 +395,7 @@ int lazy_rotsum_impl(BE &be, const CtxView &c, int ell, int nout, u64 *out, cons
   u64 *acc = work, *tmp = work + (size_t)nout * 2 * (ell + 1) * N;
   LazyRotSumArgs A;
   memset(&A, 0, sizeof(A));
-  A.t = a + (size_t)ell * N; A.c0 = a; A.ext = ext; A.acc = acc; A.primes = c.primes; A.n = n; A.nout = nout; A.ell = ell; A.k = c.k; A.N = (int)N;
+  A.t = a + (size_t)ell * N; A.ext = ext; A.acc = acc; A.primes = c.primes; A.n = n; A.nout = nout; A.ell = ell; A.k = c.k; A.N = (int)N;
   for (int i = 0; i < n; i++) { A.perm[i] = perms[i]; A.key[i] = keys[i]; A.cadd[i] = cadds[i]; }
   for (int o = 0; o < nout; o++) for (int i = 0; i < n; i++) A.wt[o][i] = wts[(size_t)o * n + i];
   if (int rc = be.lazy_rotsum(A)) return rc;

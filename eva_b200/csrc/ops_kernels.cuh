@@ -202,6 +202,53 @@ EVAB_HD void ks_inner_elem(const IpArgs &A, int mi, int j, long long off = 0) {
   st2(A.acc + off + ((size_t)1 * (A.ell + 1) + mi) * N + j, r1);
 }
 
+// The shared extended digits ext[m][J] have no entry for m == q_J (the digit itself is used): rotate_modup_prepare_impl stores
+// P * c0 mod q_m there, for the batched rotation kernels below.
+EVAB_HD void scale_c0_elem(const u64 *c0, u64 *ext, const PrimeDev *primes, int ell, int k, int N, int mi, int j, long long off = 0) {
+  const PrimeDev P = primes[mi];
+  const u64 pm = primes[k - 1].p % P.p;
+  ext[off + ((size_t)mi * ell + mi) * N + j] = mulmod_p(c0[off + (size_t)mi * N + j], pm, P);
+}
+// ---- all rotations of one ciphertext in one launch (exact; ops_impl.hpp rotate_modup_many_impl): rotation i's inner product through
+// its permutation + cadd_i, and P * perm_i(c0) added to polynomial 0 -- the division by P that follows returns exactly
+// perm_i(c0) + the key-switched part, the same residues as adding the permuted c0 afterwards ((x + P c - corr) P^-1 = (x - corr) P^-1 + c).
+#define ROTMANY_MAX 16
+struct RotManyArgs {
+  const u64 *t, *ext;             // source c1 [ell][N], shared extended digits [ell+1][ell][N] (diagonal: P * c0, see scale_c0_elem)
+  const u32 *perm[ROTMANY_MAX];
+  const u64 *key[ROTMANY_MAX], *cadd[ROTMANY_MAX];
+  u64 *acc;                       // [n][2][ell+1][N]
+  const PrimeDev *primes;
+  int n, ell, k, N;
+};
+EVAB_HD void rot_many_elem(const RotManyArgs &A, int i, int mi, int j, long long off = 0) {
+  const int row = (mi == A.ell) ? A.k - 1 : mi;
+  const PrimeDev P = A.primes[row];
+  const size_t N = A.N;
+  const u32 pj0 = EVAB_LDG(A.perm[i] + j), pj1 = EVAB_LDG(A.perm[i] + j + 1);
+  u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
+#pragma unroll 4
+  for (int J = 0; J < A.ell; J++) {
+    const u64 *src = (row == J) ? A.t + off + (size_t)J * N : A.ext + off + ((size_t)mi * A.ell + J) * N;
+    const u64 vx = EVAB_LDG(src + pj0), vy = EVAB_LDG(src + pj1);
+    const u64x2 k0 = ld2(A.key[i] + (((size_t)J * 2 + 0) * A.k + row) * N + j);
+    const u64x2 k1 = ld2(A.key[i] + (((size_t)J * 2 + 1) * A.k + row) * N + j);
+    mac128(l0x, h0x, vx, k0.x); mac128(l0y, h0y, vy, k0.y);
+    mac128(l1x, h1x, vx, k1.x); mac128(l1y, h1y, vy, k1.y);
+  }
+  const u64x2 c0 = ld2(A.cadd[i] + ((size_t)0 * (A.ell + 1) + mi) * N + j), c1 = ld2(A.cadd[i] + ((size_t)1 * (A.ell + 1) + mi) * N + j);
+  u64x2 r0, r1;
+  r0.x = addmod(reduce128(l0x, h0x, P), c0.x, P.p); r0.y = addmod(reduce128(l0y, h0y, P), c0.y, P.p);
+  r1.x = addmod(reduce128(l1x, h1x, P), c1.x, P.p); r1.y = addmod(reduce128(l1y, h1y, P), c1.y, P.p);
+  if (mi < A.ell) {   // + perm_i(P * c0), which rotate_modup_prepare_impl left on the diagonal of ext
+    const u64 *c0p = A.ext + off + ((size_t)mi * A.ell + mi) * N;
+    r0.x = addmod(r0.x, EVAB_LDG(c0p + pj0), P.p);
+    r0.y = addmod(r0.y, EVAB_LDG(c0p + pj1), P.p);
+  }
+  st2(A.acc + off + (((size_t)i * 2 + 0) * (A.ell + 1) + mi) * N + j, r0);
+  st2(A.acc + off + (((size_t)i * 2 + 1) * (A.ell + 1) + mi) * N + j, r1);
+}
+
 // ---- shared mod-up of a rotation group (exact): per Galois key and level, the constant
 //   cadd[c][m] = NTT_m(I_g) (.) sum_{J < ell} (q_J mod m) * key[J][c][row(m)]          (mod m)
 // where I_g is the indicator polynomial of the coefficients the automorphism negates (ops_impl.hpp: hoisted_modup).
@@ -242,7 +289,7 @@ EVAB_HD void hoist_indicator_elem(u64 *out, const u32 *ctab, int N, int mi, int 
 #define LRS_MAX 16
 #define LRS_OUT 4
 struct LazyRotSumArgs {
-  const u64 *t, *c0, *ext;        // source c1 [ell][N], c0 [ell][N], shared extended digits [ell+1][ell][N]
+  const u64 *t, *ext;             // source c1 [ell][N], shared extended digits [ell+1][ell][N] (diagonal: P * c0, see scale_c0_elem)
   const u32 *perm[LRS_MAX];
   const u64 *key[LRS_MAX], *cadd[LRS_MAX];
   const u64 *wt[LRS_OUT][LRS_MAX]; // plaintext weights [ell+1][N], last row mod P (batch instance offset applies); null: rotation not in that sum
@@ -271,11 +318,10 @@ EVAB_HD void lazy_rotsum_part(const LazyRotSumArgs &A, int mi, int j, int i, lon
   const u64x2 c0 = ld2(A.cadd[i] + ((size_t)0 * (A.ell + 1) + mi) * N + j), c1 = ld2(A.cadd[i] + ((size_t)1 * (A.ell + 1) + mi) * N + j);
   u64 a0x = addmod(reduce128(l0x, h0x, P), c0.x, P.p), a0y = addmod(reduce128(l0y, h0y, P), c0.y, P.p);
   const u64 a1x = addmod(reduce128(l1x, h1x, P), c1.x, P.p), a1y = addmod(reduce128(l1y, h1y, P), c1.y, P.p);
-  if (mi < A.ell) {   // + P * perm(c0): comes back as perm(c0) from the division by P
-    const u64 *c0p = A.c0 + off + (size_t)mi * N;
-    const u64 pm = A.primes[A.k - 1].p % P.p;
-    a0x = addmod(a0x, mulmod_p(EVAB_LDG(c0p + pj0), pm, P), P.p);
-    a0y = addmod(a0y, mulmod_p(EVAB_LDG(c0p + pj1), pm, P), P.p);
+  if (mi < A.ell) {   // + perm(P * c0) (the diagonal of ext): comes back as perm(c0) from the division by P
+    const u64 *c0p = A.ext + off + ((size_t)mi * A.ell + mi) * N;
+    a0x = addmod(a0x, EVAB_LDG(c0p + pj0), P.p);
+    a0y = addmod(a0y, EVAB_LDG(c0p + pj1), P.p);
   }
 #pragma unroll
   for (int o = 0; o < LRS_OUT; o++) {

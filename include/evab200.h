@@ -195,6 +195,11 @@ int evab_rotate_modup_prepare(evab_ctx *ctx, int ell, uint64_t *d_that, uint64_t
 int evab_rotate_hoist_const(evab_ctx *ctx, int ell, uint64_t galois_elt, const uint64_t *d_key, uint64_t *d_cadd, uint64_t *d_tmp, void *stream);
 int evab_rotate_modup_prepared(evab_ctx *ctx, int ell, uint64_t *d_out, const uint64_t *d_a, const uint64_t *d_ext, uint64_t galois_elt,
                                const uint64_t *d_key, const uint64_t *d_cadd, void *d_work, void *stream);
+/* n <= 16 rotations of ONE ciphertext (seal::Evaluator::rotate_vector, seal_executor.h:176-189) in three kernel launches instead of
+ * 3 n: d_out [n][2][ell][N], rotation i by galois_elts[i]; same bits as n calls of evab_rotate_modup_prepared.  d_ext, keys, cadds as there. */
+size_t evab_rotate_modup_many_work_bytes(const evab_ctx *ctx, int ell, int n);
+int evab_rotate_modup_many(evab_ctx *ctx, int ell, int n, uint64_t *d_out, const uint64_t *d_a, const uint64_t *d_ext, const uint64_t *galois_elts,
+                           const uint64_t *const *d_keys, const uint64_t *const *d_cadds, void *d_work, void *stream);
 /* OPT-IN, NOT bit-exact (graded by the reference's MSE criterion only): d_out [nout][2][ell][N],
  * out_o = sum_i w_oi (.) rotate(x, g_i) for n <= 16 rotations of ONE ciphertext x = d_a and nout <= 4 sets of plaintext weights, rounding
  * each weighted sum down by P ONCE instead of every rotation (2 + 2 ell transforms per sum instead of n (2 + 2 ell)); the key-switch

@@ -205,8 +205,22 @@ class EmuBackend:
             work = np.zeros(self.lib.emu_rotate_modup_work_bytes(self.h, ell) // 8, dtype=np.uint64)
             self._chk(self.lib.emu_rotate_modup_prepared(self.h, ell, _p(out), _p(a), _p(ext), elt, _p(gk), _p(cadd), _p(work)))
             outs.append(out)
+        # the same rotations in one call (evab_rotate_modup_many)
+        n = len(steps_list)
+        cadds = []
+        for s_, gk in zip(steps_list, gks):
+            cadd = np.empty((2, ell + 1, self.N), dtype=np.uint64)
+            tmp = np.empty((ell + 1, self.N), dtype=np.uint64)
+            self._chk(self.lib.emu_rotate_hoist_const(self.h, ell, C.c_uint64(_elt(self.N, s_)), _p(gk), _p(cadd), _p(tmp)))
+            cadds.append(cadd)
+        gkc = [np.ascontiguousarray(g) for g in gks]
+        self.lib.emu_rotate_modup_many_work_bytes.restype = C.c_size_t
+        mw = np.zeros(self.lib.emu_rotate_modup_many_work_bytes(self.h, ell, n) // 8, dtype=np.uint64)
+        many = np.empty((n, 2, ell, self.N), dtype=np.uint64)
+        self._chk(self.lib.emu_rotate_modup_many(self.h, ell, n, _p(many), _p(a), _p(ext), (C.c_uint64 * n)(*[_elt(self.N, s_) for s_ in steps_list]),
+                                                 (C.c_void_p * n)(*[g.ctypes.data for g in gkc]), (C.c_void_p * n)(*[c_.ctypes.data for c_ in cadds]), _p(mw)))
+        self.many = [many[i] for i in range(n)]
         return outs, int(zflag[0])
-
 
     def lazy_rotsum(self, a, steps_list, gks, weight_sets, scale):
         """out_o = sum_i encode(weight_sets[o][i]) (.) rotate(a, steps[i]) (None: rotation i not in sum o) with ONE mod-down per
@@ -458,7 +472,7 @@ class GpuBackend:
         self._chk(lib.evab_memset_zero(self.h, zf, 8, None))
         self._chk(lib.evab_rotate_modup_prepare(self.h, ell, that, ext, da, zf, None))
         work = self._alloc(lib.evab_rotate_modup_work_bytes(self.h, ell))
-        outs = []
+        outs, elts, dks, dcs = [], [], [], []
         for s_, gk in zip(steps_list, gks):
             elt = _elt(self.N, s_)
             if elt not in self._prepared:
@@ -471,9 +485,17 @@ class GpuBackend:
             do = self._alloc(2 * ell * self.N * 8)
             self._chk(lib.evab_rotate_modup_prepared(self.h, ell, do, da, ext, C.c_uint64(elt), dk, cadd, work, None))
             outs.append(self._down(do, (2, ell, self.N)))
-            self._free(dk, do, cadd, tmp)
+            self._free(do, tmp)
+            elts.append(elt); dks.append(dk); dcs.append(cadd)
+        # the same rotations in one call (evab_rotate_modup_many)
+        n = len(steps_list)
+        mw = self._alloc(lib.evab_rotate_modup_many_work_bytes(self.h, ell, n))
+        dm = self._alloc(n * 2 * ell * self.N * 8)
+        self._chk(lib.evab_rotate_modup_many(self.h, ell, n, dm, da, ext, (C.c_uint64 * n)(*elts), (C.c_void_p * n)(*dks), (C.c_void_p * n)(*dcs), mw, None))
+        many = self._down(dm, (n, 2, ell, self.N))
+        self.many = [many[i] for i in range(n)]
         flag = int(self._down(zf, (1,))[0])
-        self._free(da, that, ext, work, zf)
+        self._free(da, that, ext, work, zf, mw, dm, *dks, *dcs)
         return outs, flag
 
     def rotate(self, a, steps, gk):

@@ -156,6 +156,14 @@ struct EmuBE {
       for (int j = 0; j < A.N; j += 2) ks_inner_elem(A, mi, j);
     return 0;
   }
+  int scale_c0(const u64 *c0, u64 *ext, int ell) {
+    for (int mi = 0; mi < ell; mi++) for (int j = 0; j < (int)c->v.N; j++) scale_c0_elem(c0, ext, c->v.primes, ell, c->v.k, (int)c->v.N, mi, j);
+    return 0;
+  }
+  int rot_many(const RotManyArgs &A) {
+    for (int i = 0; i < A.n; i++) for (int mi = 0; mi <= A.ell; mi++) for (int j = 0; j < A.N; j += 2) rot_many_elem(A, i, mi, j);
+    return 0;
+  }
   int lazy_rotsum(const LazyRotSumArgs &A) {
     for (int mi = 0; mi <= A.ell; mi++) for (int j = 0; j < A.N; j += 2) {
       u64 sum[LRS_OUT][4] = {}, part[LRS_OUT][4];
@@ -257,6 +265,17 @@ int emu_encode_ext(EmuCtx *c, int count, const double *const *vals, const uint32
 int emu_encode_uniform_ext(EmuCtx *c, int count, const double *values, const double *scales, int ell, int with_p, uint64_t *out) {
   EmuBE be{c};
   return encode_uniform_impl(be, c->v, count, values, scales, ell, out, with_p);
+}
+size_t emu_rotate_modup_many_work_bytes(EmuCtx *c, int ell, int n) { return rotate_modup_many_work_elems(c->v, ell, n) * 8; }
+int emu_rotate_modup_many(EmuCtx *c, int ell, int n, uint64_t *o, const uint64_t *a, const uint64_t *ext, const uint64_t *elts, const uint64_t *const *keys,
+                          const uint64_t *const *cadds, void *work) {
+  const u32 *perms[ROTMANY_MAX];
+  for (int i = 0; i < n && i < ROTMANY_MAX; i++) {
+    if (!c->perms.count(elts[i])) evab_host::galois_table(c->v.N, c->v.logN, elts[i], c->perms[elts[i]]);
+    perms[i] = c->perms[elts[i]].data();
+  }
+  EmuBE be{c};
+  return rotate_modup_many_impl(be, c->v, ell, n, o, a, ext, perms, keys, cadds, (u64 *)work);
 }
 size_t emu_lazy_rotsum_work_bytes(EmuCtx *c, int ell, int nout) { return lazy_rotsum_work_elems(c->v, ell, nout) * 8; }
 int emu_lazy_rotsum(EmuCtx *c, int ell, int nout, uint64_t *o, const uint64_t *a, const uint64_t *ext, int n, const uint64_t *elts, const uint64_t *const *keys,
