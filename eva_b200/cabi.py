@@ -46,6 +46,7 @@ _SIGS = {
     "evab_rotate_hoist_const": (ci, [vp, ci, u64, vp, vp, vp, vp]),
     "evab_rotate_modup_prepared": (ci, [vp, ci, vp, vp, vp, u64, vp, vp, vp, vp]),
     "evab_memset_zero": (ci, [vp, vp, szt, vp]),
+    "evab_rotate_modup_scale_c0": (ci, [vp, ci, vp, vp, vp]),
     "evab_rotate_modup_many_work_bytes": (szt, [vp, ci, ci]),
     "evab_rotate_modup_many": (ci, [vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
     "evab_lazy_rotsum_work_bytes": (szt, [vp, ci, ci]),

@@ -822,6 +822,9 @@ extern "C" int evab_rotate_modup_prepared(evab_ctx *c, int ell, uint64_t *o, con
   if (galois_tables(c, elt, &perm, &ctab, "evab_rotate_modup_prepared")) return 1;
   BE_BEGIN return rotate_modup_prepared_impl(be, c->v, ell, o, a, ext, perm, key, cadd, (u64 *)work);
 }
+extern "C" int evab_rotate_modup_scale_c0(evab_ctx *c, int ell, uint64_t *ext, const uint64_t *a, void *stream) {
+  BE_BEGIN return rotate_modup_scale_c0_impl(be, c->v, ell, ext, a);
+}
 extern "C" size_t evab_rotate_modup_many_work_bytes(const evab_ctx *c, int ell, int n) { return rotate_modup_many_work_elems(c->v, ell, n) * sizeof(u64); }
 extern "C" int evab_rotate_modup_many(evab_ctx *c, int ell, int n, uint64_t *o, const uint64_t *a, const uint64_t *ext, const uint64_t *elts,
                                       const uint64_t *const *keys, const uint64_t *const *cadds, void *work, void *stream) {

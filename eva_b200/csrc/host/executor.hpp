@@ -651,6 +651,9 @@ private:
           }
         }
       }
+    hoistNeedsC0_.assign(hoistSrc.size(), 0);
+    for (auto &ch : chunks_) hoistNeedsC0_[ch.gid] = 1;
+    for (auto &Lz : lazy_) hoistNeedsC0_[Lz.gid] = 1;
     for (auto &ch : chunks_)
       for (const Term *r : ch.rots) {
         const u64 elt = galoisElt(*r);
@@ -829,8 +832,11 @@ private:
     }
     if (st.op == Op::Undef) {   // shared inverse NTT of a rotation group's input
       if (opt_.hoistModUp)
+      {
         check(evab_rotate_modup_prepare(c, o.ell, arena_.get() + hoistOff_[st.hoist], arena_.get() + hoistExtOff_[st.hoist], arena_.get() + o.off,
                                         arena_.get() + flagsOff_ + 8 * (std::size_t)st.hoist, stream));
+        if (hoistNeedsC0_[st.hoist]) check(evab_rotate_modup_scale_c0(c, o.ell, arena_.get() + hoistExtOff_[st.hoist], arena_.get() + o.off, stream));
+      }
       else
         check(evab_rotate_prepare(c, o.ell, arena_.get() + hoistOff_[st.hoist], arena_.get() + o.off, stream));
       return;
@@ -934,6 +940,7 @@ private:
   std::unordered_map<std::uint64_t, int> groupIndex_;
   std::unordered_map<std::uint64_t, std::size_t> rawOff_;
   std::vector<std::size_t> hoistOff_;   // arena word offset of every hoist buffer
+  std::vector<char> hoistNeedsC0_;                           // hoist group feeds evab_rotate_modup_many / evab_lazy_rotsum
   std::vector<RotChunk> chunks_;                             // rotationChunk
   std::unordered_map<std::uint64_t, int> chunkOf_;
   std::vector<LazySum> lazy_;                                // approxHoist

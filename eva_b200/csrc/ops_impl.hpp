@@ -297,8 +297,12 @@ template <class BE> int rotate_modup_prepare_impl(BE &be, const CtxView &c, int 
   A.epi = EPI_STORE_ZFLAG; A.zflag = zflag;
   for (int J = 0; J < ell; J++) A.pmap[J] = (unsigned char)J;
   if (int rc = be.inv(A, ell)) return rc;
-  if (int rc = ks_modup(be, c, ell, that, ext, nullptr)) return rc;
-  return be.scale_c0(a, ext, ell);   // P * c0 on the (otherwise unused) diagonal of ext: evab_rotate_modup_many / evab_lazy_rotsum
+  return ks_modup(be, c, ell, that, ext, nullptr);
+}
+// P * c0 on the (otherwise unused) diagonal of ext: required by rotate_modup_many_impl / lazy_rotsum_impl, after the prepare step
+template <class BE> int rotate_modup_scale_c0_impl(BE &be, const CtxView &c, int ell, u64 *ext, const u64 *a) {
+  if (ell < 1 || ell > c.k - 1) return be.error("rotate needs 1 <= ell <= k-1");
+  return be.scale_c0(a, ext, ell);
 }
 inline size_t hoist_const_elems(const CtxView &c, int ell) { return (size_t)2 * (ell + 1) * c.N; }
 // cadd_g for one Galois key at one level; `tmp` holds (ell + 1) * N words

@@ -197,6 +197,9 @@ int evab_rotate_modup_prepared(evab_ctx *ctx, int ell, uint64_t *d_out, const ui
                                const uint64_t *d_key, const uint64_t *d_cadd, void *d_work, void *stream);
 /* n <= 16 rotations of ONE ciphertext (seal::Evaluator::rotate_vector, seal_executor.h:176-189) in three kernel launches instead of
  * 3 n: d_out [n][2][ell][N], rotation i by galois_elts[i]; same bits as n calls of evab_rotate_modup_prepared.  d_ext, keys, cadds as there. */
+/* evab_rotate_modup_many and evab_lazy_rotsum read P * c0 from the diagonal of d_ext (ext[m][J] has no entry for m = q_J): call this once
+ * per ciphertext after evab_rotate_modup_prepare and before either of them. */
+int evab_rotate_modup_scale_c0(evab_ctx *ctx, int ell, uint64_t *d_ext, const uint64_t *d_a, void *stream);
 size_t evab_rotate_modup_many_work_bytes(const evab_ctx *ctx, int ell, int n);
 int evab_rotate_modup_many(evab_ctx *ctx, int ell, int n, uint64_t *d_out, const uint64_t *d_a, const uint64_t *d_ext, const uint64_t *galois_elts,
                            const uint64_t *const *d_keys, const uint64_t *const *d_cadds, void *d_work, void *stream);

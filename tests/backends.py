@@ -214,6 +214,7 @@ class EmuBackend:
             self._chk(self.lib.emu_rotate_hoist_const(self.h, ell, C.c_uint64(_elt(self.N, s_)), _p(gk), _p(cadd), _p(tmp)))
             cadds.append(cadd)
         gkc = [np.ascontiguousarray(g) for g in gks]
+        self._chk(self.lib.emu_rotate_modup_scale_c0(self.h, ell, _p(ext), _p(a)))
         self.lib.emu_rotate_modup_many_work_bytes.restype = C.c_size_t
         mw = np.zeros(self.lib.emu_rotate_modup_many_work_bytes(self.h, ell, n) // 8, dtype=np.uint64)
         many = np.empty((n, 2, ell, self.N), dtype=np.uint64)
@@ -230,6 +231,7 @@ class EmuBackend:
         ext = np.zeros((ell + 1, ell, self.N), dtype=np.uint64)
         zflag = np.zeros(1, dtype=np.uint64)
         self._chk(self.lib.emu_rotate_modup_prepare(self.h, ell, _p(that), _p(ext), _p(a), _p(zflag)))
+        self._chk(self.lib.emu_rotate_modup_scale_c0(self.h, ell, _p(ext), _p(a)))
         n, nout = len(steps_list), len(weight_sets)
         where = [(o, i) for o in range(nout) for i in range(n) if weight_sets[o][i] is not None]
         vecs = [np.ascontiguousarray(weight_sets[o][i], dtype=np.float64) for o, i in where]
@@ -489,6 +491,7 @@ class GpuBackend:
             elts.append(elt); dks.append(dk); dcs.append(cadd)
         # the same rotations in one call (evab_rotate_modup_many)
         n = len(steps_list)
+        self._chk(lib.evab_rotate_modup_scale_c0(self.h, ell, ext, da, None))
         mw = self._alloc(lib.evab_rotate_modup_many_work_bytes(self.h, ell, n))
         dm = self._alloc(n * 2 * ell * self.N * 8)
         self._chk(lib.evab_rotate_modup_many(self.h, ell, n, dm, da, ext, (C.c_uint64 * n)(*elts), (C.c_void_p * n)(*dks), (C.c_void_p * n)(*dcs), mw, None))
@@ -521,6 +524,7 @@ class GpuBackend:
         zf = self._alloc(8)
         self._chk(lib.evab_memset_zero(self.h, zf, 8, None))
         self._chk(lib.evab_rotate_modup_prepare(self.h, ell, that, ext, da, zf, None))
+        self._chk(lib.evab_rotate_modup_scale_c0(self.h, ell, ext, da, None))
         n, nout = len(steps_list), len(weight_sets)
         where = [(o, i) for o in range(nout) for i in range(n) if weight_sets[o][i] is not None]
         vecs = [np.ascontiguousarray(weight_sets[o][i], dtype=np.float64) for o, i in where]

@@ -266,6 +266,10 @@ int emu_encode_uniform_ext(EmuCtx *c, int count, const double *values, const dou
   EmuBE be{c};
   return encode_uniform_impl(be, c->v, count, values, scales, ell, out, with_p);
 }
+int emu_rotate_modup_scale_c0(EmuCtx *c, int ell, uint64_t *ext, const uint64_t *a) {
+  EmuBE be{c};
+  return rotate_modup_scale_c0_impl(be, c->v, ell, ext, a);
+}
 size_t emu_rotate_modup_many_work_bytes(EmuCtx *c, int ell, int n) { return rotate_modup_many_work_elems(c->v, ell, n) * 8; }
 int emu_rotate_modup_many(EmuCtx *c, int ell, int n, uint64_t *o, const uint64_t *a, const uint64_t *ext, const uint64_t *elts, const uint64_t *const *keys,
                           const uint64_t *const *cadds, void *work) {
