@@ -124,6 +124,18 @@ public:
   Executor(const Executor &) = delete;
 
   std::size_t cipherOpCount() const { return cipherOps_; }
+  // shape of the plan (test / tooling hook)
+  std::map<std::string, long> planStats() const {
+    std::map<std::string, long> m;
+    m["steps"] = (long)steps_.size(); m["streams"] = usedStreams_; m["hoist_groups"] = (long)hoistOff_.size();
+    m["rotation_chunks"] = (long)chunks_.size(); m["lazy_sums"] = 0; m["lazy_calls"] = (long)lazy_.size(); m["lazy_rotations"] = 0; m["chunked_rotations"] = 0;
+    for (auto &L : lazy_) { m["lazy_sums"] += (long)L.roots.size(); m["lazy_rotations"] += (long)L.rots.size(); }
+    for (auto &c : chunks_) m["chunked_rotations"] += (long)c.rots.size();
+    long elided = 0;
+    for (auto &t : order_) if ((t->op == Op::RotateLeftConst || t->op == Op::RotateRightConst) && vals_[t->index].fused) elided++;
+    m["elided_rotations"] = elided;
+    return m;
+  }
   // private stream used by B200Public::execute for H2D -> run -> D2H of this plan,
   // so that execute() calls on different programs overlap on the GPU
   std::size_t arenaBytes() const { return (stride_ * (std::size_t)opt_.batch + 8 + rawStride_ * (std::size_t)opt_.batch + 8) * 8; }
@@ -375,8 +387,12 @@ private:
           byGroup[h->second].push_back(i);
         }
         std::vector<char> drop(leaves.size(), 0);
-        for (auto &kv : byGroup) {
-          if (kv.second.size() < 2 || kv.second.size() > 16) continue;
+        std::vector<std::pair<int, std::vector<int>>> slices;   // at most 16 rotations per call: longer sums are cut
+        for (auto &kv : byGroup)
+          for (std::size_t b = 0; b < kv.second.size(); b += 16)
+            slices.emplace_back(kv.first, std::vector<int>(kv.second.begin() + b, kv.second.begin() + std::min(kv.second.size(), b + 16)));
+        for (auto &kv : slices) {
+          if (kv.second.size() < 2) continue;
           // sums over rotations of the same ciphertext share one call (and the inner products of the rotations they have in
           // common), as long as the later sum's weights are available when the first one runs
           int li = -1;

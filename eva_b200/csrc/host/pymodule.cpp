@@ -157,6 +157,8 @@ PYBIND11_MODULE(_eva_b200, m) {
       .def("set_input_sizes", [](B200Public &p, const std::map<std::string, int> &sizes) { p.options.inputSizes = sizes; },
            "ciphertext inputs that are not size 2 (name -> polynomials); applies to plans built afterwards")
       .def("drop_plan", &B200Public::dropExecutor, py::arg("program"), py::arg("batch") = 1, py::arg("replica") = 0)
+      .def("plan_stats", [](B200Public &p, Program &prog, int batch, int replica) { return p.executorFor(prog, batch, replica).planStats(); },
+           py::arg("program"), py::arg("batch") = 1, py::arg("replica") = 0, "shape of the execution plan: steps, hoist groups, rotation chunks, lazy rotation sums")
       .def("cipher_op_count", [](B200Public &p, Program &prog) { return p.executorFor(prog).cipherOpCount(); })
       // serialization (eva_b200/serialization.py): public key material only (never the secret key)
       .def("_export", [](B200Public &x) {

@@ -317,3 +317,72 @@ def test_approx_hoist_is_opt_in_and_accurate():
         assert e_approx < 4 * e_exact + 1e-12, (e_exact, e_approx)
         assert valuation_mse(approx, exact) < 4 * (e_exact + e_approx) + 1e-12   # two noisy results of the same computation
         assert valuation_mse(again, exact) == 0.0          # switching the option back rebuilds the exact plan
+
+
+def test_approx_hoist_plan_shapes():
+    """approx_hoist on the plan shapes that take its special cases: more than 16 taps of one ciphertext, a rotation that is
+    also used outside the weighted sum (it must still be materialised), the same rotation twice in one sum, vector weights,
+    weights that depend on an unencrypted input (encoded inside every execute), sums at two levels"""
+    import numpy as np
+    from eva import EvaProgram, Input, Output, evaluate
+    from eva.ckks import CKKSCompiler
+    from eva.metric import valuation_mse
+    from eva.seal import generate_keys
+    n = 1024
+    rng = np.random.default_rng(5)
+    vecs = [list(rng.uniform(-1, 1, n)) for _ in range(24)]
+
+    def many_taps():
+        acc = None
+        x = Input('x')
+        for k in range(20):
+            t = (x << (k + 1)) * (0.05 * (k + 1))
+            acc = t if acc is None else acc + t
+        Output('y', acc)
+
+    def shared_rotation():
+        x = Input('x')
+        r1, r2, r3 = x << 1, x << 2, x >> 3
+        s = r1 * 0.5 + r2 * vecs[0] + r3 * -0.25
+        Output('y', s + r2)              # r2 is needed as a ciphertext as well
+        Output('z', r1 * r1)             # and r1 feeds a ciphertext product
+
+    def repeated_rotation():
+        x = Input('x')
+        r = x << 5
+        Output('y', r * 0.5 + (x << 6) * vecs[1] + r * vecs[2] + (x >> 1) * 2.0)
+
+    def input_weights():
+        x, w = Input('x'), Input('w', is_encrypted=False)
+        Output('y', (x << 1) * w + (x << 2) * 0.75 + (x << 3) * w)
+
+    def two_levels():
+        x = Input('x')
+        a = (x << 1) * 0.5 + (x << 2) * 0.25 + (x << 4) * vecs[3]
+        b = a * a
+        Output('y', (b << 1) * 0.5 + (b << 2) * vecs[4] + (b >> 7) * -1.5 + b)
+
+    for body in (many_taps, shared_rotation, repeated_rotation, input_weights, two_levels):
+        prog = EvaProgram(body.__name__, vec_size=n)
+        with prog:
+            body()
+        prog.set_input_scales(30)
+        prog.set_output_ranges(20)
+        compiled, params, signature = CKKSCompiler({'warn_vec_size': 'false'}).compile(prog)
+        inputs = {'x': list(rng.uniform(-1, 1, n))}
+        if body is input_weights:
+            inputs['w'] = list(rng.uniform(-1, 1, n))
+        reference = evaluate(prog, inputs)
+        public_ctx, secret_ctx = generate_keys(params)
+        enc = public_ctx.encrypt(inputs, signature)
+        exact = secret_ctx.decrypt(public_ctx.execute(compiled, enc), signature)
+        public_ctx.set_options(approx_hoist=True)
+        approx = secret_ctx.decrypt(public_ctx.execute(compiled, enc), signature)
+        approx2 = secret_ctx.decrypt(public_ctx.execute(compiled, enc), signature)     # the captured graph
+        st = public_ctx.plan_stats(compiled)
+        want = {'many_taps': (2, 20, 20), 'shared_rotation': (1, 3, 1), 'repeated_rotation': (1, 3, 2), 'input_weights': (1, 3, 3),
+                'two_levels': (2, 6, 6)}[body.__name__]   # lazy sums, rotations in them, rotations never materialised
+        assert (st['lazy_sums'], st['lazy_rotations'], st['elided_rotations']) == want, (body.__name__, st)
+        e_exact, e_approx = valuation_mse(exact, reference), valuation_mse(approx, reference)
+        assert e_exact < 1e-6 and e_approx < 4 * e_exact + 1e-12, (body.__name__, e_exact, e_approx)
+        assert valuation_mse(approx, approx2) == 0.0, body.__name__
