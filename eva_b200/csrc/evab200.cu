@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) k_scale_c0(const u64 *c0, u64 *ext, const
   const long long off = (long long)blockIdx.z * bstride;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) scale_c0_elem(c0, ext, primes, ell, k, N, blockIdx.y, j, off);
 }
-__global__ void __launch_bounds__(256) k_rot_many(const RotManyArgs A, const long long bstride) {
+__global__ void __launch_bounds__(256, 4) k_rot_many(const RotManyArgs A, const long long bstride) {
   const long long off = (long long)blockIdx.z * bstride;
   const int i = blockIdx.y / (A.ell + 1), mi = blockIdx.y % (A.ell + 1);
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2; j < A.N; j += gridDim.x * blockDim.x * 2) rot_many_elem(A, i, mi, j, off);

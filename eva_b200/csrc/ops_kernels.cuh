@@ -227,7 +227,6 @@ EVAB_HD void rot_many_elem(const RotManyArgs &A, int i, int mi, int j, long long
   const size_t N = A.N;
   const u32 pj0 = EVAB_LDG(A.perm[i] + j), pj1 = EVAB_LDG(A.perm[i] + j + 1);
   u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
-#pragma unroll 4
   for (int J = 0; J < A.ell; J++) {
     const u64 *src = (row == J) ? A.t + off + (size_t)J * N : A.ext + off + ((size_t)mi * A.ell + J) * N;
     const u64 vx = EVAB_LDG(src + pj0), vy = EVAB_LDG(src + pj1);

@@ -80,6 +80,49 @@ for name, fn, algo in ops:
     lib.evab_set_batch(1, 0, 0)
     torch.cuda.synchronize()
     print(json.dumps({"op": name, "launches": int(n), "instances": B, "algorithmic_bytes_per_instance": algo}), flush=True)
+# ---- 8 rotations of one ciphertext in one call (evab_rotate_modup_many) and two weighted sums over them (evab_lazy_rotsum, opt-in,
+# not bit-exact): their own instance stride (a | that | ext | flag | 2 weights | out | work), 16 instances per launch
+nrot, B2 = 8, 16
+elts = [pow(3, i + 1, 2 * N) for i in range(nrot)]
+for e_ in elts:
+    assert lib.evab_galois_prepare(h, C.c_uint64(e_)) == 0
+wm = max(lib.evab_rotate_modup_many_work_bytes(h, ell, nrot), lib.evab_lazy_rotsum_work_bytes(h, ell, 2)) // 8
+o_a, o_that = 0, 2 * ell * N
+o_ext = o_that + ell * N
+o_flag = o_ext + (ell + 1) * ell * N
+o_w = o_flag + 8
+o_out = o_w + 2 * (ell + 1) * N
+o_work = o_out + nrot * 2 * ell * N
+stride3 = (o_work + wm + 63) // 64 * 64
+big3 = torch.randint(0, 1 << 59, (B2, stride3), dtype=torch.int64, device="cuda")
+sl = lambda off: C.c_void_p(big3.data_ptr() + 8 * off)
+keys = (C.c_void_p * nrot)(*[key.data_ptr()] * nrot)
+cadds = (C.c_void_p * nrot)(*[cadd.data_ptr()] * nrot)
+eltsA = (C.c_uint64 * nrot)(*elts)
+wts = (C.c_void_p * (2 * nrot))(*([big3.data_ptr() + 8 * o_w] * nrot + [big3.data_ptr() + 8 * (o_w + (ell + 1) * N)] * nrot))
+ops2 = [
+    ("rotate_modup_prepare + scale_c0 (once per ciphertext)", lambda: lib.evab_rotate_modup_prepare(h, ell, sl(o_that), sl(o_ext), sl(o_a), sl(o_flag), st)
+     or lib.evab_rotate_modup_scale_c0(h, ell, sl(o_ext), sl(o_a), st), (ell + ell + (ell + 1) * ell + 2 * ell) * R),
+    ("rotate_modup_many (8 rotations of one ciphertext)", lambda: lib.evab_rotate_modup_many(h, ell, nrot, sl(o_out), sl(o_a), sl(o_ext), eltsA, keys, cadds, sl(o_work), st),
+     (ell * (ell + 1) + nrot * (2 * ell * (ell + 1) + 2 * 2 * (ell + 1) + 2 * ell)) * R),
+    ("lazy_rotsum (2 weighted sums over 8 rotations; opt-in, not bit-exact)", lambda: lib.evab_lazy_rotsum(h, ell, 2, sl(o_out), sl(o_a), sl(o_ext), nrot, eltsA, keys, cadds, wts, sl(o_work), st),
+     (ell * (ell + 1) + nrot * 2 * ell * (ell + 1) + 2 * (ell + 1) + 2 * (2 * 2 * (ell + 1) + 2 * ell)) * R),
+]
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()            # warm-up outside the profiled range
+for name, fn, _ in ops2:
+    lib.evab_set_batch(B2, stride3, 0); assert fn() == 0; lib.evab_set_batch(1, 0, 0)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+for name, fn, algo in ops2:
+    flush.zero_()
+    lib.evab_set_batch(B2, stride3, 0)
+    l0 = lib.evab_launch_count(h)
+    assert fn() == 0
+    n = lib.evab_launch_count(h) - l0
+    lib.evab_set_batch(1, 0, 0)
+    torch.cuda.synchronize()
+    print(json.dumps({"op": name, "launches": int(n), "instances": B2, "algorithmic_bytes_per_instance": algo}), flush=True)
 # the encoder (E row): one batch of 23 vectors as in a Sobel execute (dense 4096-slot vectors) + replicated scalars
 cnt = 8
 vals = torch.rand((cnt, N // 2), dtype=torch.float64, device="cuda")
