@@ -179,18 +179,13 @@ def measure_workload(args, wl, steps, rank, world, local):
     pub.set_options(use_graph=False, **opts)
     pub.drop_plan(prog, 1)   # (cipher_op_count above built a batch-1 plan)
     pub.drop_plan(prog, F)
-    def count_launches(replica):
-        pub.stage_inputs(prog, groups[replica], main.cuda_stream, replica)
-        pub.run_resident(prog, main.cuda_stream, F, replica)
-        torch.cuda.synchronize()
-        l0 = pub.launch_count()
-        pub.run_resident(prog, main.cuda_stream, F, replica)
-        torch.cuda.synchronize()
-        n = pub.launch_count() - l0
-        pub.drop_plan(prog, F, replica)
-        return n
-    # (the plan of replica 0 batches the rotations of a ciphertext -- fewer launches, see backend.hpp executorFor; the others do not)
-    launches_per_step = count_launches(0) + (count_launches(1) * (G - 1) if G > 1 else 0)
+    pub.stage_inputs(prog, groups[0], main.cuda_stream)
+    pub.run_resident(prog, main.cuda_stream, F)
+    torch.cuda.synchronize()
+    l0 = pub.launch_count()
+    pub.run_resident(prog, main.cuda_stream, F)
+    torch.cuda.synchronize()
+    launches_per_step = (pub.launch_count() - l0) * G
     pub.set_options(use_graph=not args.no_graph, **opts)
     pub.drop_plan(prog, F)
     for g in range(G):
@@ -429,7 +424,7 @@ def main():
     ap.add_argument("--no-dedup", action="store_true", help="encode every Encode term separately even when constants repeat")
     ap.add_argument("--approx-hoist", action="store_true",
                     help="NOT bit-exact with the reference: one mod-down per weighted sum of rotations (SURVEY 8f-4); off in every reported line")
-    ap.add_argument("--rotation-chunk", type=int, default=0, help="rotations of one ciphertext per evab_rotate_modup_many call (1: one call each; 0: per plan, see backend.hpp executorFor)")
+    ap.add_argument("--rotation-chunk", type=int, default=16, help="rotations of one ciphertext per evab_rotate_modup_many call (1: one call each)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the Harris / polynomial lines (other_workloads)")
     ap.add_argument("--no-dag-sharded", action="store_true", help="N > 1: skip the DAG-sharded wide4096 / Harris measurement (dag_sharded)")

@@ -119,10 +119,6 @@ public:
       ExecOptions o = options;
       o.batch = batch;
       h->opt = o;   // as requested (what the staleness test above compares)
-      // rotationChunk 0 = automatic.  Batching the rotations of a ciphertext cuts launches and the serialised device time (Harris:
-      // single-program latency 0.62 -> 0.43 ms), but measured 7 % slower when many plan replicas run concurrently (coarser
-      // dependencies, larger working set per kernel): the plan of plain execute() batches, throughput replicas and fused batches do not.
-      if (o.rotationChunk == 0) o.rotationChunk = (batch == 1 && replica == 0) ? 16 : 1;
       h->exec = std::make_unique<Executor>(s_->dev, s_->client->encoder(), s_->keys, program, o);
       h->termCount = program.termCount();
       program.attach(key, h);

@@ -93,8 +93,7 @@ struct ExecOptions {
   bool hoistModUp = true;      // ... and the mod-up of its digits (exact, ops_impl.hpp hoisted_modup); a zero coefficient in a digit
                                // raises a flag and the caller redoes the run without this option (B200Public::executeMany)
   bool fuseSums = true;        // trees of Add over multiply_plain results / ciphertexts run as one kernel
-  int rotationChunk = 0;       // with hoistModUp: rotations of one ciphertext computed per evab_rotate_modup_many call (same bits); 1: one call each;
-                               // 0: chosen per plan (B200Public::executorFor)
+  int rotationChunk = 16;      // with hoistModUp: rotations of one ciphertext computed per evab_rotate_modup_many call (same bits); < 2: one call each
   bool approxHoist = false;    // OPT-IN, NOT bit-exact: sums of plaintext-weighted rotations of one ciphertext are rounded down by P
                                // once per sum instead of once per rotation (evab_lazy_rotsum); graded by the MSE criterion only
   bool dedupConstants = true;  // Encode terms of identical constants at the same (level, scale) share one plaintext
