@@ -64,6 +64,20 @@ struct PlanHolder {
   ExecOptions opt;
 };
 
+// a batch that has been enqueued (H2D, plan replays, D2H) and not yet collected: B200Public::submitMany / collect
+struct PendingBatch {
+  Program *program = nullptr;
+  std::vector<const B200Valuation *> inputs;   // the caller keeps them alive until collect()
+  std::vector<B200Valuation> outs;
+  std::vector<void *> streams;
+  std::vector<Executor *> execs;
+  int slot = 0;
+  bool collected = false;
+  std::shared_ptr<Shared> keep;
+  // dropped without collect(): the copies into `outs` must not outlive their buffers
+  ~PendingBatch() { if (!collected && keep) for (void *st : streams) keep->dev->sync(st); }
+};
+
 class B200Public {
 public:
   explicit B200Public(std::shared_ptr<Shared> s) : s_(std::move(s)) {
@@ -176,40 +190,66 @@ public:
   // replica (arena + captured graph) and all replicas are in flight at once: H2D, graph and D2H of
   // different chunks overlap, and 148 SMs are filled by concurrency rather than by launch width.
   std::vector<B200Valuation> executeMany(Program &program, const std::vector<const B200Valuation *> &inputs) {
+    auto p = submitMany(program, inputs, 0);
+    return collect(*p);
+  }
+  // Pipelined form of executeMany: submitMany enqueues a batch (H2D of its inputs, the plan replays, D2H of its outputs) and returns;
+  // collect waits for it and hands out the results.  Batches submitted with different `slot` numbers (0..7) use disjoint plan
+  // replicas, so the head of one overlaps the tail of the other (each batch alone ramps up replica by replica and drains the same way).
+  std::shared_ptr<PendingBatch> submitMany(Program &program, const std::vector<const B200Valuation *> &inputs, int slot = 0) {
     if (inputs.empty()) throw std::invalid_argument("execute needs at least one valuation");
+    if (slot < 0 || slot > 7) throw std::invalid_argument("slot out of range (0..7)");
     for (auto *v : inputs) requireAllInputs(program, *v);
     // one caller at a time per context: plan replicas own single arenas and raw-input buffers (the reference's
     // execute is re-entrant because it builds a new executor per call; concurrent callers are serialised here)
     std::lock_guard<std::mutex> guard(s_->execMutex);
+    if (auto prev = inFlight_[slot].lock(); prev && !prev->collected) throw std::runtime_error("slot in use: collect the batch submitted before");
+    auto p = std::make_shared<PendingBatch>();
+    p->program = &program; p->inputs = inputs; p->slot = slot; p->keep = s_;
+    enqueueLocked(*p);
+    inFlight_[slot] = p;
+    return p;
+  }
+  std::vector<B200Valuation> collect(PendingBatch &p) {
+    if (p.collected) throw std::runtime_error("this batch has been collected already");
+    std::lock_guard<std::mutex> guard(s_->execMutex);
+    p.collected = true;
+    for (void *st : p.streams) s_->dev->sync(st);
     bool redo = false;
-    std::vector<B200Valuation> outs = executeManyLocked(program, inputs, redo);
+    for (Executor *ex : p.execs) if (ex->flagsRaised()) redo = true;
     if (redo) {
       // a digit of a rotated ciphertext held a zero coefficient: the shared mod-up of that rotation group is not SEAL's value
       // (ops_impl.hpp hoisted_modup).  Redo the call on plans without it -- exact, and from now on for this context.
       if (verbosity() >= 1) std::fprintf(stderr, "EVA: zero digit coefficient met; rotation groups of this context no longer share their mod-up\n");
       options.hoistModUp = false;      // executorFor rebuilds every plan whose option differs
-      outs = executeManyLocked(program, inputs, redo);
+      p.outs.clear(); p.streams.clear(); p.execs.clear();
+      enqueueLocked(p);
+      for (void *st : p.streams) s_->dev->sync(st);
     }
-    return outs;
+    return std::move(p.outs);
   }
-  std::vector<B200Valuation> executeManyLocked(Program &program, const std::vector<const B200Valuation *> &inputs, bool &redo) {
+  static constexpr int kSlotReplicas = 4096;   // replica numbers of slot s: s * kSlotReplicas + r
+  void enqueueLocked(PendingBatch &p) {
+    Program &program = *p.program;
+    const std::vector<const B200Valuation *> &inputs = p.inputs;
     const int B = (int)inputs.size();
-    redo = false;
     const int F = std::max(1, std::min(options.fuse, B));
-    std::vector<B200Valuation> outs(B);
-    std::vector<void *> streams;
+    const int base = p.slot * kSlotReplicas;
+    std::vector<B200Valuation> &outs = p.outs;
+    outs.assign(B, B200Valuation());
+    std::vector<void *> &streams = p.streams;
     const u64 N = s_->dev->N();
     static const bool trace = std::getenv("EVAB_TRACE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
-    double tPlan = 0, tStage = 0, tRun = 0, tDown = 0;
+    double tPlan = 0, tStage = 0, tRun = 0;
     auto t00 = now();
     // replicas are bounded by device memory (an arena each): with R replicas chunk g runs on replica g % R
     // after that replica's previous chunk has completed (its outputs are already on their way to the host)
-    int R = (B + F - 1) / F;
+    int R = std::min((B + F - 1) / F, kSlotReplicas);
     {
-      Executor &first = executorFor(program, std::min(F, B), 0);
-      std::size_t have = 1;   // replica 0 exists; count the ones already built for this program
-      while ((int)have < R && program.attachment(planKey(std::min(F, B), (int)have))) have++;
+      Executor &first = executorFor(program, std::min(F, B), base);
+      std::size_t have = 1;   // the slot's first replica exists; count the ones already built for this program
+      while ((int)have < R && program.attachment(planKey(std::min(F, B), base + (int)have))) have++;
       if ((int)have < R) {    // new arenas are needed: how many fit?  (cudaMemGetInfo is slow: never on the steady path)
         std::size_t freeB = 0, totalB = 0;
         check(evab_mem_info(s_->dev->ctx(), &freeB, &totalB));
@@ -224,11 +264,12 @@ public:
       const int nb = std::min(F, B - b0);
       const int r = g % R;
       auto t0 = now();
-      Executor &ex = executorFor(program, nb, r);
+      Executor &ex = executorFor(program, nb, base + r);
       void *st = ex.mainStream();
       if (busy[r]) s_->dev->sync(st);   // the replica's arena is reused: wait for its previous chunk
       busy[r] = 1;
       if (std::find(streams.begin(), streams.end(), st) == streams.end()) streams.push_back(st);
+      if (std::find(p.execs.begin(), p.execs.end(), &ex) == p.execs.end()) p.execs.push_back(&ex);
       auto t1 = now();
       for (int b = 0; b < nb; b++) stageInputs(ex, program, *inputs[b0 + b], st, b);
       auto t2 = now();
@@ -253,17 +294,9 @@ public:
           }
         }
     }
-    auto t4 = now();
-    for (void *st : streams) s_->dev->sync(st);
-    for (int b0 = 0, g = 0; b0 < B; b0 += F, g++)
-      if (g < R && executorFor(program, std::min(F, B - b0), g % R).flagsRaised()) redo = true;
-    if (trace) {
-      auto t5 = now();
-      std::fprintf(stderr, "[evab] executeMany B=%d F=%d: plan %.3f stage %.3f run %.3f enqueue-total %.3f sync %.3f ms\n", B, F, tPlan * 1e3, tStage * 1e3, tRun * 1e3,
-                   std::chrono::duration<double>(t4 - t00).count() * 1e3, std::chrono::duration<double>(t5 - t4).count() * 1e3);
-    }
-    (void)tDown;
-    return outs;
+    if (trace)
+      std::fprintf(stderr, "[evab] enqueue B=%d F=%d slot=%d: plan %.3f stage %.3f run %.3f enqueue-total %.3f ms\n", B, F, p.slot, tPlan * 1e3, tStage * 1e3, tRun * 1e3,
+                   std::chrono::duration<double>(now() - t00).count() * 1e3);
   }
   std::shared_ptr<Shared> shared() const { return s_; }
   ExecOptions options;
@@ -271,6 +304,7 @@ public:
 private:
   std::shared_ptr<Shared> s_;
   std::uint64_t id_ = 0;
+  std::weak_ptr<PendingBatch> inFlight_[8];
 };
 
 class B200Secret {

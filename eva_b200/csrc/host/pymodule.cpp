@@ -140,6 +140,7 @@ PYBIND11_MODULE(_eva_b200, m) {
         return py::make_tuple("raw", std::get<std::shared_ptr<ConstantValue>>(sv)->values(), 0.0);
       });
 
+  py::class_<PendingBatch, std::shared_ptr<PendingBatch>>(mb, "PendingBatch", "a submitted, not yet collected execute_batch");
   py::class_<B200Public>(mb, "B200Public", "The public part of the context: encryption and execution on the GPU")
       .def("encrypt", &B200Public::encrypt, py::arg("inputs"), py::arg("signature"))
       .def("execute", &B200Public::execute, py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>())
@@ -147,6 +148,16 @@ PYBIND11_MODULE(_eva_b200, m) {
       .def("execute_batch", [](B200Public &p, Program &prog, const std::vector<const B200Valuation *> &in) { return p.executeMany(prog, in); },
            py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>(),
            "Execute one compiled program on a list of valuations with batched kernels; returns a list of valuations")
+      // pipelined execute_batch: the handle keeps the caller's valuations alive until result()
+      .def("execute_batch_async", [](B200Public &p, Program &prog, py::list inputs, int slot) {
+             std::vector<const B200Valuation *> in;
+             for (auto h : inputs) in.push_back(h.cast<const B200Valuation *>());
+             std::shared_ptr<PendingBatch> pb;
+             { py::gil_scoped_release rel; pb = p.submitMany(prog, in, slot); }
+             return py::make_tuple(pb, inputs);
+           }, py::arg("program"), py::arg("inputs"), py::arg("slot") = 0,
+           "Enqueue execute_batch (H2D, plan replays, D2H) and return (handle, inputs); collect with execute_batch_result(handle).  Batches in different slots (0..7) overlap")
+      .def("execute_batch_result", [](B200Public &p, std::shared_ptr<PendingBatch> pb) { py::gil_scoped_release rel; return p.collect(*pb); }, py::arg("handle"))
       .def("set_options", [](B200Public &p, int streams, bool graph, bool cache, bool dedup, int fuse, bool fuseSums, bool hoist, bool uniformEncode, bool dedupTerms, bool hoistModUp, bool approxHoist, int rotationChunk) {
              p.options.numStreams = streams; p.options.useGraph = graph; p.options.cacheConstants = cache; p.options.dedupConstants = dedup;
              p.options.fuse = fuse; p.options.fuseSums = fuseSums; p.options.hoistRotations = hoist; p.options.uniformEncode = uniformEncode;

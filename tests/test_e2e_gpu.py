@@ -386,3 +386,35 @@ def test_approx_hoist_plan_shapes():
         e_exact, e_approx = valuation_mse(exact, reference), valuation_mse(approx, reference)
         assert e_exact < 1e-6 and e_approx < 4 * e_exact + 1e-12, (body.__name__, e_exact, e_approx)
         assert valuation_mse(approx, approx2) == 0.0, body.__name__
+
+
+def test_pipelined_execute_batch():
+    """execute_batch_async / execute_batch_result: two batches in flight on disjoint plan replicas give the bits of the blocking
+    call; a slot takes one batch at a time; a handle that is dropped uncollected waits for its copies"""
+    import numpy as np
+    from eva.ckks import CKKSCompiler
+    from eva.seal import generate_keys
+    from tests_programs import sobel
+    compiled, params, signature = CKKSCompiler({'warn_vec_size': 'false'}).compile(sobel(32, 32))
+    public_ctx, secret_ctx = generate_keys(params)
+    rng = np.random.default_rng(2)
+    batches = [[public_ctx.encrypt({'image': list(rng.uniform(0, 1, 1024))}, signature) for _ in range(3)] for _ in range(3)]
+    want = [public_ctx.execute_batch(compiled, b) for b in batches]
+
+    def same(a, b):
+        for x, y in zip(a, b):
+            for name in x.names():
+                assert np.array_equal(np.asarray(x.get(name)[1]), np.asarray(y.get(name)[1]))
+    h0 = public_ctx.execute_batch_async(compiled, batches[0], 0)
+    h1 = public_ctx.execute_batch_async(compiled, batches[1], 1)
+    with pytest.raises(RuntimeError, match="slot in use"):
+        public_ctx.execute_batch_async(compiled, batches[2], 1)
+    same(public_ctx.execute_batch_result(h0[0]), want[0])
+    h2 = public_ctx.execute_batch_async(compiled, batches[2], 0)
+    same(public_ctx.execute_batch_result(h1[0]), want[1])
+    same(public_ctx.execute_batch_result(h2[0]), want[2])
+    with pytest.raises(RuntimeError, match="collected already"):
+        public_ctx.execute_batch_result(h2[0])
+    h3 = public_ctx.execute_batch_async(compiled, batches[0], 2)
+    del h3                                   # never collected
+    same(public_ctx.execute_batch(compiled, batches[0]), want[0])
