@@ -197,7 +197,7 @@ def measure_workload(args, wl, steps, rank, world, local):
     for _ in range(max(3, args.warmup)):       # warm the e2e path (same plan replicas; fills the pinned-buffer pool)
         outs = pub.execute_batch(prog, all_vals)
     for _ in range(max(3, args.warmup)):       # ... and the second slot of the pipelined form
-        outs = pub.execute_batch_result(pub.execute_batch_async(prog, all_vals, 1)[0])
+        outs = pub.execute_batch_result(pub.execute_batch_async(prog, all_vals, 1))
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -242,9 +242,9 @@ def measure_workload(args, wl, steps, rank, world, local):
     for i in range(steps):
         nxt = pub.execute_batch_async(prog, all_vals, i & 1)
         if pending is not None:
-            outs = pub.execute_batch_result(pending[0])
+            outs = pub.execute_batch_result(pending)
         pending = nxt
-    outs = pub.execute_batch_result(pending[0])
+    outs = pub.execute_batch_result(pending)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()

@@ -70,7 +70,7 @@ struct PendingBatch {
   std::vector<const B200Valuation *> inputs;   // the caller keeps them alive until collect()
   std::vector<B200Valuation> outs;
   std::vector<void *> streams;
-  std::vector<Executor *> execs;
+  std::vector<std::shared_ptr<PlanHolder>> plans;   // the plans it runs on stay alive until it is collected (set_options may replace them meanwhile)
   int slot = 0;
   bool collected = false;
   std::shared_ptr<Shared> keep;
@@ -123,7 +123,8 @@ public:
   // one plan (arena, streams, captured graph) per (context, batch, replica); replicas of the same
   // batch size run concurrently in executeMany
   std::uint64_t planKey(int batch, int replica) const { return (id_ << 32) | ((std::uint64_t)replica << 16) | (std::uint64_t)batch; }
-  Executor &executorFor(Program &program, int batch = 1, int replica = 0) {
+  Executor &executorFor(Program &program, int batch = 1, int replica = 0) { return *holderFor(program, batch, replica)->exec; }
+  std::shared_ptr<PlanHolder> holderFor(Program &program, int batch = 1, int replica = 0) {
     if (batch < 1 || batch > 65535 || replica < 0 || replica > 65535) throw std::invalid_argument("batch / replica out of range");
     const std::uint64_t key = planKey(batch, replica);
     auto h = std::static_pointer_cast<PlanHolder>(program.attachment(key));
@@ -137,7 +138,7 @@ public:
       h->termCount = program.termCount();
       program.attach(key, h);
     }
-    return *h->exec;
+    return h;
   }
   void dropExecutor(Program &program, int batch = 1, int replica = 0) { program.attach(planKey(batch, replica), nullptr); }
 
@@ -216,13 +217,13 @@ public:
     p.collected = true;
     for (void *st : p.streams) s_->dev->sync(st);
     bool redo = false;
-    for (Executor *ex : p.execs) if (ex->flagsRaised()) redo = true;
+    for (auto &h : p.plans) if (h->exec->flagsRaised()) redo = true;
     if (redo) {
       // a digit of a rotated ciphertext held a zero coefficient: the shared mod-up of that rotation group is not SEAL's value
       // (ops_impl.hpp hoisted_modup).  Redo the call on plans without it -- exact, and from now on for this context.
       if (verbosity() >= 1) std::fprintf(stderr, "EVA: zero digit coefficient met; rotation groups of this context no longer share their mod-up\n");
       options.hoistModUp = false;      // executorFor rebuilds every plan whose option differs
-      p.outs.clear(); p.streams.clear(); p.execs.clear();
+      p.outs.clear(); p.streams.clear(); p.plans.clear();
       enqueueLocked(p);
       for (void *st : p.streams) s_->dev->sync(st);
     }
@@ -264,12 +265,13 @@ public:
       const int nb = std::min(F, B - b0);
       const int r = g % R;
       auto t0 = now();
-      Executor &ex = executorFor(program, nb, base + r);
+      std::shared_ptr<PlanHolder> holder = holderFor(program, nb, base + r);
+      Executor &ex = *holder->exec;
       void *st = ex.mainStream();
       if (busy[r]) s_->dev->sync(st);   // the replica's arena is reused: wait for its previous chunk
       busy[r] = 1;
       if (std::find(streams.begin(), streams.end(), st) == streams.end()) streams.push_back(st);
-      if (std::find(p.execs.begin(), p.execs.end(), &ex) == p.execs.end()) p.execs.push_back(&ex);
+      if (std::find(p.plans.begin(), p.plans.end(), holder) == p.plans.end()) p.plans.push_back(holder);
       auto t1 = now();
       for (int b = 0; b < nb; b++) stageInputs(ex, program, *inputs[b0 + b], st, b);
       auto t2 = now();

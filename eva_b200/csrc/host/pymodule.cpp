@@ -26,6 +26,14 @@ static void requireShape(const u64arr &a, std::initializer_list<std::size_t> sha
   if (!ok) throw std::runtime_error(std::string(what) + " does not match the parameters (modulus count / degree)");
 }
 
+// execute_batch_async handle: the batch plus the Python objects it reads from.  Destroyed with the GIL held (the batch first:
+// it waits for its copies before the valuations may go)
+struct PyPending {
+  std::shared_ptr<evab::PendingBatch> batch;
+  py::object program, inputs;
+  ~PyPending() { batch.reset(); }
+};
+
 PYBIND11_MODULE(_eva_b200, m) {
   m.doc() = "B200-native EVA backend";
 
@@ -140,7 +148,7 @@ PYBIND11_MODULE(_eva_b200, m) {
         return py::make_tuple("raw", std::get<std::shared_ptr<ConstantValue>>(sv)->values(), 0.0);
       });
 
-  py::class_<PendingBatch, std::shared_ptr<PendingBatch>>(mb, "PendingBatch", "a submitted, not yet collected execute_batch");
+  py::class_<PyPending, std::shared_ptr<PyPending>>(mb, "PendingBatch", "a submitted, not yet collected execute_batch");
   py::class_<B200Public>(mb, "B200Public", "The public part of the context: encryption and execution on the GPU")
       .def("encrypt", &B200Public::encrypt, py::arg("inputs"), py::arg("signature"))
       .def("execute", &B200Public::execute, py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>())
@@ -148,16 +156,22 @@ PYBIND11_MODULE(_eva_b200, m) {
       .def("execute_batch", [](B200Public &p, Program &prog, const std::vector<const B200Valuation *> &in) { return p.executeMany(prog, in); },
            py::arg("program"), py::arg("inputs"), py::call_guard<py::gil_scoped_release>(),
            "Execute one compiled program on a list of valuations with batched kernels; returns a list of valuations")
-      // pipelined execute_batch: the handle keeps the caller's valuations alive until result()
-      .def("execute_batch_async", [](B200Public &p, Program &prog, py::list inputs, int slot) {
+      // pipelined execute_batch: the handle keeps the program and the caller's valuations alive until it is collected
+      .def("execute_batch_async", [](B200Public &p, py::object program, py::list inputs, int slot) {
+             Program &prog = program.cast<Program &>();
              std::vector<const B200Valuation *> in;
              for (auto h : inputs) in.push_back(h.cast<const B200Valuation *>());
-             std::shared_ptr<PendingBatch> pb;
-             { py::gil_scoped_release rel; pb = p.submitMany(prog, in, slot); }
-             return py::make_tuple(pb, inputs);
+             auto out = std::make_shared<PyPending>();
+             { py::gil_scoped_release rel; out->batch = p.submitMany(prog, in, slot); }
+             out->program = program; out->inputs = inputs;
+             return out;
            }, py::arg("program"), py::arg("inputs"), py::arg("slot") = 0,
-           "Enqueue execute_batch (H2D, plan replays, D2H) and return (handle, inputs); collect with execute_batch_result(handle).  Batches in different slots (0..7) overlap")
-      .def("execute_batch_result", [](B200Public &p, std::shared_ptr<PendingBatch> pb) { py::gil_scoped_release rel; return p.collect(*pb); }, py::arg("handle"))
+           "Enqueue execute_batch (H2D, plan replays, D2H) and return a handle; collect with execute_batch_result(handle).  Batches in different slots (0..7) overlap")
+      .def("execute_batch_result", [](B200Public &p, std::shared_ptr<PyPending> h) {
+             std::vector<B200Valuation> outs;
+             { py::gil_scoped_release rel; outs = p.collect(*h->batch); }
+             return outs;
+           }, py::arg("handle"))
       .def("set_options", [](B200Public &p, int streams, bool graph, bool cache, bool dedup, int fuse, bool fuseSums, bool hoist, bool uniformEncode, bool dedupTerms, bool hoistModUp, bool approxHoist, int rotationChunk) {
              p.options.numStreams = streams; p.options.useGraph = graph; p.options.cacheConstants = cache; p.options.dedupConstants = dedup;
              p.options.fuse = fuse; p.options.fuseSums = fuseSums; p.options.hoistRotations = hoist; p.options.uniformEncode = uniformEncode;

@@ -409,12 +409,12 @@ def test_pipelined_execute_batch():
     h1 = public_ctx.execute_batch_async(compiled, batches[1], 1)
     with pytest.raises(RuntimeError, match="slot in use"):
         public_ctx.execute_batch_async(compiled, batches[2], 1)
-    same(public_ctx.execute_batch_result(h0[0]), want[0])
+    same(public_ctx.execute_batch_result(h0), want[0])
     h2 = public_ctx.execute_batch_async(compiled, batches[2], 0)
-    same(public_ctx.execute_batch_result(h1[0]), want[1])
-    same(public_ctx.execute_batch_result(h2[0]), want[2])
+    same(public_ctx.execute_batch_result(h1), want[1])
+    same(public_ctx.execute_batch_result(h2), want[2])
     with pytest.raises(RuntimeError, match="collected already"):
-        public_ctx.execute_batch_result(h2[0])
+        public_ctx.execute_batch_result(h2)
     h3 = public_ctx.execute_batch_async(compiled, batches[0], 2)
     del h3                                   # never collected
     same(public_ctx.execute_batch(compiled, batches[0]), want[0])
