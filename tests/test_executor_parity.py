@@ -129,6 +129,20 @@ def test_without_hoisted_rotations():
         b200.B200Public.set_options = orig
 
 
+@pytest.mark.parametrize("chunk", [1, 3])
+def test_rotation_chunk_sizes(chunk):
+    """rotation_chunk=1: one evab_rotate_modup_prepared call per rotation; 3: the 8 rotations of Sobel's image in chunks of 3 + 3 + 2
+    (default 16: all in one evab_rotate_modup_many call) -- every intermediate identical to the oracle either way"""
+    from eva_b200 import b200
+    orig = b200.B200Public.set_options
+    try:
+        b200.B200Public.set_options = lambda self, **kw: orig(self, **{**kw, "rotation_chunk": chunk})
+        run_both("sobel", lo=0.0, hi=0.2)
+        run_both("harris")
+    finally:
+        b200.B200Public.set_options = orig
+
+
 @pytest.mark.parametrize("name,min_fused", [("sobel", 30), ("harris", 40), ("polynomial", 0), ("feat_hsum", 0), ("feat_mixed", 0), ("wide64", 1)])
 def test_fused_sums_bit_exact(name, min_fused):
     """default executor mode: trees of multiply_plain / add evaluated by one kernel (evab_sum_terms);
