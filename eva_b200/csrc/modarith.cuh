@@ -55,7 +55,18 @@ struct FoldPrime {
 constexpr int NTT_MAX_PRIMES = 24;
 
 // x >= c ? x - c : x
-EVAB_HD u64 csub(u64 x, u64 c) { return x >= c ? x - c : x; }
+EVAB_HD u64 csub(u64 x, u64 c) {
+#if defined(__CUDA_ARCH__)
+  // x - c with the borrow selecting the result: ptxas keeps the borrow in the carry-out predicate of IADD3.X and selects on it
+  // (IADD3, IADD3.X, SEL, SEL) instead of comparing first (two ISETP more)
+  u32 lo, hi, b;
+  asm("sub.cc.u32 %0, %3, %5;\n\tsubc.cc.u32 %1, %4, %6;\n\tsubc.u32 %2, 0, 0;"
+      : "=r"(lo), "=r"(hi), "=r"(b) : "r"((u32)x), "r"((u32)(x >> 32)), "r"((u32)c), "r"((u32)(c >> 32)));
+  return b ? x : (((u64)hi << 32) | lo);
+#else
+  return x >= c ? x - c : x;
+#endif
+}
 
 // Shoup multiplication by a constant w (ws = floor(w*2^64/p)); any u64 y.
 // Result is congruent to w*y mod p and lies in [0, 2p).
@@ -132,8 +143,7 @@ EVAB_HD u64 madw32(u32 a, u32 b, u64 c) {
 EVAB_HD u64 fold61(u64 x, u32 eps) { return madw32((u32)(x >> 61), eps, x & ((1ull << 61) - 1)); }
 // x < 16p -> canonical [0,p): x = h*2^60 + l == l + h*delta, which is < p + 2^29; one conditional subtraction
 EVAB_HD u64 fold_canon(u64 x, u32 eps, u64 p) {
-  const u64 r = madw32((u32)(x >> 60), eps >> 1, x & ((1ull << 60) - 1));
-  return r >= p ? r - p : r;
+  return csub(madw32((u32)(x >> 60), eps >> 1, x & ((1ull << 60) - 1)), p);
 }
 EVAB_HD u64 fold_mul(u64 y, u64 w, u64 v, u32 eps) {
   const u32 y0 = (u32)y, y1 = (u32)(y >> 32);
