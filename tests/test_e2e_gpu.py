@@ -418,3 +418,23 @@ def test_pipelined_execute_batch():
     h3 = public_ctx.execute_batch_async(compiled, batches[0], 2)
     del h3                                   # never collected
     same(public_ctx.execute_batch(compiled, batches[0]), want[0])
+
+
+def test_approx_hoist_batched_equals_single():
+    """approx_hoist is deterministic: instances fused into one launch (fuse=2, execute_batch) give the bits of separate execute() calls"""
+    import numpy as np
+    from eva.ckks import CKKSCompiler
+    from eva.seal import generate_keys
+    from tests_programs import sobel
+    compiled, params, signature = CKKSCompiler({'warn_vec_size': 'false'}).compile(sobel(32, 32))
+    public_ctx, secret_ctx = generate_keys(params)
+    rng = np.random.default_rng(9)
+    vals = [public_ctx.encrypt({'image': list(rng.uniform(0, 1, 1024))}, signature) for _ in range(4)]
+    public_ctx.set_options(approx_hoist=True, fuse=2)
+    batched = public_ctx.execute_batch(compiled, vals)
+    public_ctx.set_options(approx_hoist=True, fuse=1)
+    for v, b in zip(vals, batched):
+        single = public_ctx.execute(compiled, v)
+        for name in single.names():
+            assert np.array_equal(np.asarray(single.get(name)[1]), np.asarray(b.get(name)[1]))
+    assert public_ctx.plan_stats(compiled)['lazy_sums'] == 2
